@@ -1,0 +1,164 @@
+/*
+ * mrs_b200.h -- C ABI of libmrs_b200.so, the B200 (sm_100a) engine for the rating-prediction hot
+ * path of EloDoyard/movie-recommender-system.
+ *
+ * The reference has no FFI of its own: its boundary is the public surface of the Scala package
+ * object `shared.predictions` (src/main/scala/shared/predictions.scala, "P:" below).  Each entry
+ * point here names the reference function(s) it replaces; the JNI/Scala binding a maintainer
+ * would add is shown in INTEGRATION.md.  Plain pointers and sizes only; no exceptions cross the
+ * boundary.  Every function returns 0 (MRS_OK) or a negative mrs_status; mrs_last_error() gives a
+ * thread-local message for the last failure on the calling thread.
+ *
+ * Model of use (fit -> device-resident model -> batched query):
+ *   engine  = one CUDA device + one stream (one process per GPU; multi-GPU is sharded by the host
+ *             layer with one collective on the exchange buffer, see mrs_fit_local/mrs_fit_finish)
+ *   ratings = a device-resident rating set: user-major CSR + item-major CSC (+ sorted COO)
+ *   model   = global / per-user / per-item averages, item average deviations      (P:94-237, 246-391)
+ *   sim     = user-user similarity (uniform | cosine | jaccard) with optional top-k (P:400-481, 596-649)
+ * Ids are the reference's original Int ids (>= 0); tables are direct-indexed by id.
+ * Handles are not thread-safe; use one engine per host thread.
+ */
+#ifndef MRS_B200_H
+#define MRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MRS_API __attribute__((visibility("default")))
+#else
+#define MRS_API
+#endif
+
+typedef struct mrs_engine mrs_engine;
+typedef struct mrs_ratings mrs_ratings;
+typedef struct mrs_model mrs_model;
+typedef struct mrs_sim mrs_sim;
+
+typedef enum {
+  MRS_OK = 0,
+  MRS_ERR_INVALID = -1,     /* bad argument (NULL handle, negative id, unknown kind ...) */
+  MRS_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has the CUDA error string) */
+  MRS_ERR_NOMEM = -3,
+  MRS_ERR_DUPLICATE = -4,   /* duplicate (user,item) pair in a rating set (P:168 keeps the last; unsupported here) */
+  MRS_ERR_IO = -5,          /* file missing / malformed row (the reference throws at P:41) */
+  MRS_ERR_UNSUPPORTED = -6  /* shape outside what this build handles; never a silent CPU fallback */
+} mrs_status;
+
+/* vectors / scalars of a fitted model */
+typedef enum {
+  MRS_GLOBAL_AVG = 0,   /* average            P:94,  getGlobalAvg     P:265 */
+  MRS_USER_AVG = 1,     /* usersAvg           P:113, getUsersAvg      P:274 */
+  MRS_ITEM_AVG = 2,     /* itemsAvg           P:134, getItemsAvg      P:295 */
+  MRS_ITEM_AVG_DEV = 3  /* itemsAvgDev        P:176, getItemsAvgDev   P:336 */
+} mrs_vec_kind;
+
+/* predictors ((Int,Int) => Double closures of the reference) */
+typedef enum {
+  MRS_PRED_GLOBAL = 0,       /* computeAvgRating   P:101 */
+  MRS_PRED_USER = 1,         /* computeUserAvg     P:120, usersAvgSpark    P:281 */
+  MRS_PRED_ITEM = 2,         /* computeItemAvg     P:141, itemsAvgSpark    P:302 */
+  MRS_PRED_ITEMDEV = 3,      /* computeItemAvgDev  P:193, itemsAvgDevSpark P:350 */
+  MRS_PRED_BASELINE = 4,     /* computePrediction  P:205, baselinePredictorSpark P:362 */
+  MRS_PRED_PERSONALIZED = 5, /* predictor(ratings, weightedSumDeviation(ratings, sim))  P:489-586; needs an mrs_sim */
+  MRS_PRED_WSD = 6           /* weightedSumDeviation(ratings, sim) itself              P:489-549; needs an mrs_sim; mrs_predict only */
+} mrs_pred_kind;
+
+typedef enum {
+  MRS_SIM_UNIFORM = 0,  /* similarityOne                      P:400 */
+  MRS_SIM_COSINE = 1,   /* adjustedCosineSimilarityFunction   P:407-433 (+ preprocessedRating P:470-481) */
+  MRS_SIM_JACCARD = 2   /* jaccardCoefficient                 P:440-464 */
+} mrs_sim_kind;
+
+/* ---- library ---- */
+MRS_API const char* mrs_last_error(void);
+MRS_API const char* mrs_version(void);
+/* number of kernel launches issued by this library on this process so far (bench.py's gpu_launches) */
+MRS_API int64_t mrs_launch_count(void);
+
+/* ---- engine ---- */
+/* cuda_stream: a cudaStream_t to enqueue on (e.g. the caller's current stream), or NULL to create one. */
+MRS_API int32_t mrs_engine_create(int32_t device, void* cuda_stream, mrs_engine** out);
+MRS_API void mrs_engine_destroy(mrs_engine* e);
+MRS_API int32_t mrs_engine_sync(mrs_engine* e);
+
+/* Per-kernel device timing (diagnostics; what bench.py's roofline uses): between begin and end every kernel the
+ * library launches on this engine is bracketed by CUDA events on the engine's stream.  mrs_profile_end syncs and
+ * returns one '\n'-separated label per launch in names_out and its duration in milliseconds in ms_out. */
+MRS_API int32_t mrs_profile_begin(mrs_engine* e);
+MRS_API int32_t mrs_profile_end(mrs_engine* e, char* names_out, int64_t names_cap, float* ms_out, int32_t cap, int32_t* n_out);
+
+/* ---- ratings: replaces `load(...).collect()` / RDD[Rating] materialisation (P:35-49; call sites
+ * predict/Baseline.scala:40-42, distributed/DistributedBaseline.scala:41-43) ---- */
+/* Inputs are host arrays (Rating.user, Rating.item, Rating.rating); they are copied, never retained.
+ * n_users_dim / n_items_dim: minimum table sizes (max id + 1) to allocate, or 0 to derive them from the data;
+ * ranks of a sharded run pass the global values so that their exchange buffers line up. */
+MRS_API int32_t mrs_ratings_from_coo(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings,
+                                     int64_t n, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
+/* Same parse rules as P:35-49: split on `sep`, trim, keep the row iff column 0 parses as an Int. */
+MRS_API int32_t mrs_ratings_from_file(mrs_engine* e, const char* path, const char* sep, mrs_ratings** out);
+/* value_kind: 0 = every rating is a multiple of 0.5 in [0,127.5] and is stored as a 1-byte code; 1 = fp64 values */
+MRS_API int32_t mrs_ratings_info(const mrs_ratings* r, int64_t* n, int32_t* n_users_dim, int32_t* n_items_dim, int32_t* value_kind);
+/* bytes of device memory the hot kernels read per pass over this set: [0] user-major payload, [1] item-major payload,
+ * [2] sorted-COO payload (the figures bench.py's roofline uses) */
+MRS_API int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* bytes3);
+MRS_API void mrs_ratings_destroy(mrs_ratings* r);
+
+/* ---- fit: replaces the eager part of computePrediction (P:205-214) / baselinePredictorSpark (P:362-368)
+ * and of computeAvgRating/computeUserAvg/computeItemAvg/computeItemAvgDev ---- */
+/* `train` must outlive the model.  mrs_fit == mrs_fit_local + mrs_fit_finish (+ a stream sync). */
+MRS_API int32_t mrs_fit(mrs_engine* e, const mrs_ratings* train, mrs_model** out);
+/* Asynchronous pieces (enqueue on the engine's stream, no host sync); *out may be an existing model of the same
+ * train set, in which case its buffers are reused (this is what a timed loop calls). */
+MRS_API int32_t mrs_fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
+/* The exchange buffer written by mrs_fit_local: n_doubles fp64 values on the device,
+ * [ sum of deviations per item | sum of ratings per item | count per item | sum of all ratings | count ].
+ * A sharded run all-reduces (sum) it across ranks between mrs_fit_local and mrs_fit_finish: this is the one
+ * collective that replaces the reduceByKey/collect shuffles of P:267-268 and the sum/count of P:247. */
+MRS_API int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, int64_t* n_doubles);
+MRS_API int32_t mrs_fit_finish(mrs_model* m);
+MRS_API void mrs_model_destroy(mrs_model* m);
+
+MRS_API int32_t mrs_model_scalar(const mrs_model* m, int32_t vec_kind, double* out);
+/* value for one original id with the reference's fallbacks (unknown user/item -> global average; unknown item
+ * deviation -> 0.0).  known_out (optional) = 1 iff the id occurs in the train set. */
+MRS_API int32_t mrs_model_lookup(const mrs_model* m, int32_t vec_kind, int32_t id, double* out, int32_t* known_out);
+/* whole table, direct-indexed by id (entries of unknown ids hold the fallback); counts_out optional */
+MRS_API int32_t mrs_model_vector(const mrs_model* m, int32_t vec_kind, double* vals_out, int32_t* counts_out, int64_t cap, int64_t* n_out);
+
+/* ---- similarity: replaces adjustedCosineSimilarityFunction / jaccardCoefficient / similarityOne and
+ * getNeighbors / getSimilarity (P:596-649).  k <= 0: no neighbourhood restriction. ---- */
+MRS_API int32_t mrs_fit_similarity(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** out);
+MRS_API int32_t mrs_fit_similarity_async(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** inout);
+/* change k without recomputing similarities (the sorted lists have the prefix property) */
+MRS_API int32_t mrs_sim_set_k(mrs_sim* s, int32_t k);
+MRS_API int32_t mrs_similarity(const mrs_sim* s, int32_t u, int32_t v, double* out);
+/* first min(k, candidates) neighbours of u, order (similarity desc, user id asc); P:603-616 */
+MRS_API int32_t mrs_neighbors(const mrs_sim* s, int32_t u, int32_t k, int32_t* ids_out, double* sims_out, int32_t cap, int32_t* n_out);
+/* per-rating values in user-major order (user asc, item asc): which = 0 -> computeNormalizeDeviation (P:155-169),
+ * which = 1 -> preprocessedRating (P:470-481).  Any of the output arrays may be NULL; n_out gets the entry count. */
+MRS_API int32_t mrs_sim_entry_values(const mrs_sim* s, int32_t which, int32_t* users_out, int32_t* items_out, double* vals_out,
+                                     int64_t cap, int64_t* n_out);
+MRS_API void mrs_sim_destroy(mrs_sim* s);
+
+/* ---- batched prediction and fused MAE: replace `predict(u,i)` closures and MAE / MeanAbsoluteErrorSpark
+ * (P:69-86, P:256-258; call sites predict/Baseline.scala:46-67, distributed/DistributedBaseline.scala:46,
+ * predict/Personalized.scala:61-67, predict/kNN.scala:43-44) ---- */
+MRS_API int32_t mrs_predict(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind,
+                            const int32_t* users, const int32_t* items, int64_t n, double* out);
+MRS_API int32_t mrs_mae(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind, const mrs_ratings* test, double* mae_out);
+/* asynchronous form: writes {sum |r - p|, count} as two fp64 to device memory (a sharded run adds them across ranks) */
+MRS_API int32_t mrs_mae_async(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind, const mrs_ratings* test,
+                              void* device_out2);
+
+/* ---- recommendations (P:651-674; call site recommend/Recommender.scala:82-88) ---- */
+MRS_API int32_t mrs_recommend(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind, int32_t user, int32_t n,
+                              int32_t* items_out, double* scores_out, int32_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRS_B200_H */

@@ -1,0 +1,343 @@
+// baseline.cu -- the baseline family of shared/predictions.scala as segmented-reduction kernels:
+//   global / per-user / per-item averages (P:94-148, Spark twins P:265-309), scale()-normalised deviations
+//   (P:155-169, P:316-329), per-item average deviation (P:176-198, P:336-355), the baseline predictor
+//   (P:205-237, P:362-391) and the fused prediction + |error| reduction of MAE (P:69-86, P:256-258).
+//
+// Every kernel here is HBM/L2-bound integer/byte + fp64 work: no tensor cores.  Accumulation is fp64; rating
+// sums of half-star data are exact in any order, deviation sums are reduced in a fixed order
+// (lane-strided inside a chunk, xor-shuffle tree, chunks of a column in ascending order), so results are
+// run-to-run bit-reproducible.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace mrs {
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- K1: per-user chunk sums of ratings (user-major values only: 1 B/rating for half-star codes)
+template <typename VT>
+__global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restrict__ uval, const int32_t* __restrict__ urow,
+                                                            const int32_t* __restrict__ chunk_seg,
+                                                            const int32_t* __restrict__ chunk_begin, int32_t n_chunks,
+                                                            double* __restrict__ upart) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int32_t c = blockIdx.x * warps_per_block + (threadIdx.x >> 5); c < n_chunks; c += gridDim.x * warps_per_block) {
+    const int32_t seg = chunk_seg[c];
+    const int32_t b = chunk_begin[c];
+    const int32_t e = min(b + kUserChunk, urow[seg + 1]);
+    double s;
+    if (sizeof(VT) == 1) {
+      uint32_t acc = 0;  // <= 2048 * 255: exact
+      for (int32_t p = b + lane; p < e; p += 32) acc += (uint32_t)uval[p];
+      acc = __reduce_add_sync(0xffffffffu, acc);
+      s = 0.5 * (double)acc;
+    } else {
+      double acc = 0.0;
+      for (int32_t p = b + lane; p < e; p += 32) acc += (double)uval[p];
+      s = warp_sum(acc);
+    }
+    if (lane == 0) upart[c] = s;
+  }
+}
+
+// ---- K1b: per-user average (-1.0 sentinel for users without ratings) + global rating sum / count
+__global__ void __launch_bounds__(256) user_finalize_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ seg_chunk_ptr,
+                                                           const double* __restrict__ upart, int32_t n_users,
+                                                           double* __restrict__ uavg, double* __restrict__ gsum_gcnt) {
+  __shared__ double sh[8];
+  const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (u < n_users) {
+    const int32_t cnt = urow[u + 1] - urow[u];
+    for (int32_t c = seg_chunk_ptr[u]; c < seg_chunk_ptr[u + 1]; ++c) s += upart[c];
+    uavg[u] = cnt ? s / (double)cnt : -1.0;  // P:18 sum/length; unknown user marked like P:222 getOrElse(user,-1.0)
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0 && t != 0.0) atomicAdd(&gsum_gcnt[0], t);  // exact for half-star data => order-independent
+  }
+  if (u == 0) gsum_gcnt[1] = (double)urow[n_users];
+}
+
+// ---- K2: per-item chunk sums of normalised deviations and of ratings (item-major: user id + value),
+//      gathering the rater's average from the per-user table
+template <typename VT>
+__global__ void __launch_bounds__(256) item_chunk_dev_kernel(const int32_t* __restrict__ irow, const VT* __restrict__ ival,
+                                                            const int32_t* __restrict__ icolp,
+                                                            const int32_t* __restrict__ chunk_seg,
+                                                            const int32_t* __restrict__ chunk_begin, int32_t n_chunks,
+                                                            const double* __restrict__ uavg, double* __restrict__ ipart) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int32_t c = blockIdx.x * warps_per_block + (threadIdx.x >> 5); c < n_chunks; c += gridDim.x * warps_per_block) {
+    const int32_t seg = chunk_seg[c];
+    const int32_t b = chunk_begin[c];
+    const int32_t e = min(b + kItemChunk, icolp[seg + 1]);
+    double dsum = 0.0, rsum = 0.0;
+#pragma unroll 4
+    for (int32_t p = b + lane; p < e; p += 32) {
+      const double r = decode_value(ival[p]);
+      const double a = __ldg(&uavg[irow[p]]);
+      dsum += deviation_fn(r, a);  // P:167 / P:327
+      rsum += r;
+    }
+    dsum = warp_sum(dsum);
+    rsum = warp_sum(rsum);
+    if (lane == 0) {
+      ipart[c] = dsum;
+      ipart[n_chunks + c] = rsum;
+    }
+  }
+}
+
+// ---- K2b: chunk partials -> exchange buffer [devsum | ratesum | count] (P:176-186 (sum,count); P:267 reduceByKey)
+__global__ void __launch_bounds__(256) item_partial_kernel(const int32_t* __restrict__ icolp, const int32_t* __restrict__ seg_chunk_ptr,
+                                                          const double* __restrict__ ipart, int32_t n_chunks, int32_t n_items,
+                                                          double* __restrict__ xbuf) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  double ds = 0.0, rs = 0.0;
+  for (int32_t c = seg_chunk_ptr[i]; c < seg_chunk_ptr[i + 1]; ++c) {
+    ds += ipart[c];
+    rs += ipart[n_chunks + c];
+  }
+  xbuf[i] = ds;
+  xbuf[n_items + i] = rs;
+  xbuf[2 * n_items + i] = (double)(icolp[i + 1] - icolp[i]);
+}
+
+// ---- K2c: (after the optional cross-rank sum of xbuf) per-item averages and the global average
+__global__ void __launch_bounds__(256) item_finalize_kernel(const double* __restrict__ xbuf, int32_t n_items,
+                                                           double* __restrict__ idevavg, double* __restrict__ iavg,
+                                                           double* __restrict__ gavg) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    const double gs = xbuf[3 * n_items], gc = xbuf[3 * n_items + 1];
+    gavg[0] = gc > 0.0 ? gs / gc : 0.0;  // P:18 mean of an empty Seq is 0.0
+  }
+  if (i >= n_items) return;
+  const double cnt = xbuf[2 * n_items + i];
+  idevavg[i] = cnt > 0.0 ? xbuf[i] / cnt : 0.0;                 // P:185 x._1/x._2 ; unknown item -> 0.0 (P:197)
+  iavg[i] = cnt > 0.0 ? xbuf[n_items + i] / cnt : nan("");      // unknown item -> global average at query time (P:147)
+}
+
+// ---- prediction of one (u,i) for the five closed-form predictors
+template <int KIND>
+__device__ __forceinline__ double predict_one(int32_t u, int32_t i, int32_t n_users, int32_t n_items,
+                                              const double* __restrict__ uavg, const double* __restrict__ idevavg,
+                                              const double* __restrict__ iavg, double gavg) {
+  if (KIND == MRS_PRED_GLOBAL) return gavg;  // P:105
+  if (KIND == MRS_PRED_USER) {               // P:126
+    const double a = (u >= 0 && u < n_users) ? __ldg(&uavg[u]) : -1.0;
+    return a < 0.0 ? gavg : a;
+  }
+  if (KIND == MRS_PRED_ITEM) {  // P:147
+    const double a = (i >= 0 && i < n_items) ? __ldg(&iavg[i]) : nan("");
+    return isnan(a) ? gavg : a;
+  }
+  if (KIND == MRS_PRED_ITEMDEV) return (i >= 0 && i < n_items) ? __ldg(&idevavg[i]) : 0.0;  // P:197
+  // baseline, P:217-236
+  const double a = (u >= 0 && u < n_users) ? __ldg(&uavg[u]) : -1.0;
+  if (a < 0.0) return gavg;  // P:222-224
+  const double d = (i >= 0 && i < n_items) ? __ldg(&idevavg[i]) : 0.0;
+  return combine_fn(a, d);  // P:229
+}
+
+// ---- K3: fused predict + |r - p| + reduction over the sorted COO of the test set (P:69-86).
+// Per-block partials are combined by the last block in block order: deterministic.
+template <typename VT, int KIND>
+__global__ void __launch_bounds__(256) predict_mae_kernel(const int32_t* __restrict__ tu, const int32_t* __restrict__ ti,
+                                                         const VT* __restrict__ tv, int64_t n, int32_t n_users, int32_t n_items,
+                                                         const double* __restrict__ uavg, const double* __restrict__ idevavg,
+                                                         const double* __restrict__ iavg, const double* __restrict__ gavg_p,
+                                                         double* __restrict__ part, unsigned int* __restrict__ counter,
+                                                         double* __restrict__ out2) {
+  __shared__ double sh[8];
+  __shared__ bool is_last;
+  const double gavg = gavg_p[0];
+  double acc = 0.0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const double r = decode_value(tv[p]);
+    const double pr = predict_one<KIND>(tu[p], ti[p], n_users, n_items, uavg, idevavg, iavg, gavg);
+    acc += fabs(r - pr);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      part[blockIdx.x] = t;
+      __threadfence();
+      const unsigned int done = atomicAdd(counter, 1u);
+      is_last = (done == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(&part[b]);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+      out2[0] = s;
+      out2[1] = (double)n;
+      *counter = 0;  // re-arm for the next launch
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) predict_pairs_kernel(const int32_t* __restrict__ us, const int32_t* __restrict__ is, int64_t n,
+                                                           int32_t n_users, int32_t n_items, const double* __restrict__ uavg,
+                                                           const double* __restrict__ idevavg, const double* __restrict__ iavg,
+                                                           const double* __restrict__ gavg_p, double* __restrict__ out) {
+  const double gavg = gavg_p[0];
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    out[p] = predict_one<KIND>(us[p], is[p], n_users, n_items, uavg, idevavg, iavg, gavg);
+}
+
+inline int chunk_grid(int32_t n_chunks, int sm_count) {
+  const int per_block = 8;  // warps per 256-thread block
+  int g = (n_chunks + per_block - 1) / per_block;
+  return std::max(1, std::min(g, sm_count * 8));
+}
+
+template <typename VT>
+int32_t launch_fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model* m) {
+  cudaStream_t st = e->stream;
+  const int32_t NI = R->n_items, NU = R->n_users;
+  MRS_CUDA(cudaMemsetAsync(m->xbuf + 3 * (size_t)NI, 0, 2 * sizeof(double), st));
+  if (R->uch.n_chunks > 0) {
+    user_chunk_sum_kernel<VT><<<chunk_grid(R->uch.n_chunks, e->sm_count), 256, 0, st>>>(
+        (const VT*)R->uval, R->urow, R->uch.chunk_seg, R->uch.chunk_begin, R->uch.n_chunks, m->upart);
+    mark(e, "user_chunk_sum");
+  }
+  user_finalize_kernel<<<(NU + 255) / 256, 256, 0, st>>>(R->urow, R->uch.seg_chunk_ptr, m->upart, NU, m->uavg, m->xbuf + 3 * (size_t)NI);
+  mark(e, "user_finalize");
+  if (R->ich.n_chunks > 0) {
+    item_chunk_dev_kernel<VT><<<chunk_grid(R->ich.n_chunks, e->sm_count), 256, 0, st>>>(
+        R->irow, (const VT*)R->ival, R->icolp, R->ich.chunk_seg, R->ich.chunk_begin, R->ich.n_chunks, m->uavg, m->ipart);
+    mark(e, "item_chunk_dev");
+  }
+  item_partial_kernel<<<(NI + 255) / 256, 256, 0, st>>>(R->icolp, R->ich.seg_chunk_ptr, m->ipart, R->ich.n_chunks, NI, m->xbuf);
+  mark(e, "item_partial");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+template <typename VT, int KIND>
+int32_t launch_mae(const mrs_model* m, const mrs_ratings* T, double* d_out2) {
+  mrs_engine* e = m->eng;
+  int grid = (int)std::min<int64_t>((T->n + 255) / 256, (int64_t)m->mae_part_cap);
+  if (grid < 1) grid = 1;
+  predict_mae_kernel<VT, KIND><<<grid, 256, 0, e->stream>>>(T->coo_u, T->ucol, (const VT*)T->uval, T->n, m->n_users, m->n_items,
+                                                            m->uavg, m->idevavg, m->iavg, m->gavg, m->mae_part, m->counters, d_out2);
+  mark(e, "predict_mae");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+template <typename VT>
+int32_t dispatch_mae(const mrs_model* m, int32_t kind, const mrs_ratings* T, double* d_out2) {
+  switch (kind) {
+    case MRS_PRED_GLOBAL: return launch_mae<VT, MRS_PRED_GLOBAL>(m, T, d_out2);
+    case MRS_PRED_USER: return launch_mae<VT, MRS_PRED_USER>(m, T, d_out2);
+    case MRS_PRED_ITEM: return launch_mae<VT, MRS_PRED_ITEM>(m, T, d_out2);
+    case MRS_PRED_ITEMDEV: return launch_mae<VT, MRS_PRED_ITEMDEV>(m, T, d_out2);
+    case MRS_PRED_BASELINE: return launch_mae<VT, MRS_PRED_BASELINE>(m, T, d_out2);
+    default: set_error("mrs_mae: predictor kind %d needs a similarity handle", kind); return MRS_ERR_INVALID;
+  }
+}
+
+}  // namespace
+
+int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout) {
+  MRS_REQUIRE(e && R && inout, MRS_ERR_INVALID, "mrs_fit: NULL argument");
+  MRS_CUDA(cudaSetDevice(e->device));
+  mrs_model* m = *inout;
+  if (m && m->train != R) {
+    set_error("mrs_fit_local: the model passed for reuse was fitted on a different rating set");
+    return MRS_ERR_INVALID;
+  }
+  if (!m) {
+    m = new mrs_model();
+    m->eng = e;
+    m->train = R;
+    m->n_users = R->n_users;
+    m->n_items = R->n_items;
+    m->mae_part_cap = e->sm_count * 16;
+    int32_t s = MRS_OK;
+    if (s == MRS_OK) s = dev_alloc(&m->upart, (size_t)R->uch.n_chunks);
+    if (s == MRS_OK) s = dev_alloc(&m->uavg, (size_t)R->n_users);
+    if (s == MRS_OK) s = dev_alloc(&m->ipart, 2 * (size_t)R->ich.n_chunks);
+    if (s == MRS_OK) s = dev_alloc(&m->xbuf, 3 * (size_t)R->n_items + 2);
+    if (s == MRS_OK) s = dev_alloc(&m->idevavg, (size_t)R->n_items);
+    if (s == MRS_OK) s = dev_alloc(&m->iavg, (size_t)R->n_items);
+    if (s == MRS_OK) s = dev_alloc(&m->gavg, 1);
+    if (s == MRS_OK) s = dev_alloc(&m->mae_part, (size_t)m->mae_part_cap);
+    if (s == MRS_OK) s = dev_alloc(&m->counters, 8);
+    if (s == MRS_OK && cudaMemsetAsync(m->counters, 0, 8 * sizeof(unsigned int), e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+    if (s != MRS_OK) { mrs_model_destroy(m); return s; }
+    *inout = m;
+  }
+  m->finished = false;
+  m->host_valid = false;
+  return R->value_kind == kValueCode ? launch_fit_local<uint8_t>(e, R, m) : launch_fit_local<double>(e, R, m);
+}
+
+int32_t fit_finish(mrs_model* m) {
+  MRS_REQUIRE(m, MRS_ERR_INVALID, "mrs_fit_finish: NULL model");
+  item_finalize_kernel<<<(m->n_items + 255) / 256, 256, 0, m->eng->stream>>>(m->xbuf, m->n_items, m->idevavg, m->iavg, m->gavg);
+  mark(m->eng, "item_finalize");
+  MRS_CUDA(cudaGetLastError());
+  m->finished = true;
+  m->host_valid = false;
+  return MRS_OK;
+}
+
+int32_t mae_baseline_async(const mrs_model* m, int32_t kind, const mrs_ratings* T, double* d_out2) {
+  MRS_REQUIRE(m && T && d_out2, MRS_ERR_INVALID, "mrs_mae: NULL argument");
+  MRS_REQUIRE(m->finished, MRS_ERR_INVALID, "mrs_mae: model not finished (call mrs_fit_finish)");
+  return T->value_kind == kValueCode ? dispatch_mae<uint8_t>(m, kind, T, d_out2) : dispatch_mae<double>(m, kind, T, d_out2);
+}
+
+int32_t predict_baseline_async(const mrs_model* m, int32_t kind, const int32_t* d_users, const int32_t* d_items, int64_t n,
+                               double* d_out) {
+  MRS_REQUIRE(m && m->finished, MRS_ERR_INVALID, "mrs_predict: model missing or not finished");
+  if (n == 0) return MRS_OK;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)m->eng->sm_count * 16);
+  cudaStream_t st = m->eng->stream;
+#define MRS_LAUNCH_PRED(K) \
+  predict_pairs_kernel<K><<<grid, 256, 0, st>>>(d_users, d_items, n, m->n_users, m->n_items, m->uavg, m->idevavg, m->iavg, m->gavg, d_out)
+  switch (kind) {
+    case MRS_PRED_GLOBAL: MRS_LAUNCH_PRED(MRS_PRED_GLOBAL); break;
+    case MRS_PRED_USER: MRS_LAUNCH_PRED(MRS_PRED_USER); break;
+    case MRS_PRED_ITEM: MRS_LAUNCH_PRED(MRS_PRED_ITEM); break;
+    case MRS_PRED_ITEMDEV: MRS_LAUNCH_PRED(MRS_PRED_ITEMDEV); break;
+    case MRS_PRED_BASELINE: MRS_LAUNCH_PRED(MRS_PRED_BASELINE); break;
+    default: set_error("mrs_predict: predictor kind %d needs a similarity handle", kind); return MRS_ERR_INVALID;
+  }
+#undef MRS_LAUNCH_PRED
+  mark(m->eng, "predict_pairs");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+}  // namespace mrs

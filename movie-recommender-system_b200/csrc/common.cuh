@@ -1,0 +1,208 @@
+// common.cuh -- shared declarations of libmrs_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/mrs_b200.h"
+
+namespace mrs {
+
+// ---------- error plumbing (no exceptions across the C ABI) ----------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define MRS_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      mrs::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return MRS_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define MRS_TRY(expr)                 \
+  do {                                \
+    int32_t _s = (expr);              \
+    if (_s != MRS_OK) return _s;      \
+  } while (0)
+
+#define MRS_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      mrs::set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+constexpr int kWarp = 32;
+// rows (users) / columns (items) longer than this are split into chunks handled by different warps
+constexpr int kUserChunk = 2048;
+constexpr int kItemChunk = 1024;
+
+// value kinds of a rating set
+enum : int32_t { kValueCode = 0, kValueF64 = 1 };
+
+__host__ __device__ inline double decode_value(uint8_t c) { return 0.5 * (double)c; }
+__host__ __device__ inline double decode_value(double v) { return v; }
+
+// P:57-61 -- strict comparisons, equality -> 1
+__host__ __device__ inline double scale_fn(double x, double y) {
+  if (x > y) return 5.0 - y;
+  if (x < y) return y - 1.0;
+  return 1.0;
+}
+// P:229 / P:383 / P:578: the branch is taken on the rounded sum avg+dev.  No FMA contraction:
+// the JVM evaluates the multiply and the add separately.
+__device__ inline double combine_fn(double avg, double dev) {
+  return __dadd_rn(avg, __dmul_rn(dev, scale_fn(__dadd_rn(avg, dev), avg)));
+}
+// P:167 / P:327 / P:516: (r - avg) / scale(r, avg), correctly rounded subtract and divide
+__device__ inline double deviation_fn(double r, double avg) { return __ddiv_rn(__dsub_rn(r, avg), scale_fn(r, avg)); }
+
+}  // namespace mrs
+
+// ---------- handle layouts ----------
+struct mrs_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  void* scratch = nullptr;  // reusable device scratch (CUB temp storage etc.)
+  size_t scratch_bytes = 0;
+  double* h_pinned = nullptr;  // small pinned staging area for scalar read-backs
+  // diagnostics: event after every launch while profiling (mrs_profile_begin/end)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<const char*> prof_names;
+};
+
+struct mrs_chunks {
+  // Segments ("rows" = users or item columns) longer than the chunk size are split; one warp per chunk.
+  int32_t n_chunks = 0;
+  int32_t* chunk_seg = nullptr;    // [n_chunks] owning segment
+  int32_t* chunk_begin = nullptr;  // [n_chunks] first entry
+  int32_t* seg_chunk_ptr = nullptr;  // [n_seg+1] chunks of a segment are contiguous
+};
+
+struct mrs_ratings {
+  mrs_engine* eng = nullptr;
+  int64_t n = 0;
+  int32_t n_users = 0;  // table size = max user id + 1 (or the caller's dim)
+  int32_t n_items = 0;
+  int32_t value_kind = mrs::kValueCode;
+  // user-major CSR, items ascending inside a row
+  int32_t* urow = nullptr;  // [n_users+1]
+  int32_t* ucol = nullptr;  // [n] item id
+  void* uval = nullptr;     // [n] uint8 code or double
+  int32_t* coo_u = nullptr;  // [n] user id of each CSR entry (sorted COO = coo_u, ucol, uval)
+  // item-major CSC, users ascending inside a column
+  int32_t* icolp = nullptr;  // [n_items+1]
+  int32_t* irow = nullptr;   // [n] user id
+  void* ival = nullptr;      // [n]
+  int32_t* csc_src = nullptr;  // [n] position of the same rating in the CSR arrays
+  mrs_chunks uch, ich;
+  size_t value_size() const { return value_kind == mrs::kValueCode ? 1 : 8; }
+  // ---- lazily built layout for the user-user similarity kernels (knn.cu): depends only on the sparsity pattern
+  struct sim_layout {
+    bool built = false;
+    int32_t n_known = 0;           // users with at least one rating
+    int32_t n_slices = 0;          // ceil(n_known / 32)
+    int32_t* known_user = nullptr; // [n_known] original id, ascending            (compact index c -> user)
+    int32_t* cidx = nullptr;       // [n_users] compact index or -1
+    int32_t* perm = nullptr;       // [n_slices*32] compact index handled by (slice, lane), rows sorted by length desc; -1 = padding
+    int32_t* slice_off = nullptr;  // [n_slices+1] offset (in units of 32 entries) of each slice in the ELL arrays
+    int32_t* ell_col = nullptr;    // [slice_off[n_slices]*32] item id (0 for padding)
+    int32_t* ell_src = nullptr;    // [same] position of the entry in the CSR arrays, -1 for padding
+    int64_t ell_entries = 0;
+  };
+  mutable sim_layout sl;
+};
+
+struct mrs_model {
+  mrs_engine* eng = nullptr;
+  const mrs_ratings* train = nullptr;
+  int32_t n_users = 0, n_items = 0;
+  double* upart = nullptr;      // [uch.n_chunks] chunk partial sums of ratings
+  double* uavg = nullptr;       // [n_users]  average, -1.0 for unknown users (the reference's own sentinel, P:222)
+  double* ipart = nullptr;      // [2 * ich.n_chunks] chunk partials: deviations | ratings
+  double* xbuf = nullptr;       // [3*n_items + 2] exchange buffer: devsum | ratesum | count | gsum | gcount
+  double* idevavg = nullptr;    // [n_items]  0.0 for unknown items (P:197)
+  double* iavg = nullptr;       // [n_items]  NaN for unknown items (replaced by the global average at query time, P:147)
+  double* gavg = nullptr;       // [1] device scalar
+  double* mae_part = nullptr;   // per-block partials of |err| sums
+  unsigned int* counters = nullptr;  // small set of device counters (last-block-done patterns)
+  int32_t mae_part_cap = 0;
+  bool finished = false;
+  // host mirrors, filled lazily by queries
+  mutable bool host_valid = false;
+  mutable double h_gavg = 0.0;
+};
+
+struct mrs_sim {
+  mrs_model* model = nullptr;
+  int32_t kind = MRS_SIM_COSINE;
+  int32_t k = 0;
+  int32_t n_known = 0;
+  double* udev = nullptr;   // [n] deviation of each CSR entry (exact ops, P:167)
+  double* upre = nullptr;   // [n] preprocessed rating r~ (P:470-481)
+  double* unorm = nullptr;  // [n_known]
+  double* cdev = nullptr;   // [n] deviation of each CSC entry
+  double* ell_val = nullptr;  // r~ (cosine) or 1.0 (jaccard) in sliced-ELL order
+  double* S = nullptr;      // [n_known^2] similarity matrix in compact indices (cosine / jaccard)
+  int32_t* rank = nullptr;  // [n_known^2] position of v in u's sorted neighbour list (INT_MAX for v == u)
+  int32_t* nbr_id = nullptr;  // [n_known * (n_known-1)] neighbours of each user, original ids, (sim desc, id asc)
+  double* nbr_sim = nullptr;
+  double* mae_part = nullptr;
+  int32_t mae_part_cap = 0;
+  unsigned int* counter = nullptr;
+};
+
+namespace mrs {
+// called right after each kernel launch: counts it and, while profiling, records an event behind it
+inline void mark(mrs_engine* e, const char* name, int n = 1) {
+  count_launch(n);
+  if (e->profiling) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) == cudaSuccess) {
+      cudaEventRecord(ev, e->stream);
+      e->prof_events.push_back(ev);
+      e->prof_names.push_back(name);
+    }
+  }
+}
+int32_t ensure_scratch(mrs_engine* e, size_t bytes);
+template <typename T>
+int32_t dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t err = cudaMalloc((void**)p, count * sizeof(T));
+  if (err != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(err));
+    return MRS_ERR_NOMEM;
+  }
+  return MRS_OK;
+}
+inline void dev_free(void* p) {
+  if (p) cudaFree(p);
+}
+
+// loader.cu
+int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
+                      int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
+// baseline.cu
+int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
+int32_t fit_finish(mrs_model* m);
+int32_t mae_baseline_async(const mrs_model* m, int32_t pred_kind, const mrs_ratings* test, double* d_out2);
+int32_t predict_baseline_async(const mrs_model* m, int32_t pred_kind, const int32_t* d_users, const int32_t* d_items,
+                               int64_t n, double* d_out);
+// knn.cu
+int32_t sim_fit_async(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** inout);
+int32_t mae_personalized_async(const mrs_model* m, const mrs_sim* s, const mrs_ratings* test, double* d_out2);
+int32_t predict_personalized_async(const mrs_model* m, const mrs_sim* s, const int32_t* d_users, const int32_t* d_items,
+                                   int64_t n, double* d_out, bool wsd_only);
+void free_sim_layout(const mrs_ratings* r);
+}  // namespace mrs

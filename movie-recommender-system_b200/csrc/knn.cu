@@ -1,0 +1,651 @@
+// knn.cu -- personalized / kNN predictors of shared/predictions.scala:
+//   preprocessedRating (P:470-481), adjustedCosineSimilarityFunction (P:407-433), jaccardCoefficient (P:440-464),
+//   getNeighbors / getSimilarity (P:596-649), weightedSumDeviation (P:489-549), predictor (P:557-586).
+//
+// This file is the "similarity matrix fits on one GPU" path (ml-100k shape: U <= 16384 known users): S is
+// materialised as a dense n_known x n_known fp64 matrix, every row is fully sorted once (so any k is a prefix,
+// SURVEY A.6) and prediction looks similarities up by (u, v).
+//
+// Bit-exact neighbour sets need the similarity bits to equal the oracle's, so everything that feeds the ranking
+// uses correctly-rounded, non-fused fp64 ops in ONE canonical order: deviations (sub, div), squared
+// norm (sequential, ascending item id), r~ (div), dot product (sequential, ascending item id).  The similarity
+// kernel is a shared-memory-staged SpGEMM: the dense r~ rows of a block of UB users sit in shared memory and
+// every other user's sparse row is streamed once per block from a sliced-ELL layout (coalesced); items the block
+// user did not rate contribute an exact +/-0 product, which leaves the running sum unchanged, so the result is
+// bit-identical to a sum over the item intersection.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mrs {
+namespace {
+
+constexpr int32_t kMaxDenseUsers = 16384;
+constexpr int kSimMaxSmem = 220 * 1024;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------- sliced-ELL structure (sparsity pattern only; cached on the rating set) ----------------
+__global__ void ell_fill_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol,
+                                const int32_t* __restrict__ known_user, const int32_t* __restrict__ perm,
+                                const int32_t* __restrict__ slice_off, int32_t n_slices, int32_t* __restrict__ ell_col,
+                                int32_t* __restrict__ ell_src) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t slice = t >> 5, lane = t & 31;
+  if (slice >= n_slices) return;
+  const int32_t c = perm[t];
+  const int32_t base = slice_off[slice], width = slice_off[slice + 1] - base;
+  int32_t b = 0, len = 0;
+  if (c >= 0) {
+    const int32_t u = known_user[c];
+    b = urow[u];
+    len = urow[u + 1] - b;
+  }
+  for (int32_t j = 0; j < width; ++j) {
+    const int64_t q = ((int64_t)(base + j) << 5) + lane;
+    ell_col[q] = j < len ? ucol[b + j] : 0;
+    ell_src[q] = j < len ? b + j : -1;
+  }
+}
+
+int32_t build_sim_layout(const mrs_ratings* R) {
+  mrs_ratings::sim_layout& L = R->sl;
+  if (L.built) return MRS_OK;
+  cudaStream_t st = R->eng->stream;
+  std::vector<int32_t> urow((size_t)R->n_users + 1);
+  MRS_CUDA(cudaMemcpyAsync(urow.data(), R->urow, sizeof(int32_t) * urow.size(), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  std::vector<int32_t> known, cidx((size_t)R->n_users, -1);
+  for (int32_t u = 0; u < R->n_users; ++u)
+    if (urow[u + 1] > urow[u]) { cidx[u] = (int32_t)known.size(); known.push_back(u); }
+  const int32_t nk = (int32_t)known.size();
+  std::vector<int32_t> order(nk);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    return urow[known[a] + 1] - urow[known[a]] > urow[known[b] + 1] - urow[known[b]];
+  });
+  const int32_t ns = (nk + 31) / 32;
+  std::vector<int32_t> perm((size_t)ns * 32, -1), soff((size_t)ns + 1, 0);
+  for (int32_t t = 0; t < nk; ++t) perm[t] = order[t];
+  for (int32_t s = 0; s < ns; ++s) {
+    const int32_t c = perm[(size_t)s * 32];
+    const int32_t w = urow[known[c] + 1] - urow[known[c]];  // longest row of the slice (rows sorted by length)
+    soff[s + 1] = soff[s] + w;
+  }
+  L.n_known = nk;
+  L.n_slices = ns;
+  L.ell_entries = (int64_t)soff[ns] * 32;
+  MRS_TRY(dev_alloc(&L.known_user, (size_t)nk));
+  MRS_TRY(dev_alloc(&L.cidx, (size_t)R->n_users));
+  MRS_TRY(dev_alloc(&L.perm, perm.size()));
+  MRS_TRY(dev_alloc(&L.slice_off, soff.size()));
+  MRS_TRY(dev_alloc(&L.ell_col, (size_t)L.ell_entries));
+  MRS_TRY(dev_alloc(&L.ell_src, (size_t)L.ell_entries));
+  MRS_CUDA(cudaMemcpyAsync(L.known_user, known.data(), sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
+  MRS_CUDA(cudaMemcpyAsync(L.cidx, cidx.data(), sizeof(int32_t) * cidx.size(), cudaMemcpyHostToDevice, st));
+  MRS_CUDA(cudaMemcpyAsync(L.perm, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice, st));
+  MRS_CUDA(cudaMemcpyAsync(L.slice_off, soff.data(), sizeof(int32_t) * soff.size(), cudaMemcpyHostToDevice, st));
+  if (ns > 0) {
+    ell_fill_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(R->urow, R->ucol, L.known_user, L.perm, L.slice_off, ns, L.ell_col, L.ell_src);
+    count_launch();
+  }
+  MRS_CUDA(cudaGetLastError());
+  MRS_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+  L.built = true;
+  return MRS_OK;
+}
+
+// ---------------- P1: deviations, squared norm, r~ (one warp per known user, canonical sequential order) -------------
+template <typename VT>
+__global__ void __launch_bounds__(256) dev_pre_kernel(const VT* __restrict__ uval, const int32_t* __restrict__ urow,
+                                                     const int32_t* __restrict__ known_user, int32_t n_known,
+                                                     const double* __restrict__ uavg, double* __restrict__ udev,
+                                                     double* __restrict__ upre, double* __restrict__ unorm) {
+  const int lane = threadIdx.x & 31;
+  const int32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n_known) return;
+  const int32_t u = known_user[c];
+  const int32_t b = urow[u], e = urow[u + 1];
+  const double a = uavg[u];
+  double ss = 0.0;
+  for (int32_t base = b; base < e; base += 32) {
+    const int32_t p = base + lane;
+    double d = 0.0;
+    if (p < e) {
+      d = deviation_fn(decode_value(uval[p]), a);  // P:167
+      udev[p] = d;
+    }
+    const double d2 = __dmul_rn(d, d);  // math.pow(y, 2), P:474
+    const int cnt = min(32, e - base);
+    for (int j = 0; j < cnt; ++j) ss = __dadd_rn(ss, __shfl_sync(0xffffffffu, d2, j));  // ascending item id
+  }
+  const double w = __dsqrt_rn(ss);
+  if (lane == 0) unorm[c] = w;
+  for (int32_t p = b + lane; p < e; p += 32) upre[p] = (w != 0.0) ? __ddiv_rn(udev[p], w) : 0.0;  // P:478-479
+}
+
+// ---------------- P2: values in the layouts the next kernels stream (ELL for similarity, CSC for prediction) --------
+template <int MODE>  // 0: deviations only (uniform); 1: cosine; 2: jaccard
+__global__ void gather_values_kernel(const double* __restrict__ udev, const double* __restrict__ upre,
+                                     const int32_t* __restrict__ csc_src, int64_t n, const int32_t* __restrict__ ell_src,
+                                     int64_t ell_entries, double* __restrict__ cdev, double* __restrict__ ell_val) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += stride) cdev[p] = udev[csc_src[p]];
+  if (MODE != 0) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < ell_entries; q += stride) {
+      const int32_t s = ell_src[q];
+      ell_val[q] = s >= 0 ? (MODE == 1 ? upre[s] : 1.0) : 0.0;
+    }
+  }
+}
+
+// ---------------- P3: user-user similarity, shared-memory-staged SpGEMM --------------------------------------------
+template <int UB, int MODE>  // MODE 1: cosine (P:424-426), 2: jaccard (P:454-458)
+__global__ void __launch_bounds__(256) similarity_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol,
+                                                        const double* __restrict__ upre, const int32_t* __restrict__ known_user,
+                                                        int32_t n_known, int32_t n_items, const int32_t* __restrict__ perm,
+                                                        const int32_t* __restrict__ slice_off, int32_t n_slices,
+                                                        const int32_t* __restrict__ ell_col, const double* __restrict__ ell_val,
+                                                        double* __restrict__ S) {
+  extern __shared__ double su[];  // [n_items][UB]: r~ of the block's users, 0.0 where unrated
+  const int32_t cu0 = blockIdx.x * UB;
+  for (int32_t x = threadIdx.x; x < n_items * UB; x += blockDim.x) su[x] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < UB; ++t) {
+    const int32_t cu = cu0 + t;
+    if (cu < n_known) {
+      const int32_t u = known_user[cu];
+      for (int32_t p = urow[u] + threadIdx.x; p < urow[u + 1]; p += blockDim.x) su[ucol[p] * UB + t] = (MODE == 1) ? upre[p] : 1.0;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int32_t slice = threadIdx.x >> 5; slice < n_slices; slice += (blockDim.x >> 5)) {
+    const int32_t cv = perm[slice * 32 + lane];
+    const int32_t base = slice_off[slice], width = slice_off[slice + 1] - base;
+    double acc[UB];
+#pragma unroll
+    for (int t = 0; t < UB; ++t) acc[t] = 0.0;
+    const int32_t* colp = ell_col + ((int64_t)base << 5) + lane;
+    const double* valp = ell_val + ((int64_t)base << 5) + lane;
+#pragma unroll 2
+    for (int32_t j = 0; j < width; ++j) {
+      const int32_t col = __ldg(colp + ((int64_t)j << 5));
+      const double val = __ldg(valp + ((int64_t)j << 5));
+      const double* row = su + col * UB;
+#pragma unroll
+      for (int t = 0; t < UB; ++t) acc[t] = __dadd_rn(acc[t], __dmul_rn(row[t], val));  // ascending item id, no FMA
+    }
+    if (cv >= 0) {
+      int32_t nv = 0;
+      if (MODE == 2) { const int32_t v = known_user[cv]; nv = urow[v + 1] - urow[v]; }
+#pragma unroll
+      for (int t = 0; t < UB; ++t) {
+        const int32_t cu = cu0 + t;
+        if (cu < n_known) {
+          double s = acc[t];
+          if (MODE == 2) {
+            const int32_t u = known_user[cu];
+            const int32_t nu = urow[u + 1] - urow[u];
+            s = acc[t] / (double)(nu + nv - (int32_t)acc[t]);  // P:458
+          }
+          S[(int64_t)cu * n_known + cv] = s;
+        }
+      }
+    }
+  }
+}
+
+// ---------------- P4: full sort of every row by (similarity desc, user id asc); P:610 + SURVEY A.6 ----------------
+__device__ __forceinline__ bool before(double ka, int32_t ia, double kb, int32_t ib) {
+  return (ka > kb) || (ka == kb && ia < ib);
+}
+
+// in-shared-memory bitonic sort of P (power of two) (key,id) pairs into `before` order
+__device__ void bitonic_sort_shared(double* key, int32_t* id, int32_t P) {
+  for (int32_t size = 2; size <= P; size <<= 1) {
+    for (int32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int32_t t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int32_t lo = 2 * t - (t & (stride - 1));
+        const int32_t hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double ka = key[lo], kb = key[hi];
+        const int32_t ia = id[lo], ib = id[hi];
+        const bool swap = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
+        if (swap) { key[lo] = kb; key[hi] = ka; id[lo] = ib; id[hi] = ia; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) sort_rank_kernel(const double* __restrict__ S, const int32_t* __restrict__ known_user,
+                                                       int32_t n_known, int32_t P, int32_t* __restrict__ rank,
+                                                       int32_t* __restrict__ nbr_id, double* __restrict__ nbr_sim) {
+  extern __shared__ double sh_key[];
+  int32_t* sh_id = (int32_t*)(sh_key + P);
+  const int32_t cu = blockIdx.x;
+  for (int32_t x = threadIdx.x; x < P; x += blockDim.x) {
+    const bool cand = (x < n_known && x != cu);  // P:608 allUsers - u
+    sh_key[x] = cand ? S[(int64_t)cu * n_known + x] : -INFINITY;
+    sh_id[x] = cand ? x : INT_MAX;
+  }
+  bitonic_sort_shared(sh_key, sh_id, P);
+  const int32_t nn = n_known - 1;
+  for (int32_t j = threadIdx.x; j < nn; j += blockDim.x) {
+    const int32_t cv = sh_id[j];
+    nbr_id[(int64_t)cu * nn + j] = known_user[cv];
+    nbr_sim[(int64_t)cu * nn + j] = sh_key[j];
+    rank[(int64_t)cu * n_known + cv] = j;
+  }
+  if (threadIdx.x == 0) rank[(int64_t)cu * n_known + cu] = INT_MAX;  // s_k(u,u) = 0 (A.5)
+}
+
+// ---------------- P5: weighted-sum deviation + prediction (+ |error| reduction), one warp per (u,i) ----------------
+// SIMMODE 0: uniform (s == 1, P:400); 1: matrix, no neighbourhood; 2: matrix restricted to the first k neighbours of u
+template <int SIMMODE, bool WSD = false>
+__device__ __forceinline__ double predict_pair(int32_t u, int32_t i, int lane, int32_t n_users, int32_t n_items,
+                                               const double* __restrict__ uavg, double gavg, const int32_t* __restrict__ icolp,
+                                               const int32_t* __restrict__ irow, const double* __restrict__ cdev,
+                                               const int32_t* __restrict__ cidx, const double* __restrict__ S,
+                                               const int32_t* __restrict__ rank, int32_t n_known, int32_t k) {
+  const double ua = (u >= 0 && u < n_users) ? uavg[u] : -1.0;
+  if (ua < 0.0) {
+    if (!WSD) return gavg;              // P:572-573
+    if (SIMMODE != 0) return 0.0;       // wsd of a user without ratings: every similarity is 0 -> denominator 0 (P:527-529)
+  }
+  double num = 0.0, den = 0.0;
+  if (i >= 0 && i < n_items) {
+    const int32_t b = icolp[i], e = icolp[i + 1];
+    const int64_t rowbase = (SIMMODE == 0) ? 0 : (int64_t)cidx[u] * n_known;
+    for (int32_t p = b + lane; p < e; p += 32) {
+      double s;
+      if (SIMMODE == 0) {
+        s = 1.0;
+      } else {
+        const int32_t cv = cidx[irow[p]];
+        s = S[rowbase + cv];
+        if (SIMMODE == 2 && rank[rowbase + cv] >= k) s = 0.0;  // P:638-641
+      }
+      num += cdev[p] * s;  // P:522
+      den += fabs(s);
+    }
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  const double w = den > 0.0 ? num / den : 0.0;  // P:527-529
+  if (WSD) return w;
+  return combine_fn(ua, w);                       // P:578
+}
+
+template <typename VT, int SIMMODE>
+__global__ void __launch_bounds__(256) pers_mae_kernel(const int32_t* __restrict__ tu, const int32_t* __restrict__ ti,
+                                                      const VT* __restrict__ tv, int64_t n, int32_t n_users, int32_t n_items,
+                                                      const double* __restrict__ uavg, const double* __restrict__ gavg_p,
+                                                      const int32_t* __restrict__ icolp, const int32_t* __restrict__ irow,
+                                                      const double* __restrict__ cdev, const int32_t* __restrict__ cidx,
+                                                      const double* __restrict__ S, const int32_t* __restrict__ rank,
+                                                      int32_t n_known, int32_t k, double* __restrict__ part,
+                                                      unsigned int* __restrict__ counter, double* __restrict__ out2) {
+  __shared__ double sh[8];
+  __shared__ bool is_last;
+  const double gavg = gavg_p[0];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double acc = 0.0;  // identical in every lane of the warp
+  for (int64_t q = blockIdx.x * (int64_t)wpb + wid; q < n; q += (int64_t)gridDim.x * wpb) {
+    const double pr = predict_pair<SIMMODE>(tu[q], ti[q], lane, n_users, n_items, uavg, gavg, icolp, irow, cdev, cidx, S, rank, n_known, k);
+    acc += fabs(decode_value(tv[q]) - pr);  // P:71
+  }
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < wpb; ++w) t += sh[w];
+    part[blockIdx.x] = t;
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(&part[b]);
+    t = warp_sum(t);
+    if (lane == 0) sh[wid] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < wpb; ++w) s += sh[w];
+      out2[0] = s;
+      out2[1] = (double)n;
+      *counter = 0;
+    }
+  }
+}
+
+template <int SIMMODE, bool WSD>
+__global__ void __launch_bounds__(256) pers_pairs_kernel(const int32_t* __restrict__ us, const int32_t* __restrict__ is, int64_t n,
+                                                        int32_t n_users, int32_t n_items, const double* __restrict__ uavg,
+                                                        const double* __restrict__ gavg_p, const int32_t* __restrict__ icolp,
+                                                        const int32_t* __restrict__ irow, const double* __restrict__ cdev,
+                                                        const int32_t* __restrict__ cidx, const double* __restrict__ S,
+                                                        const int32_t* __restrict__ rank, int32_t n_known, int32_t k,
+                                                        double* __restrict__ out) {
+  const double gavg = gavg_p[0];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int64_t q = blockIdx.x * (int64_t)wpb + wid; q < n; q += (int64_t)gridDim.x * wpb) {
+    const double pr = predict_pair<SIMMODE, WSD>(us[q], is[q], lane, n_users, n_items, uavg, gavg, icolp, irow, cdev, cidx, S, rank, n_known, k);
+    if (lane == 0) out[q] = pr;
+  }
+}
+
+int sim_mode(const mrs_sim* s) {
+  if (s->kind == MRS_SIM_UNIFORM) return 0;
+  return s->k > 0 ? 2 : 1;
+}
+
+template <int UB, int MODE>
+int32_t launch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
+  const auto& L = R->sl;
+  const size_t smem = (size_t)R->n_items * UB * sizeof(double);
+  MRS_CUDA(cudaFuncSetAttribute(similarity_kernel<UB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (L.n_known + UB - 1) / UB;
+  similarity_kernel<UB, MODE><<<grid, 256, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.n_known, R->n_items, L.perm,
+                                                       L.slice_off, L.n_slices, L.ell_col, s->ell_val, s->S);
+  mark(R->eng, "similarity");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+template <int MODE>
+int32_t dispatch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
+  const size_t row = (size_t)R->n_items * sizeof(double);
+  if (row * 8 <= (size_t)kSimMaxSmem) return launch_similarity<8, MODE>(R, s, st);
+  if (row * 4 <= (size_t)kSimMaxSmem) return launch_similarity<4, MODE>(R, s, st);
+  if (row * 2 <= (size_t)kSimMaxSmem) return launch_similarity<2, MODE>(R, s, st);
+  return launch_similarity<1, MODE>(R, s, st);
+}
+
+}  // namespace
+
+void free_sim_layout(const mrs_ratings* r) {
+  auto& L = r->sl;
+  dev_free(L.known_user); dev_free(L.cidx); dev_free(L.perm); dev_free(L.slice_off); dev_free(L.ell_col); dev_free(L.ell_src);
+  L = mrs_ratings::sim_layout();
+}
+
+int32_t sim_fit_async(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout) {
+  MRS_REQUIRE(m && inout, MRS_ERR_INVALID, "mrs_fit_similarity: NULL argument");
+  MRS_REQUIRE(m->finished, MRS_ERR_INVALID, "mrs_fit_similarity: model not finished");
+  MRS_REQUIRE(kind == MRS_SIM_UNIFORM || kind == MRS_SIM_COSINE || kind == MRS_SIM_JACCARD, MRS_ERR_INVALID,
+              "mrs_fit_similarity: unknown similarity kind %d", kind);
+  MRS_REQUIRE(!(kind == MRS_SIM_UNIFORM && k > 0), MRS_ERR_UNSUPPORTED,
+              "mrs_fit_similarity: a neighbourhood over the uniform similarity is not supported (no call site in the reference)");
+  const mrs_ratings* R = m->train;
+  mrs_engine* e = m->eng;
+  cudaStream_t st = e->stream;
+  MRS_CUDA(cudaSetDevice(e->device));
+  MRS_TRY(build_sim_layout(R));
+  const auto& L = R->sl;
+  const bool matrix = (kind != MRS_SIM_UNIFORM);
+  if (matrix) {
+    MRS_REQUIRE(L.n_known <= kMaxDenseUsers, MRS_ERR_UNSUPPORTED,
+                "mrs_fit_similarity: %d users exceed the dense-similarity path (max %d); the row-block streaming path is not built yet",
+                L.n_known, kMaxDenseUsers);
+    MRS_REQUIRE((size_t)R->n_items * sizeof(double) <= (size_t)kSimMaxSmem, MRS_ERR_UNSUPPORTED,
+                "mrs_fit_similarity: item dimension %d does not fit the shared-memory staged similarity kernel", R->n_items);
+  }
+  mrs_sim* s = *inout;
+  if (s && (s->model != m || s->kind != kind)) {
+    set_error("mrs_fit_similarity_async: the handle passed for reuse belongs to another model or similarity kind");
+    return MRS_ERR_INVALID;
+  }
+  if (!s) {
+    s = new mrs_sim();
+    s->model = m;
+    s->kind = kind;
+    s->n_known = L.n_known;
+    s->mae_part_cap = e->sm_count * 8;
+    const size_t nk = (size_t)L.n_known;
+    int32_t rc = MRS_OK;
+    if (rc == MRS_OK) rc = dev_alloc(&s->udev, (size_t)R->n);
+    if (rc == MRS_OK) rc = dev_alloc(&s->upre, (size_t)R->n);
+    if (rc == MRS_OK) rc = dev_alloc(&s->unorm, nk);
+    if (rc == MRS_OK) rc = dev_alloc(&s->cdev, (size_t)R->n);
+    if (rc == MRS_OK) rc = dev_alloc(&s->mae_part, (size_t)s->mae_part_cap);
+    if (rc == MRS_OK) rc = dev_alloc(&s->counter, 4);
+    if (rc == MRS_OK && cudaMemsetAsync(s->counter, 0, 4 * sizeof(unsigned int), st) != cudaSuccess) rc = MRS_ERR_CUDA;
+    if (matrix) {
+      if (rc == MRS_OK) rc = dev_alloc(&s->ell_val, (size_t)L.ell_entries);
+      if (rc == MRS_OK) rc = dev_alloc(&s->S, nk * nk);
+      if (rc == MRS_OK) rc = dev_alloc(&s->rank, nk * nk);
+      if (rc == MRS_OK) rc = dev_alloc(&s->nbr_id, nk * (nk ? nk - 1 : 0));
+      if (rc == MRS_OK) rc = dev_alloc(&s->nbr_sim, nk * (nk ? nk - 1 : 0));
+    }
+    if (rc != MRS_OK) { mrs_sim_destroy(s); return rc; }
+    *inout = s;
+  }
+  s->k = k;
+  if (L.n_known == 0) return MRS_OK;
+  // P1
+  const int wpb = 8;
+  if (R->value_kind == kValueCode)
+    dev_pre_kernel<uint8_t><<<(L.n_known + wpb - 1) / wpb, 256, 0, st>>>((const uint8_t*)R->uval, R->urow, L.known_user, L.n_known, m->uavg, s->udev, s->upre, s->unorm);
+  else
+    dev_pre_kernel<double><<<(L.n_known + wpb - 1) / wpb, 256, 0, st>>>((const double*)R->uval, R->urow, L.known_user, L.n_known, m->uavg, s->udev, s->upre, s->unorm);
+  mark(e, "dev_pre");
+  // P2
+  const int64_t work = std::max<int64_t>(R->n, matrix ? L.ell_entries : 0);
+  const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)e->sm_count * 8));
+  if (kind == MRS_SIM_UNIFORM) gather_values_kernel<0><<<g2, 256, 0, st>>>(s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val);
+  else if (kind == MRS_SIM_COSINE) gather_values_kernel<1><<<g2, 256, 0, st>>>(s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val);
+  else gather_values_kernel<2><<<g2, 256, 0, st>>>(s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val);
+  mark(e, "gather_values");
+  MRS_CUDA(cudaGetLastError());
+  if (!matrix) return MRS_OK;
+  // P3
+  if (kind == MRS_SIM_COSINE) MRS_TRY(dispatch_similarity<1>(R, s, st));
+  else MRS_TRY(dispatch_similarity<2>(R, s, st));
+  // P4
+  int32_t P = 2;
+  while (P < L.n_known) P <<= 1;
+  const size_t smem = (size_t)P * (sizeof(double) + sizeof(int32_t));
+  MRS_CUDA(cudaFuncSetAttribute(sort_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sort_rank_kernel<<<L.n_known, 512, smem, st>>>(s->S, L.known_user, L.n_known, P, s->rank, s->nbr_id, s->nbr_sim);
+  mark(e, "sort_rank");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+int32_t mae_personalized_async(const mrs_model* m, const mrs_sim* s, const mrs_ratings* T, double* d_out2) {
+  MRS_REQUIRE(m && s && T && d_out2, MRS_ERR_INVALID, "mrs_mae: NULL argument");
+  MRS_REQUIRE(s->model == m, MRS_ERR_INVALID, "mrs_mae: similarity handle belongs to another model");
+  const mrs_ratings* R = m->train;
+  const auto& L = R->sl;
+  cudaStream_t st = m->eng->stream;
+  const int wpb = 8;
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>((T->n + wpb - 1) / wpb, (int64_t)s->mae_part_cap));
+  const int mode = sim_mode(s);
+#define MRS_PERS_MAE(VT, MODE)                                                                                              \
+  pers_mae_kernel<VT, MODE><<<grid, 256, 0, st>>>(T->coo_u, T->ucol, (const VT*)T->uval, T->n, m->n_users, m->n_items, m->uavg, \
+                                                  m->gavg, R->icolp, R->irow, s->cdev, L.cidx, s->S, s->rank, L.n_known, s->k,  \
+                                                  s->mae_part, s->counter, d_out2)
+  if (T->value_kind == kValueCode) {
+    if (mode == 0) MRS_PERS_MAE(uint8_t, 0); else if (mode == 1) MRS_PERS_MAE(uint8_t, 1); else MRS_PERS_MAE(uint8_t, 2);
+  } else {
+    if (mode == 0) MRS_PERS_MAE(double, 0); else if (mode == 1) MRS_PERS_MAE(double, 1); else MRS_PERS_MAE(double, 2);
+  }
+#undef MRS_PERS_MAE
+  mark(m->eng, "pers_mae");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+int32_t predict_personalized_async(const mrs_model* m, const mrs_sim* s, const int32_t* d_users, const int32_t* d_items, int64_t n,
+                                   double* d_out, bool wsd_only) {
+  MRS_REQUIRE(m && s, MRS_ERR_INVALID, "mrs_predict: NULL argument");
+  MRS_REQUIRE(s->model == m, MRS_ERR_INVALID, "mrs_predict: similarity handle belongs to another model");
+  if (n == 0) return MRS_OK;
+  const mrs_ratings* R = m->train;
+  const auto& L = R->sl;
+  cudaStream_t st = m->eng->stream;
+  const int wpb = 8;
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)m->eng->sm_count * 16));
+  const int mode = sim_mode(s);
+#define MRS_PERS_PAIRS(MODE, W)                                                                                               \
+  pers_pairs_kernel<MODE, W><<<grid, 256, 0, st>>>(d_users, d_items, n, m->n_users, m->n_items, m->uavg, m->gavg, R->icolp, R->irow, \
+                                                   s->cdev, L.cidx, s->S, s->rank, L.n_known, s->k, d_out)
+  if (wsd_only) {
+    if (mode == 0) MRS_PERS_PAIRS(0, true); else if (mode == 1) MRS_PERS_PAIRS(1, true); else MRS_PERS_PAIRS(2, true);
+  } else {
+    if (mode == 0) MRS_PERS_PAIRS(0, false); else if (mode == 1) MRS_PERS_PAIRS(1, false); else MRS_PERS_PAIRS(2, false);
+  }
+#undef MRS_PERS_PAIRS
+  mark(m->eng, "pers_pairs");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+}  // namespace mrs
+
+// ------------------------------------------------------------------ C ABI
+using namespace mrs;
+
+extern "C" int32_t mrs_fit_similarity_async(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** inout) {
+  return sim_fit_async(m, sim_kind, k, inout);
+}
+
+extern "C" int32_t mrs_fit_similarity(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** out) {
+  MRS_REQUIRE(out, MRS_ERR_INVALID, "mrs_fit_similarity: NULL output");
+  *out = nullptr;
+  MRS_TRY(sim_fit_async(m, sim_kind, k, out));
+  cudaError_t ce = cudaStreamSynchronize(m->eng->stream);
+  if (ce != cudaSuccess) {
+    set_error("mrs_fit_similarity: %s", cudaGetErrorString(ce));
+    mrs_sim_destroy(*out);
+    *out = nullptr;
+    return MRS_ERR_CUDA;
+  }
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_sim_set_k(mrs_sim* s, int32_t k) {
+  MRS_REQUIRE(s, MRS_ERR_INVALID, "mrs_sim_set_k: NULL handle");
+  s->k = k;
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_sim_entry_values(const mrs_sim* s, int32_t which, int32_t* users_out, int32_t* items_out, double* vals_out,
+                                        int64_t cap, int64_t* n_out) {
+  MRS_REQUIRE(s && n_out, MRS_ERR_INVALID, "mrs_sim_entry_values: NULL argument");
+  MRS_REQUIRE(which == 0 || which == 1, MRS_ERR_INVALID, "mrs_sim_entry_values: which must be 0 (deviation) or 1 (preprocessed)");
+  const mrs_ratings* R = s->model->train;
+  *n_out = R->n;
+  if (!users_out && !items_out && !vals_out) return MRS_OK;
+  MRS_REQUIRE(cap >= R->n, MRS_ERR_INVALID, "mrs_sim_entry_values: capacity %lld < %lld", (long long)cap, (long long)R->n);
+  cudaStream_t st = R->eng->stream;
+  if (users_out) MRS_CUDA(cudaMemcpyAsync(users_out, R->coo_u, sizeof(int32_t) * R->n, cudaMemcpyDeviceToHost, st));
+  if (items_out) MRS_CUDA(cudaMemcpyAsync(items_out, R->ucol, sizeof(int32_t) * R->n, cudaMemcpyDeviceToHost, st));
+  if (vals_out) MRS_CUDA(cudaMemcpyAsync(vals_out, which == 0 ? s->udev : s->upre, sizeof(double) * R->n, cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  return MRS_OK;
+}
+
+extern "C" void mrs_sim_destroy(mrs_sim* s) {
+  if (!s) return;
+  if (s->model && s->model->eng) { cudaSetDevice(s->model->eng->device); cudaStreamSynchronize(s->model->eng->stream); }
+  dev_free(s->udev); dev_free(s->upre); dev_free(s->unorm); dev_free(s->cdev); dev_free(s->ell_val); dev_free(s->S);
+  dev_free(s->rank); dev_free(s->nbr_id); dev_free(s->nbr_sim); dev_free(s->mae_part); dev_free(s->counter);
+  delete s;
+}
+
+static int32_t host_user_len(const mrs_ratings* R, int32_t u, int32_t* len) {
+  *len = 0;
+  if (u < 0 || u >= R->n_users) return MRS_OK;
+  int32_t p[2];
+  MRS_CUDA(cudaMemcpyAsync(p, R->urow + u, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, R->eng->stream));
+  MRS_CUDA(cudaStreamSynchronize(R->eng->stream));
+  *len = p[1] - p[0];
+  return MRS_OK;
+}
+
+static int32_t host_cidx(const mrs_ratings* R, int32_t u, int32_t* c) {
+  *c = -1;
+  if (u < 0 || u >= R->n_users) return MRS_OK;
+  MRS_CUDA(cudaMemcpyAsync(c, R->sl.cidx + u, sizeof(int32_t), cudaMemcpyDeviceToHost, R->eng->stream));
+  MRS_CUDA(cudaStreamSynchronize(R->eng->stream));
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_similarity(const mrs_sim* s, int32_t u, int32_t v, double* out) {
+  MRS_REQUIRE(s && out, MRS_ERR_INVALID, "mrs_similarity: NULL argument");
+  const mrs_ratings* R = s->model->train;
+  cudaStream_t st = R->eng->stream;
+  int32_t cu = -1, cv = -1;
+  MRS_TRY(host_cidx(R, u, &cu));
+  MRS_TRY(host_cidx(R, v, &cv));
+  if (s->kind == MRS_SIM_UNIFORM) { *out = 1.0; return MRS_OK; }  // P:400
+  if (cu < 0 || cv < 0) {
+    if (s->kind == MRS_SIM_JACCARD && s->k <= 0) {
+      int32_t lu = 0, lv = 0;
+      MRS_TRY(host_user_len(R, u, &lu));
+      MRS_TRY(host_user_len(R, v, &lv));
+      *out = (lu + lv) ? 0.0 : nan("");  // 0/0 on the JVM (P:458)
+    } else {
+      *out = 0.0;  // empty intersection -> empty sum (P:424-426); zero-similarity fillers weigh 0 either way
+    }
+    return MRS_OK;
+  }
+  double val = 0.0;
+  int32_t rk = 0;
+  const int64_t off = (int64_t)cu * s->n_known + cv;
+  MRS_CUDA(cudaMemcpyAsync(&val, s->S + off, sizeof(double), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaMemcpyAsync(&rk, s->rank + off, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  *out = (s->k > 0 && rk >= s->k) ? 0.0 : val;
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_neighbors(const mrs_sim* s, int32_t u, int32_t k, int32_t* ids_out, double* sims_out, int32_t cap, int32_t* n_out) {
+  MRS_REQUIRE(s && n_out, MRS_ERR_INVALID, "mrs_neighbors: NULL argument");
+  const mrs_ratings* R = s->model->train;
+  cudaStream_t st = R->eng->stream;
+  int32_t cu = -1;
+  MRS_TRY(host_cidx(R, u, &cu));
+  const int32_t nk = s->n_known;
+  const int32_t cand = nk - (cu >= 0 ? 1 : 0);
+  int32_t w = std::max(0, std::min(std::min(k, cand), cap));
+  *n_out = w;
+  if (w == 0) return MRS_OK;
+  if (s->kind != MRS_SIM_UNIFORM && cu >= 0) {
+    const int64_t off = (int64_t)cu * (nk - 1);
+    if (ids_out) MRS_CUDA(cudaMemcpyAsync(ids_out, s->nbr_id + off, sizeof(int32_t) * w, cudaMemcpyDeviceToHost, st));
+    if (sims_out) MRS_CUDA(cudaMemcpyAsync(sims_out, s->nbr_sim + off, sizeof(double) * w, cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    return MRS_OK;
+  }
+  // all similarities equal (uniform: 1.0; unknown u: 0.0) -> stable sort keeps ascending user id
+  std::vector<int32_t> known((size_t)std::min(nk, w + 1));
+  MRS_CUDA(cudaMemcpyAsync(known.data(), R->sl.known_user, sizeof(int32_t) * known.size(), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  const double val = (s->kind == MRS_SIM_UNIFORM) ? 1.0 : 0.0;
+  int32_t j = 0;
+  for (size_t t = 0; t < known.size() && j < w; ++t) {
+    if (known[t] == u) continue;
+    if (ids_out) ids_out[j] = known[t];
+    if (sims_out) sims_out[j] = val;
+    ++j;
+  }
+  *n_out = j;
+  return MRS_OK;
+}

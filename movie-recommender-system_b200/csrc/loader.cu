@@ -1,0 +1,389 @@
+// loader.cu -- host COO (Rating(user,item,rating), P:9) -> device-resident user-major CSR, item-major CSC
+// and sorted COO.  Replaces `load(...).collect()` materialisation (P:35-49).  Not on the timed hot path of the
+// reference either (predict/Baseline.scala:40-42 load before timing); it is inside bench.py's e2e figure.
+//
+// The two sorts use cub::DeviceRadixSort (library code, like calling cuBLAS); everything else is ours.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mrs {
+
+namespace {
+
+// one pass over the raw input: id ranges and whether every rating is a half-star code
+__global__ void scan_input_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ it,
+                                  const double* __restrict__ r, int64_t n, int32_t* __restrict__ stats) {
+  // stats: [0]=max user, [1]=max item, [2]=min id, [3]=number of ratings that are not k*0.5 in [0,127.5]
+  int32_t mu = -1, mi = -1, mn = 0x7fffffff, bad = 0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    int32_t a = u[p], b = it[p];
+    mu = max(mu, a);
+    mi = max(mi, b);
+    mn = min(mn, min(a, b));
+    double v = r[p] * 2.0;
+    if (!(v >= 0.0 && v <= 255.0 && v == floor(v))) bad++;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mu = max(mu, __shfl_xor_sync(0xffffffffu, mu, o));
+    mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&stats[0], mu);
+    atomicMax(&stats[1], mi);
+    atomicMin(&stats[2], mn);
+    if (bad) atomicAdd(&stats[3], bad);
+  }
+}
+
+__global__ void make_keys_kernel(const int32_t* __restrict__ hi, const int32_t* __restrict__ lo, int64_t n,
+                                 uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    keys[p] = ((uint64_t)(uint32_t)hi[p] << 32) | (uint32_t)lo[p];
+    idx[p] = (int32_t)p;
+  }
+}
+
+// sorted (major<<32|minor) keys -> major array, minor array, gathered values, segment pointer, duplicate count
+template <typename VT, bool kEncode>
+__global__ void scatter_sorted_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ src, int64_t n,
+                                      int32_t n_seg, const void* __restrict__ values_in, int32_t* __restrict__ major_out,
+                                      int32_t* __restrict__ minor_out, VT* __restrict__ values_out,
+                                      int32_t* __restrict__ seg_ptr, int32_t* __restrict__ dup_count) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t k = keys[p];
+    int32_t major = (int32_t)(k >> 32), minor = (int32_t)(k & 0xffffffffu);
+    if (major_out) major_out[p] = major;
+    minor_out[p] = minor;
+    if (kEncode) {
+      double v = ((const double*)values_in)[src[p]];
+      if (sizeof(VT) == 1) values_out[p] = (VT)(v * 2.0); else values_out[p] = (VT)v;
+    } else {
+      values_out[p] = ((const VT*)values_in)[src[p]];
+    }
+    int32_t prev = -1;
+    if (p > 0) {
+      uint64_t kp = keys[p - 1];
+      prev = (int32_t)(kp >> 32);
+      if (kp == k) atomicAdd(dup_count, 1);
+    }
+    for (int32_t s = prev + 1; s <= major; ++s) seg_ptr[s] = (int32_t)p;
+    if (p == n - 1)
+      for (int32_t s = major + 1; s <= n_seg; ++s) seg_ptr[s] = (int32_t)n;
+  }
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void chunk_count_kernel(const int32_t* __restrict__ seg_ptr, int32_t n_seg, int32_t chunk, int32_t* __restrict__ counts) {
+  int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_seg) {
+    int32_t len = seg_ptr[s + 1] - seg_ptr[s];
+    counts[s] = (len + chunk - 1) / chunk;
+  }
+}
+
+__global__ void chunk_fill_kernel(const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_chunk_ptr, int32_t n_seg,
+                                  int32_t chunk, int32_t* __restrict__ chunk_seg, int32_t* __restrict__ chunk_begin) {
+  int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_seg) {
+    int32_t c0 = seg_chunk_ptr[s], c1 = seg_chunk_ptr[s + 1], b = seg_ptr[s];
+    for (int32_t c = c0; c < c1; ++c) {
+      chunk_seg[c] = s;
+      chunk_begin[c] = b + (c - c0) * chunk;
+    }
+  }
+}
+
+int grid_for(int64_t n, int block, int sm_count) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)sm_count * 16;
+  return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+int bits_for(uint32_t v) {
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return std::max(b, 1);
+}
+
+int32_t build_chunks(mrs_engine* e, const int32_t* seg_ptr, int32_t n_seg, int32_t chunk, mrs_chunks* out) {
+  cudaStream_t st = e->stream;
+  int32_t* counts = nullptr;
+  MRS_TRY(dev_alloc(&counts, (size_t)n_seg + 1));
+  MRS_TRY(dev_alloc(&out->seg_chunk_ptr, (size_t)n_seg + 1));
+  MRS_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * ((size_t)n_seg + 1), st));
+  chunk_count_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(seg_ptr, n_seg, chunk, counts);
+  count_launch();
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, counts, out->seg_chunk_ptr, n_seg + 1, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceScan::ExclusiveSum(e->scratch, tmp, counts, out->seg_chunk_ptr, n_seg + 1, st);
+  count_launch();
+  int32_t total = 0;
+  MRS_CUDA(cudaMemcpyAsync(&total, out->seg_chunk_ptr + n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  out->n_chunks = total;
+  MRS_TRY(dev_alloc(&out->chunk_seg, (size_t)total));
+  MRS_TRY(dev_alloc(&out->chunk_begin, (size_t)total));
+  chunk_fill_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(seg_ptr, out->seg_chunk_ptr, n_seg, chunk, out->chunk_seg, out->chunk_begin);
+  count_launch();
+  MRS_CUDA(cudaGetLastError());
+  dev_free(counts);
+  return MRS_OK;
+}
+
+template <typename VT>
+int32_t build_sorted(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_t* d_i, const double* d_r, int32_t* d_dup) {
+  cudaStream_t st = e->stream;
+  const int64_t n = R->n;
+  const int block = 256;
+  const int grid = grid_for(n, block, e->sm_count);
+  uint64_t *k_in = nullptr, *k_out = nullptr;
+  int32_t *v_in = nullptr, *v_out = nullptr;
+  MRS_TRY(dev_alloc(&k_in, (size_t)n));
+  MRS_TRY(dev_alloc(&k_out, (size_t)n));
+  MRS_TRY(dev_alloc(&v_in, (size_t)n));
+  MRS_TRY(dev_alloc(&v_out, (size_t)n));
+  VT *uval = nullptr, *ival = nullptr;
+  MRS_TRY(dev_alloc(&uval, (size_t)n));
+  MRS_TRY(dev_alloc(&ival, (size_t)n));
+  R->uval = uval;
+  R->ival = ival;
+  MRS_TRY(dev_alloc(&R->ucol, (size_t)n));
+  MRS_TRY(dev_alloc(&R->coo_u, (size_t)n));
+  MRS_TRY(dev_alloc(&R->irow, (size_t)n));
+  MRS_TRY(dev_alloc(&R->csc_src, (size_t)n));
+  MRS_TRY(dev_alloc(&R->urow, (size_t)R->n_users + 1));
+  MRS_TRY(dev_alloc(&R->icolp, (size_t)R->n_items + 1));
+
+  if (n == 0) {
+    MRS_CUDA(cudaMemsetAsync(R->urow, 0, sizeof(int32_t) * ((size_t)R->n_users + 1), st));
+    MRS_CUDA(cudaMemsetAsync(R->icolp, 0, sizeof(int32_t) * ((size_t)R->n_items + 1), st));
+  } else {
+    const int ubits = bits_for((uint32_t)(R->n_users - 1)), ibits = bits_for((uint32_t)(R->n_items - 1));
+    // ---- user-major: sort by (user, item)
+    make_keys_kernel<<<grid, block, 0, st>>>(d_u, d_i, n, k_in, v_in);
+    count_launch();
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ubits, st);
+    MRS_TRY(ensure_scratch(e, tmp));
+    cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ubits, st);
+    count_launch(4);
+    scatter_sorted_kernel<VT, true><<<grid, block, 0, st>>>(k_out, v_out, n, R->n_users, d_r, R->coo_u, R->ucol, uval, R->urow, d_dup);
+    count_launch();
+    // ---- item-major: sort by (item, user); payload = position in the user-major arrays
+    make_keys_kernel<<<grid, block, 0, st>>>(R->ucol, R->coo_u, n, k_in, v_in);
+    count_launch();
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ibits, st);
+    MRS_TRY(ensure_scratch(e, tmp));
+    cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ibits, st);
+    count_launch(4);
+    scatter_sorted_kernel<VT, false><<<grid, block, 0, st>>>(k_out, v_out, n, R->n_items, uval, nullptr, R->irow, ival, R->icolp, d_dup);
+    count_launch();
+    MRS_CUDA(cudaMemcpyAsync(R->csc_src, v_out, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+    MRS_CUDA(cudaGetLastError());
+  }
+  MRS_TRY(build_chunks(e, R->urow, R->n_users, kUserChunk, &R->uch));
+  MRS_TRY(build_chunks(e, R->icolp, R->n_items, kItemChunk, &R->ich));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  dev_free(k_in); dev_free(k_out); dev_free(v_in); dev_free(v_out);
+  return MRS_OK;
+}
+
+}  // namespace
+
+int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
+                      int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {
+  MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL engine or output");
+  MRS_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, MRS_ERR_UNSUPPORTED, "mrs_ratings_from_coo: n=%lld outside [0, 2^31)", (long long)n);
+  MRS_REQUIRE(n == 0 || (users && items && ratings), MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL input array");
+  MRS_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  int32_t *d_u = nullptr, *d_i = nullptr, *d_stats = nullptr;
+  double* d_r = nullptr;
+  MRS_TRY(dev_alloc(&d_u, (size_t)n));
+  MRS_TRY(dev_alloc(&d_i, (size_t)n));
+  MRS_TRY(dev_alloc(&d_r, (size_t)n));
+  MRS_TRY(dev_alloc(&d_stats, 8));
+  int32_t h_stats[5] = {-1, -1, 0x7fffffff, 0, 0};
+  MRS_CUDA(cudaMemcpyAsync(d_stats, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, st));
+  if (n) {
+    MRS_CUDA(cudaMemcpyAsync(d_u, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    MRS_CUDA(cudaMemcpyAsync(d_i, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    MRS_CUDA(cudaMemcpyAsync(d_r, ratings, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    scan_input_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(d_u, d_i, d_r, n, d_stats);
+    count_launch();
+  }
+  MRS_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  if (n && h_stats[2] < 0) {
+    dev_free(d_u); dev_free(d_i); dev_free(d_r); dev_free(d_stats);
+    set_error("mrs_ratings_from_coo: negative user or item id (%d)", h_stats[2]);
+    return MRS_ERR_INVALID;
+  }
+  mrs_ratings* R = new mrs_ratings();
+  R->eng = e;
+  R->n = n;
+  R->n_users = std::max(n_users_dim, h_stats[0] + 1);
+  R->n_items = std::max(n_items_dim, h_stats[1] + 1);
+  if (R->n_users < 1) R->n_users = 1;
+  if (R->n_items < 1) R->n_items = 1;
+  R->value_kind = (h_stats[3] == 0) ? kValueCode : kValueF64;
+  int32_t* d_dup = d_stats + 4;
+  int32_t s = (R->value_kind == kValueCode) ? build_sorted<uint8_t>(e, R, d_u, d_i, d_r, d_dup)
+                                             : build_sorted<double>(e, R, d_u, d_i, d_r, d_dup);
+  int32_t dup = 0;
+  if (s == MRS_OK) {
+    cudaError_t ce = cudaMemcpy(&dup, d_dup, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(ce)); s = MRS_ERR_CUDA; }
+  }
+  dev_free(d_u); dev_free(d_i); dev_free(d_r); dev_free(d_stats);
+  if (s == MRS_OK && dup != 0) {
+    // each duplicate pair is seen once in the CSR pass and once in the CSC pass
+    set_error("mrs_ratings_from_coo: %d duplicate (user,item) pair(s); the reference keeps the last one (P:168), this engine rejects them", dup / 2);
+    s = MRS_ERR_DUPLICATE;
+  }
+  if (s != MRS_OK) {
+    mrs_ratings_destroy(R);
+    return s;
+  }
+  *out = R;
+  return MRS_OK;
+}
+
+}  // namespace mrs
+
+// ------------------------------------------------------------------ C ABI
+using namespace mrs;
+
+extern "C" int32_t mrs_ratings_from_coo(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings,
+                                        int64_t n, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {
+  return build_ratings(e, users, items, ratings, n, n_users_dim, n_items_dim, out);
+}
+
+// Java semantics of Integer.parseInt after trim (P:27-33 toInt): optional sign, then decimal digits only.
+static bool parse_java_int(const char* b, const char* e, int32_t* out) {
+  while (b < e && (unsigned char)*b <= ' ') ++b;  // String.trim strips chars <= U+0020
+  while (e > b && (unsigned char)e[-1] <= ' ') --e;
+  if (b == e) return false;
+  bool neg = false;
+  if (*b == '-' || *b == '+') { neg = (*b == '-'); ++b; }
+  if (b == e) return false;
+  int64_t v = 0;
+  for (; b < e; ++b) {
+    if (*b < '0' || *b > '9') return false;
+    v = v * 10 + (*b - '0');
+    if (v > (int64_t)0x80000000LL) return false;
+  }
+  v = neg ? -v : v;
+  if (v > 0x7fffffffLL || v < -(int64_t)0x80000000LL) return false;
+  *out = (int32_t)v;
+  return true;
+}
+
+extern "C" int32_t mrs_ratings_from_file(mrs_engine* e, const char* path, const char* sep, mrs_ratings** out) {
+  MRS_REQUIRE(e && path && sep && out && sep[0], MRS_ERR_INVALID, "mrs_ratings_from_file: NULL/empty argument");
+  FILE* f = fopen(path, "rb");
+  MRS_REQUIRE(f != nullptr, MRS_ERR_IO, "mrs_ratings_from_file: cannot open %s", path);
+  std::vector<char> buf;
+  {
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize((size_t)std::max(0L, sz) + 1);
+    size_t got = fread(buf.data(), 1, (size_t)std::max(0L, sz), f);
+    buf.resize(got + 1);
+    buf[got] = '\n';
+    fclose(f);
+  }
+  const size_t seplen = strlen(sep);
+  std::vector<int32_t> us, is;
+  std::vector<double> rs;
+  const char* p = buf.data();
+  const char* end = buf.data() + buf.size();
+  int64_t lineno = 0;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    if (!nl) nl = end;
+    const char* le = nl;
+    if (le > p && le[-1] == '\r') --le;  // textFile strips \r\n as well as \n
+    ++lineno;
+    {
+      // split(sep): first three columns
+      const char* c[4] = {p, nullptr, nullptr, nullptr};
+      const char* ce[4] = {le, le, le, le};
+      int nc = 1;
+      const char* q = p;
+      while (nc < 4) {
+        const char* hit = nullptr;
+        for (const char* t = q; t + seplen <= le; ++t)
+          if (memcmp(t, sep, seplen) == 0) { hit = t; break; }
+        if (!hit) break;
+        ce[nc - 1] = hit;
+        c[nc] = hit + seplen;
+        q = hit + seplen;
+        ++nc;
+      }
+      int32_t uu = 0, ii = 0;
+      if (parse_java_int(c[0], ce[0], &uu)) {  // P:40: rows whose column 0 is not an Int are dropped (header skip)
+        if (nc < 3 || !parse_java_int(c[1], ce[1], &ii)) {
+          set_error("mrs_ratings_from_file: %s:%lld: malformed row (the reference throws at predictions.scala:41)", path, (long long)lineno);
+          return MRS_ERR_IO;
+        }
+        std::string tok(c[2], ce[2]);
+        char* endp = nullptr;
+        double rr = strtod(tok.c_str(), &endp);
+        while (endp && *endp && (unsigned char)*endp <= ' ') ++endp;
+        if (endp == tok.c_str() || (endp && *endp)) {
+          set_error("mrs_ratings_from_file: %s:%lld: rating is not a number", path, (long long)lineno);
+          return MRS_ERR_IO;
+        }
+        us.push_back(uu); is.push_back(ii); rs.push_back(rr);
+      }
+    }
+    p = nl + 1;
+  }
+  return build_ratings(e, us.data(), is.data(), rs.data(), (int64_t)us.size(), 0, 0, out);
+}
+
+extern "C" int32_t mrs_ratings_info(const mrs_ratings* r, int64_t* n, int32_t* n_users_dim, int32_t* n_items_dim, int32_t* value_kind) {
+  MRS_REQUIRE(r, MRS_ERR_INVALID, "mrs_ratings_info: NULL handle");
+  if (n) *n = r->n;
+  if (n_users_dim) *n_users_dim = r->n_users;
+  if (n_items_dim) *n_items_dim = r->n_items;
+  if (value_kind) *value_kind = r->value_kind;
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* b) {
+  MRS_REQUIRE(r && b, MRS_ERR_INVALID, "mrs_ratings_bytes: NULL argument");
+  const int64_t vs = (int64_t)r->value_size();
+  b[0] = r->n * vs;          // user-major pass reads the values only (the user is implicit in the row pointer)
+  b[1] = r->n * (4 + vs);    // item-major pass: user id + value
+  b[2] = r->n * (8 + vs);    // sorted COO pass: user id + item id + value
+  return MRS_OK;
+}
+
+static void free_chunks(mrs_chunks* c) {
+  dev_free(c->chunk_seg); dev_free(c->chunk_begin); dev_free(c->seg_chunk_ptr);
+}
+
+extern "C" void mrs_ratings_destroy(mrs_ratings* r) {
+  if (!r) return;
+  dev_free(r->urow); dev_free(r->ucol); dev_free(r->uval); dev_free(r->coo_u);
+  dev_free(r->icolp); dev_free(r->irow); dev_free(r->ival); dev_free(r->csc_src);
+  free_chunks(&r->uch); free_chunks(&r->ich);
+  free_sim_layout(r);
+  delete r;
+}

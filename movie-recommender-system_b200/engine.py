@@ -1,0 +1,317 @@
+"""ctypes binding of libmrs_b200.so (the C ABI in include/mrs_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is present,
+everything here raises.  PyTorch is not imported; pass ``stream=torch.cuda.current_stream().cuda_stream``
+to run on torch's stream when torch owns the timing events or the NCCL collectives.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmrs_b200.so")
+
+# mrs_vec_kind / mrs_pred_kind / mrs_sim_kind
+GLOBAL_AVG, USER_AVG, ITEM_AVG, ITEM_AVG_DEV = range(4)
+PRED_GLOBAL, PRED_USER, PRED_ITEM, PRED_ITEMDEV, PRED_BASELINE, PRED_PERSONALIZED, PRED_WSD = range(7)
+SIM_UNIFORM, SIM_COSINE, SIM_JACCARD = range(3)
+
+ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4: "MRS_ERR_DUPLICATE",
+             -5: "MRS_ERR_IO", -6: "MRS_ERR_UNSUPPORTED"}
+
+EXPORTS = [
+    "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
+    "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_destroy",
+    "mrs_fit", "mrs_fit_local", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_model_scalar",
+    "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_sim_set_k",
+    "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
+    "mrs_mae_async", "mrs_recommend",
+]
+
+
+class MrsError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{ERR_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+def build_library(force=False):
+    """Compile csrc/*.cu for sm_100a with nvcc (works without a GPU) into libmrs_b200.so, in-tree."""
+    src = os.path.join(_HERE, "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src) if f.endswith((".cu", ".cuh")))
+    newest = max(newest, os.path.getmtime(os.path.join(_HERE, "..", "include", "mrs_b200.h")))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        subprocess.run(["make", "-C", src, "-j8"], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def lib():
+    """Load libmrs_b200.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MrsError(-6, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    sig = {
+        "mrs_last_error": (C.c_char_p, []),
+        "mrs_version": (C.c_char_p, []),
+        "mrs_launch_count": (i64, []),
+        "mrs_engine_create": (i32, [i32, vp, P(vp)]),
+        "mrs_engine_destroy": (None, [vp]),
+        "mrs_engine_sync": (i32, [vp]),
+        "mrs_profile_begin": (i32, [vp]),
+        "mrs_profile_end": (i32, [vp, C.c_char_p, i64, P(C.c_float), i32, P(i32)]),
+        "mrs_ratings_from_coo": (i32, [vp, vp, vp, vp, i64, i32, i32, P(vp)]),
+        "mrs_ratings_from_file": (i32, [vp, C.c_char_p, C.c_char_p, P(vp)]),
+        "mrs_ratings_info": (i32, [vp, P(i64), P(i32), P(i32), P(i32)]),
+        "mrs_ratings_bytes": (i32, [vp, P(i64)]),
+        "mrs_ratings_destroy": (None, [vp]),
+        "mrs_fit": (i32, [vp, vp, P(vp)]),
+        "mrs_fit_local": (i32, [vp, vp, P(vp)]),
+        "mrs_model_exchange_buffer": (i32, [vp, P(vp), P(i64)]),
+        "mrs_fit_finish": (i32, [vp]),
+        "mrs_model_destroy": (None, [vp]),
+        "mrs_model_scalar": (i32, [vp, i32, P(dbl)]),
+        "mrs_model_lookup": (i32, [vp, i32, i32, P(dbl), P(i32)]),
+        "mrs_model_vector": (i32, [vp, i32, vp, vp, i64, P(i64)]),
+        "mrs_fit_similarity": (i32, [vp, i32, i32, P(vp)]),
+        "mrs_fit_similarity_async": (i32, [vp, i32, i32, P(vp)]),
+        "mrs_sim_set_k": (i32, [vp, i32]),
+        "mrs_similarity": (i32, [vp, i32, i32, P(dbl)]),
+        "mrs_neighbors": (i32, [vp, i32, i32, vp, vp, i32, P(i32)]),
+        "mrs_sim_entry_values": (i32, [vp, i32, vp, vp, vp, i64, P(i64)]),
+        "mrs_sim_destroy": (None, [vp]),
+        "mrs_predict": (i32, [vp, vp, i32, vp, vp, i64, vp]),
+        "mrs_mae": (i32, [vp, vp, i32, vp, P(dbl)]),
+        "mrs_mae_async": (i32, [vp, vp, i32, vp, vp]),
+        "mrs_recommend": (i32, [vp, vp, i32, i32, i32, vp, vp, P(i32)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != 0:
+        raise MrsError(status, lib().mrs_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def launch_count():
+    return int(lib().mrs_launch_count())
+
+
+class Engine:
+    """One CUDA device + one stream."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        _check(lib().mrs_engine_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self.device = int(device)
+
+    def sync(self):
+        _check(lib().mrs_engine_sync(self._h))
+
+    def profile_begin(self):
+        _check(lib().mrs_profile_begin(self._h))
+
+    def profile_end(self):
+        """[(kernel label, milliseconds)] for every launch since profile_begin (CUDA events on the engine's stream)."""
+        cap = 4096
+        names = C.create_string_buffer(cap * 24)
+        ms = (C.c_float * cap)()
+        n = C.c_int32()
+        _check(lib().mrs_profile_end(self._h, names, len(names), ms, cap, C.byref(n)))
+        labels = names.value.decode().split("\n")[:n.value]
+        return [(labels[j], float(ms[j])) for j in range(min(n.value, cap))]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_engine_destroy(self._h)
+            self._h = None
+
+    def ratings(self, users, items, ratings, n_users_dim=0, n_items_dim=0):
+        return Ratings(self, users, items, ratings, n_users_dim, n_items_dim)
+
+    def ratings_from_file(self, path, sep):
+        return Ratings.from_file(self, path, sep)
+
+
+class Ratings:
+    """Device-resident rating set (user-major CSR + item-major CSC + sorted COO)."""
+
+    def __init__(self, engine, users, items, ratings, n_users_dim=0, n_items_dim=0, _handle=None):
+        self.engine = engine
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            u = np.ascontiguousarray(users, dtype=np.int32)
+            i = np.ascontiguousarray(items, dtype=np.int32)
+            r = np.ascontiguousarray(ratings, dtype=np.float64)
+            if not (u.shape == i.shape == r.shape and u.ndim == 1):
+                raise ValueError("users, items, ratings must be 1-D arrays of equal length")
+            _check(lib().mrs_ratings_from_coo(engine._h, _ptr(u), _ptr(i), _ptr(r), u.size, int(n_users_dim), int(n_items_dim),
+                                              C.byref(self._h)))
+        n, nu, ni, vk = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().mrs_ratings_info(self._h, C.byref(n), C.byref(nu), C.byref(ni), C.byref(vk)))
+        self.n, self.n_users_dim, self.n_items_dim, self.value_kind = n.value, nu.value, ni.value, vk.value
+
+    @classmethod
+    def from_file(cls, engine, path, sep):
+        h = C.c_void_p()
+        _check(lib().mrs_ratings_from_file(engine._h, os.fsencode(path), sep.encode(), C.byref(h)))
+        return cls(engine, None, None, None, _handle=h)
+
+    def bytes(self):
+        b = (C.c_int64 * 3)()
+        _check(lib().mrs_ratings_bytes(self._h, b))
+        return {"user_major": b[0], "item_major": b[1], "sorted_coo": b[2]}
+
+    def __len__(self):
+        return self.n
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_ratings_destroy(self._h)
+            self._h = None
+
+
+class Model:
+    """Fitted baseline model of a train set (global / user / item averages, item average deviations)."""
+
+    def __init__(self, engine, train, sync=True):
+        self.engine, self.train = engine, train
+        self._h = C.c_void_p()
+        if sync:
+            _check(lib().mrs_fit(engine._h, train._h, C.byref(self._h)))
+        else:
+            self.refit()
+
+    def refit(self, between=None):
+        """Enqueue the fit again on the same buffers (no host sync). ``between(ptr, n_doubles)`` is called after the
+        local pass with the device exchange buffer -- a sharded run all-reduces it there."""
+        _check(lib().mrs_fit_local(self.engine._h, self.train._h, C.byref(self._h)))
+        if between is not None:
+            between(*self.exchange_buffer())
+        _check(lib().mrs_fit_finish(self._h))
+
+    def exchange_buffer(self):
+        p, n = C.c_void_p(), C.c_int64()
+        _check(lib().mrs_model_exchange_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    @property
+    def global_avg(self):
+        out = C.c_double()
+        _check(lib().mrs_model_scalar(self._h, GLOBAL_AVG, C.byref(out)))
+        return out.value
+
+    def lookup(self, kind, ident):
+        out, known = C.c_double(), C.c_int32()
+        _check(lib().mrs_model_lookup(self._h, kind, int(ident), C.byref(out), C.byref(known)))
+        return out.value, bool(known.value)
+
+    def vector(self, kind):
+        n = C.c_int64()
+        _check(lib().mrs_model_vector(self._h, kind, None, None, 0, C.byref(n)))
+        vals = np.empty(n.value, dtype=np.float64)
+        cnts = np.empty(n.value, dtype=np.int32)
+        _check(lib().mrs_model_vector(self._h, kind, _ptr(vals), _ptr(cnts), n.value, C.byref(n)))
+        return vals, cnts
+
+    def predict(self, users, items, kind=PRED_BASELINE, sim=None):
+        u = np.ascontiguousarray(users, dtype=np.int32)
+        i = np.ascontiguousarray(items, dtype=np.int32)
+        out = np.empty(u.size, dtype=np.float64)
+        _check(lib().mrs_predict(self._h, sim._h if sim is not None else None, int(kind), _ptr(u), _ptr(i), u.size, _ptr(out)))
+        return out
+
+    def mae(self, test, kind=PRED_BASELINE, sim=None):
+        out = C.c_double()
+        _check(lib().mrs_mae(self._h, sim._h if sim is not None else None, int(kind), test._h, C.byref(out)))
+        return out.value
+
+    def mae_async(self, test, device_out_ptr, kind=PRED_BASELINE, sim=None):
+        """Enqueue predict+|err| reduction; {sum, count} (2 fp64) land at ``device_out_ptr``; no host sync."""
+        _check(lib().mrs_mae_async(self._h, sim._h if sim is not None else None, int(kind), test._h, C.c_void_p(device_out_ptr)))
+
+    def similarity(self, kind=SIM_COSINE, k=0, sync=True):
+        return Sim(self, kind, k, sync=sync)
+
+    def recommend(self, user, n, kind=PRED_PERSONALIZED, sim=None):
+        items = np.empty(max(n, 1), dtype=np.int32)
+        scores = np.empty(max(n, 1), dtype=np.float64)
+        w = C.c_int32()
+        _check(lib().mrs_recommend(self._h, sim._h if sim is not None else None, int(kind), int(user), int(n), _ptr(items),
+                                   _ptr(scores), C.byref(w)))
+        return items[:w.value].copy(), scores[:w.value].copy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_model_destroy(self._h)
+            self._h = None
+
+
+class Sim:
+    """User-user similarity of a fitted model (uniform | cosine | jaccard), optionally restricted to k neighbours."""
+
+    def __init__(self, model, kind=SIM_COSINE, k=0, sync=True):
+        self.model, self.kind, self.k = model, int(kind), int(k)
+        self._h = C.c_void_p()
+        if sync:
+            _check(lib().mrs_fit_similarity(model._h, self.kind, self.k, C.byref(self._h)))
+        else:
+            self.refit()
+
+    def refit(self, k=None):
+        if k is not None:
+            self.k = int(k)
+        _check(lib().mrs_fit_similarity_async(self.model._h, self.kind, self.k, C.byref(self._h)))
+
+    def set_k(self, k):
+        self.k = int(k)
+        _check(lib().mrs_sim_set_k(self._h, self.k))
+
+    def __call__(self, u, v):
+        out = C.c_double()
+        _check(lib().mrs_similarity(self._h, int(u), int(v), C.byref(out)))
+        return out.value
+
+    def neighbors(self, u, k):
+        cap = max(int(k), 1)
+        ids = np.empty(cap, dtype=np.int32)
+        sims = np.empty(cap, dtype=np.float64)
+        w = C.c_int32()
+        _check(lib().mrs_neighbors(self._h, int(u), int(k), _ptr(ids), _ptr(sims), cap, C.byref(w)))
+        return ids[:w.value].copy(), sims[:w.value].copy()
+
+    def entry_values(self, which):
+        n = C.c_int64()
+        _check(lib().mrs_sim_entry_values(self._h, int(which), None, None, None, 0, C.byref(n)))
+        u = np.empty(n.value, dtype=np.int32)
+        i = np.empty(n.value, dtype=np.int32)
+        v = np.empty(n.value, dtype=np.float64)
+        _check(lib().mrs_sim_entry_values(self._h, int(which), _ptr(u), _ptr(i), _ptr(v), n.value, C.byref(n)))
+        return u, i, v
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_sim_destroy(self._h)
+            self._h = None

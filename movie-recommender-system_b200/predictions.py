@@ -1,0 +1,373 @@
+"""Host-side mirror of the reference's ``package object shared.predictions`` (src/main/scala/shared/
+predictions.scala, "P:" below): same function names, argument meaning and fallbacks, so that code written
+against the Scala library reads the same here.  The Scala/JNI form of this facade is in INTEGRATION.md (no
+JVM exists in this image, so the executable mirror is Python over the same C ABI).
+
+The reference returns closures; here every factory returns a *tagged* callable that carries an engine handle
+and a kind, so ``MAE`` / ``MeanAbsoluteErrorSpark`` / ``recommendations`` issue ONE fused native call, and
+``f(u, i)`` answers single probes.  Arbitrary Python callables cannot run on the GPU and there is no CPU
+fallback: passing one raises ``UnsupportedOperationError`` (hard part 5).
+
+A "Seq[Rating]" / "RDD[Rating]" is a :class:`RatingSet` (device resident).  ``load`` builds one from a text
+file with the reference's parse rules; ``RatingSet.from_arrays`` / ``from_ratings`` from host data.
+"""
+import math
+import time
+from collections import namedtuple
+
+import numpy as np
+
+from . import engine as E
+
+Rating = namedtuple("Rating", ["user", "item", "rating"])  # P:9
+
+
+class UnsupportedOperationError(TypeError):
+    """An untagged (arbitrary) function reached an entry point that must run fused on the GPU."""
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = E.Engine(0)
+    return _default_engine
+
+
+def set_default_engine(engine):
+    global _default_engine
+    _default_engine = engine
+
+
+# ------------------------------------------------------------------ utilities (P:11-33)
+def timingInMs(f):  # P:11
+    start = time.perf_counter_ns()
+    out = f()
+    end = time.perf_counter_ns()
+    return out, (end - start) / 1000000.0
+
+
+def mean(s):  # P:18
+    s = list(s)
+    if len(s) > 0:
+        acc = s[0]
+        for v in s[1:]:
+            acc = acc + v
+        return acc / len(s)
+    return 0.0
+
+
+def std(s):  # P:19-25 (population standard deviation)
+    s = list(s)
+    if len(s) == 0:
+        return 0.0
+    m = mean(s)
+    return math.sqrt(sum((m - x) ** 2 for x in s) / float(len(s)))
+
+
+def toInt(s):  # P:27-33
+    try:
+        return int(s.strip()) if s.strip().lstrip("+-").isdigit() else None
+    except Exception:
+        return None
+
+
+def scale(x, y):  # P:57-61
+    if x > y:
+        return 5 - y
+    elif x < y:
+        return y - 1
+    else:
+        return 1
+
+
+# ------------------------------------------------------------------ rating sets
+class RatingSet:
+    """Device-resident Seq[Rating] / RDD[Rating]."""
+
+    def __init__(self, handle):
+        self._r = handle
+        self._model = None
+        self._sims = {}
+
+    @classmethod
+    def from_arrays(cls, users, items, ratings, engine=None, n_users_dim=0, n_items_dim=0):
+        eng = engine or default_engine()
+        return cls(E.Ratings(eng, users, items, ratings, n_users_dim, n_items_dim))
+
+    @classmethod
+    def from_ratings(cls, ratings, engine=None):
+        ratings = list(ratings)
+        return cls.from_arrays([r[0] for r in ratings], [r[1] for r in ratings], [r[2] for r in ratings], engine)
+
+    def __len__(self):
+        return self._r.n
+
+    length = property(__len__)
+
+    @property
+    def engine(self):
+        return self._r.engine
+
+    # fit (or re-run the fit kernels on the same buffers): this is the eager part of every computeX(ratings)
+    def _fit(self):
+        if self._model is None:
+            self._model = E.Model(self.engine, self._r, sync=False)
+        else:
+            self._model.refit()
+        return self._model
+
+    def _sim(self, kind, k):
+        m = self._fit()
+        s = self._sims.get(kind)
+        if s is None:
+            s = self._sims[kind] = E.Sim(m, kind, k, sync=False)
+        else:
+            s.refit(k)
+        return s
+
+
+def _as_set(ratings):
+    if isinstance(ratings, RatingSet):
+        return ratings
+    return RatingSet.from_ratings(ratings)
+
+
+def load(spark, path, sep):  # P:35-49 (the SparkSession argument is accepted and ignored)
+    eng = default_engine()
+    return RatingSet(E.Ratings.from_file(eng, path, sep))
+
+
+# ------------------------------------------------------------------ tagged function objects
+class GpuPredictor:
+    """(Int, Int) => Double backed by the engine."""
+
+    def __init__(self, train, kind, sim=None):
+        self.train, self.kind, self.sim = train, kind, sim
+
+    def __call__(self, u, i):
+        return float(self.train._model.predict([u], [i], self.kind, self.sim._s if self.sim else None)[0])
+
+    def batch(self, users, items):
+        return self.train._model.predict(users, items, self.kind, self.sim._s if self.sim else None)
+
+
+class GpuSimilarity:
+    """(Int, Int) => Double similarity; k > 0 restricts it to the first k neighbours of the first argument."""
+
+    def __init__(self, train, kind, k=0, fitted=None):
+        self.train, self.kind, self.k = train, kind, k
+        self._s = fitted
+
+    def __call__(self, u, v):
+        self._s.set_k(self.k)
+        return self._s(u, v)
+
+
+class GpuWsd:
+    def __init__(self, train, sim):
+        self.train, self.sim = train, sim
+
+    def __call__(self, u, i):
+        self.sim._s.set_k(self.sim.k)
+        return float(self.train._model.predict([u], [i], E.PRED_WSD, self.sim._s)[0])
+
+
+class IdMap:
+    """Map[Int, Double] view of a model vector (only ids that occur in the train set are members)."""
+
+    def __init__(self, vals, counts):
+        self._v, self._c = vals, counts
+
+    def __contains__(self, k):
+        return 0 <= k < self._c.size and self._c[k] > 0
+
+    def __getitem__(self, k):
+        if k not in self:
+            raise KeyError(k)
+        return float(self._v[k])
+
+    def get(self, k, default=None):
+        return float(self._v[k]) if k in self else default
+
+    getOrElse = get
+
+    def keys(self):
+        return [int(k) for k in np.flatnonzero(self._c > 0)]
+
+    def __len__(self):
+        return int((self._c > 0).sum())
+
+    def items(self):
+        return [(k, float(self._v[k])) for k in self.keys()]
+
+
+def _require_tagged(f, what):
+    if not isinstance(f, what):
+        raise UnsupportedOperationError(
+            f"expected a function object made by this library ({what.__name__}); arbitrary functions cannot run on the "
+            "GPU and there is no CPU fallback")
+    return f
+
+
+# ------------------------------------------------------------------ baseline family (P:69-237)
+def MAE(predict, data):  # P:69-86
+    p = _require_tagged(predict, GpuPredictor)
+    data = _as_set(data)
+    if p.sim is not None:
+        p.sim._s.set_k(p.sim.k)
+    return p.train._model.mae(data._r, p.kind, p.sim._s if p.sim else None)
+
+
+def average(ratings):  # P:94
+    return _as_set(ratings)._fit().global_avg
+
+
+def computeAvgRating(ratings):  # P:101
+    t = _as_set(ratings); t._fit()
+    return GpuPredictor(t, E.PRED_GLOBAL)
+
+
+def _vector(ratings, kind):
+    t = _as_set(ratings)
+    return IdMap(*t._fit().vector(kind))
+
+
+def usersAvg(ratings):  # P:113
+    return _vector(ratings, E.USER_AVG)
+
+
+def computeUserAvg(ratings):  # P:120
+    t = _as_set(ratings); t._fit()
+    return GpuPredictor(t, E.PRED_USER)
+
+
+def itemsAvg(ratings):  # P:134
+    return _vector(ratings, E.ITEM_AVG)
+
+
+def computeItemAvg(ratings):  # P:141
+    t = _as_set(ratings); t._fit()
+    return GpuPredictor(t, E.PRED_ITEM)
+
+
+def _entry_map(ratings, which):
+    t = _as_set(ratings)
+    s = t._sim(E.SIM_COSINE, 0)
+    u, i, v = s.entry_values(which)
+    return {(int(a), int(b)): float(c) for a, b, c in zip(u, i, v)}
+
+
+def computeNormalizeDeviation(ratings):  # P:155-169
+    return _entry_map(ratings, 0)
+
+
+def itemsAvgDev(ratings):  # P:176-186
+    return _vector(ratings, E.ITEM_AVG_DEV)
+
+
+def computeItemAvgDev(ratings):  # P:193
+    t = _as_set(ratings); t._fit()
+    return GpuPredictor(t, E.PRED_ITEMDEV)
+
+
+def computePrediction(ratings):  # P:205
+    t = _as_set(ratings); t._fit()
+    return GpuPredictor(t, E.PRED_BASELINE)
+
+
+# ------------------------------------------------------------------ Spark twins (P:246-391): same engine, RDD = RatingSet
+def meanSpark(values):  # P:246
+    vals = list(values)
+    return sum(vals) / len(vals) if len(vals) else float("nan")
+
+
+def MeanAbsoluteErrorSpark(predictor, real):  # P:256
+    return MAE(predictor, real)
+
+
+def getGlobalAvg(ratings):  # P:265
+    return average(ratings)
+
+
+getUsersAvg = usersAvg          # P:274
+usersAvgSpark = computeUserAvg  # P:281
+getItemsAvg = itemsAvg          # P:295
+itemsAvgSpark = computeItemAvg  # P:302
+getItemsAvgDev = itemsAvgDev    # P:336
+itemsAvgDevSpark = computeItemAvgDev       # P:350
+baselinePredictorSpark = computePrediction  # P:362
+
+
+# ------------------------------------------------------------------ personalized / kNN (P:400-649)
+class _SimilarityOne(GpuSimilarity):
+    def __init__(self):
+        super().__init__(None, E.SIM_UNIFORM, 0)
+
+    def __call__(self, u, v):  # P:400
+        return 1.0
+
+
+similarityOne = _SimilarityOne()
+
+
+def _bind(sim, train):
+    """Attach a similarity object to the train set whose similarities it must use and (re)compute it."""
+    _require_tagged(sim, GpuSimilarity)
+    t = _as_set(train)
+    return GpuSimilarity(t, sim.kind, sim.k, fitted=t._sim(sim.kind, sim.k))
+
+
+def adjustedCosineSimilarityFunction(ratings):  # P:407
+    t = _as_set(ratings)
+    return GpuSimilarity(t, E.SIM_COSINE, 0, fitted=t._sim(E.SIM_COSINE, 0))
+
+
+def jaccardCoefficient(ratings):  # P:440
+    t = _as_set(ratings)
+    return GpuSimilarity(t, E.SIM_JACCARD, 0, fitted=t._sim(E.SIM_JACCARD, 0))
+
+
+def preprocessedRating(ratings):  # P:470
+    return _entry_map(ratings, 1)
+
+
+def weightedSumDeviation(ratings, similarityFunction):  # P:489
+    t = _as_set(ratings)
+    return GpuWsd(t, _bind(similarityFunction, t))
+
+
+def predictor(ratings, wsd):  # P:557
+    w = _require_tagged(wsd, GpuWsd)
+    t = _as_set(ratings)
+    if w.train is not t:
+        w = GpuWsd(t, _bind(w.sim, t))
+    return GpuPredictor(t, E.PRED_PERSONALIZED, w.sim)
+
+
+def getNeighbors(ratings, k, similarityFunction):  # P:596
+    s = _bind(similarityFunction, ratings)
+
+    def neighbors(u):
+        ids, sims = s._s.neighbors(u, k)
+        return list(zip(ids.tolist(), sims.tolist()))
+    return neighbors
+
+
+def getSimilarity(ratings, k, similarityFunction):  # P:626
+    _require_tagged(similarityFunction, GpuSimilarity)
+    t = _as_set(ratings)
+    return GpuSimilarity(t, similarityFunction.kind, k, fitted=t._sim(similarityFunction.kind, k))
+
+
+def recommendations(ratings, predictor):  # P:651
+    p = _require_tagged(predictor, GpuPredictor)
+
+    def recommend(user, n):
+        if p.sim is not None:
+            p.sim._s.set_k(p.sim.k)
+        items, scores = p.train._model.recommend(user, n, p.kind, p.sim._s if p.sim else None)
+        return list(zip(items.tolist(), scores.tolist()))
+    return recommend
