@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline benchmark on B200: the ml-25m-shape baseline "MAE pass"
+(distributed/DistributedBaseline.scala:45-47: MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test))
+in ratings/s, plus the kNN k=300 ml-100k-shape fit+predict+MAE time (predict/kNN.scala:42-45) as an extra key.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      (the reference's CPU algorithm on the host cores)
+
+One JSON line on stdout (rank 0).  Data are synthetic MovieLens-shaped sets (mrs_b200/synth.py, seed 449).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ml25m_baseline_mae_pass_ratings_per_s"
+UNIT = "ratings/s"
+# distributed-25m-4.json:16-21, 66,147.47 ms for ~25,000,095 ratings on Spark local[4]
+# (hardware unstated, text parsing inside the timer)
+PUBLISHED_RATINGS_PER_S = 25_000_095 / 66.14747
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for r in self.rows if len(r) >= 9]
+        busy = [r for r in rows if r[4].isdigit() and int(r[4]) >= 50] or rows
+        for r in busy:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for j, nme in enumerate(names):
+                if r[5 + j].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(busy), "reasons": sorted(reasons)}
+
+
+def load_workload(rank):
+    import mrs_b200  # noqa: F401
+    from mrs_b200 import synth
+    t0 = time.time()
+    d = synth.cached("ml25m")
+    log(f"[rank {rank}] ml25m-shaped synthetic set ready in {time.time() - t0:.1f}s "
+        f"(train {d['train'][0].size}, test {d['test'][0].size})")
+    return d
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's CPU algorithm (oracle port of the Spark twin, partitions = host threads) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    d = load_workload(0)
+    tr, te = d["train"], d["test"]
+    n = tr[0].size + te[0].size
+    threads = oracle.max_threads()
+    for _ in range(max(args.warmup, 0)):
+        oracle.spark_baseline_mae(tr, te, nthreads=threads)
+    times = []
+    mae = None
+    for _ in range(max(args.steps, 1)):
+        t0 = time.perf_counter()
+        mae, _g = oracle.spark_baseline_mae(tr, te, nthreads=threads)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / PUBLISHED_RATINGS_PER_S, "dtype": "f64", "data": "synthetic ml-25m shape (seed 449)",
+        "config": workload_config(d, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "whole workload per step (fit on 20,000,076 train + MAE on 5,000,019 test), arrays already parsed"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mae": mae,
+        "note": "the Scala/Spark reference cannot run here (no JVM); this is oracle/mrs_oracle.c orc_baseline_mae_spark, "
+                "the C restatement of P:246-391 with partitions = threads",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(d, world):
+    return {
+        "workload": "distributed.DistributedBaseline on synthetic ml-25m shape: baselinePredictorSpark(train) fit + "
+                    "MeanAbsoluteErrorSpark on test (BASELINE.json configs[3])",
+        "train_ratings_per_gpu": int(d["train"][0].size), "test_ratings_per_gpu": int(d["test"][0].size),
+        "users_per_gpu": int(d["n_users"]), "items": int(d["n_items"]),
+        "layout": "user-major CSR (1 B half-star code/rating), item-major CSC (int32 user + 1 B code), sorted COO test "
+                  "(int32 u, int32 i, 1 B code)",
+        "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
+        "parallelism": f"user-sharded x{world}, one all-reduce of the per-item exchange buffer" if world > 1 else "single GPU",
+    }
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mrs_b200  # noqa: F401
+    from mrs_b200 import engine as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    d = load_workload(rank)
+    tr, te = d["train"], d["test"]
+    n_step = int(tr[0].size + te[0].size)
+
+    stream = torch.cuda.Stream(device=dev)
+    eng = E.Engine(local_rank, stream=stream.cuda_stream)
+    # global table sizes so that every rank's exchange buffer lines up (here all shards have the same shape)
+    R = eng.ratings(*tr)
+    T = eng.ratings(*te)
+    model = E.Model(eng, R)
+    bytes_r, bytes_t = R.bytes(), T.bytes()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out2 = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    class _Wrap:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    xptr, xn = model.exchange_buffer()
+    xbuf = torch.as_tensor(_Wrap(xptr, xn), device=dev) if world > 1 else None
+
+    def allreduce_x(ptr, n):
+        if world > 1:
+            dist.all_reduce(xbuf)
+
+    def step():
+        model.refit(between=allreduce_x if world > 1 else None)
+        model.mae_async(T, out2.data_ptr())
+        if world > 1:
+            dist.all_reduce(out2)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            flush.zero_()
+            step()
+        barrier()
+        launches0 = E.launch_count()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        t_wall0 = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()          # L2 flush, outside the timed pair
+            a.record(stream)
+            step()
+            b.record(stream)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = E.launch_count() - launches0
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        total_ms = sum(step_ms)
+        tot = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        total_ms = float(tot.item())
+        res = out2.cpu().numpy()
+        mae = float(res[0] / res[1])
+
+        # ---- per-kernel durations (CUDA events on the launching stream) for the roofline
+        per_kernel = {}
+        reps = 10
+        for _ in range(reps):
+            flush.zero_()
+            eng.profile_begin()
+            model.refit()
+            model.mae_async(T, out2.data_ptr())
+            for name, ms in eng.profile_end():
+                per_kernel.setdefault(name, []).append(ms)
+        per_kernel = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+
+        # ---- sustained repetition so that nvidia-smi (100 ms sampling) sees the same step under load
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 1.5:
+            for _ in range(50):
+                step()
+            torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if sampler else None
+
+    value = world * n_step * args.steps / (total_ms / 1000.0)
+    peak, peak_src = measured_peak()
+    alg = {"user_chunk_sum": bytes_r["user_major"], "item_chunk_dev": bytes_r["item_major"], "predict_mae": bytes_t["sorted_coo"]}
+    alg_total = sum(alg.values())
+    dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k])
+    dom_gbs = alg[dom] / (per_kernel[dom] * 1e-3) / 1e9
+    step_ms_mean = total_ms / args.steps
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+        "kernel_ms": per_kernel[dom], "per_kernel_ms": per_kernel,
+        "step": {"algorithmic_bytes": alg_total, "achieved": alg_total / (step_ms_mean * 1e-3) / 1e9,
+                 "frac": alg_total / (step_ms_mean * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + layout build + fit + MAE + D2H per step
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+    host = [pinned(x) for x in (*tr, *te)]
+    hu, hi, hr, tu, ti, tv = [h[0] for h in host]
+    e2e_steps = max(1, min(args.steps, 5))
+    keep = []
+
+    def e2e_step():
+        R2 = eng.ratings(hu, hi, hr)
+        T2 = eng.ratings(tu, ti, tv)
+        m2 = E.Model(eng, R2, sync=False) if world == 1 else None
+        if world > 1:
+            m2 = E.Model.__new__(E.Model)
+            m2.engine, m2.train, m2._h = eng, R2, E.C.c_void_p()
+            E._check(E.lib().mrs_fit_local(eng._h, R2._h, E.C.byref(m2._h)))
+            p2, n2 = m2.exchange_buffer()
+            dist.all_reduce(torch.as_tensor(_Wrap(p2, n2), device=dev))
+            E._check(E.lib().mrs_fit_finish(m2._h))
+        m2.mae_async(T2, out2.data_ptr())
+        if world > 1:
+            dist.all_reduce(out2)
+        r = out2.cpu().numpy()           # D2H read of the result
+        keep.append((m2, T2, R2))
+        return float(r[0] / r[1])
+
+    with torch.cuda.stream(stream):
+        e2e_step()
+        for h in keep.pop():
+            h.close()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_mae = e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_step * e2e_steps / float(e2e_t.item())
+    h2d = sum(int(x.nbytes) for x in (hu, hi, hr, tu, ti, tv))
+    for hs in keep:
+        for h in hs:
+            h.close()
+
+    line = None
+    if rank == 0:
+        # ---- CPU baseline on this box's host cores (oracle port, single thread), bounded sample
+        import oracle
+        t0 = time.perf_counter()
+        cpu_mae, _ = oracle.spark_baseline_mae(tr, te, nthreads=1)
+        cpu_s = time.perf_counter() - t0
+        cpu = {"value": n_step / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "whole workload once (fit on 20,000,076 train + MAE on 5,000,019 test), arrays already parsed",
+               "seconds": cpu_s, "mae": cpu_mae, "host_cores_available": os.cpu_count()}
+        knn = bench_knn(eng, stream, torch) if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms_mean, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / PUBLISHED_RATINGS_PER_S, "dtype": "f64", "data": "synthetic ml-25m shape (seed 449)",
+            "config": workload_config(d, world),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "steps": e2e_steps,
+                    "ms_per_step": 1000.0 * float(e2e_t.item()) / e2e_steps, "mae": e2e_mae,
+                    "note": "pinned host COO (int32,int32,f64) -> H2D -> CSR/CSC build -> fit -> MAE -> D2H, per step"},
+            "gpu_launches": int(launches), "clocks": clocks, "mae": mae, "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae),
+            "wall_ms_per_step_incl_flush": 1000.0 * t_wall / args.steps,
+            "step_ms_min_max": [min(step_ms), max(step_ms)],
+            "knn": knn,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_knn(eng, stream, torch):
+    """kNN k=300 on ml-100k shape: the closure timed by predict/kNN.scala:42-45 (similarities + top-k + predict + MAE)."""
+    from mrs_b200 import engine as E, synth
+    d = synth.cached("ml100k")
+    tr, te = d["train"], d["test"]
+    R, T = eng.ratings(*tr), eng.ratings(*te)
+    m = E.Model(eng, R)
+    s = m.similarity(E.SIM_COSINE, 300)
+    out2 = torch.zeros(2, dtype=torch.float64, device=f"cuda:{eng.device}")
+    reps = 30
+
+    def closure():
+        m.refit()
+        s.refit(300)
+        m.mae_async(T, out2.data_ptr(), E.PRED_PERSONALIZED, s)
+
+    for _ in range(5):
+        closure()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record(stream)
+        closure()
+        b.record(stream)
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    r = out2.cpu().numpy()
+    per_kernel = {}
+    for _ in range(5):
+        eng.profile_begin()
+        closure()
+        for name, t in eng.profile_end():
+            per_kernel.setdefault(name, []).append(t)
+    per_kernel = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+    # CPU port of the same closure (single thread)
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    o = O.Oracle(*tr)
+    cpu_mae = o.mae(te, kind=O.PERSONALIZED, simkind=O.SIM_COSINE, k=300)
+    cpu_ms = 1000.0 * (time.perf_counter() - t0)
+    mae = float(r[0] / r[1])
+    for h in (s, m, T, R):
+        h.close()
+    return {"metric": "knn_k300_ml100k_fit_predict_mae_ms", "value": statistics.median(ms), "unit": "ms", "min_ms": min(ms),
+            "mean_ms": sum(ms) / len(ms), "reps": reps, "mae": mae, "per_kernel_ms": per_kernel,
+            "l2": "not flushed: the whole working set (about 25 MB) is L2-resident by design",
+            "cpu_port_ms": cpu_ms, "cpu_port_mae": cpu_mae, "published_reference_ms": 26198.54,
+            "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.steps = max(args.steps, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
