@@ -105,6 +105,10 @@ MRS_API int32_t mrs_ratings_info(const mrs_ratings* r, int64_t* n, int32_t* n_us
 /* bytes of device memory the hot kernels read per pass over this set: [0] user-major payload, [1] item-major payload,
  * [2] sorted-COO payload (the figures bench.py's roofline uses) */
 MRS_API int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* bytes3);
+/* diagnostics: sizes of the lazily built kernel layouts (0 until built):
+ * [0] user tiles, [1] units, [2] slices, [3] slots of the tiled item-major layout; [4] item tiles, [5] chunks, [6] slots of the
+ * item-tiled test layout; [7] 16-code vectors of the padded user-major code array */
+MRS_API int32_t mrs_ratings_layout_info(const mrs_ratings* r, int64_t* out8);
 MRS_API void mrs_ratings_destroy(mrs_ratings* r);
 
 /* ---- fit: replaces the eager part of computePrediction (P:205-214) / baselinePredictorSpark (P:362-368)
@@ -114,10 +118,16 @@ MRS_API int32_t mrs_fit(mrs_engine* e, const mrs_ratings* train, mrs_model** out
 /* Asynchronous pieces (enqueue on the engine's stream, no host sync); *out may be an existing model of the same
  * train set, in which case its buffers are reused (this is what a timed loop calls). */
 MRS_API int32_t mrs_fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
+/* single-GPU asynchronous fit: mrs_fit_local and mrs_fit_finish fused (no exchange step, one kernel fewer) */
+MRS_API int32_t mrs_fit_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
 /* The exchange buffer written by mrs_fit_local: n_doubles fp64 values on the device,
  * [ sum of deviations per item | sum of ratings per item | count per item | sum of all ratings | count ].
  * A sharded run all-reduces (sum) it across ranks between mrs_fit_local and mrs_fit_finish: this is the one
  * collective that replaces the reduceByKey/collect shuffles of P:267-268 and the sum/count of P:247. */
+/* Per-item rating averages (itemsAvg, P:134) are accumulated in the same pass as the deviations by default.  The
+ * baseline predictor (P:205 / P:362) does not use them: a caller that only needs that predictor can switch them off
+ * for subsequent fits of this model; item-average queries then fail with MRS_ERR_INVALID. */
+MRS_API int32_t mrs_model_set_item_averages(mrs_model* m, int32_t enabled);
 MRS_API int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, int64_t* n_doubles);
 MRS_API int32_t mrs_fit_finish(mrs_model* m);
 MRS_API void mrs_model_destroy(mrs_model* m);

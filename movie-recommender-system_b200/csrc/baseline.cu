@@ -7,6 +7,7 @@
 // sums of half-star data are exact in any order, deviation sums are reduced in a fixed order
 // (lane-strided inside a chunk, xor-shuffle tree, chunks of a column in ascending order), so results are
 // run-to-run bit-reproducible.
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -44,6 +45,40 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
       s = warp_sum(acc);
     }
     if (lane == 0) upart[c] = s;
+  }
+}
+
+// ---- K1 (half-star codes): flat streaming of the padded user-major code array, one 128-bit load (16 codes of ONE
+// user) per thread; lanes of the same user are contiguous, so a segmented shuffle reduction leaves one integer
+// atomicAdd per (warp, user).  Integer sums are exact: the result does not depend on the order of the atomics.
+__global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
+                                                      uint32_t* __restrict__ usum, unsigned long long* __restrict__ block_part) {
+  __shared__ uint32_t sh[8];
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t s = 0;
+  int32_t row = -1;
+  if (t < n_vec) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(uval16) + t);
+    row = __ldg(vec_row + t);
+    s = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+  }
+  const uint32_t total = __reduce_add_sync(0xffffffffu, s);
+  // segmented suffix sums over runs of equal row ids
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_down_sync(0xffffffffu, s, o);
+    const int32_t r = __shfl_down_sync(0xffffffffu, row, o);
+    if (lane + o < 32 && r == row) s += v;
+  }
+  const int32_t prev = __shfl_up_sync(0xffffffffu, row, 1);
+  if (row >= 0 && (lane == 0 || prev != row)) atomicAdd(usum + row, s);
+  if (lane == 0) sh[threadIdx.x >> 5] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += sh[k];
+    block_part[blockIdx.x] = a;
   }
 }
 
@@ -203,6 +238,84 @@ __global__ void __launch_bounds__(256) predict_mae_kernel(const int32_t* __restr
   }
 }
 
+// ---- K3 (half-star codes): same as predict_mae_kernel with 4 consecutive test entries per thread (128-bit loads of the
+// user and item ids, 32-bit load of the codes) so that enough bytes are in flight; the tail (n % 4) is done by block 0.
+template <int KIND>
+__global__ void __launch_bounds__(256) predict_mae4_kernel(const int32_t* __restrict__ tu, const int32_t* __restrict__ ti,
+                                                          const uint8_t* __restrict__ tv, int64_t n, int32_t n_users, int32_t n_items,
+                                                          const double* __restrict__ uavg, const double* __restrict__ idevavg,
+                                                          const double* __restrict__ iavg, const double* __restrict__ gavg_p,
+                                                          double* __restrict__ part, unsigned int* __restrict__ counter,
+                                                          double* __restrict__ out2) {
+  __shared__ double sh[8];
+  __shared__ bool is_last;
+  const double gavg = gavg_p[0];
+  const int64_t n4 = n >> 2;
+  double acc = 0.0;
+  constexpr int Q = 2;  // quads per thread per iteration: 2 x (16 + 16 + 4) bytes requested before the first use
+  const int64_t T = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q0 < n4; q0 += Q * T) {
+    int4 u4[Q], i4[Q];
+    uchar4 c4[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const int64_t q = min(q0 + k * T, n4 - 1);
+      u4[k] = __ldg(reinterpret_cast<const int4*>(tu) + q);
+      i4[k] = __ldg(reinterpret_cast<const int4*>(ti) + q);
+      c4[k] = __ldg(reinterpret_cast<const uchar4*>(tv) + q);
+    }
+    double pr[Q][4];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      pr[k][0] = predict_one<KIND>(u4[k].x, i4[k].x, n_users, n_items, uavg, idevavg, iavg, gavg);
+      pr[k][1] = predict_one<KIND>(u4[k].y, i4[k].y, n_users, n_items, uavg, idevavg, iavg, gavg);
+      pr[k][2] = predict_one<KIND>(u4[k].z, i4[k].z, n_users, n_items, uavg, idevavg, iavg, gavg);
+      pr[k][3] = predict_one<KIND>(u4[k].w, i4[k].w, n_users, n_items, uavg, idevavg, iavg, gavg);
+    }
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      if (q0 + k * T < n4) {
+        acc += fabs(0.5 * (double)c4[k].x - pr[k][0]);
+        acc += fabs(0.5 * (double)c4[k].y - pr[k][1]);
+        acc += fabs(0.5 * (double)c4[k].z - pr[k][2]);
+        acc += fabs(0.5 * (double)c4[k].w - pr[k][3]);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    const int64_t p = (n4 << 2) + threadIdx.x;
+    if (p < n) acc += fabs(0.5 * (double)tv[p] - predict_one<KIND>(tu[p], ti[p], n_users, n_items, uavg, idevavg, iavg, gavg));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      part[blockIdx.x] = t;
+      __threadfence();
+      is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(&part[b]);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+      out2[0] = s;
+      out2[1] = (double)n;
+      *counter = 0;
+    }
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) predict_pairs_kernel(const int32_t* __restrict__ us, const int32_t* __restrict__ is, int64_t n,
                                                            int32_t n_users, int32_t n_items, const double* __restrict__ uavg,
@@ -217,6 +330,15 @@ inline int chunk_grid(int32_t n_chunks, int sm_count) {
   const int per_block = 8;  // warps per 256-thread block
   int g = (n_chunks + per_block - 1) / per_block;
   return std::max(1, std::min(g, sm_count * 8));
+}
+
+// code path: K1 (user code sums) -> K2 tiled item pass (forms the user averages on the way) -> K2b finalize
+int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused) {
+  MRS_CUDA(cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream));
+  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part);
+  mark(e, "user_sum");
+  MRS_CUDA(cudaGetLastError());
+  return launch_item_tiled(e, R, m, fused);
 }
 
 template <typename VT>
@@ -247,6 +369,14 @@ int32_t launch_mae(const mrs_model* m, const mrs_ratings* T, double* d_out2) {
   mrs_engine* e = m->eng;
   int grid = (int)std::min<int64_t>((T->n + 255) / 256, (int64_t)m->mae_part_cap);
   if (grid < 1) grid = 1;
+  if (sizeof(VT) == 1) {
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(((T->n >> 3) + 255) / 256, (int64_t)m->mae_part_cap));
+    predict_mae4_kernel<KIND><<<grid, 256, 0, e->stream>>>(T->coo_u, T->ucol, (const uint8_t*)T->uval, T->n, m->n_users, m->n_items,
+                                                           m->uavg, m->idevavg, m->iavg, m->gavg, m->mae_part, m->counters, d_out2);
+    mark(e, "predict_mae");
+    MRS_CUDA(cudaGetLastError());
+    return MRS_OK;
+  }
   predict_mae_kernel<VT, KIND><<<grid, 256, 0, e->stream>>>(T->coo_u, T->ucol, (const VT*)T->uval, T->n, m->n_users, m->n_items,
                                                             m->uavg, m->idevavg, m->iavg, m->gavg, m->mae_part, m->counters, d_out2);
   mark(e, "predict_mae");
@@ -268,9 +398,11 @@ int32_t dispatch_mae(const mrs_model* m, int32_t kind, const mrs_ratings* T, dou
 
 }  // namespace
 
-int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout) {
+int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool fused_finalize) {
   MRS_REQUIRE(e && R && inout, MRS_ERR_INVALID, "mrs_fit: NULL argument");
   MRS_CUDA(cudaSetDevice(e->device));
+  const bool codes = (R->value_kind == kValueCode);
+  if (codes) MRS_TRY(build_tiled_layout(R));
   mrs_model* m = *inout;
   if (m && m->train != R) {
     set_error("mrs_fit_local: the model passed for reuse was fitted on a different rating set");
@@ -283,9 +415,19 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout) {
     m->n_users = R->n_users;
     m->n_items = R->n_items;
     m->mae_part_cap = e->sm_count * 16;
+    m->k1_blocks = std::max(1, (R->n_vec + 255) / 256);
     int32_t s = MRS_OK;
+    if (codes) {
+      if (s == MRS_OK) s = dev_alloc(&m->usum, (size_t)R->n_users);
+      if (s == MRS_OK) s = dev_alloc(&m->k1_part, (size_t)m->k1_blocks);
+      if (s == MRS_OK) s = dev_alloc(&m->xdev_fix, (size_t)R->n_items);
+      if (s == MRS_OK) s = dev_alloc(&m->xcode_sum, (size_t)R->n_items);
+      if (s == MRS_OK && cudaMemsetAsync(m->xdev_fix, 0, sizeof(long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+      if (s == MRS_OK && cudaMemsetAsync(m->xcode_sum, 0, sizeof(unsigned long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+    }
     if (s == MRS_OK) s = dev_alloc(&m->upart, (size_t)R->uch.n_chunks);
-    if (s == MRS_OK) s = dev_alloc(&m->uavg, (size_t)R->n_users);
+    // padded to whole user tiles: the tiled kernel stages a tile's averages with one 64 KB bulk copy
+    if (s == MRS_OK) s = dev_alloc(&m->uavg, ((size_t)R->n_users + kTileUsers - 1) / kTileUsers * kTileUsers + kTileUsers);
     if (s == MRS_OK) s = dev_alloc(&m->ipart, 2 * (size_t)R->ich.n_chunks);
     if (s == MRS_OK) s = dev_alloc(&m->xbuf, 3 * (size_t)R->n_items + 2);
     if (s == MRS_OK) s = dev_alloc(&m->idevavg, (size_t)R->n_items);
@@ -299,7 +441,14 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout) {
   }
   m->finished = false;
   m->host_valid = false;
-  return R->value_kind == kValueCode ? launch_fit_local<uint8_t>(e, R, m) : launch_fit_local<double>(e, R, m);
+  if (codes) {
+    MRS_TRY(launch_fit_codes(e, R, m, fused_finalize));
+    if (fused_finalize) m->finished = true;
+    return MRS_OK;
+  }
+  MRS_TRY(launch_fit_local<double>(e, R, m));
+  if (fused_finalize) return fit_finish(m);
+  return MRS_OK;
 }
 
 int32_t fit_finish(mrs_model* m) {
@@ -315,12 +464,15 @@ int32_t fit_finish(mrs_model* m) {
 int32_t mae_baseline_async(const mrs_model* m, int32_t kind, const mrs_ratings* T, double* d_out2) {
   MRS_REQUIRE(m && T && d_out2, MRS_ERR_INVALID, "mrs_mae: NULL argument");
   MRS_REQUIRE(m->finished, MRS_ERR_INVALID, "mrs_mae: model not finished (call mrs_fit_finish)");
+  MRS_REQUIRE(kind != MRS_PRED_ITEM || m->want_item_avg, MRS_ERR_INVALID, "mrs_mae: item averages were switched off for this model");
+  if (kind == MRS_PRED_BASELINE && T->value_kind == kValueCode && T->n > 0) return launch_mae_tiled_baseline(m, T, d_out2);
   return T->value_kind == kValueCode ? dispatch_mae<uint8_t>(m, kind, T, d_out2) : dispatch_mae<double>(m, kind, T, d_out2);
 }
 
 int32_t predict_baseline_async(const mrs_model* m, int32_t kind, const int32_t* d_users, const int32_t* d_items, int64_t n,
                                double* d_out) {
   MRS_REQUIRE(m && m->finished, MRS_ERR_INVALID, "mrs_predict: model missing or not finished");
+  MRS_REQUIRE(kind != MRS_PRED_ITEM || m->want_item_avg, MRS_ERR_INVALID, "mrs_predict: item averages were switched off for this model");
   if (n == 0) return MRS_OK;
   int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)m->eng->sm_count * 16);
   cudaStream_t st = m->eng->stream;

@@ -133,20 +133,29 @@ extern "C" int32_t mrs_profile_end(mrs_engine* e, char* names_out, int64_t names
 }
 
 // ------------------------------------------------------------------ fit
-extern "C" int32_t mrs_fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout) { return fit_local(e, train, inout); }
+extern "C" int32_t mrs_fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout) { return fit_local(e, train, inout, false); }
+extern "C" int32_t mrs_fit_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout) { return fit_local(e, train, inout, true); }
 extern "C" int32_t mrs_fit_finish(mrs_model* m) { return fit_finish(m); }
 
 extern "C" int32_t mrs_fit(mrs_engine* e, const mrs_ratings* train, mrs_model** out) {
   MRS_REQUIRE(out, MRS_ERR_INVALID, "mrs_fit: NULL output");
   *out = nullptr;
-  MRS_TRY(fit_local(e, train, out));
-  int32_t s = fit_finish(*out);
+  int32_t s = fit_local(e, train, out, true);
+  if (s != MRS_OK) { mrs_model_destroy(*out); *out = nullptr; return s; }
   if (s == MRS_OK) {
     cudaError_t ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) { set_error("mrs_fit: %s", cudaGetErrorString(ce)); s = MRS_ERR_CUDA; }
   }
   if (s != MRS_OK) { mrs_model_destroy(*out); *out = nullptr; }
   return s;
+}
+
+extern "C" int32_t mrs_model_set_item_averages(mrs_model* m, int32_t enabled) {
+  MRS_REQUIRE(m, MRS_ERR_INVALID, "mrs_model_set_item_averages: NULL model");
+  m->want_item_avg = enabled != 0;
+  m->finished = false;  // the next query needs a fit made with the new setting
+  m->host_valid = false;
+  return MRS_OK;
 }
 
 extern "C" int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, int64_t* n_doubles) {
@@ -159,6 +168,8 @@ extern "C" int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, in
 extern "C" void mrs_model_destroy(mrs_model* m) {
   if (!m) return;
   if (m->eng) { cudaSetDevice(m->eng->device); cudaStreamSynchronize(m->eng->stream); }
+  dev_free(m->uinv_hi); dev_free(m->uinv_lo);
+  dev_free(m->usum); dev_free(m->k1_part); dev_free(m->xdev_fix); dev_free(m->xcode_sum);
   dev_free(m->upart); dev_free(m->uavg); dev_free(m->ipart); dev_free(m->xbuf); dev_free(m->idevavg); dev_free(m->iavg);
   dev_free(m->gavg); dev_free(m->mae_part); dev_free(m->counters);
   delete m;
@@ -190,7 +201,9 @@ static int32_t fetch_table(const mrs_model* m, int32_t kind, int64_t first, int6
   const int32_t* ptr = nullptr;
   switch (kind) {
     case MRS_USER_AVG: src = m->uavg; ptr = R->urow; break;
-    case MRS_ITEM_AVG: src = m->iavg; ptr = R->icolp; break;
+    case MRS_ITEM_AVG:
+      MRS_REQUIRE(m->want_item_avg, MRS_ERR_INVALID, "item averages were switched off for this model (mrs_model_set_item_averages)");
+      src = m->iavg; ptr = R->icolp; break;
     case MRS_ITEM_AVG_DEV: src = m->idevavg; ptr = R->icolp; break;
     default: set_error("unknown vector kind %d", kind); return MRS_ERR_INVALID;
   }

@@ -99,6 +99,11 @@ struct mrs_ratings {
   int32_t* ucol = nullptr;  // [n] item id
   void* uval = nullptr;     // [n] uint8 code or double
   int32_t* coo_u = nullptr;  // [n] user id of each CSR entry (sorted COO = coo_u, ucol, uval)
+  // code path, fit kernel K1: every user's codes padded with zeros to a multiple of 16 so that each 128-bit vector
+  // belongs to exactly one user
+  uint8_t* uval16 = nullptr;   // [n_vec * 16]
+  int32_t* vec_row = nullptr;  // [n_vec] user of each vector
+  int32_t n_vec = 0;
   // item-major CSC, users ascending inside a column
   int32_t* icolp = nullptr;  // [n_items+1]
   int32_t* irow = nullptr;   // [n] user id
@@ -120,14 +125,50 @@ struct mrs_ratings {
     int64_t ell_entries = 0;
   };
   mutable sim_layout sl;
+  // ---- lazily built tiled item-major layout for the fit kernel (tiled.cu); half-star codes only
+  struct tiled_layout {
+    bool built = false;
+    int32_t n_tiles = 0;
+    int32_t n_units = 0;
+    int32_t n_slices = 0;
+    int64_t n_slots = 0;               // 32 * (rows of all slices)
+    uint32_t* entry = nullptr;         // [n_slots] bit31 valid | code << 16 | user id local to the tile
+    int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
+    int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
+    int32_t* item_unit_ptr = nullptr;  // [n_items+1]
+    int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
+  };
+  mutable tiled_layout tl;
+  // ---- lazily built item-tiled layout for the fused predict + |error| kernel (mae_tiled.cu); half-star codes only
+  struct mae_layout {
+    bool built = false;
+    int32_t n_tiles = 0;        // item tiles of kMaeTileItems
+    int32_t n_chunks = 0;
+    int64_t n_slots = 0;        // entries incl. padding (every tile starts at a multiple of 16)
+    int32_t* user = nullptr;    // [n_slots] user id
+    uint16_t* item_local = nullptr;  // [n_slots] item id inside the tile
+    uint8_t* code = nullptr;    // [n_slots] half-star code, 0xFF = padding
+    int32_t* chunk_tile = nullptr;   // [n_chunks]
+    int32_t* chunk_begin = nullptr;  // [n_chunks]
+    int32_t* chunk_end = nullptr;    // [n_chunks]
+  };
+  mutable mae_layout ml;
 };
 
 struct mrs_model {
   mrs_engine* eng = nullptr;
   const mrs_ratings* train = nullptr;
   int32_t n_users = 0, n_items = 0;
-  double* upart = nullptr;      // [uch.n_chunks] chunk partial sums of ratings
+  uint32_t* usum = nullptr;     // [n_users] sum of half-star codes per user (code path)
+  unsigned long long* k1_part = nullptr;  // per-block sums of usum (code path)
+  int32_t k1_blocks = 0;
+  long long* xdev_fix = nullptr;            // [n_items] per-item deviation sums in units of 2^-40 (exact integer accumulation)
+  unsigned long long* xcode_sum = nullptr;  // [n_items] per-item sums of half-star codes
+  bool want_item_avg = true;                // also accumulate per-item rating sums during the fit (P:134; not needed by P:362)
+  double* upart = nullptr;      // [uch.n_chunks] chunk partial sums of ratings (fp64-value path)
   double* uavg = nullptr;       // [n_users]  average, -1.0 for unknown users (the reference's own sentinel, P:222)
+  double* uinv_hi = nullptr;    // [n_users]  1 / (5 - avg)   (code path: reciprocal of scale() for ratings above the average)
+  double* uinv_lo = nullptr;    // [n_users]  1 / (avg - 1)   (                              ... below the average)
   double* ipart = nullptr;      // [2 * ich.n_chunks] chunk partials: deviations | ratings
   double* xbuf = nullptr;       // [3*n_items + 2] exchange buffer: devsum | ratesum | count | gsum | gcount
   double* idevavg = nullptr;    // [n_items]  0.0 for unknown items (P:197)
@@ -193,8 +234,21 @@ inline void dev_free(void* p) {
 // loader.cu
 int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
                       int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
+// tiled.cu
+constexpr int kTileUsers = 8192;  // users per tile: 64 KB of fp64 averages in shared memory
+constexpr int kUnitLen = 64;      // (tile,item) segments are cut into units of at most this many entries
+constexpr int kUnitBits = 7;      // bits of (kUnitLen - len) in the unit sort key
+int32_t build_tiled_layout(const mrs_ratings* R);
+void free_tiled_layout(const mrs_ratings* R);
+int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize);
+// mae_tiled.cu
+constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item deviations in shared memory
+constexpr int kMaeChunk = 8192;      // test entries per CTA
+int32_t build_mae_layout(const mrs_ratings* T);
+void free_mae_layout(const mrs_ratings* T);
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2);
 // baseline.cu
-int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
+int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize);
 int32_t fit_finish(mrs_model* m);
 int32_t mae_baseline_async(const mrs_model* m, int32_t pred_kind, const mrs_ratings* test, double* d_out2);
 int32_t predict_baseline_async(const mrs_model* m, int32_t pred_kind, const int32_t* d_users, const int32_t* d_items,

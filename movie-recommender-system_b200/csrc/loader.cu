@@ -117,6 +117,63 @@ int bits_for(uint32_t v) {
   return std::max(b, 1);
 }
 
+__global__ void vec_count_kernel(const int32_t* __restrict__ urow, int32_t n_users, int32_t* __restrict__ cnt) {
+  const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n_users) cnt[u] = (urow[u + 1] - urow[u] + 15) >> 4;
+}
+
+__global__ void pad_fill_kernel(const uint8_t* __restrict__ uval, const int32_t* __restrict__ coo_u, const int32_t* __restrict__ urow,
+                                const int32_t* __restrict__ vrow, int64_t n, uint8_t* __restrict__ uval16) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t u = coo_u[p];
+    uval16[((int64_t)vrow[u] << 4) + (p - urow[u])] = uval[p];
+  }
+}
+
+// user of every 16-code vector of the padded array (largest u with vrow[u] <= t)
+__global__ void vec_row_kernel(const int32_t* __restrict__ vrow, int32_t n_users, int32_t n_vec, int32_t* __restrict__ vec_row) {
+  for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_vec; t += gridDim.x * blockDim.x) {
+    int32_t lo = 0, hi = n_users;
+    while (hi - lo > 1) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (vrow[mid] <= t) lo = mid; else hi = mid;
+    }
+    vec_row[t] = lo;
+  }
+}
+
+int grid_for(int64_t n, int block, int sm_count);
+
+int32_t build_padded_codes(mrs_engine* e, mrs_ratings* R) {
+  cudaStream_t st = e->stream;
+  const int32_t NU = R->n_users;
+  int32_t *cnt = nullptr, *vrow = nullptr;
+  MRS_TRY(dev_alloc(&cnt, (size_t)NU + 1));
+  MRS_TRY(dev_alloc(&vrow, (size_t)NU + 1));
+  MRS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)NU + 1), st));
+  vec_count_kernel<<<(NU + 255) / 256, 256, 0, st>>>(R->urow, NU, cnt);
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, vrow, NU + 1, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceScan::ExclusiveSum(e->scratch, tmp, cnt, vrow, NU + 1, st);
+  int32_t n_vec = 0;
+  MRS_CUDA(cudaMemcpyAsync(&n_vec, vrow + NU, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  R->n_vec = n_vec;
+  MRS_TRY(dev_alloc(&R->uval16, (size_t)n_vec * 16));
+  MRS_TRY(dev_alloc(&R->vec_row, (size_t)n_vec));
+  if (n_vec) {
+    MRS_CUDA(cudaMemsetAsync(R->uval16, 0, (size_t)n_vec * 16, st));
+    pad_fill_kernel<<<grid_for(R->n, 256, e->sm_count), 256, 0, st>>>((const uint8_t*)R->uval, R->coo_u, R->urow, vrow, R->n, R->uval16);
+    vec_row_kernel<<<grid_for(n_vec, 256, e->sm_count), 256, 0, st>>>(vrow, NU, n_vec, R->vec_row);
+    count_launch(4);
+  }
+  MRS_CUDA(cudaGetLastError());
+  MRS_CUDA(cudaStreamSynchronize(st));
+  dev_free(cnt); dev_free(vrow);
+  return MRS_OK;
+}
+
 int32_t build_chunks(mrs_engine* e, const int32_t* seg_ptr, int32_t n_seg, int32_t chunk, mrs_chunks* out) {
   cudaStream_t st = e->stream;
   int32_t* counts = nullptr;
@@ -156,8 +213,8 @@ int32_t build_sorted(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const in
   MRS_TRY(dev_alloc(&v_in, (size_t)n));
   MRS_TRY(dev_alloc(&v_out, (size_t)n));
   VT *uval = nullptr, *ival = nullptr;
-  MRS_TRY(dev_alloc(&uval, (size_t)n));
-  MRS_TRY(dev_alloc(&ival, (size_t)n));
+  MRS_TRY(dev_alloc(&uval, (size_t)n + 32));  // +32: 128-bit loads may read past the last rating (masked)
+  MRS_TRY(dev_alloc(&ival, (size_t)n + 32));
   R->uval = uval;
   R->ival = ival;
   MRS_TRY(dev_alloc(&R->ucol, (size_t)n));
@@ -194,6 +251,7 @@ int32_t build_sorted(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const in
     MRS_CUDA(cudaMemcpyAsync(R->csc_src, v_out, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
     MRS_CUDA(cudaGetLastError());
   }
+  if (sizeof(VT) == 1) MRS_TRY(build_padded_codes(e, R));
   MRS_TRY(build_chunks(e, R->urow, R->n_users, kUserChunk, &R->uch));
   MRS_TRY(build_chunks(e, R->icolp, R->n_items, kItemChunk, &R->ich));
   MRS_CUDA(cudaStreamSynchronize(st));
@@ -370,8 +428,18 @@ extern "C" int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* b) {
   MRS_REQUIRE(r && b, MRS_ERR_INVALID, "mrs_ratings_bytes: NULL argument");
   const int64_t vs = (int64_t)r->value_size();
   b[0] = r->n * vs;          // user-major pass reads the values only (the user is implicit in the row pointer)
+  if (r->uval16) b[0] = (int64_t)r->n_vec * 20;  // padded codes (16 per vector) + one user id per vector
+  if (r->ml.built) b[2] = r->n * 7;  // item-tiled test layout: int32 user + 16-bit local item + 1 B code (padding not counted)
   b[1] = r->n * (4 + vs);    // item-major pass: user id + value
+  if (r->tl.built) b[1] = r->n * 4;  // tiled item-major layout: one packed 32-bit word per rating (padding not counted)
   b[2] = r->n * (8 + vs);    // sorted COO pass: user id + item id + value
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_ratings_layout_info(const mrs_ratings* r, int64_t* o) {
+  MRS_REQUIRE(r && o, MRS_ERR_INVALID, "mrs_ratings_layout_info: NULL argument");
+  o[0] = r->tl.n_tiles; o[1] = r->tl.n_units; o[2] = r->tl.n_slices; o[3] = r->tl.n_slots;
+  o[4] = r->ml.n_tiles; o[5] = r->ml.n_chunks; o[6] = r->ml.n_slots; o[7] = r->n_vec;
   return MRS_OK;
 }
 
@@ -381,9 +449,11 @@ static void free_chunks(mrs_chunks* c) {
 
 extern "C" void mrs_ratings_destroy(mrs_ratings* r) {
   if (!r) return;
-  dev_free(r->urow); dev_free(r->ucol); dev_free(r->uval); dev_free(r->coo_u);
+  dev_free(r->urow); dev_free(r->ucol); dev_free(r->uval); dev_free(r->coo_u); dev_free(r->vec_row); dev_free(r->uval16);
   dev_free(r->icolp); dev_free(r->irow); dev_free(r->ival); dev_free(r->csc_src);
   free_chunks(&r->uch); free_chunks(&r->ich);
   free_sim_layout(r);
+  free_tiled_layout(r);
+  free_mae_layout(r);
   delete r;
 }

@@ -23,8 +23,8 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
-    "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_destroy",
-    "mrs_fit", "mrs_fit_local", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_model_scalar",
+    "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
+    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
     "mrs_mae_async", "mrs_recommend",
@@ -76,9 +76,12 @@ def lib():
         "mrs_ratings_from_file": (i32, [vp, C.c_char_p, C.c_char_p, P(vp)]),
         "mrs_ratings_info": (i32, [vp, P(i64), P(i32), P(i32), P(i32)]),
         "mrs_ratings_bytes": (i32, [vp, P(i64)]),
+        "mrs_ratings_layout_info": (i32, [vp, P(i64)]),
         "mrs_ratings_destroy": (None, [vp]),
         "mrs_fit": (i32, [vp, vp, P(vp)]),
         "mrs_fit_local": (i32, [vp, vp, P(vp)]),
+        "mrs_fit_async": (i32, [vp, vp, P(vp)]),
+        "mrs_model_set_item_averages": (i32, [vp, i32]),
         "mrs_model_exchange_buffer": (i32, [vp, P(vp), P(i64)]),
         "mrs_fit_finish": (i32, [vp]),
         "mrs_model_destroy": (None, [vp]),
@@ -184,6 +187,12 @@ class Ratings:
         _check(lib().mrs_ratings_bytes(self._h, b))
         return {"user_major": b[0], "item_major": b[1], "sorted_coo": b[2]}
 
+    def layout_info(self):
+        o = (C.c_int64 * 8)()
+        _check(lib().mrs_ratings_layout_info(self._h, o))
+        keys = ("user_tiles", "units", "slices", "tiled_slots", "item_tiles", "mae_chunks", "mae_slots", "code_vectors")
+        return dict(zip(keys, [int(x) for x in o]))
+
     def __len__(self):
         return self.n
 
@@ -207,10 +216,16 @@ class Model:
     def refit(self, between=None):
         """Enqueue the fit again on the same buffers (no host sync). ``between(ptr, n_doubles)`` is called after the
         local pass with the device exchange buffer -- a sharded run all-reduces it there."""
+        if between is None:
+            _check(lib().mrs_fit_async(self.engine._h, self.train._h, C.byref(self._h)))
+            return
         _check(lib().mrs_fit_local(self.engine._h, self.train._h, C.byref(self._h)))
-        if between is not None:
-            between(*self.exchange_buffer())
+        between(*self.exchange_buffer())
         _check(lib().mrs_fit_finish(self._h))
+
+    def set_item_averages(self, enabled):
+        """Per-item rating averages are not needed by the baseline predictor; switching them off saves work in the fit."""
+        _check(lib().mrs_model_set_item_averages(self._h, 1 if enabled else 0))
 
     def exchange_buffer(self):
         p, n = C.c_void_p(), C.c_int64()
