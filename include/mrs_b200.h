@@ -37,6 +37,7 @@ typedef struct mrs_engine mrs_engine;
 typedef struct mrs_ratings mrs_ratings;
 typedef struct mrs_model mrs_model;
 typedef struct mrs_sim mrs_sim;
+typedef struct mrs_graph mrs_graph;
 
 typedef enum {
   MRS_OK = 0,
@@ -84,6 +85,15 @@ MRS_API int64_t mrs_launch_count(void);
 MRS_API int32_t mrs_engine_create(int32_t device, void* cuda_stream, mrs_engine** out);
 MRS_API void mrs_engine_destroy(mrs_engine* e);
 MRS_API int32_t mrs_engine_sync(mrs_engine* e);
+
+/* CUDA-graph capture of any sequence of the asynchronous entry points (mrs_fit_async, mrs_fit_local, mrs_fit_finish,
+ * mrs_fit_similarity_async, mrs_mae_async) on this engine's stream: the kernels of a pass take tens of microseconds, so
+ * replaying one graph instead of launching them one by one removes the launch latency from the step.  Every handle used
+ * between begin and end must have been used once before (layouts and buffers are allocated on first use). */
+MRS_API int32_t mrs_graph_begin(mrs_engine* e);
+MRS_API int32_t mrs_graph_end(mrs_engine* e, mrs_graph** out);
+MRS_API int32_t mrs_graph_launch(mrs_graph* g);
+MRS_API void mrs_graph_destroy(mrs_graph* g);
 
 /* Per-kernel device timing (diagnostics; what bench.py's roofline uses): between begin and end every kernel the
  * library launches on this engine is bracketed by CUDA events on the engine's stream.  mrs_profile_end syncs and

@@ -95,6 +95,51 @@ extern "C" int32_t mrs_engine_sync(mrs_engine* e) {
   return MRS_OK;
 }
 
+struct mrs_graph {
+  mrs_engine* eng = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+extern "C" int32_t mrs_graph_begin(mrs_engine* e) {
+  MRS_REQUIRE(e, MRS_ERR_INVALID, "mrs_graph_begin: NULL engine");
+  MRS_REQUIRE(!e->profiling, MRS_ERR_INVALID, "mrs_graph_begin: per-kernel profiling is active");
+  MRS_CUDA(cudaSetDevice(e->device));
+  MRS_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_graph_end(mrs_engine* e, mrs_graph** out) {
+  MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_graph_end: NULL argument");
+  *out = nullptr;
+  cudaGraph_t g = nullptr;
+  MRS_CUDA(cudaStreamEndCapture(e->stream, &g));
+  cudaGraphExec_t ex = nullptr;
+  cudaError_t ce = cudaGraphInstantiate(&ex, g, 0);
+  if (ce != cudaSuccess) {
+    cudaGraphDestroy(g);
+    set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    return MRS_ERR_CUDA;
+  }
+  mrs_graph* h = new mrs_graph();
+  h->eng = e; h->graph = g; h->exec = ex;
+  *out = h;
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_graph_launch(mrs_graph* g) {
+  MRS_REQUIRE(g, MRS_ERR_INVALID, "mrs_graph_launch: NULL graph");
+  MRS_CUDA(cudaGraphLaunch(g->exec, g->eng->stream));
+  return MRS_OK;
+}
+
+extern "C" void mrs_graph_destroy(mrs_graph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
 extern "C" int32_t mrs_profile_begin(mrs_engine* e) {
   MRS_REQUIRE(e, MRS_ERR_INVALID, "mrs_profile_begin: NULL engine");
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);

@@ -23,7 +23,7 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
-    "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
+    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
     "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
@@ -70,6 +70,10 @@ def lib():
         "mrs_engine_create": (i32, [i32, vp, P(vp)]),
         "mrs_engine_destroy": (None, [vp]),
         "mrs_engine_sync": (i32, [vp]),
+        "mrs_graph_begin": (i32, [vp]),
+        "mrs_graph_end": (i32, [vp, P(vp)]),
+        "mrs_graph_launch": (i32, [vp]),
+        "mrs_graph_destroy": (None, [vp]),
         "mrs_profile_begin": (i32, [vp]),
         "mrs_profile_end": (i32, [vp, C.c_char_p, i64, P(C.c_float), i32, P(i32)]),
         "mrs_ratings_from_coo": (i32, [vp, vp, vp, vp, i64, i32, i32, P(vp)]),
@@ -131,6 +135,17 @@ class Engine:
     def sync(self):
         _check(lib().mrs_engine_sync(self._h))
 
+    def capture(self, fn):
+        """Run ``fn()`` (asynchronous engine calls only) under CUDA-graph capture and return a replayable Graph."""
+        _check(lib().mrs_graph_begin(self._h))
+        try:
+            fn()
+        finally:
+            h = C.c_void_p()
+            status = lib().mrs_graph_end(self._h, C.byref(h))
+        _check(status)
+        return Graph(h)
+
     def profile_begin(self):
         _check(lib().mrs_profile_begin(self._h))
 
@@ -154,6 +169,21 @@ class Engine:
 
     def ratings_from_file(self, path, sep):
         return Ratings.from_file(self, path, sep)
+
+
+class Graph:
+    """A captured sequence of kernels (cudaGraphExec); ``launch()`` replays it on the engine's stream."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def launch(self):
+        _check(lib().mrs_graph_launch(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_graph_destroy(self._h)
+            self._h = None
 
 
 class Ratings:
