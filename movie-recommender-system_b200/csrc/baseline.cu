@@ -400,7 +400,7 @@ int32_t dispatch_mae(const mrs_model* m, int32_t kind, const mrs_ratings* T, dou
 
 int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool fused_finalize) {
   MRS_REQUIRE(e && R && inout, MRS_ERR_INVALID, "mrs_fit: NULL argument");
-  MRS_CUDA(cudaSetDevice(e->device));
+  use_engine(e);
   const bool codes = (R->value_kind == kValueCode);
   if (codes) MRS_TRY(build_tiled_layout(R));
   mrs_model* m = *inout;

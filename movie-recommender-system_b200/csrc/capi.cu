@@ -11,6 +11,56 @@
 namespace mrs {
 
 static thread_local char g_err[1024] = "";
+thread_local mrs_engine* tls_engine = nullptr;
+
+constexpr size_t kCacheCap = (size_t)64 << 30;  // keep at most this many bytes of released buffers per engine
+
+void* cache_alloc(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  mrs_engine* e = tls_engine;
+  if (e) {
+    auto it = e->free_blocks.find(bytes);
+    if (it != e->free_blocks.end()) {
+      void* p = it->second;
+      e->free_blocks.erase(it);
+      e->cached_bytes -= bytes;
+      e->live_blocks[p] = bytes;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, bytes);
+  if (err != cudaSuccess && e && !e->free_blocks.empty()) {  // give the cache back to the driver and retry
+    cudaStreamSynchronize(e->stream);
+    for (auto& kv : e->free_blocks) cudaFree(kv.second);
+    e->free_blocks.clear();
+    e->cached_bytes = 0;
+    err = cudaMalloc(&p, bytes);
+  }
+  if (err != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+    return nullptr;
+  }
+  if (e) e->live_blocks[p] = bytes;
+  return p;
+}
+
+void cache_free(void* p) {
+  mrs_engine* e = tls_engine;
+  if (e) {
+    auto it = e->live_blocks.find(p);
+    if (it != e->live_blocks.end()) {
+      const size_t bytes = it->second;
+      e->live_blocks.erase(it);
+      if (e->cached_bytes + bytes <= kCacheCap) {
+        e->free_blocks.emplace(bytes, p);
+        e->cached_bytes += bytes;
+        return;
+      }
+    }
+  }
+  cudaFree(p);
+}
 std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -73,6 +123,7 @@ extern "C" int32_t mrs_engine_create(int32_t device, void* cuda_stream, mrs_engi
     if (se != cudaSuccess) { delete e; set_error("cudaStreamCreate failed: %s", cudaGetErrorString(se)); return MRS_ERR_CUDA; }
     e->own_stream = true;
   }
+  use_engine(e);
   cudaError_t he = cudaMallocHost((void**)&e->h_pinned, 64 * sizeof(double));
   if (he != cudaSuccess) { set_error("cudaMallocHost failed: %s", cudaGetErrorString(he)); mrs_engine_destroy(e); return MRS_ERR_NOMEM; }
   *out = e;
@@ -84,6 +135,9 @@ extern "C" void mrs_engine_destroy(mrs_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->scratch) cudaFree(e->scratch);
+  for (auto& kv : e->free_blocks) cudaFree(kv.second);
+  e->free_blocks.clear();
+  if (tls_engine == e) tls_engine = nullptr;
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -212,7 +266,7 @@ extern "C" int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, in
 
 extern "C" void mrs_model_destroy(mrs_model* m) {
   if (!m) return;
-  if (m->eng) { cudaSetDevice(m->eng->device); cudaStreamSynchronize(m->eng->stream); }
+  if (m->eng) use_engine(m->eng);
   dev_free(m->uinv_hi); dev_free(m->uinv_lo);
   dev_free(m->usum); dev_free(m->k1_part); dev_free(m->xdev_fix); dev_free(m->xcode_sum);
   dev_free(m->upart); dev_free(m->uavg); dev_free(m->ipart); dev_free(m->xbuf); dev_free(m->idevavg); dev_free(m->iavg);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <atomic>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mrs_b200.h"
@@ -74,6 +75,12 @@ struct mrs_engine {
   void* scratch = nullptr;  // reusable device scratch (CUB temp storage etc.)
   size_t scratch_bytes = 0;
   double* h_pinned = nullptr;  // small pinned staging area for scalar read-backs
+  // device block cache: buffers released by destroyed handles are kept (exact size match) and handed out again, so
+  // rebuilding a rating set or a model does not go back to the driver (cudaMalloc/cudaFree of ~1 GB of layouts cost
+  // 100+ ms per build).  Everything runs on one stream, so reuse is ordered.
+  std::unordered_multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> live_blocks;
+  size_t cached_bytes = 0;
   // diagnostics: event after every launch while profiling (mrs_profile_begin/end)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -203,6 +210,13 @@ struct mrs_sim {
 };
 
 namespace mrs {
+extern thread_local mrs_engine* tls_engine;  // engine whose block cache serves dev_alloc / dev_free on this thread
+inline void use_engine(const mrs_engine* e) {
+  cudaSetDevice(e->device);
+  tls_engine = const_cast<mrs_engine*>(e);
+}
+void* cache_alloc(size_t bytes);
+void cache_free(void* p);
 // called right after each kernel launch: counts it and, while profiling, records an event behind it
 inline void mark(mrs_engine* e, const char* name, int n = 1) {
   count_launch(n);
@@ -218,17 +232,12 @@ inline void mark(mrs_engine* e, const char* name, int n = 1) {
 int32_t ensure_scratch(mrs_engine* e, size_t bytes);
 template <typename T>
 int32_t dev_alloc(T** p, size_t count) {
-  *p = nullptr;
   if (count == 0) count = 1;
-  cudaError_t err = cudaMalloc((void**)p, count * sizeof(T));
-  if (err != cudaSuccess) {
-    set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(err));
-    return MRS_ERR_NOMEM;
-  }
-  return MRS_OK;
+  *p = (T*)cache_alloc(count * sizeof(T));
+  return *p ? MRS_OK : MRS_ERR_NOMEM;
 }
 inline void dev_free(void* p) {
-  if (p) cudaFree(p);
+  if (p) cache_free(p);
 }
 
 // loader.cu

@@ -394,7 +394,7 @@ int32_t sim_fit_async(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout) {
   const mrs_ratings* R = m->train;
   mrs_engine* e = m->eng;
   cudaStream_t st = e->stream;
-  MRS_CUDA(cudaSetDevice(e->device));
+  use_engine(e);
   MRS_TRY(build_sim_layout(R));
   const auto& L = R->sl;
   const bool matrix = (kind != MRS_SIM_UNIFORM);
@@ -563,7 +563,7 @@ extern "C" int32_t mrs_sim_entry_values(const mrs_sim* s, int32_t which, int32_t
 
 extern "C" void mrs_sim_destroy(mrs_sim* s) {
   if (!s) return;
-  if (s->model && s->model->eng) { cudaSetDevice(s->model->eng->device); cudaStreamSynchronize(s->model->eng->stream); }
+  if (s->model && s->model->eng) use_engine(s->model->eng);
   dev_free(s->udev); dev_free(s->upre); dev_free(s->unorm); dev_free(s->cdev); dev_free(s->ell_val); dev_free(s->S);
   dev_free(s->rank); dev_free(s->nbr_id); dev_free(s->nbr_sim); dev_free(s->mae_part); dev_free(s->counter);
   delete s;

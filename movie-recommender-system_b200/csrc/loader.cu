@@ -266,7 +266,7 @@ int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items,
   MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL engine or output");
   MRS_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, MRS_ERR_UNSUPPORTED, "mrs_ratings_from_coo: n=%lld outside [0, 2^31)", (long long)n);
   MRS_REQUIRE(n == 0 || (users && items && ratings), MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL input array");
-  MRS_CUDA(cudaSetDevice(e->device));
+  use_engine(e);
   cudaStream_t st = e->stream;
   int32_t *d_u = nullptr, *d_i = nullptr, *d_stats = nullptr;
   double* d_r = nullptr;
@@ -449,6 +449,7 @@ static void free_chunks(mrs_chunks* c) {
 
 extern "C" void mrs_ratings_destroy(mrs_ratings* r) {
   if (!r) return;
+  if (r->eng) use_engine(r->eng);
   dev_free(r->urow); dev_free(r->ucol); dev_free(r->uval); dev_free(r->coo_u); dev_free(r->vec_row); dev_free(r->uval16);
   dev_free(r->icolp); dev_free(r->irow); dev_free(r->ival); dev_free(r->csc_src);
   free_chunks(&r->uch); free_chunks(&r->ich);

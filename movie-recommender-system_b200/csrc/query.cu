@@ -66,6 +66,7 @@ using namespace mrs;
 
 extern "C" int32_t mrs_mae_async(const mrs_model* m, const mrs_sim* sim, int32_t kind, const mrs_ratings* test, void* device_out2) {
   MRS_REQUIRE(m && test && device_out2, MRS_ERR_INVALID, "mrs_mae_async: NULL argument");
+  use_engine(m->eng);
   MRS_REQUIRE(m->eng == test->eng, MRS_ERR_INVALID, "mrs_mae: model and test set live on different engines");
   if (kind == MRS_PRED_PERSONALIZED) {
     MRS_REQUIRE(sim, MRS_ERR_INVALID, "mrs_mae: the personalized predictor needs a similarity handle");
@@ -77,7 +78,7 @@ extern "C" int32_t mrs_mae_async(const mrs_model* m, const mrs_sim* sim, int32_t
 extern "C" int32_t mrs_mae(const mrs_model* m, const mrs_sim* sim, int32_t kind, const mrs_ratings* test, double* mae_out) {
   MRS_REQUIRE(m && test && mae_out, MRS_ERR_INVALID, "mrs_mae: NULL argument");
   mrs_engine* e = m->eng;
-  MRS_CUDA(cudaSetDevice(e->device));
+  use_engine(e);
   double* d_out = nullptr;
   MRS_TRY(dev_alloc(&d_out, 2));
   int32_t s = mrs_mae_async(m, sim, kind, test, d_out);
@@ -98,7 +99,7 @@ extern "C" int32_t mrs_predict(const mrs_model* m, const mrs_sim* sim, int32_t k
   MRS_REQUIRE(n >= 0, MRS_ERR_INVALID, "mrs_predict: negative n");
   if (n == 0) return MRS_OK;
   mrs_engine* e = m->eng;
-  MRS_CUDA(cudaSetDevice(e->device));
+  use_engine(e);
   int32_t *d_u = nullptr, *d_i = nullptr;
   double* d_o = nullptr;
   int32_t s = dev_alloc(&d_u, (size_t)n);
@@ -131,7 +132,7 @@ extern "C" int32_t mrs_recommend(const mrs_model* m, const mrs_sim* sim, int32_t
   int32_t P = 2;
   while (P < NI) P <<= 1;
   MRS_REQUIRE(P <= (1 << 20), MRS_ERR_UNSUPPORTED, "mrs_recommend: item dimension %d too large for the single-block sort", NI);
-  MRS_CUDA(cudaSetDevice(e->device));
+  use_engine(e);
   cudaStream_t st = e->stream;
   int32_t *d_u = nullptr, *d_i = nullptr, *d_id = nullptr;
   double *d_score = nullptr, *d_key = nullptr;

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Wall-clock phases of the end-to-end path (host COO -> layouts -> fit -> MAE) on the ml-25m shape."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import mrs_b200
+from mrs_b200 import engine as E, synth
+
+d = synth.cached("ml25m")
+eng = E.Engine(0)
+def pin(a):
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory(); return t.numpy(), t
+host = [pin(x) for x in (*d["train"], *d["test"])]
+hu, hi, hr, tu, ti, tv = [h[0] for h in host]
+out = torch.zeros(2, dtype=torch.float64, device="cuda")
+for rep in range(3):
+    t = [time.perf_counter()]
+    R = eng.ratings(hu, hi, hr); eng.sync(); t.append(time.perf_counter())
+    T = eng.ratings(tu, ti, tv); eng.sync(); t.append(time.perf_counter())
+    m = E.Model(eng, R, sync=False); eng.sync(); t.append(time.perf_counter())
+    m.mae_async(T, out.data_ptr()); eng.sync(); t.append(time.perf_counter())
+    r = out.cpu().numpy(); t.append(time.perf_counter())
+    print("rep", rep, "train build %.2f ms | test build %.2f | first fit (tiled layout + kernels) %.2f | first mae (mae layout + kernel) %.2f | d2h %.2f | total %.2f ms  mae=%.6f" % (
+        *(1e3 * (t[k + 1] - t[k]) for k in range(5)), 1e3 * (t[-1] - t[0]), r[0] / r[1]))
+    t0 = time.perf_counter(); m.close(); T.close(); R.close(); print("  destroy %.2f ms" % (1e3 * (time.perf_counter() - t0)))
