@@ -173,31 +173,26 @@ def run_ours(args):
     # global table sizes so that every rank's exchange buffer lines up (here all shards have the same shape)
     R = eng.ratings(*tr)
     T = eng.ratings(*te)
-    model = E.Model(eng, R)
+    model = E.Model(eng, R) if world == 1 else None
     # the timed closure is baselinePredictorSpark + MeanAbsoluteErrorSpark: it never forms per-item rating averages
     # (P:362-391), so that optional part of the fit is switched off (it costs about 8 % of the item pass)
-    model.set_item_averages(False)
-    model.refit()
+    if model is not None:
+        model.set_item_averages(False)
+        model.refit()
     bytes_r, bytes_t = R.bytes(), T.bytes()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
-    class _Wrap:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-    xptr, xn = model.exchange_buffer()
-    xbuf = torch.as_tensor(_Wrap(xptr, xn), device=dev) if world > 1 else None
-
-    def allreduce_x(ptr, n):
-        if world > 1:
-            dist.all_reduce(xbuf)
+    from mrs_b200 import sharded
+    sb = sharded.ShardedBaseline(eng, R, T) if world > 1 else None
 
     def enqueue():
-        model.refit(between=allreduce_x if world > 1 else None)
-        model.mae_async(T, out2.data_ptr())
-        if world > 1:
-            dist.all_reduce(out2)
+        if sb is not None:       # local pass -> all-reduce of the exchange buffer -> finish -> MAE -> 16-byte all-reduce
+            sb.fit()
+            sb.mae_async()
+        else:
+            model.refit()
+            model.mae_async(T, out2.data_ptr())
 
     graph = None
 
@@ -242,17 +237,18 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         total_ms = float(tot.item())
-        res = out2.cpu().numpy()
+        res = (sb.out2 if sb is not None else out2).cpu().numpy()
         mae = float(res[0] / res[1])
 
         # ---- per-kernel durations (CUDA events on the launching stream) for the roofline
         per_kernel = {}
         reps = 10
+        pm = model if model is not None else sb.model
         for _ in range(reps):
             flush.zero_()
             eng.profile_begin()
-            model.refit()
-            model.mae_async(T, out2.data_ptr())
+            pm.refit()
+            pm.mae_async(T, out2.data_ptr())
             for name, ms in eng.profile_end():
                 per_kernel.setdefault(name, []).append(ms)
         per_kernel = {k: sum(v) / len(v) for k, v in per_kernel.items()}
@@ -299,25 +295,24 @@ def run_ours(args):
     def e2e_step():
         R2 = eng.ratings(hu, hi, hr)
         T2 = eng.ratings(tu, ti, tv)
-        m2 = E.Model(eng, R2, sync=False) if world == 1 else None
-        if world > 1:
-            m2 = E.Model.__new__(E.Model)
-            m2.engine, m2.train, m2._h = eng, R2, E.C.c_void_p()
-            E._check(E.lib().mrs_fit_local(eng._h, R2._h, E.C.byref(m2._h)))
-            p2, n2 = m2.exchange_buffer()
-            dist.all_reduce(torch.as_tensor(_Wrap(p2, n2), device=dev))
-            E._check(E.lib().mrs_fit_finish(m2._h))
-        m2.mae_async(T2, out2.data_ptr())
-        if world > 1:
-            dist.all_reduce(out2)
-        r = out2.cpu().numpy()           # D2H read of the result
-        keep.append((m2, T2, R2))
+        if world == 1:
+            m2 = E.Model(eng, R2, sync=False)
+            m2.mae_async(T2, out2.data_ptr())
+            r = out2.cpu().numpy()       # D2H read of the result
+            handles = (m2, T2, R2)
+        else:
+            s2 = sharded.ShardedBaseline(eng, R2, T2)
+            s2.fit()
+            s2.mae_async()
+            r = s2.out2.cpu().numpy()
+            handles = (s2.model, T2, R2)
+        for h in handles:                # a caller drops the handles; their device blocks go back to the engine's cache
+            h.close()
         return float(r[0] / r[1])
 
     with torch.cuda.stream(stream):
         e2e_step()
-        for h in keep.pop():
-            h.close()
+        e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -352,7 +347,8 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "steps": e2e_steps,
                     "ms_per_step": 1000.0 * float(e2e_t.item()) / e2e_steps, "mae": e2e_mae,
-                    "note": "pinned host COO (int32,int32,f64) -> H2D -> CSR/CSC build -> fit -> MAE -> D2H, per step"},
+                    "note": "pinned host COO (int32,int32,f64) -> H2D -> CSR/CSC + kernel layouts build -> fit -> MAE -> D2H -> handles "
+                            "released, per step (2 untimed warm-up steps fill the engine's device block cache)"},
             "gpu_launches": int(launches) if graph is None else int(args.steps * kernels_per_step),
             "launch_mode": "cuda graph replay (1 cudaGraphLaunch per step)" if graph is not None else "stream launches", "clocks": clocks, "mae": mae, "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae),
             "wall_ms_per_step_incl_flush": 1000.0 * t_wall / args.steps,

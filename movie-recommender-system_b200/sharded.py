@@ -1,0 +1,102 @@
+"""User-sharded baseline pass: one process per GPU, one collective.
+
+The reference distributes the baseline with Spark: `reduceByKey` + `collect` per keyed average (P:267-268) and
+`sum`/`count` for the global mean (P:247).  Here users are partitioned into contiguous id ranges balanced by rating
+count; a rank holds the train rows and the test pairs of its users, so user sums/averages are local.  The only exchange
+is ONE all-reduce (sum) of the per-item exchange buffer written by ``mrs_fit_local``:
+
+    [ sum of deviations per item | sum of ratings per item | count per item | sum of all ratings | count ]   (3*I+2 fp64)
+
+followed by ``mrs_fit_finish`` on every rank, and a 16-byte all-reduce of {sum |err|, n} for the MAE.
+The collective itself is `torch.distributed` (NCCL on GPUs; gloo in the CPU tests of this host logic).
+"""
+import numpy as np
+
+
+def partition_users(user_counts, world):
+    """Cut points b[0]=0 <= ... <= b[world]=len(user_counts): rank r owns user ids [b[r], b[r+1]); contiguous ranges
+    whose rating counts are as equal as a contiguous split allows."""
+    counts = np.asarray(user_counts, dtype=np.int64)
+    total = int(counts.sum())
+    csum = np.cumsum(counts)
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r // world
+        cut = int(np.searchsorted(csum, target, side="left")) + 1 if total else 0
+        bounds.append(min(max(cut, bounds[-1]), counts.size))
+    bounds.append(int(counts.size))
+    return bounds
+
+
+def shard_of(users, bounds, rank):
+    """Boolean mask of the entries owned by `rank` (its users are [bounds[rank], bounds[rank+1]))."""
+    u = np.asarray(users)
+    return (u >= bounds[rank]) & (u < bounds[rank + 1])
+
+
+def exchange_size(n_items_dim):
+    return 3 * int(n_items_dim) + 2
+
+
+def split_exchange(buf, n_items_dim):
+    """Views of an exchange buffer: (dev_sum[I], rating_sum[I], count[I], global_sum, global_count)."""
+    n = int(n_items_dim)
+    return buf[:n], buf[n:2 * n], buf[2 * n:3 * n], buf[3 * n], buf[3 * n + 1]
+
+
+def finish_from_exchange(buf, n_items_dim):
+    """What ``mrs_fit_finish`` computes from the (all-reduced) buffer -- numpy statement used by the CPU tests of the
+    exchange protocol: item average deviation (0.0 for unknown items, P:197), item average, global average."""
+    dev, rate, cnt, gs, gc = split_exchange(np.asarray(buf, dtype=np.float64), n_items_dim)
+    known = cnt > 0
+    idev = np.where(known, dev / np.where(known, cnt, 1.0), 0.0)
+    iavg = np.where(known, rate / np.where(known, cnt, 1.0), np.nan)
+    gavg = gs / gc if gc > 0 else 0.0
+    return idev, iavg, gavg
+
+
+def all_reduce_sum(tensor, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor
+
+
+class _CudaView:
+    """Zero-copy `__cuda_array_interface__` view of a device buffer owned by the engine (n fp64 values)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class ShardedBaseline:
+    """Fit + MAE of the baseline predictor over this rank's shard, with the one exchange of the module docstring.
+
+    `engine` must have been created on the CUDA stream the collectives run on (``torch.cuda.current_stream()``)."""
+
+    def __init__(self, engine, train, test, group=None):
+        import torch
+        from . import engine as E
+        self.E, self.torch, self.group = E, torch, group
+        self.engine, self.train, self.test = engine, train, test
+        self.model = E.Model(engine, train, sync=False)
+        ptr, n = self.model.exchange_buffer()
+        self.device = torch.device("cuda", engine.device)
+        self.xbuf = torch.as_tensor(_CudaView(ptr, n), device=self.device)
+        self.out2 = torch.zeros(2, dtype=torch.float64, device=self.device)
+
+    def _exchange(self, ptr, n):
+        all_reduce_sum(self.xbuf, self.group)
+
+    def fit(self):
+        """Enqueue: local pass -> all-reduce of the exchange buffer -> finish (no host sync)."""
+        self.model.refit(between=self._exchange)
+
+    def mae_async(self):
+        self.model.mae_async(self.test, self.out2.data_ptr(), self.E.PRED_BASELINE)
+        all_reduce_sum(self.out2, self.group)
+
+    def mae(self):
+        self.mae_async()
+        r = self.out2.cpu().numpy()
+        return float(r[0] / r[1])
