@@ -130,10 +130,11 @@ MRS_API int32_t mrs_fit(mrs_engine* e, const mrs_ratings* train, mrs_model** out
 MRS_API int32_t mrs_fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
 /* single-GPU asynchronous fit: mrs_fit_local and mrs_fit_finish fused (no exchange step, one kernel fewer) */
 MRS_API int32_t mrs_fit_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
-/* The exchange buffer written by mrs_fit_local: n_doubles fp64 values on the device,
- * [ sum of deviations per item | sum of ratings per item | count per item | sum of all ratings | count ].
+/* The exchange buffer written by mrs_fit_local: n_doubles = 3*I+2 fp64 values on the device (I = item table size),
+ * [ sum of deviations per item | count per item | sum of all ratings | count | sum of ratings per item ].
  * A sharded run all-reduces (sum) it across ranks between mrs_fit_local and mrs_fit_finish: this is the one
- * collective that replaces the reduceByKey/collect shuffles of P:267-268 and the sum/count of P:247. */
+ * collective that replaces the reduceByKey/collect shuffles of P:267-268 and the sum/count of P:247.  The first
+ * 2*I+2 values are all the baseline predictor needs: with item averages switched off only that prefix has to travel. */
 /* Per-item rating averages (itemsAvg, P:134) are accumulated in the same pass as the deviations by default.  The
  * baseline predictor (P:205 / P:362) does not use them: a caller that only needs that predictor can switch them off
  * for subsequent fits of this model; item-average queries then fail with MRS_ERR_INVALID. */

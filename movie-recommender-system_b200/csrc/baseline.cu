@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) item_chunk_dev_kernel(const int32_t* __re
   }
 }
 
-// ---- K2b: chunk partials -> exchange buffer [devsum | ratesum | count] (P:176-186 (sum,count); P:267 reduceByKey)
+// ---- K2b: chunk partials -> exchange buffer [devsum | count | gsum gcount | ratesum] (P:176-186 (sum,count); P:267 reduceByKey)
 __global__ void __launch_bounds__(256) item_partial_kernel(const int32_t* __restrict__ icolp, const int32_t* __restrict__ seg_chunk_ptr,
                                                           const double* __restrict__ ipart, int32_t n_chunks, int32_t n_items,
                                                           double* __restrict__ xbuf) {
@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(256) item_partial_kernel(const int32_t* __rest
     rs += ipart[n_chunks + c];
   }
   xbuf[i] = ds;
-  xbuf[n_items + i] = rs;
-  xbuf[2 * n_items + i] = (double)(icolp[i + 1] - icolp[i]);
+  xbuf[(size_t)n_items + i] = (double)(icolp[i + 1] - icolp[i]);
+  xbuf[2 * (size_t)n_items + 2 + i] = rs;
 }
 
 // ---- K2c: (after the optional cross-rank sum of xbuf) per-item averages and the global average
@@ -158,13 +158,13 @@ __global__ void __launch_bounds__(256) item_finalize_kernel(const double* __rest
                                                            double* __restrict__ gavg) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
-    const double gs = xbuf[3 * n_items], gc = xbuf[3 * n_items + 1];
+    const double gs = xbuf[2 * (size_t)n_items], gc = xbuf[2 * (size_t)n_items + 1];
     gavg[0] = gc > 0.0 ? gs / gc : 0.0;  // P:18 mean of an empty Seq is 0.0
   }
   if (i >= n_items) return;
-  const double cnt = xbuf[2 * n_items + i];
-  idevavg[i] = cnt > 0.0 ? xbuf[i] / cnt : 0.0;                 // P:185 x._1/x._2 ; unknown item -> 0.0 (P:197)
-  iavg[i] = cnt > 0.0 ? xbuf[n_items + i] / cnt : nan("");      // unknown item -> global average at query time (P:147)
+  const double cnt = xbuf[(size_t)n_items + i];
+  idevavg[i] = cnt > 0.0 ? xbuf[i] / cnt : 0.0;                                     // P:185 x._1/x._2 ; unknown item -> 0.0 (P:197)
+  iavg[i] = cnt > 0.0 ? xbuf[2 * (size_t)n_items + 2 + i] / cnt : nan("");          // unknown item -> global average at query time (P:147)
 }
 
 // ---- prediction of one (u,i) for the five closed-form predictors
@@ -345,13 +345,13 @@ template <typename VT>
 int32_t launch_fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model* m) {
   cudaStream_t st = e->stream;
   const int32_t NI = R->n_items, NU = R->n_users;
-  MRS_CUDA(cudaMemsetAsync(m->xbuf + 3 * (size_t)NI, 0, 2 * sizeof(double), st));
+  MRS_CUDA(cudaMemsetAsync(m->xbuf + 2 * (size_t)NI, 0, 2 * sizeof(double), st));
   if (R->uch.n_chunks > 0) {
     user_chunk_sum_kernel<VT><<<chunk_grid(R->uch.n_chunks, e->sm_count), 256, 0, st>>>(
         (const VT*)R->uval, R->urow, R->uch.chunk_seg, R->uch.chunk_begin, R->uch.n_chunks, m->upart);
     mark(e, "user_chunk_sum");
   }
-  user_finalize_kernel<<<(NU + 255) / 256, 256, 0, st>>>(R->urow, R->uch.seg_chunk_ptr, m->upart, NU, m->uavg, m->xbuf + 3 * (size_t)NI);
+  user_finalize_kernel<<<(NU + 255) / 256, 256, 0, st>>>(R->urow, R->uch.seg_chunk_ptr, m->upart, NU, m->uavg, m->xbuf + 2 * (size_t)NI);
   mark(e, "user_finalize");
   if (R->ich.n_chunks > 0) {
     item_chunk_dev_kernel<VT><<<chunk_grid(R->ich.n_chunks, e->sm_count), 256, 0, st>>>(

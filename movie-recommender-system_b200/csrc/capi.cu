@@ -313,7 +313,7 @@ static int32_t fetch_table(const mrs_model* m, int32_t kind, int64_t first, int6
   if (item_kind) {
     // counts of items come from the (possibly all-reduced) exchange buffer, not the local column pointer
     xcnt.resize((size_t)count);
-    MRS_CUDA(cudaMemcpyAsync(xcnt.data(), m->xbuf + 2 * (size_t)m->n_items + first, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaMemcpyAsync(xcnt.data(), m->xbuf + (size_t)m->n_items + first, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
   } else {
     MRS_CUDA(cudaMemcpyAsync(p.data(), ptr + first, sizeof(int32_t) * (count + 1), cudaMemcpyDeviceToHost, st));
   }

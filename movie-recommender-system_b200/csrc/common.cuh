@@ -177,7 +177,7 @@ struct mrs_model {
   double* uinv_hi = nullptr;    // [n_users]  1 / (5 - avg)   (code path: reciprocal of scale() for ratings above the average)
   double* uinv_lo = nullptr;    // [n_users]  1 / (avg - 1)   (                              ... below the average)
   double* ipart = nullptr;      // [2 * ich.n_chunks] chunk partials: deviations | ratings
-  double* xbuf = nullptr;       // [3*n_items + 2] exchange buffer: devsum | ratesum | count | gsum | gcount
+  double* xbuf = nullptr;       // [3*n_items + 2] exchange buffer: devsum | count | gsum gcount | ratesum
   double* idevavg = nullptr;    // [n_items]  0.0 for unknown items (P:197)
   double* iavg = nullptr;       // [n_items]  NaN for unknown items (replaced by the global average at query time, P:147)
   double* gavg = nullptr;       // [1] device scalar

@@ -147,7 +147,7 @@ extern "C" int32_t mrs_recommend(const mrs_model* m, const mrs_sim* sim, int32_t
     s = predict_async(m, sim, kind, d_u, d_i, NI, d_score);
   }
   if (s == MRS_OK) {
-    reco_mask_kernel<<<(NI + 255) / 256, 256, 0, st>>>(user, R->n_users, NI, R->urow, R->ucol, m->xbuf + 2 * (size_t)NI, d_score);
+    reco_mask_kernel<<<(NI + 255) / 256, 256, 0, st>>>(user, R->n_users, NI, R->urow, R->ucol, m->xbuf + (size_t)NI, d_score);
     reco_sort_kernel<<<1, 1024, 0, st>>>(d_score, NI, P, d_key, d_id);
     count_launch(2);
     const int32_t w = n < NI ? n : NI;

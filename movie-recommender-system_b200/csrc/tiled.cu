@@ -343,8 +343,8 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
     }
     if (threadIdx.x == 0) {
       const double gs = 0.5 * (double)sh[0];  // integer sum of codes: exact, order independent
-      xbuf[3 * (size_t)n_items] = gs;
-      xbuf[3 * (size_t)n_items + 1] = n_total;
+      xbuf[2 * (size_t)n_items] = gs;
+      xbuf[2 * (size_t)n_items + 1] = n_total;
       if (fused) gavg[0] = n_total > 0.0 ? gs / n_total : 0.0;
     }
   }
@@ -356,8 +356,8 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
   xcode_sum[i] = 0;
   const double cnt = (double)(icolp[i + 1] - icolp[i]);
   xbuf[i] = ds;
-  xbuf[n_items + i] = rs;
-  xbuf[2 * (size_t)n_items + i] = cnt;
+  xbuf[(size_t)n_items + i] = cnt;
+  xbuf[2 * (size_t)n_items + 2 + i] = rs;
   if (fused) {
     idevavg[i] = cnt > 0.0 ? ds / cnt : 0.0;
     iavg[i] = cnt > 0.0 ? rs / cnt : nan("");

@@ -5,7 +5,8 @@ The reference distributes the baseline with Spark: `reduceByKey` + `collect` per
 count; a rank holds the train rows and the test pairs of its users, so user sums/averages are local.  The only exchange
 is ONE all-reduce (sum) of the per-item exchange buffer written by ``mrs_fit_local``:
 
-    [ sum of deviations per item | sum of ratings per item | count per item | sum of all ratings | count ]   (3*I+2 fp64)
+    [ sum of deviations per item | count per item | sum of all ratings | count | sum of ratings per item ]   (3*I+2 fp64;
+    the first 2*I+2 values are all the baseline predictor needs)
 
 followed by ``mrs_fit_finish`` on every rank, and a 16-byte all-reduce of {sum |err|, n} for the MAE.
 The collective itself is `torch.distributed` (NCCL on GPUs; gloo in the CPU tests of this host logic).
@@ -38,10 +39,15 @@ def exchange_size(n_items_dim):
     return 3 * int(n_items_dim) + 2
 
 
+def mandatory_size(n_items_dim):
+    """Length of the prefix that must be exchanged when per-item rating averages are switched off."""
+    return 2 * int(n_items_dim) + 2
+
+
 def split_exchange(buf, n_items_dim):
     """Views of an exchange buffer: (dev_sum[I], rating_sum[I], count[I], global_sum, global_count)."""
     n = int(n_items_dim)
-    return buf[:n], buf[n:2 * n], buf[2 * n:3 * n], buf[3 * n], buf[3 * n + 1]
+    return buf[:n], buf[2 * n + 2:3 * n + 2], buf[n:2 * n], buf[2 * n], buf[2 * n + 1]
 
 
 def finish_from_exchange(buf, n_items_dim):
@@ -74,27 +80,56 @@ class ShardedBaseline:
 
     `engine` must have been created on the CUDA stream the collectives run on (``torch.cuda.current_stream()``)."""
 
-    def __init__(self, engine, train, test, group=None):
+    def __init__(self, engine, train, test, group=None, item_averages=False):
         import torch
         from . import engine as E
         self.E, self.torch, self.group = E, torch, group
         self.engine, self.train, self.test = engine, train, test
         self.model = E.Model(engine, train, sync=False)
+        self.model.set_item_averages(item_averages)
         ptr, n = self.model.exchange_buffer()
         self.device = torch.device("cuda", engine.device)
         self.xbuf = torch.as_tensor(_CudaView(ptr, n), device=self.device)
+        if not item_averages:            # only [dev sums | counts | global sum, count] has to travel
+            self.xbuf = self.xbuf[:mandatory_size(train.n_items_dim)]
         self.out2 = torch.zeros(2, dtype=torch.float64, device=self.device)
 
-    def _exchange(self, ptr, n):
-        all_reduce_sum(self.xbuf, self.group)
+    # ---- the five pieces of a step (all asynchronous on the engine's stream)
+    def fit_local(self):
+        self.E._check(self.E.lib().mrs_fit_local(self.engine._h, self.train._h, self.E.C.byref(self.model._h)))
+
+    def exchange(self):
+        all_reduce_sum(self.xbuf, self.group)          # THE collective of the fit (P:267-268, P:247)
+
+    def fit_finish(self):
+        self.E._check(self.E.lib().mrs_fit_finish(self.model._h))
+
+    def mae_local(self):
+        self.model.mae_async(self.test, self.out2.data_ptr(), self.E.PRED_BASELINE)
+
+    def mae_exchange(self):
+        all_reduce_sum(self.out2, self.group)          # 16 bytes: {sum |err|, n}
+
+    def capture(self):
+        """Capture the kernel runs between the collectives as two CUDA graphs; `step()` then issues
+        graph, all-reduce, graph, all-reduce instead of ~10 separate launches."""
+        self.step()                                    # first use allocates layouts
+        self.torch.cuda.synchronize(self.device)
+        self._g1 = self.engine.capture(self.fit_local)
+        self._g2 = self.engine.capture(lambda: (self.fit_finish(), self.mae_local()))
+
+    def step(self):
+        if getattr(self, "_g1", None) is not None:
+            self._g1.launch(); self.exchange(); self._g2.launch(); self.mae_exchange()
+        else:
+            self.fit_local(); self.exchange(); self.fit_finish(); self.mae_local(); self.mae_exchange()
 
     def fit(self):
         """Enqueue: local pass -> all-reduce of the exchange buffer -> finish (no host sync)."""
-        self.model.refit(between=self._exchange)
+        self.fit_local(); self.exchange(); self.fit_finish()
 
     def mae_async(self):
-        self.model.mae_async(self.test, self.out2.data_ptr(), self.E.PRED_BASELINE)
-        all_reduce_sum(self.out2, self.group)
+        self.mae_local(); self.mae_exchange()
 
     def mae(self):
         self.mae_async()

@@ -32,8 +32,8 @@ def _local_exchange(tr, n_users, n_items):
     d += np.bincount(i, weights=dev, minlength=n_items)
     rs += np.bincount(i, weights=r, minlength=n_items)
     c += np.bincount(i, minlength=n_items)
-    buf[3 * n_items] = r.sum()
-    buf[3 * n_items + 1] = r.size
+    buf[2 * n_items] = r.sum()
+    buf[2 * n_items + 1] = r.size
     return buf, avg
 
 
@@ -81,8 +81,8 @@ def test_exchange_layout_helpers():
     n = 7
     buf = np.arange(sharded.exchange_size(n), dtype=np.float64)
     d, r, c, gs, gc = sharded.split_exchange(buf, n)
-    assert d[0] == 0 and r[0] == 7 and c[0] == 14 and gs == 21 and gc == 22
-    buf2 = np.zeros(sharded.exchange_size(2)); buf2[:] = [1.0, 0.0, 8.0, 0.0, 2.0, 0.0, 8.0, 2.0]
+    assert d[0] == 0 and c[0] == 7 and gs == 14 and gc == 15 and r[0] == 16 and sharded.mandatory_size(n) == 16
+    buf2 = np.zeros(sharded.exchange_size(2)); buf2[:] = [1.0, 0.0, 2.0, 0.0, 8.0, 2.0, 8.0, 0.0]
     idev, iavg, g = sharded.finish_from_exchange(buf2, 2)
     assert idev.tolist() == [0.5, 0.0] and iavg[0] == 4.0 and np.isnan(iavg[1]) and g == 4.0
 
