@@ -139,7 +139,7 @@ def workload_config(d, world):
         "train_ratings_per_gpu": int(d["train"][0].size), "test_ratings_per_gpu": int(d["test"][0].size),
         "users_per_gpu": int(d["n_users"]), "items": int(d["n_items"]),
         "layout": "train: user-major codes padded to 16 B vectors (1 B/rating + 4 B/vector), user-tiled item-major sliced-ELL "
-                  "(4 B/rating: valid|code|16-bit local user); test: item-tiled (int32 user, 16-bit local item, 1 B code = 7 B/rating)",
+                  "(4 B/rating: valid|code|16-bit local user); test: item-tiled, one packed 8-byte word per rating (int32 user | 16-bit local item | code)",
         "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
         "parallelism": f"user-sharded x{world}, one all-reduce of the per-item exchange buffer" if world > 1 else "single GPU",
     }

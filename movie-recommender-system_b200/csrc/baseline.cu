@@ -52,33 +52,42 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
 // user) per thread; lanes of the same user are contiguous, so a segmented shuffle reduction leaves one integer
 // atomicAdd per (warp, user).  Integer sums are exact: the result does not depend on the order of the atomics.
 __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
-                                                      uint32_t* __restrict__ usum, unsigned long long* __restrict__ block_part) {
+                                                      uint32_t* __restrict__ usum, unsigned long long* __restrict__ gsum_codes) {
   __shared__ uint32_t sh[8];
-  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  uint32_t s = 0;
-  int32_t row = -1;
-  if (t < n_vec) {
-    const uint4 x = __ldg(reinterpret_cast<const uint4*>(uval16) + t);
-    row = __ldg(vec_row + t);
-    s = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
-  }
-  const uint32_t total = __reduce_add_sync(0xffffffffu, s);
-  // segmented suffix sums over runs of equal row ids
+  constexpr int V = 2;  // vectors per thread (both loads are issued before the first use)
+  const int32_t t0 = blockIdx.x * (blockDim.x * V) + threadIdx.x;
+  uint4 x[V];
+  int32_t row[V];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_down_sync(0xffffffffu, s, o);
-    const int32_t r = __shfl_down_sync(0xffffffffu, row, o);
-    if (lane + o < 32 && r == row) s += v;
+  for (int k = 0; k < V; ++k) {
+    const int32_t t = t0 + k * blockDim.x;
+    const bool in = t < n_vec;
+    x[k] = in ? __ldg(reinterpret_cast<const uint4*>(uval16) + t) : make_uint4(0u, 0u, 0u, 0u);
+    row[k] = in ? __ldg(vec_row + t) : -1;
   }
-  const int32_t prev = __shfl_up_sync(0xffffffffu, row, 1);
-  if (row >= 0 && (lane == 0 || prev != row)) atomicAdd(usum + row, s);
+  uint32_t total = 0;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    uint32_t s = __dp4a(x[k].x, 0x01010101u, __dp4a(x[k].y, 0x01010101u, __dp4a(x[k].z, 0x01010101u, __dp4a(x[k].w, 0x01010101u, 0u))));
+    total += s;
+    // segmented suffix sums over runs of equal row ids (lanes of one user are contiguous)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_down_sync(0xffffffffu, s, o);
+      const int32_t r = __shfl_down_sync(0xffffffffu, row[k], o);
+      if (lane + o < 32 && r == row[k]) s += v;
+    }
+    const int32_t prev = __shfl_up_sync(0xffffffffu, row[k], 1);
+    if (row[k] >= 0 && (lane == 0 || prev != row[k])) atomicAdd(usum + row[k], s);
+  }
+  total = __reduce_add_sync(0xffffffffu, total);
   if (lane == 0) sh[threadIdx.x >> 5] = total;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long a = 0;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += sh[k];
-    block_part[blockIdx.x] = a;
+    atomicAdd(gsum_codes, a);  // integer: exact, order independent
   }
 }
 
@@ -415,11 +424,12 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
     m->n_users = R->n_users;
     m->n_items = R->n_items;
     m->mae_part_cap = e->sm_count * 16;
-    m->k1_blocks = std::max(1, (R->n_vec + 255) / 256);
+    m->k1_blocks = std::max(1, (R->n_vec + 511) / 512);
     int32_t s = MRS_OK;
     if (codes) {
       if (s == MRS_OK) s = dev_alloc(&m->usum, (size_t)R->n_users);
-      if (s == MRS_OK) s = dev_alloc(&m->k1_part, (size_t)m->k1_blocks);
+      if (s == MRS_OK) s = dev_alloc(&m->k1_part, 1);
+      if (s == MRS_OK && cudaMemsetAsync(m->k1_part, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
       if (s == MRS_OK) s = dev_alloc(&m->xdev_fix, (size_t)R->n_items);
       if (s == MRS_OK) s = dev_alloc(&m->xcode_sum, (size_t)R->n_items);
       if (s == MRS_OK && cudaMemsetAsync(m->xdev_fix, 0, sizeof(long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;

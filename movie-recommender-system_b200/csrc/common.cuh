@@ -150,14 +150,9 @@ struct mrs_ratings {
   struct mae_layout {
     bool built = false;
     int32_t n_tiles = 0;        // item tiles of kMaeTileItems
-    int32_t n_chunks = 0;
-    int64_t n_slots = 0;        // entries incl. padding (every tile starts at a multiple of 16)
-    int32_t* user = nullptr;    // [n_slots] user id
-    uint16_t* item_local = nullptr;  // [n_slots] item id inside the tile
-    uint8_t* code = nullptr;    // [n_slots] half-star code, 0xFF = padding
-    int32_t* chunk_tile = nullptr;   // [n_chunks]
-    int32_t* chunk_begin = nullptr;  // [n_chunks]
-    int32_t* chunk_end = nullptr;    // [n_chunks]
+    int64_t n_rows = 0;         // 32-entry rows incl. padding (every tile starts at a row boundary)
+    uint2* entry = nullptr;     // [n_rows*32] .x = user id, .y = local item | code << 16 (code 0xFF = padding)
+    int32_t* tile_row_ptr = nullptr;  // [n_tiles+1] first row of every tile
   };
   mutable mae_layout ml;
 };
@@ -167,7 +162,7 @@ struct mrs_model {
   const mrs_ratings* train = nullptr;
   int32_t n_users = 0, n_items = 0;
   uint32_t* usum = nullptr;     // [n_users] sum of half-star codes per user (code path)
-  unsigned long long* k1_part = nullptr;  // per-block sums of usum (code path)
+  unsigned long long* k1_part = nullptr;  // [1] sum of all half-star codes (integer atomics in K1, re-armed by K2b)
   int32_t k1_blocks = 0;
   long long* xdev_fix = nullptr;            // [n_items] per-item deviation sums in units of 2^-40 (exact integer accumulation)
   unsigned long long* xcode_sum = nullptr;  // [n_items] per-item sums of half-star codes
@@ -252,7 +247,6 @@ void free_tiled_layout(const mrs_ratings* R);
 int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize);
 // mae_tiled.cu
 constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item deviations in shared memory
-constexpr int kMaeChunk = 8192;      // test entries per CTA
 int32_t build_mae_layout(const mrs_ratings* T);
 void free_mae_layout(const mrs_ratings* T);
 int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2);

@@ -429,7 +429,7 @@ extern "C" int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* b) {
   const int64_t vs = (int64_t)r->value_size();
   b[0] = r->n * vs;          // user-major pass reads the values only (the user is implicit in the row pointer)
   if (r->uval16) b[0] = (int64_t)r->n_vec * 20;  // padded codes (16 per vector) + one user id per vector
-  if (r->ml.built) b[2] = r->n * 7;  // item-tiled test layout: int32 user + 16-bit local item + 1 B code (padding not counted)
+  if (r->ml.built) b[2] = r->n * 8;  // item-tiled test layout: one packed 8-byte word per rating (padding not counted)
   b[1] = r->n * (4 + vs);    // item-major pass: user id + value
   if (r->tl.built) b[1] = r->n * 4;  // tiled item-major layout: one packed 32-bit word per rating (padding not counted)
   b[2] = r->n * (8 + vs);    // sorted COO pass: user id + item id + value
@@ -439,7 +439,7 @@ extern "C" int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* b) {
 extern "C" int32_t mrs_ratings_layout_info(const mrs_ratings* r, int64_t* o) {
   MRS_REQUIRE(r && o, MRS_ERR_INVALID, "mrs_ratings_layout_info: NULL argument");
   o[0] = r->tl.n_tiles; o[1] = r->tl.n_units; o[2] = r->tl.n_slices; o[3] = r->tl.n_slots;
-  o[4] = r->ml.n_tiles; o[5] = r->ml.n_chunks; o[6] = r->ml.n_slots; o[7] = r->n_vec;
+  o[4] = r->ml.n_tiles; o[5] = r->ml.n_rows; o[6] = r->ml.n_rows * 32; o[7] = r->n_vec;
   return MRS_OK;
 }
 

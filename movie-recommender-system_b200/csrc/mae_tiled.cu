@@ -1,17 +1,19 @@
 // mae_tiled.cu -- fused baseline prediction + |error| reduction (P:69-86 over P:217-236) on an item-tiled test layout.
 //
 // The generic kernel (baseline.cu predict_mae_kernel) gathers avg[u] and dev[i] from global memory: scattered 8-byte
-// gathers cost one L1 tag cycle per distinct line (capture B: the test pass was bound by that, not by HBM).  Here the
+// gathers cost one L1 tag cycle per distinct line (capture A: the test pass was bound by that, not by HBM).  Here the
 // test entries are grouped by item tile (kMaeTileItems items): a CTA stages the tile's item deviations in shared
-// memory (64 KB) and streams a chunk of entries; inside a tile the entries stay in (user, item) order, so the
-// remaining global gather -- the user average -- touches one or two lines per warp.  An entry is 7 bytes:
-// int32 user | 16-bit item id local to the tile | half-star code.
+// memory (64 KB) and its warps stream contiguous runs of 32-entry rows through private TMA rings (cp.async.bulk +
+// mbarrier), exactly like the item pass of the fit (tiled.cu).  Inside a tile the entries stay in (user, item) order,
+// so the remaining global gather -- the user average -- touches one or two lines per warp.
+// An entry is one 8-byte word: int32 user | 16-bit item id local to the tile | half-star code (0xFF = padding).
 #include <cub/cub.cuh>
 
 #include <algorithm>
 #include <vector>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mrs {
 namespace {
@@ -40,82 +42,115 @@ __global__ void tile_ptr_kernel(const uint16_t* __restrict__ key, int64_t n, int
   }
 }
 
+__global__ void mae_fill_kernel(uint2* __restrict__ entry, int64_t n_slots) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_slots; q += (int64_t)gridDim.x * blockDim.x)
+    entry[q] = make_uint2(0u, 0xffu << 16);  // padding slot
+}
+
 __global__ void mae_scatter_kernel(const uint16_t* __restrict__ key, const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_ptr,
-                                   const int32_t* __restrict__ padded_ptr, const int32_t* __restrict__ users, const int32_t* __restrict__ items,
-                                   const uint8_t* __restrict__ codes, int64_t n, int32_t* __restrict__ o_user,
-                                   uint16_t* __restrict__ o_item, uint8_t* __restrict__ o_code) {
+                                   const int32_t* __restrict__ tile_row_ptr, const int32_t* __restrict__ users,
+                                   const int32_t* __restrict__ items, const uint8_t* __restrict__ codes, int64_t n, uint2* __restrict__ entry) {
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     const int32_t t = key[q], p = perm[q];
-    const int64_t dst = (int64_t)padded_ptr[t] + (q - tile_ptr[t]);
-    o_user[dst] = users[p];
-    o_item[dst] = (uint16_t)(items[p] - t * kMaeTileItems);
-    o_code[dst] = codes[p];
+    const int64_t dst = ((int64_t)tile_row_ptr[t] << 5) + (q - tile_ptr[t]);
+    entry[dst] = make_uint2((uint32_t)users[p], (uint32_t)(items[p] - t * kMaeTileItems) | ((uint32_t)codes[p] << 16));
   }
 }
 
-constexpr int kMaeThreads = 512;
-constexpr int kMaeQuads = kMaeChunk / (4 * kMaeThreads);  // quads (4 entries) per thread
-static_assert(kMaeQuads * 4 * kMaeThreads == kMaeChunk, "chunk must be a multiple of 4 * threads");
+constexpr int kMaeThreads = 1024;
+constexpr int kMaeRows = 8;    // rows (32 entries of 8 bytes = 256 B) per ring stage: 2 KB
+constexpr int kMaeStages = 2;
+constexpr size_t kMaeSmem = (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 32) * kMaeStages * kMaeRows * 256 + (size_t)(kMaeThreads / 32) * kMaeStages * 8;
 
-// one CTA per chunk of one item tile
-__global__ void __launch_bounds__(kMaeThreads, 2) predict_mae_tiled_kernel(const int32_t* __restrict__ user, const uint16_t* __restrict__ item_local,
-                                                                          const uint8_t* __restrict__ code, const int32_t* __restrict__ chunk_tile,
-                                                                          const int32_t* __restrict__ chunk_begin, const int32_t* __restrict__ chunk_end,
-                                                                          int32_t n_users, int32_t n_items, const double* __restrict__ uavg,
-                                                                          const double* __restrict__ idevavg, const double* __restrict__ gavg_p,
-                                                                          double n_total, double* __restrict__ part, unsigned int* __restrict__ counter,
+// one CTA = (item tile, share of the tile's rows); 32 warps, one CTA per SM
+__global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const uint2* __restrict__ entry, const int32_t* __restrict__ tile_row_ptr,
+                                                                          int32_t ctas_per_tile, int32_t n_users, int32_t n_items,
+                                                                          const double* __restrict__ uavg, const double* __restrict__ idevavg,
+                                                                          const double* __restrict__ gavg_p, double n_total,
+                                                                          double* __restrict__ part, unsigned int* __restrict__ counter,
                                                                           double* __restrict__ out2) {
-  extern __shared__ double s_dev[];  // [kMaeTileItems]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* s_dev = reinterpret_cast<double*>(smem_raw);                                     // [kMaeTileItems]
+  uint2* s_ring = reinterpret_cast<uint2*>(smem_raw + (size_t)kMaeTileItems * 8);          // [warps][stages][rows*32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 32) * kMaeStages * kMaeRows * 256);
   __shared__ double sh[kMaeThreads / 32];
   __shared__ bool is_last;
-  // ---- every load of this thread goes out first: kMaeQuads x (4 users, 4 local items, 4 codes), then the user averages
-  // the chunk starts at a multiple of 16 entries; slots past the tile's last entry are padding (code 0xFF)
-  const int32_t b4 = chunk_begin[blockIdx.x] >> 2, e4 = (chunk_end[blockIdx.x] + 3) >> 2;
-  int4 u4[kMaeQuads];
-  uint2 i2[kMaeQuads];
-  uchar4 c4[kMaeQuads];
+  const int32_t tile = blockIdx.x / ctas_per_tile, share = blockIdx.x % ctas_per_tile;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int32_t wpb = kMaeThreads >> 5;
+  uint64_t* bar = s_bar + wid * kMaeStages;
+  uint2* ring = s_ring + (size_t)wid * kMaeStages * kMaeRows * 32;
+  if (lane == 0) {
 #pragma unroll
-  for (int k = 0; k < kMaeQuads; ++k) {
-    const int32_t q = min(b4 + (int32_t)threadIdx.x + k * kMaeThreads, e4 - 1);
-    u4[k] = __ldg(reinterpret_cast<const int4*>(user) + q);
-    i2[k] = __ldg(reinterpret_cast<const uint2*>(item_local) + q);
-    c4[k] = __ldg(reinterpret_cast<const uchar4*>(code) + q);
+    for (int st = 0; st < kMaeStages; ++st) tma::mbar_init(bar + st, 1);
+    tma::fence_barrier_init();
   }
-  const int32_t tile = chunk_tile[blockIdx.x];
+  __syncwarp();
+  // ---- this warp's rows: an equal share of the tile's rows
+  const int32_t ra = tile_row_ptr[tile], rb = tile_row_ptr[tile + 1];
+  const int32_t nw = ctas_per_tile * wpb, w = share * wpb + wid;
+  const int32_t r0 = ra + (int32_t)(((int64_t)(rb - ra) * w) / nw);
+  const int32_t r_end = ra + (int32_t)(((int64_t)(rb - ra) * (w + 1)) / nw);
+  const int32_t n_chunks = (r_end - r0 + kMaeRows - 1) / kMaeRows;
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kMaeStages; ++st) {
+      if (st < n_chunks) {
+        const int32_t rr = r0 + st * kMaeRows;
+        const uint32_t bytes = (uint32_t)min(kMaeRows, r_end - rr) * 256u;
+        tma::mbar_arrive_expect_tx(bar + st, bytes);
+        tma::bulk_g2s(ring + st * kMaeRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
+      }
+    }
+  }
+  // ---- the tile's item deviations (unknown item -> 0.0, P:226-227)
   const int32_t i0 = tile * kMaeTileItems;
 #pragma unroll 4
   for (int32_t x = threadIdx.x; x < kMaeTileItems; x += kMaeThreads) {
     const int32_t i = i0 + x;
-    s_dev[x] = (i < n_items) ? __ldg(idevavg + i) : 0.0;  // unknown item -> 0.0 (P:226-227)
-  }
-  double ua[kMaeQuads][4];
-#pragma unroll
-  for (int k = 0; k < kMaeQuads; ++k) {
-    const int32_t us[4] = {u4[k].x, u4[k].y, u4[k].z, u4[k].w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ua[k][j] = (us[j] >= 0 && us[j] < n_users) ? __ldg(uavg + us[j]) : -1.0;
+    s_dev[x] = (i < n_items) ? __ldg(idevavg + i) : 0.0;
   }
   const double gavg = gavg_p[0];
   __syncthreads();
+
   double acc = 0.0;
+  for (int32_t c = 0; c < n_chunks; ++c) {
+    const int st = c % kMaeStages;
+    const int32_t r = r0 + c * kMaeRows;
+    const int32_t nrows = min(kMaeRows, r_end - r);
+    tma::mbar_wait(bar + st, (uint32_t)(c / kMaeStages) & 1u);
+    const uint2* rp = ring + st * kMaeRows * 32 + lane;
+    uint2 ev[kMaeRows];
 #pragma unroll
-  for (int k = 0; k < kMaeQuads; ++k) {
-    const uint32_t il[4] = {i2[k].x & 0xffffu, i2[k].x >> 16, i2[k].y & 0xffffu, i2[k].y >> 16};
-    const uint32_t cs[4] = {c4[k].x, c4[k].y, c4[k].z, c4[k].w};
-    const bool live = (b4 + (int32_t)threadIdx.x + k * kMaeThreads < e4);
+    for (int k = 0; k < kMaeRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : make_uint2(0u, 0xffu << 16);
+    __syncwarp();
+    if (lane == 0 && c + kMaeStages < n_chunks) {
+      const int32_t rr = r + kMaeStages * kMaeRows;
+      const uint32_t bytes = (uint32_t)min(kMaeRows, r_end - rr) * 256u;
+      tma::fence_proxy_async();
+      tma::mbar_arrive_expect_tx(bar + st, bytes);
+      tma::bulk_g2s(ring + st * kMaeRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
+    }
+    double ua[kMaeRows];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double d = s_dev[il[j]];
-      const double p = ua[k][j] < 0.0 ? gavg : combine_fn(ua[k][j], d);  // P:222-229
-      const double err = fabs(0.5 * (double)cs[j] - p);                     // P:71
-      acc += (live && cs[j] != 0xffu) ? err : 0.0;                         // 0xFF = padding slot
+    for (int k = 0; k < kMaeRows; ++k) {  // the user averages: all gathers of the stage go out together
+      const int32_t u = (int32_t)ev[k].x;
+      ua[k] = (u >= 0 && u < n_users) ? __ldg(uavg + u) : -1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaeRows; ++k) {
+      const uint32_t code = ev[k].y >> 16;
+      const double d = s_dev[ev[k].y & 0xffffu];
+      const double p = ua[k] < 0.0 ? gavg : combine_fn(ua[k], d);   // P:222-229
+      const double err = fabs(fma((double)code, 0.5, -p));          // |r - p|, P:71
+      acc += (code != 0xffu) ? err : 0.0;                           // 0xFF = padding slot
     }
   }
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  if (lane == 0) sh[wid] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
-    double t = (threadIdx.x < (kMaeThreads >> 5)) ? sh[threadIdx.x] : 0.0;
+    double t = (threadIdx.x < wpb) ? sh[threadIdx.x] : 0.0;
     t = warp_sum(t);
     if (threadIdx.x == 0) {
       part[blockIdx.x] = t;
@@ -129,11 +164,11 @@ __global__ void __launch_bounds__(kMaeThreads, 2) predict_mae_tiled_kernel(const
     double t = 0.0;
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(&part[b]);
     t = warp_sum(t);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    if (lane == 0) sh[wid] = t;
     __syncthreads();
     if (threadIdx.x == 0) {
       double s = 0.0;
-      for (int w = 0; w < (kMaeThreads >> 5); ++w) s += sh[w];
+      for (int k = 0; k < wpb; ++k) s += sh[k];
       out2[0] = s;
       out2[1] = n_total;
       *counter = 0;
@@ -149,7 +184,7 @@ int grid_for(int64_t n, int block, int sm_count) {
 
 void free_mae_layout(const mrs_ratings* T) {
   auto& L = T->ml;
-  dev_free(L.user); dev_free(L.item_local); dev_free(L.code); dev_free(L.chunk_tile); dev_free(L.chunk_begin); dev_free(L.chunk_end);
+  dev_free(L.entry); dev_free(L.tile_row_ptr);
   L = mrs_ratings::mae_layout();
 }
 
@@ -165,10 +200,11 @@ int32_t build_mae_layout(const mrs_ratings* T) {
   L.n_tiles = NT;
   const int grid = grid_for(n, 256, e->sm_count);
   uint16_t *k_in = nullptr, *k_out = nullptr;
-  int32_t *p_in = nullptr, *perm = nullptr, *tile_ptr = nullptr, *d_padded = nullptr;
+  int32_t *p_in = nullptr, *perm = nullptr, *tile_ptr = nullptr;
   MRS_TRY(dev_alloc(&k_in, (size_t)n)); MRS_TRY(dev_alloc(&k_out, (size_t)n));
   MRS_TRY(dev_alloc(&p_in, (size_t)n)); MRS_TRY(dev_alloc(&perm, (size_t)n));
-  MRS_TRY(dev_alloc(&tile_ptr, (size_t)NT + 1)); MRS_TRY(dev_alloc(&d_padded, (size_t)NT + 1));
+  MRS_TRY(dev_alloc(&tile_ptr, (size_t)NT + 1));
+  MRS_TRY(dev_alloc(&L.tile_row_ptr, (size_t)NT + 1));
   mae_keys_kernel<<<grid, 256, 0, st>>>(T->ucol, n, k_in, p_in);
   int tbits = 1;
   while ((1 << tbits) < NT) ++tbits;
@@ -177,39 +213,19 @@ int32_t build_mae_layout(const mrs_ratings* T) {
   MRS_TRY(ensure_scratch(e, tmp));
   cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k_in, k_out, p_in, perm, (int)n, 0, tbits, st);  // stable: (user, item) order kept
   tile_ptr_kernel<<<grid, 256, 0, st>>>(k_out, n, NT, tile_ptr);
-  std::vector<int32_t> h_ptr((size_t)NT + 1), h_pad((size_t)NT + 1, 0);
+  std::vector<int32_t> h_ptr((size_t)NT + 1), h_rows((size_t)NT + 1, 0);
   MRS_CUDA(cudaMemcpyAsync(h_ptr.data(), tile_ptr, sizeof(int32_t) * ((size_t)NT + 1), cudaMemcpyDeviceToHost, st));
   MRS_CUDA(cudaStreamSynchronize(st));
-  std::vector<int32_t> c_tile, c_begin, c_end;
-  for (int32_t t = 0; t < NT; ++t) {
-    const int32_t cnt = h_ptr[t + 1] - h_ptr[t];
-    h_pad[t + 1] = h_pad[t] + ((cnt + 15) / 16) * 16;
-    for (int32_t b = 0; b < cnt; b += kMaeChunk) {
-      c_tile.push_back(t);
-      c_begin.push_back(h_pad[t] + b);
-      c_end.push_back(h_pad[t] + std::min(cnt, b + kMaeChunk));
-    }
-  }
-  L.n_slots = h_pad[NT];
-  L.n_chunks = (int32_t)c_tile.size();
-  MRS_TRY(dev_alloc(&L.user, (size_t)L.n_slots + 16));
-  MRS_TRY(dev_alloc(&L.item_local, (size_t)L.n_slots + 16));
-  MRS_TRY(dev_alloc(&L.code, (size_t)L.n_slots + 16));
-  MRS_TRY(dev_alloc(&L.chunk_tile, c_tile.size()));
-  MRS_TRY(dev_alloc(&L.chunk_begin, c_tile.size()));
-  MRS_TRY(dev_alloc(&L.chunk_end, c_tile.size()));
-  MRS_CUDA(cudaMemsetAsync(L.user, 0, sizeof(int32_t) * ((size_t)L.n_slots + 16), st));
-  MRS_CUDA(cudaMemsetAsync(L.item_local, 0, sizeof(uint16_t) * ((size_t)L.n_slots + 16), st));
-  MRS_CUDA(cudaMemsetAsync(L.code, 0xff, (size_t)L.n_slots + 16, st));
-  MRS_CUDA(cudaMemcpyAsync(d_padded, h_pad.data(), sizeof(int32_t) * ((size_t)NT + 1), cudaMemcpyHostToDevice, st));
-  MRS_CUDA(cudaMemcpyAsync(L.chunk_tile, c_tile.data(), sizeof(int32_t) * c_tile.size(), cudaMemcpyHostToDevice, st));
-  MRS_CUDA(cudaMemcpyAsync(L.chunk_begin, c_begin.data(), sizeof(int32_t) * c_tile.size(), cudaMemcpyHostToDevice, st));
-  MRS_CUDA(cudaMemcpyAsync(L.chunk_end, c_end.data(), sizeof(int32_t) * c_tile.size(), cudaMemcpyHostToDevice, st));
-  mae_scatter_kernel<<<grid, 256, 0, st>>>(k_out, perm, tile_ptr, d_padded, T->coo_u, T->ucol, (const uint8_t*)T->uval, n, L.user, L.item_local, L.code);
+  for (int32_t t = 0; t < NT; ++t) h_rows[t + 1] = h_rows[t] + (h_ptr[t + 1] - h_ptr[t] + 31) / 32;
+  L.n_rows = h_rows[NT];
+  MRS_TRY(dev_alloc(&L.entry, (size_t)L.n_rows * 32 + 32));
+  MRS_CUDA(cudaMemcpyAsync(L.tile_row_ptr, h_rows.data(), sizeof(int32_t) * ((size_t)NT + 1), cudaMemcpyHostToDevice, st));
+  mae_fill_kernel<<<grid_for(L.n_rows * 32, 256, e->sm_count), 256, 0, st>>>(L.entry, L.n_rows * 32);
+  mae_scatter_kernel<<<grid, 256, 0, st>>>(k_out, perm, tile_ptr, L.tile_row_ptr, T->coo_u, T->ucol, (const uint8_t*)T->uval, n, L.entry);
   count_launch(6);
   MRS_CUDA(cudaGetLastError());
   MRS_CUDA(cudaStreamSynchronize(st));
-  dev_free(k_in); dev_free(k_out); dev_free(p_in); dev_free(perm); dev_free(tile_ptr); dev_free(d_padded);
+  dev_free(k_in); dev_free(k_out); dev_free(p_in); dev_free(perm); dev_free(tile_ptr);
   L.built = true;
   return MRS_OK;
 }
@@ -218,18 +234,17 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
   MRS_TRY(build_mae_layout(T));
   const auto& L = T->ml;
   mrs_engine* e = m->eng;
-  MRS_REQUIRE(L.n_chunks <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set has %d chunks, more than the %d partial slots of the model",
-              L.n_chunks, m->mae_part_cap);
-  const size_t smem = (size_t)kMaeTileItems * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
     attr_set = true;
   }
-  predict_mae_tiled_kernel<<<L.n_chunks, kMaeThreads, smem, e->stream>>>(L.user, L.item_local, L.code, L.chunk_tile, L.chunk_begin, L.chunk_end,
-                                                                         m->n_users, m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n,
-                                                                         m->mae_part, m->counters, d_out2);
+  const int32_t ctas_per_tile = std::max(1, e->sm_count / L.n_tiles);
+  const int32_t grid = L.n_tiles * ctas_per_tile;
+  MRS_REQUIRE(grid <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set needs %d CTAs, more than the %d partial slots of the model", grid,
+              m->mae_part_cap);
+  predict_mae_tiled_kernel<<<grid, kMaeThreads, kMaeSmem, e->stream>>>(L.entry, L.tile_row_ptr, ctas_per_tile, m->n_users, m->n_items, m->uavg,
+                                                                       m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2);
   mark(e, "predict_mae_tiled");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

@@ -328,25 +328,15 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
 // K2b: per item, integer accumulators -> exchange buffer (and re-arm them for the next pass); optionally finish the fit
 __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __restrict__ xdev_fix, unsigned long long* __restrict__ xcode_sum,
                                                                  const int32_t* __restrict__ icolp, int32_t n_items,
-                                                                 const unsigned long long* __restrict__ k1_part, int32_t n_k1, double n_total,
+                                                                 unsigned long long* __restrict__ k1_part, int32_t n_k1, double n_total,
                                                                  double* __restrict__ xbuf, int fused, double* __restrict__ idevavg,
                                                                  double* __restrict__ iavg, double* __restrict__ gavg) {
-  if (blockIdx.x == 0) {
-    __shared__ unsigned long long sh[256];
-    unsigned long long t = 0;
-    for (int32_t b = threadIdx.x; b < n_k1; b += blockDim.x) t += k1_part[b];
-    sh[threadIdx.x] = t;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      const double gs = 0.5 * (double)sh[0];  // integer sum of codes: exact, order independent
-      xbuf[2 * (size_t)n_items] = gs;
-      xbuf[2 * (size_t)n_items + 1] = n_total;
-      if (fused) gavg[0] = n_total > 0.0 ? gs / n_total : 0.0;
-    }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
+    k1_part[0] = 0;                              // re-arm for the next pass
+    xbuf[2 * (size_t)n_items] = gs;
+    xbuf[2 * (size_t)n_items + 1] = n_total;
+    if (fused) gavg[0] = n_total > 0.0 ? gs / n_total : 0.0;
   }
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) return;
