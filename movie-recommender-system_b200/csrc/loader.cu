@@ -428,11 +428,11 @@ extern "C" int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* b) {
   MRS_REQUIRE(r && b, MRS_ERR_INVALID, "mrs_ratings_bytes: NULL argument");
   const int64_t vs = (int64_t)r->value_size();
   b[0] = r->n * vs;          // user-major pass reads the values only (the user is implicit in the row pointer)
-  if (r->uval16) b[0] = (int64_t)r->n_vec * 20;  // padded codes (16 per vector) + one user id per vector
-  if (r->ml.built) b[2] = r->n * 8;  // item-tiled test layout: one packed 8-byte word per rating (padding not counted)
   b[1] = r->n * (4 + vs);    // item-major pass: user id + value
-  if (r->tl.built) b[1] = r->n * 4;  // tiled item-major layout: one packed 32-bit word per rating (padding not counted)
   b[2] = r->n * (8 + vs);    // sorted COO pass: user id + item id + value
+  if (r->uval16) b[0] = (int64_t)r->n_vec * 20;  // padded codes (16 per vector) + one user id per vector
+  if (r->tl.built) b[1] = r->n * 4;              // tiled item-major layout: one packed 32-bit word per rating (padding not counted)
+  if (r->ml.built) b[2] = r->n * 8;              // item-tiled test layout: one packed 8-byte word per rating (padding not counted)
   return MRS_OK;
 }
 

@@ -127,7 +127,6 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     if (lane == 0 && c + kMaeStages < n_chunks) {
       const int32_t rr = r + kMaeStages * kMaeRows;
       const uint32_t bytes = (uint32_t)min(kMaeRows, r_end - rr) * 256u;
-      tma::fence_proxy_async();
       tma::mbar_arrive_expect_tx(bar + st, bytes);
       tma::bulk_g2s(ring + st * kMaeRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
     }

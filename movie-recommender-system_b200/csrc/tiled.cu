@@ -155,7 +155,7 @@ __device__ __forceinline__ double fast_rcp(double s) {
 }
 
 // K2: one CTA = (tile, share of the tile's work), 32 warps, one CTA per SM.
-// Shared memory: the tile's user averages (64 KB, formed here from the integer code sums of K1) + a private ring of
+// Shared memory: (code sum, rating count) of the tile's users (64 KB, code sums from K1) + a private ring of
 // kStages x kRows 128-byte rows per warp filled by 1-D bulk asynchronous copies (TMA) and signalled through mbarriers:
 // ~100 KB of entries are in flight per SM without costing registers.  Slices of a tile are contiguous in memory, so a
 // warp that owns a contiguous range of slices streams one contiguous run of rows; slice boundaries only decide when a
@@ -178,14 +178,19 @@ __device__ __forceinline__ int32_t lower_bound_cost(const int32_t* __restrict__ 
   return lo;
 }
 
-// deviation of one entry; branch free so that the rows of a batch overlap in the pipeline
-__device__ __forceinline__ double tiled_dev(uint32_t e, const double* __restrict__ s_avg) {
+// Deviation of one entry in exact integer form; branch free so that the rows of a batch overlap in the pipeline.
+// With r = code/2 and avg = S/(2c) (S = the user's code sum, c = its rating count):
+//     r - avg = (c*code - S)/(2c),   5 - avg = (10c - S)/(2c),   avg - 1 = (S - 2c)/(2c)
+// so (r - avg)/scale(r, avg) (P:57-61, P:167) = N/D with N = c*code - S and D = 10c - S (N > 0) or S - 2c (N < 0):
+// two small integers, ONE rounding (the reference rounds the average, the difference and the quotient: <= 2 ulp apart).
+// r > avg <=> N > 0 exactly (|avg - r| >= 1/(2c) whenever they differ, far above an ulp), so the branch is the reference's.
+__device__ __forceinline__ double tiled_dev(uint32_t e, const uint2* __restrict__ s_sc) {
   const uint32_t code = (e >> 16) & 0xffu;              // 0 for padding
-  const double a = s_avg[e & 0xffffu];
-  const double d = fma((double)code, 0.5, -a);          // r - avg: exact operands, one rounding (P:167)
-  const double hi = 5.0 - a, lo = a - 1.0;              // scale(r, avg), P:57-61
-  const double dev = d * fast_rcp(d > 0.0 ? hi : lo);
-  return (d != 0.0 && (int32_t)e < 0) ? dev : 0.0;      // r == avg -> 0/1 = 0; padding (valid bit clear) contributes nothing
+  const uint2 sc = s_sc[e & 0xffffu];                   // .x = S, .y = c
+  const int32_t N = (int32_t)(sc.y * code) - (int32_t)sc.x;
+  const int32_t D = N > 0 ? (int32_t)(10u * sc.y) - (int32_t)sc.x : (int32_t)sc.x - (int32_t)(2u * sc.y);
+  const double dev = (double)N * fast_rcp((double)D);
+  return (N != 0 && (int32_t)e < 0) ? dev : 0.0;        // r == avg -> 0/1 = 0; padding (valid bit clear) contributes nothing
 }
 
 template <bool WITH_SUM>
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
                                                                      double* __restrict__ uavg, long long* __restrict__ xdev_fix,
                                                                      unsigned long long* __restrict__ xcode_sum) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* s_avg = reinterpret_cast<double*>(smem_raw);                                    // [kTileUsers]
+  uint2* s_sc = reinterpret_cast<uint2*>(smem_raw);                                       // [kTileUsers] (code sum, count)
   uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTileUsers * 8);      // [warps][kStages][kRows*32]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128);
   const int32_t tile = blockIdx.x / ctas_per_tile, share = blockIdx.x % ctas_per_tile;
@@ -249,25 +254,20 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
   int32_t item1 = (cur < s_hi) ? __ldg(slot_item + cur * 32 + lane) : -1;       // item of this lane's unit in the current slice
   int32_t item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
 
-  // ---- the tile's user averages: exact integer code sum / count, one correctly rounded division each (P:18)
+  // ---- the tile's users: (code sum from K1, rating count); the first CTA of the tile also publishes the averages
   {
     const int32_t u0 = tile * kTileUsers;
     constexpr int kPer = kTileUsers / kTiledThreads;
-    uint32_t sums[kPer];
-    int32_t cnts[kPer];
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      const int32_t u = u0 + k * kTiledThreads + threadIdx.x;
-      const bool in = u < n_users;
-      sums[k] = in ? __ldg(usum + u) : 0u;
-      cnts[k] = in ? __ldg(urow + u + 1) - __ldg(urow + u) : 0;
-    }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const int32_t x = k * kTiledThreads + threadIdx.x;
-      const double a = cnts[k] ? (0.5 * (double)sums[k]) / (double)cnts[k] : -1.0;  // -1.0: no ratings (the reference's sentinel, P:222)
-      s_avg[x] = a;
-      if (share == 0 && u0 + x < n_users) uavg[u0 + x] = a;
+      const int32_t u = u0 + x;
+      const bool in = u < n_users;
+      const uint32_t S = in ? __ldg(usum + u) : 0u;
+      const uint32_t cnt = in ? (uint32_t)(__ldg(urow + u + 1) - __ldg(urow + u)) : 0u;
+      s_sc[x] = make_uint2(S, cnt);
+      if (share == 0 && in)  // exact sum, one correctly rounded division (P:18); -1.0: no ratings (the reference's sentinel, P:222)
+        uavg[u] = cnt ? (0.5 * (double)S) / (double)cnt : -1.0;
     }
   }
   __syncthreads();
@@ -293,13 +293,12 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
     if (lane == 0 && c + kStages < n_chunks) {  // the stage is free again: request the chunk kStages ahead
       const int32_t rr = r + kStages * kRows;
       const uint32_t bytes = (uint32_t)min(kRows, r_end - rr) * 128u;
-      tma::fence_proxy_async();
       tma::mbar_arrive_expect_tx(bar + st, bytes);
       tma::bulk_g2s(ring + st * kRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
     }
     double dv[kRows];
 #pragma unroll
-    for (int k = 0; k < kRows; ++k) dv[k] = tiled_dev(ev[k], s_avg);  // heavy part: no branches, 8 independent chains
+    for (int k = 0; k < kRows; ++k) dv[k] = tiled_dev(ev[k], s_sc);  // heavy part: no branches, 8 independent chains
     if (plain) {
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {

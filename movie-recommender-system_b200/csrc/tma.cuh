@@ -17,7 +17,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 // make barrier initialisation visible to the async proxy
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// order prior generic-proxy accesses to shared memory before subsequent async-proxy (bulk copy) writes
+// order prior generic-proxy accesses to shared memory before subsequent async-proxy (bulk copy) writes.
+// Not used by the ring buffers: a stage is re-armed by the same warp after __syncwarp(), i.e. after every lane has
+// read its words (ptxas turns this fence into MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, costly once per KB).
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
