@@ -142,7 +142,6 @@ struct mrs_ratings {
     uint32_t* entry = nullptr;         // [n_slots] bit31 valid | code << 16 | user id local to the tile
     int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
     int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
-    int32_t* item_unit_ptr = nullptr;  // [n_items+1]
     int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
   };
   mutable tiled_layout tl;

@@ -252,8 +252,10 @@ int32_t build_sorted(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const in
     MRS_CUDA(cudaGetLastError());
   }
   if (sizeof(VT) == 1) MRS_TRY(build_padded_codes(e, R));
-  MRS_TRY(build_chunks(e, R->urow, R->n_users, kUserChunk, &R->uch));
-  MRS_TRY(build_chunks(e, R->icolp, R->n_items, kItemChunk, &R->ich));
+  if (sizeof(VT) != 1) {  // chunk lists feed the generic (fp64-valued) fit kernels only
+    MRS_TRY(build_chunks(e, R->urow, R->n_users, kUserChunk, &R->uch));
+    MRS_TRY(build_chunks(e, R->icolp, R->n_items, kItemChunk, &R->ich));
+  }
   MRS_CUDA(cudaStreamSynchronize(st));
   dev_free(k_in); dev_free(k_out); dev_free(v_in); dev_free(v_out);
   return MRS_OK;

@@ -77,10 +77,10 @@ __global__ void unit_scatter_kernel(const int32_t* __restrict__ flag, const int3
   }
 }
 
-// length of each unit, its (tile, kUnitLen - len) sort key and the per-tile unit histogram
+// length of each unit, its (tile, kUnitLen - len) sort key and the first unit of every tile (unit ids ascend with the tile)
 __global__ void unit_len_kernel(const int32_t* __restrict__ unit_begin, const int32_t* __restrict__ unit_tile, int32_t n_units, int64_t n,
                                 int32_t* __restrict__ unit_len, uint32_t* __restrict__ sort_key, int32_t* __restrict__ ids,
-                                int32_t* __restrict__ tile_count) {
+                                int32_t* __restrict__ tile_first) {
   const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_units) return;
   const int32_t b = unit_begin[id];
@@ -89,7 +89,7 @@ __global__ void unit_len_kernel(const int32_t* __restrict__ unit_begin, const in
   unit_len[id] = len;
   sort_key[id] = ((uint32_t)unit_tile[id] << kUnitBits) | (uint32_t)(kUnitLen - len);
   ids[id] = id;
-  atomicAdd(&tile_count[unit_tile[id]], 1);
+  if (id == 0 || unit_tile[id - 1] != unit_tile[id]) tile_first[unit_tile[id]] = id;
 }
 
 // sorted index j -> slot (slice*32 + lane); lane 0 of a slice holds its longest unit
@@ -127,17 +127,6 @@ __global__ void slot_item_kernel(const int32_t* __restrict__ unit_slot, const in
                                  int32_t* __restrict__ slot_item) {
   const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id < n_units) slot_item[unit_slot[id]] = unit_item[id];
-}
-
-// sorted (by item) unit list -> item_unit_ptr
-__global__ void item_ptr_kernel(const uint32_t* __restrict__ sorted_item, int32_t n_units, int32_t n_items, int32_t* __restrict__ ptr) {
-  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_units) return;
-  const int32_t it = (int32_t)sorted_item[j];
-  const int32_t prev = j ? (int32_t)sorted_item[j - 1] : -1;
-  for (int32_t s = prev + 1; s <= it; ++s) ptr[s] = j;
-  if (j == n_units - 1)
-    for (int32_t s = it + 1; s <= n_items; ++s) ptr[s] = n_units;
 }
 
 int grid_for(int64_t n, int block, int sm_count) {
@@ -357,7 +346,7 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
 
 void free_tiled_layout(const mrs_ratings* R) {
   auto& T = R->tl;
-  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.item_unit_ptr); dev_free(T.slot_item);
+  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.slot_item);
   T = mrs_ratings::tiled_layout();
 }
 
@@ -376,10 +365,8 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   const int grid = grid_for(n, block, e->sm_count);
   std::vector<int32_t> h_tile_slice((size_t)NT + 1, 0);
   MRS_TRY(dev_alloc(&T.tile_slice_ptr, (size_t)NT + 1));
-  MRS_TRY(dev_alloc(&T.item_unit_ptr, (size_t)NI + 1));
   if (n == 0) {
     MRS_CUDA(cudaMemsetAsync(T.tile_slice_ptr, 0, sizeof(int32_t) * ((size_t)NT + 1), st));
-    MRS_CUDA(cudaMemsetAsync(T.item_unit_ptr, 0, sizeof(int32_t) * ((size_t)NI + 1), st));
     MRS_TRY(dev_alloc(&T.slice_off, 1));
     MRS_CUDA(cudaMemsetAsync(T.slice_off, 0, sizeof(int32_t), st));
     MRS_TRY(dev_alloc(&T.entry, 1));
@@ -419,13 +406,13 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   T.n_units = NUN;
   int32_t *unit_begin = nullptr, *unit_item = nullptr, *unit_tile = nullptr, *unit_len = nullptr, *ids = nullptr, *sorted_id = nullptr;
   int32_t *tile_count = nullptr, *unit_slot = nullptr, *slice_width = nullptr, *d_tile_unit_ptr = nullptr;
-  uint32_t *skey = nullptr, *skey_out = nullptr, *ikey_out = nullptr;  // ikey_out: unused scratch kept for symmetry
+  uint32_t *skey = nullptr, *skey_out = nullptr;
   MRS_TRY(dev_alloc(&unit_begin, (size_t)NUN)); MRS_TRY(dev_alloc(&unit_item, (size_t)NUN)); MRS_TRY(dev_alloc(&unit_tile, (size_t)NUN));
   MRS_TRY(dev_alloc(&unit_len, (size_t)NUN)); MRS_TRY(dev_alloc(&ids, (size_t)NUN)); MRS_TRY(dev_alloc(&sorted_id, (size_t)NUN));
-  MRS_TRY(dev_alloc(&skey, (size_t)NUN)); MRS_TRY(dev_alloc(&skey_out, (size_t)NUN)); MRS_TRY(dev_alloc(&ikey_out, (size_t)NUN));
+  MRS_TRY(dev_alloc(&skey, (size_t)NUN)); MRS_TRY(dev_alloc(&skey_out, (size_t)NUN));
   MRS_TRY(dev_alloc(&tile_count, (size_t)NT + 1)); MRS_TRY(dev_alloc(&unit_slot, (size_t)NUN));
   MRS_TRY(dev_alloc(&d_tile_unit_ptr, (size_t)NT + 1));
-  MRS_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * ((size_t)NT + 1), st));
+  MRS_CUDA(cudaMemsetAsync(tile_count, 0xff, sizeof(int32_t) * ((size_t)NT + 1), st));  // -1: tile without units
   unit_scatter_kernel<<<grid, block, 0, st>>>(flag, uid, perm, item_of, R->irow, n, unit_begin, unit_item, unit_tile);
   const int ugrid = (NUN + block - 1) / block;
   unit_len_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_tile, NUN, n, unit_len, skey, ids, tile_count);
@@ -436,9 +423,13 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   std::vector<int32_t> h_count((size_t)NT + 1, 0), h_unit_ptr((size_t)NT + 1, 0);
   MRS_CUDA(cudaMemcpyAsync(h_count.data(), tile_count, sizeof(int32_t) * (size_t)NT, cudaMemcpyDeviceToHost, st));
   MRS_CUDA(cudaStreamSynchronize(st));
+  h_count[NT] = NUN;  // h_count holds the first unit of every tile; tiles without units take the next tile's first
+  for (int32_t t = NT - 1; t >= 0; --t)
+    if (h_count[t] < 0) h_count[t] = h_count[t + 1];
   for (int32_t t = 0; t < NT; ++t) {
-    h_unit_ptr[t + 1] = h_unit_ptr[t] + h_count[t];
-    h_tile_slice[t + 1] = h_tile_slice[t] + (h_count[t] + 31) / 32;
+    const int32_t cnt = h_count[t + 1] - h_count[t];
+    h_unit_ptr[t + 1] = h_unit_ptr[t] + cnt;
+    h_tile_slice[t + 1] = h_tile_slice[t] + (cnt + 31) / 32;
   }
   const int32_t NS = h_tile_slice[NT];
   T.n_slices = NS;
@@ -467,7 +458,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   MRS_CUDA(cudaStreamSynchronize(st));
   for (void* p : {(void*)tk_in, (void*)tk_out, (void*)pos_in, (void*)perm, (void*)item_of, (void*)head, (void*)seg_start, (void*)flag,
                   (void*)uid, (void*)unit_begin, (void*)unit_item, (void*)unit_tile, (void*)unit_len, (void*)ids, (void*)sorted_id,
-                  (void*)skey, (void*)skey_out, (void*)ikey_out, (void*)tile_count, (void*)unit_slot, (void*)slice_width,
+                  (void*)skey, (void*)skey_out, (void*)tile_count, (void*)unit_slot, (void*)slice_width,
                   (void*)d_tile_unit_ptr})
     dev_free(p);
   T.built = true;

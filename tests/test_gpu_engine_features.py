@@ -1,0 +1,103 @@
+"""GPU tests of the engine features around the kernels: CUDA-graph replay, the item-average switch, the sharded
+wrapper on one rank, per-kernel profiling, layout diagnostics and the device block cache."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import mrs_b200  # noqa: F401,E402
+from mrs_b200 import engine as E  # noqa: E402
+from mrs_b200 import sharded  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    stream = torch.cuda.Stream()
+    e = E.Engine(0, stream=stream.cuda_stream)
+    e._keep = stream
+    yield e
+    e.close()
+
+
+def test_graph_replay_matches_direct_launch(eng, ml100k):
+    import torch
+    R, T = eng.ratings(*ml100k["train"]), eng.ratings(*ml100k["test"])
+    m = E.Model(eng, R)
+    direct = m.mae(T, E.PRED_BASELINE)
+    out = torch.zeros(2, dtype=torch.float64, device="cuda")
+
+    def pass_():
+        m.refit()
+        m.mae_async(T, out.data_ptr())
+
+    pass_(); eng.sync()
+    g = eng.capture(pass_)
+    for _ in range(3):
+        out.zero_()
+        g.launch()
+        eng.sync()
+        r = out.cpu().numpy()
+        assert r[0] / r[1] == direct and r[1] == 20_000       # bit-reproducible across replays
+    g.close()
+
+
+def test_item_average_switch(eng, ml100k):
+    R, T = eng.ratings(*ml100k["train"]), eng.ratings(*ml100k["test"])
+    m = E.Model(eng, R)
+    ref_dev = m.vector(E.ITEM_AVG_DEV)[0].copy()
+    ref_avg = m.vector(E.ITEM_AVG)[0].copy()
+    m.set_item_averages(False)
+    m.refit(); eng.sync()
+    assert np.array_equal(m.vector(E.ITEM_AVG_DEV)[0], ref_dev)   # the deviation pass is unchanged
+    with pytest.raises(E.MrsError):
+        m.vector(E.ITEM_AVG)
+    with pytest.raises(E.MrsError):
+        m.mae(T, E.PRED_ITEM)
+    m.set_item_averages(True)
+    m.refit(); eng.sync()
+    assert np.array_equal(m.vector(E.ITEM_AVG)[0], ref_avg, equal_nan=True)
+
+
+def test_sharded_wrapper_single_rank_and_graphs(eng, ml100k):
+    R, T = eng.ratings(*ml100k["train"]), eng.ratings(*ml100k["test"])
+    o = O.Oracle(*ml100k["train"])
+    ref = o.mae(ml100k["test"], kind=O.BASELINE)
+    sb = sharded.ShardedBaseline(eng, R, T)
+    sb.fit()
+    assert sb.mae() == pytest.approx(ref, rel=1e-6)
+    sb.capture()
+    sb.step(); eng.sync()
+    r = sb.out2.cpu().numpy()
+    assert r[0] / r[1] == pytest.approx(ref, rel=1e-6)
+    # exchange buffer prefix = [dev sums | counts | global sum, count]
+    x = sb.xbuf.cpu().numpy()
+    n_items = R.n_items_dim
+    assert x.size == sharded.mandatory_size(n_items)
+    assert x[2 * n_items + 1] == 80_000 and x[2 * n_items] == ml100k["train"][2].sum()
+    assert np.array_equal(x[n_items:2 * n_items], np.bincount(ml100k["train"][1], minlength=n_items))
+
+
+def test_profile_labels_layout_info_and_block_cache(eng, ml100k):
+    R, T = eng.ratings(*ml100k["train"]), eng.ratings(*ml100k["test"])
+    m = E.Model(eng, R)
+    m.mae(T, E.PRED_BASELINE)
+    eng.profile_begin()
+    m.refit()
+    labels = [k for k, _ in eng.profile_end()]
+    assert labels == ["user_sum", "item_tiled", "item_tiled_finalize"]
+    info = R.layout_info()
+    assert info["user_tiles"] == 1 and info["units"] > 0 and info["tiled_slots"] >= 80_000
+    assert T.layout_info()["item_tiles"] == 1
+    b = R.bytes()
+    assert b["item_major"] == 4 * 80_000 and T.bytes()["sorted_coo"] == 8 * 20_000
+    # released blocks are reused: rebuilding the same set must not grow device memory
+    import torch
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(3):
+        R2 = eng.ratings(*ml100k["train"]); m2 = E.Model(eng, R2); m2.close(); R2.close()
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)
+    before = E.launch_count()
+    m.refit(); eng.sync()
+    assert E.launch_count() - before == 3
