@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
 __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
                                                       uint32_t* __restrict__ usum, unsigned long long* __restrict__ gsum_codes) {
   __shared__ uint32_t sh[8];
+  pdl_trigger();  // the item pass may start its prologue (ring prefetch) while this kernel runs
   const int lane = threadIdx.x & 31;
   constexpr int V = 2;  // vectors per thread (both loads are issued before the first use)
   const int32_t t0 = blockIdx.x * (blockDim.x * V) + threadIdx.x;

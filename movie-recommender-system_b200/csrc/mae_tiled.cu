@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     }
   }
   // ---- the tile's item deviations (unknown item -> 0.0, P:226-227)
+  pdl_wait();  // barriers, partition and the first ring stages overlapped the end of the fit; its outputs are complete from here on
   const int32_t i0 = tile * kMaeTileItems;
 #pragma unroll 4
   for (int32_t x = threadIdx.x; x < kMaeTileItems; x += kMaeThreads) {
@@ -242,8 +243,8 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
   const int32_t grid = L.n_tiles * ctas_per_tile;
   MRS_REQUIRE(grid <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set needs %d CTAs, more than the %d partial slots of the model", grid,
               m->mae_part_cap);
-  predict_mae_tiled_kernel<<<grid, kMaeThreads, kMaeSmem, e->stream>>>(L.entry, L.tile_row_ptr, ctas_per_tile, m->n_users, m->n_items, m->uavg,
-                                                                       m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2);
+  MRS_CUDA(launch_pdl(predict_mae_tiled_kernel, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, ctas_per_tile, m->n_users,
+                      m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2));
   mark(e, "predict_mae_tiled");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

@@ -244,6 +244,8 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
   int32_t item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
 
   // ---- the tile's users: (code sum from K1, rating count); the first CTA of the tile also publishes the averages
+  pdl_trigger();  // K2b may be scheduled as SMs free up
+  pdl_wait();     // everything above (barriers, partition, first ring stages) overlapped K1; usum is complete from here on
   {
     const int32_t u0 = tile * kTileUsers;
     constexpr int kPer = kTileUsers / kTiledThreads;
@@ -319,6 +321,8 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
                                                                  unsigned long long* __restrict__ k1_part, int32_t n_k1, double n_total,
                                                                  double* __restrict__ xbuf, int fused, double* __restrict__ idevavg,
                                                                  double* __restrict__ iavg, double* __restrict__ gavg) {
+  pdl_trigger();
+  pdl_wait();  // the accumulators are complete once the item pass has finished
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
     k1_part[0] = 0;                              // re-arm for the next pass
@@ -476,17 +480,16 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
   }
   // one CTA of 1024 threads per SM; every tile gets the same number of CTAs and the grid never exceeds one wave
   const int32_t ctas_per_tile = std::max(1, e->sm_count / T.n_tiles);
+  const dim3 grid2(T.n_tiles * ctas_per_tile), block2(kTiledThreads);
   if (m->want_item_avg)
-    item_tiled_kernel<true><<<T.n_tiles * ctas_per_tile, kTiledThreads, kTiledSmem, st>>>(T.entry, T.slice_off, T.tile_slice_ptr, ctas_per_tile, m->usum,
-                                                                                          R->urow, R->n_users, T.slot_item, m->uavg, m->xdev_fix,
-                                                                                          m->xcode_sum);
+    MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.tile_slice_ptr, ctas_per_tile, m->usum, R->urow,
+                        R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
   else
-    item_tiled_kernel<false><<<T.n_tiles * ctas_per_tile, kTiledThreads, kTiledSmem, st>>>(T.entry, T.slice_off, T.tile_slice_ptr, ctas_per_tile, m->usum,
-                                                                                           R->urow, R->n_users, T.slot_item, m->uavg, m->xdev_fix,
-                                                                                           m->xcode_sum);
+    MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.tile_slice_ptr, ctas_per_tile, m->usum, R->urow,
+                        R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
   mark(e, "item_tiled");
-  item_tiled_finalize_kernel<<<(R->n_items + 255) / 256, 256, 0, st>>>(m->xdev_fix, m->xcode_sum, R->icolp, R->n_items, m->k1_part, m->k1_blocks,
-                                                                       (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg);
+  MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
+                      m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg));
   mark(e, "item_tiled_finalize");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
