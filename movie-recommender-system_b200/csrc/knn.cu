@@ -148,23 +148,29 @@ __global__ void gather_values_kernel(const double* __restrict__ udev, const doub
 }
 
 // ---------------- P3: user-user similarity, shared-memory-staged SpGEMM --------------------------------------------
+constexpr int kSimThreads = 1024;  // 32 warps: about one slice per warp at ml-100k shape (943 users = 30 slices)
 template <int UB, int MODE>  // MODE 1: cosine (P:424-426), 2: jaccard (P:454-458)
-__global__ void __launch_bounds__(256) similarity_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol,
+__global__ void __launch_bounds__(kSimThreads) similarity_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol,
                                                         const double* __restrict__ upre, const int32_t* __restrict__ known_user,
                                                         int32_t n_known, int32_t n_items, const int32_t* __restrict__ perm,
                                                         const int32_t* __restrict__ slice_off, int32_t n_slices,
                                                         const int32_t* __restrict__ ell_col, const double* __restrict__ ell_val,
                                                         double* __restrict__ S) {
-  extern __shared__ double su[];  // [n_items][UB]: r~ of the block's users, 0.0 where unrated
+  // [n_items][kStride]: r~ of the block's users, 0.0 where unrated.  A lane reads the UB values of its item with 128-bit
+  // loads; the row stride is padded from 8 to 10 doubles (80 B) so that the items of a quarter warp fall on 8 different
+  // bank groups (with a 64-byte stride every item sits on the same two: capture r01_knn counted 18.3 M bank conflicts
+  // in 23.7 M shared wavefronts, the kernel was bound by that)
+  constexpr int kStride = (UB >= 4) ? UB + 2 : UB;
+  extern __shared__ __align__(16) double su[];
   const int32_t cu0 = blockIdx.x * UB;
-  for (int32_t x = threadIdx.x; x < n_items * UB; x += blockDim.x) su[x] = 0.0;
+  for (int32_t x = threadIdx.x; x < n_items * kStride; x += blockDim.x) su[x] = 0.0;
   __syncthreads();
 #pragma unroll
   for (int t = 0; t < UB; ++t) {
     const int32_t cu = cu0 + t;
     if (cu < n_known) {
       const int32_t u = known_user[cu];
-      for (int32_t p = urow[u] + threadIdx.x; p < urow[u + 1]; p += blockDim.x) su[ucol[p] * UB + t] = (MODE == 1) ? upre[p] : 1.0;
+      for (int32_t p = urow[u] + threadIdx.x; p < urow[u + 1]; p += blockDim.x) su[ucol[p] * kStride + t] = (MODE == 1) ? upre[p] : 1.0;
     }
   }
   __syncthreads();
@@ -177,13 +183,30 @@ __global__ void __launch_bounds__(256) similarity_kernel(const int32_t* __restri
     for (int t = 0; t < UB; ++t) acc[t] = 0.0;
     const int32_t* colp = ell_col + ((int64_t)base << 5) + lane;
     const double* valp = ell_val + ((int64_t)base << 5) + lane;
-#pragma unroll 2
-    for (int32_t j = 0; j < width; ++j) {
-      const int32_t col = __ldg(colp + ((int64_t)j << 5));
-      const double val = __ldg(valp + ((int64_t)j << 5));
-      const double* row = su + col * UB;
+    constexpr int kB = 8;  // rows of the slice requested before the first use (the row walk is a serial chain otherwise)
+    for (int32_t j0 = 0; j0 < width; j0 += kB) {
+      int32_t col[kB];
+      double val[kB];
 #pragma unroll
-      for (int t = 0; t < UB; ++t) acc[t] = __dadd_rn(acc[t], __dmul_rn(row[t], val));  // ascending item id, no FMA
+      for (int k = 0; k < kB; ++k) {
+        const bool in = j0 + k < width;
+        col[k] = in ? __ldg(colp + ((int64_t)(j0 + k) << 5)) : 0;
+        val[k] = in ? __ldg(valp + ((int64_t)(j0 + k) << 5)) : 0.0;  // padding: +/-0 products leave the sums unchanged
+      }
+#pragma unroll
+      for (int k = 0; k < kB; ++k) {
+        const double* row = su + col[k] * kStride;
+        if (UB >= 2) {
+#pragma unroll
+          for (int t = 0; t < UB; t += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(row + t);
+            acc[t] = __dadd_rn(acc[t], __dmul_rn(v.x, val[k]));  // ascending item id, no FMA
+            acc[t + (UB >= 2 ? 1 : 0)] = __dadd_rn(acc[t + (UB >= 2 ? 1 : 0)], __dmul_rn(v.y, val[k]));
+          }
+        } else {
+          acc[0] = __dadd_rn(acc[0], __dmul_rn(row[0], val[k]));
+        }
+      }
     }
     if (cv >= 0) {
       int32_t nv = 0;
@@ -357,10 +380,10 @@ int sim_mode(const mrs_sim* s) {
 template <int UB, int MODE>
 int32_t launch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
   const auto& L = R->sl;
-  const size_t smem = (size_t)R->n_items * UB * sizeof(double);
+  const size_t smem = (size_t)R->n_items * ((UB >= 4) ? UB + 2 : UB) * sizeof(double);
   MRS_CUDA(cudaFuncSetAttribute(similarity_kernel<UB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (L.n_known + UB - 1) / UB;
-  similarity_kernel<UB, MODE><<<grid, 256, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.n_known, R->n_items, L.perm,
+  similarity_kernel<UB, MODE><<<grid, kSimThreads, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.n_known, R->n_items, L.perm,
                                                        L.slice_off, L.n_slices, L.ell_col, s->ell_val, s->S);
   mark(R->eng, "similarity");
   MRS_CUDA(cudaGetLastError());
@@ -370,8 +393,9 @@ int32_t launch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
 template <int MODE>
 int32_t dispatch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
   const size_t row = (size_t)R->n_items * sizeof(double);
-  if (row * 8 <= (size_t)kSimMaxSmem) return launch_similarity<8, MODE>(R, s, st);
-  if (row * 4 <= (size_t)kSimMaxSmem) return launch_similarity<4, MODE>(R, s, st);
+  // 8 users per CTA: measured 127 us against 144 us with 4 users per CTA at ml-100k shape (profiles/r01_summary.md)
+  if (row * 10 <= (size_t)kSimMaxSmem) return launch_similarity<8, MODE>(R, s, st);
+  if (row * 6 <= (size_t)kSimMaxSmem) return launch_similarity<4, MODE>(R, s, st);
   if (row * 2 <= (size_t)kSimMaxSmem) return launch_similarity<2, MODE>(R, s, st);
   return launch_similarity<1, MODE>(R, s, st);
 }
