@@ -1,0 +1,123 @@
+"""Answer documents with the reference's JSON schema, produced through the predictions mirror.
+
+Each function returns the dict that the corresponding main of the reference serialises with ``ujson.write(answers, 4)``:
+  baseline      predict/Baseline.scala:86-124              keys "B.1" "B.2" "B.3"
+  distributed   distributed/DistributedBaseline.scala:62-83 keys "D.1" "D.2"
+  personalized  predict/Personalized.scala:53-75            keys "P.1" "P.2" "P.3"
+  knn           predict/kNN.scala:59-87                     keys "N.1" "N.2" "N.3"
+  recommender   recommend/Recommender.scala:70-89           keys "R.1" "R.2"
+so that a run on the real MovieLens files diffs directly against the reference's committed answers
+(baseline-100k.json, distributed-25m-4.json, personalized-100k.json, knn-100k.json).  The CLI shells of the reference
+(scallop, Spark session) are out of scope; ``tools/run_answers.py`` is a thin argparse wrapper.
+"""
+from . import predictions as P
+
+KNN_SWEEP = [10, 30, 50, 100, 200, 300, 400, 800, 943]  # predict/kNN.scala:73
+
+
+def _timed(n, closure):
+    ts = [P.timingInMs(closure)[1] for _ in range(max(int(n), 0))]
+    return {"average (ms)": P.mean(ts), "stddev (ms)": P.std(ts)}
+
+
+def baseline(train, test, num_measurements=3, train_path="", test_path=""):
+    return {
+        "Meta": {"1.Train": train_path, "2.Test": test_path, "3.Measurements": num_measurements},
+        "B.1": {
+            "1.GlobalAvg": P.computeAvgRating(train)(1, 1),
+            "2.User1Avg": P.computeUserAvg(train)(1, 1),
+            "3.Item1Avg": P.computeItemAvg(train)(1, 1),
+            "4.Item1AvgDev": P.computeItemAvgDev(train)(1, 1),
+            "5.PredUser1Item1": P.computePrediction(train)(1, 1),
+        },
+        "B.2": {
+            "1.GlobalAvgMAE": P.MAE(P.computeAvgRating(train), test),
+            "2.UserAvgMAE": P.MAE(P.computeUserAvg(train), test),
+            "3.ItemAvgMAE": P.MAE(P.computeItemAvg(train), test),
+            "4.BaselineMAE": P.MAE(P.computePrediction(train), test),
+        },
+        "B.3": {
+            "1.GlobalAvg": _timed(num_measurements, lambda: P.MAE(P.computeAvgRating(train), test)),
+            "2.UserAvg": _timed(num_measurements, lambda: P.MAE(P.computeUserAvg(train), test)),
+            "3.ItemAvg": _timed(num_measurements, lambda: P.MAE(P.computeItemAvg(train), test)),
+            "4.Baseline": _timed(num_measurements, lambda: P.MAE(P.computePrediction(train), test)),
+        },
+    }
+
+
+def distributed(train, test, num_measurements=3, master="b200", train_path="", test_path=""):
+    return {
+        "Meta": {"1.Train": train_path, "2.Test": test_path, "3.Master": master, "4.Measurements": num_measurements},
+        "D.1": {
+            "1.GlobalAvg": P.getGlobalAvg(train),
+            "2.User1Avg": P.usersAvgSpark(train)(1, 0),
+            "3.Item1Avg": P.itemsAvgSpark(train)(0, 1),
+            "4.Item1AvgDev": P.itemsAvgDevSpark(train)(0, 1),
+            "5.PredUser1Item1": P.baselinePredictorSpark(train)(1, 1),
+            "6.Mae": P.MeanAbsoluteErrorSpark(P.baselinePredictorSpark(train), test),
+        },
+        "D.2": {"1.DistributedBaseline": _timed(num_measurements,
+                                                lambda: P.MeanAbsoluteErrorSpark(P.baselinePredictorSpark(train), test))},
+    }
+
+
+def personalized(train, test, num_measurements=0, train_path="", test_path=""):
+    ones = P.predictor(train, P.weightedSumDeviation(train, P.similarityOne))
+    cos = P.adjustedCosineSimilarityFunction(train)
+    pcos = P.predictor(train, P.weightedSumDeviation(train, cos))
+    out = {
+        "Meta": {"1.Train": train_path, "2.Test": test_path, "3.Measurements": num_measurements},
+        "P.1": {"1.PredUser1Item1": ones(1, 1), "2.OnesMAE": P.MAE(ones, test)},
+        "P.2": {"1.AdjustedCosineUser1User2": cos(2, 1), "2.PredUser1Item1": pcos(1, 1), "3.AdjustedCosineMAE": P.MAE(pcos, test)},
+    }
+    jac = P.jaccardCoefficient(train)
+    pjac = P.predictor(train, P.weightedSumDeviation(train, jac))
+    out["P.3"] = {"1.JaccardUser1User2": jac(1, 2), "2.PredUser1Item1": pjac(1, 1), "3.JaccardPersonalizedMAE": P.MAE(pjac, test)}
+    return out
+
+
+def knn(train, test, num_measurements=3, train_path="", test_path="", sweep=KNN_SWEEP):
+    def closure(k):
+        return P.MAE(P.predictor(train, P.weightedSumDeviation(train, P.getSimilarity(train, k, P.adjustedCosineSimilarityFunction(train)))), test)
+    s10 = P.getSimilarity(train, 10, P.adjustedCosineSimilarityFunction(train))
+    n1 = {"1.k10u1v1": s10(1, 1), "2.k10u1v864": s10(1, 864), "3.k10u1v886": s10(1, 886),
+          "4.PredUser1Item1": P.predictor(train, P.weightedSumDeviation(train, s10))(1, 1)}
+    return {
+        "Meta": {"1.Train": train_path, "2.Test": test_path, "3.Measurements": num_measurements},
+        "N.1": n1,
+        "N.2": {"1.kNN-Mae": [[k, closure(k)] for k in sweep]},
+        "N.3": {"1.kNN": _timed(num_measurements, lambda: closure(300))},
+    }
+
+
+def parse_personal(path):
+    """recommend/Recommender.scala:39-54: `id,title,rating` rows; rated rows become Rating(944, id, rating)."""
+    ratings, names = [], {}
+    with open(path, newline="") as f:
+        for line in f.read().splitlines():
+            cols = [c.strip() for c in line.rstrip("\r").split(",")]
+            while cols and cols[-1] == "":   # String.split drops trailing empty fields
+                cols.pop()
+            if not cols or cols[0] == "id":
+                continue
+            names[int(cols[0])] = cols[1] if len(cols) > 1 else ""
+            if len(cols) >= 3 and float(cols[2]) != 0:
+                ratings.append(P.Rating(944, int(cols[0]), float(cols[2])))
+    return ratings, names
+
+
+def recommender(data_arrays, personal_path, data_path=""):
+    """data_arrays = (users, items, ratings) of u.data; the personal ratings are appended as user 944 (Recommender.scala:68)."""
+    import numpy as np
+    personal, names = parse_personal(personal_path)
+    u = np.concatenate([np.asarray(data_arrays[0], dtype=np.int32), np.array([r.user for r in personal], dtype=np.int32)])
+    i = np.concatenate([np.asarray(data_arrays[1], dtype=np.int32), np.array([r.item for r in personal], dtype=np.int32)])
+    r = np.concatenate([np.asarray(data_arrays[2], dtype=np.float64), np.array([x.rating for x in personal], dtype=np.float64)])
+    augmented = P.RatingSet.from_arrays(u, i, r)
+    pred = P.predictor(augmented, P.weightedSumDeviation(augmented, P.getSimilarity(augmented, 300, P.adjustedCosineSimilarityFunction(augmented))))
+    top = P.recommendations(augmented, pred)(944, 3)
+    return {
+        "Meta": {"data": data_path, "personal": personal_path},
+        "R.1": {"PredUser1Item1": pred(1, 1)},
+        "R.2": [[item, names.get(item, ""), score] for item, score in top],
+    }

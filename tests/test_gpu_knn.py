@@ -159,3 +159,36 @@ def test_mirror_knn_reads_like_the_reference(eng, ml100k):
     assert [x[0] for x in rec] == o.recommend(1, 3, k=300)[0].tolist()
     with pytest.raises(P.UnsupportedOperationError):
         P.weightedSumDeviation(train, lambda u, v: 0.5)
+
+
+def test_answer_documents_have_the_reference_schema(eng, ml100k, tmp_path):
+    """the JSON documents of the five mains, key for key (values checked against the oracle)."""
+    import json
+    from mrs_b200 import answers
+    P.set_default_engine(eng)
+    train = P.RatingSet.from_arrays(*ml100k["train"])
+    test = P.RatingSet.from_arrays(*ml100k["test"])
+    o = O.Oracle(*ml100k["train"])
+    te = ml100k["test"]
+    b = answers.baseline(train, test, num_measurements=1)
+    assert list(b) == ["Meta", "B.1", "B.2", "B.3"]
+    assert list(b["B.1"]) == ["1.GlobalAvg", "2.User1Avg", "3.Item1Avg", "4.Item1AvgDev", "5.PredUser1Item1"]
+    assert b["B.1"]["1.GlobalAvg"] == o.global_avg and b["B.1"]["2.User1Avg"] == o.user_avg(1) and b["B.1"]["3.Item1Avg"] == o.item_avg(1)
+    assert b["B.2"]["4.BaselineMAE"] == pytest.approx(o.mae(te, kind=O.BASELINE), rel=REL)
+    assert set(b["B.3"]["4.Baseline"]) == {"average (ms)", "stddev (ms)"}
+    d = answers.distributed(train, test, num_measurements=1)
+    assert list(d["D.1"]) == ["1.GlobalAvg", "2.User1Avg", "3.Item1Avg", "4.Item1AvgDev", "5.PredUser1Item1", "6.Mae"]
+    assert d["D.1"]["6.Mae"] == pytest.approx(b["B.2"]["4.BaselineMAE"], rel=1e-12)          # A.9 (7)
+    p = answers.personalized(train, test)
+    assert p["P.1"]["2.OnesMAE"] == pytest.approx(b["B.2"]["4.BaselineMAE"], rel=1e-9)        # A.9 (1)
+    assert p["P.2"]["1.AdjustedCosineUser1User2"] == o.cosine(2, 1)
+    assert p["P.3"]["1.JaccardUser1User2"] == o.jaccard(1, 2)
+    k = answers.knn(train, test, num_measurements=1, sweep=[10, 943])
+    assert k["N.1"]["1.k10u1v1"] == 0.0
+    assert k["N.2"]["1.kNN-Mae"][1][1] == pytest.approx(p["P.2"]["3.AdjustedCosineMAE"], rel=1e-9)   # k=943 == cosine, A.9 (2)
+    personal = tmp_path / "personal.csv"
+    personal.write_bytes(b"id,title,rating\r\n1,Toy Story (1995),5\r\n2,GoldenEye (1995),\r\n3,Four Rooms (1995),2\r\n")
+    r = answers.recommender(ml100k["all"], str(personal))
+    assert list(r) == ["Meta", "R.1", "R.2"] and len(r["R.2"]) == 3 and all(len(x) == 3 for x in r["R.2"])
+    assert all(x[0] not in (1, 3) for x in r["R.2"])                                          # rated items are never recommended
+    json.dumps([b, d, p, k, r])
