@@ -141,7 +141,7 @@ def workload_config(d, world):
         "layout": "train: user-major codes padded to 16 B vectors (1 B/rating + 4 B/vector), user-tiled item-major sliced-ELL "
                   "(4 B/rating: valid|code|16-bit local user); test: item-tiled, one packed 8-byte word per rating (int32 user | 16-bit local item | code)",
         "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
-        "parallelism": f"user-sharded x{world}, one all-reduce of the per-item exchange buffer" if world > 1 else "single GPU",
+        "parallelism": f"user-sharded x{world}, one all-reduce of the per-item exchange buffer (own NVLink peer-memory kernel)" if world > 1 else "single GPU",
     }
 
 
@@ -186,7 +186,7 @@ def run_ours(args):
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
     from mrs_b200 import sharded
-    sb = sharded.ShardedBaseline(eng, R, T) if world > 1 else None
+    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl) if world > 1 else None
 
     def enqueue():
         if sb is not None:       # local pass -> all-reduce of the exchange buffer -> finish -> MAE -> 16-byte all-reduce
@@ -262,11 +262,13 @@ def run_ours(args):
         per_kernel = {k: sum(v) / len(v) for k, v in per_kernel.items()}
 
         # ---- sustained repetition so that nvidia-smi (100 ms sampling) sees the same step under load
-        t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 1.5:
-            for _ in range(50):
-                step()
-            torch.cuda.synchronize(dev)
+        # (a fixed count derived from the max-reduced step time: every rank must issue the same number of exchanges)
+        n_sustain = int(min(20000, max(50, 1.5e3 / max(total_ms / args.steps, 1e-3))))
+        for k in range(n_sustain):
+            step()
+            if k % 50 == 49:
+                torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
     clocks = sampler.stop() if sampler else None
 
     value = world * n_step * args.steps / (total_ms / 1000.0)
@@ -309,7 +311,7 @@ def run_ours(args):
             r = out2.cpu().numpy()       # D2H read of the result
             handles = (m2, T2, R2)
         else:
-            s2 = sharded.ShardedBaseline(eng, R2, T2)
+            s2 = sharded.ShardedBaseline(eng, R2, T2)   # NCCL here: the peer buffers belong to the long-lived pass above
             s2.fit()
             s2.mae_async()
             r = s2.out2.cpu().numpy()
@@ -359,8 +361,11 @@ def run_ours(args):
                             "released, per step (2 untimed warm-up steps fill the engine's device block cache)"},
             "gpu_launches": int(launches) if graph is None else int(args.steps * kernels_per_step),
             "launch_mode": ("cuda graph replay (1 cudaGraphLaunch per step)" if world == 1 else
-                            "2 cuda graphs + 2 NCCL all-reduces per step") if graph is not None else "stream launches", "clocks": clocks, "mae": mae, "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae),
+                            ("1 cuda graph per step incl. the 2 peer-memory exchange kernels" if not args.nccl else
+                             "2 cuda graphs + 2 NCCL all-reduces per step")) if graph is not None else "stream launches", "clocks": clocks, "mae": mae, "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae),
             "wall_ms_per_step_incl_flush": 1000.0 * t_wall / args.steps,
+            "exchange": None if sb is None else ("nccl" if sb.peer is None else
+                                                 {"kind": "own NVLink peer-memory kernel", "timed_out": sb.peer.timed_out()}),
             "step_ms_min_max": [min(step_ms), max(step_ms)],
             "knn": knn,
         }
@@ -429,6 +434,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nccl", action="store_true", help="N>1: use NCCL all-reduces instead of the library's peer-memory exchange kernel")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.steps = max(args.steps, 1)

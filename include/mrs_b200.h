@@ -38,6 +38,7 @@ typedef struct mrs_ratings mrs_ratings;
 typedef struct mrs_model mrs_model;
 typedef struct mrs_sim mrs_sim;
 typedef struct mrs_graph mrs_graph;
+typedef struct mrs_exchange mrs_exchange;
 
 typedef enum {
   MRS_OK = 0,
@@ -142,6 +143,19 @@ MRS_API int32_t mrs_model_set_item_averages(mrs_model* m, int32_t enabled);
 MRS_API int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, int64_t* n_doubles);
 MRS_API int32_t mrs_fit_finish(mrs_model* m);
 MRS_API void mrs_model_destroy(mrs_model* m);
+
+/* ---- the collective of a sharded run as our own kernel over NVLink peer memory (one process per GPU, one box).
+ * Each rank creates an exchange object (a symmetric device buffer + flags) and gets a 64-byte CUDA-IPC handle; the
+ * host layer all-gathers the handles (any transport) and passes the world x 64 bytes to mrs_exchange_connect.
+ * mrs_exchange_allreduce_async then sums `n_doubles` fp64 values in place across the ranks IN RANK ORDER (bit-identical
+ * result everywhere) with one kernel: publish, flag the peers, wait, 128-bit peer loads.  Replaces the NCCL all-reduce of
+ * the exchange buffer (P:267-268, P:247) and of {sum |err|, n}; can be captured in a CUDA graph.  Every rank must issue
+ * the same sequence of calls.  A peer that never arrives makes the kernel give up after ~2 s: mrs_exchange_status. */
+MRS_API int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t rank, int32_t world, void* ipc_handle_out64, mrs_exchange** out);
+MRS_API int32_t mrs_exchange_connect(mrs_exchange* x, const void* all_handles_world_x_64);
+MRS_API int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout, int64_t n_doubles);
+MRS_API int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out);
+MRS_API void mrs_exchange_destroy(mrs_exchange* x);
 
 MRS_API int32_t mrs_model_scalar(const mrs_model* m, int32_t vec_kind, double* out);
 /* value for one original id with the reference's fallbacks (unknown user/item -> global average; unknown item

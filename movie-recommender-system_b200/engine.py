@@ -24,7 +24,8 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
     "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
-    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_model_scalar",
+    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_status", "mrs_exchange_destroy",
+    "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
     "mrs_mae_async", "mrs_recommend",
@@ -89,6 +90,11 @@ def lib():
         "mrs_model_exchange_buffer": (i32, [vp, P(vp), P(i64)]),
         "mrs_fit_finish": (i32, [vp]),
         "mrs_model_destroy": (None, [vp]),
+        "mrs_exchange_create": (i32, [vp, i64, i32, i32, vp, P(vp)]),
+        "mrs_exchange_connect": (i32, [vp, vp]),
+        "mrs_exchange_allreduce_async": (i32, [vp, vp, i64]),
+        "mrs_exchange_status": (i32, [vp, P(i32)]),
+        "mrs_exchange_destroy": (None, [vp]),
         "mrs_model_scalar": (i32, [vp, i32, P(dbl)]),
         "mrs_model_lookup": (i32, [vp, i32, i32, P(dbl), P(i32)]),
         "mrs_model_vector": (i32, [vp, i32, vp, vp, i64, P(i64)]),
@@ -169,6 +175,35 @@ class Engine:
 
     def ratings_from_file(self, path, sep):
         return Ratings.from_file(self, path, sep)
+
+
+class PeerExchange:
+    """Sum fp64 device buffers across the ranks of one box with the library's own NVLink peer-memory kernel.
+
+    ``all_gather(bytes) -> list[bytes]`` is any host-side transport of the 64-byte IPC handles (e.g.
+    ``torch.distributed.all_gather_object``)."""
+
+    def __init__(self, engine, n_doubles, rank, world, all_gather):
+        self._h = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _check(lib().mrs_exchange_create(engine._h, int(n_doubles), int(rank), int(world), handle, C.byref(self._h)))
+        handles = all_gather(handle.raw)
+        assert len(handles) == world and all(len(h) == 64 for h in handles)
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        _check(lib().mrs_exchange_connect(self._h, blob))
+
+    def allreduce_async(self, device_ptr, n_doubles):
+        _check(lib().mrs_exchange_allreduce_async(self._h, C.c_void_p(int(device_ptr)), int(n_doubles)))
+
+    def timed_out(self):
+        t = C.c_int32()
+        _check(lib().mrs_exchange_status(self._h, C.byref(t)))
+        return bool(t.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_exchange_destroy(self._h)
+            self._h = None
 
 
 class Graph:

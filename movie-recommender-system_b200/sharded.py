@@ -80,7 +80,7 @@ class ShardedBaseline:
 
     `engine` must have been created on the CUDA stream the collectives run on (``torch.cuda.current_stream()``)."""
 
-    def __init__(self, engine, train, test, group=None, item_averages=False):
+    def __init__(self, engine, train, test, group=None, item_averages=False, peer_exchange=False):
         import torch
         from . import engine as E
         self.E, self.torch, self.group = E, torch, group
@@ -93,13 +93,28 @@ class ShardedBaseline:
         if not item_averages:            # only [dev sums | counts | global sum, count] has to travel
             self.xbuf = self.xbuf[:mandatory_size(train.n_items_dim)]
         self.out2 = torch.zeros(2, dtype=torch.float64, device=self.device)
+        # peer_exchange: the two all-reduces run as the library's own NVLink peer-memory kernel instead of NCCL
+        self.peer = None
+        if peer_exchange:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+                def gather(b):
+                    out = [None] * world
+                    dist.all_gather_object(out, b, group=group)
+                    return out
+                self.peer = E.PeerExchange(engine, max(int(self.xbuf.numel()), 2), rank, world, gather)
 
     # ---- the five pieces of a step (all asynchronous on the engine's stream)
     def fit_local(self):
         self.E._check(self.E.lib().mrs_fit_local(self.engine._h, self.train._h, self.E.C.byref(self.model._h)))
 
-    def exchange(self):
-        all_reduce_sum(self.xbuf, self.group)          # THE collective of the fit (P:267-268, P:247)
+    def exchange(self):                                # THE collective of the fit (P:267-268, P:247)
+        if self.peer is not None:
+            self.peer.allreduce_async(self.xbuf.data_ptr(), self.xbuf.numel())
+        else:
+            all_reduce_sum(self.xbuf, self.group)
 
     def fit_finish(self):
         self.E._check(self.E.lib().mrs_fit_finish(self.model._h))
@@ -107,19 +122,28 @@ class ShardedBaseline:
     def mae_local(self):
         self.model.mae_async(self.test, self.out2.data_ptr(), self.E.PRED_BASELINE)
 
-    def mae_exchange(self):
-        all_reduce_sum(self.out2, self.group)          # 16 bytes: {sum |err|, n}
+    def mae_exchange(self):                            # 16 bytes: {sum |err|, n}
+        if self.peer is not None:
+            self.peer.allreduce_async(self.out2.data_ptr(), 2)
+        else:
+            all_reduce_sum(self.out2, self.group)
 
     def capture(self):
         """Capture the kernel runs between the collectives as two CUDA graphs; `step()` then issues
         graph, all-reduce, graph, all-reduce instead of ~10 separate launches."""
         self.step()                                    # first use allocates layouts
         self.torch.cuda.synchronize(self.device)
+        if self.peer is not None:                      # our exchange kernels are plain launches: the whole step is ONE graph
+            self._g_all = self.engine.capture(lambda: (self.fit_local(), self.exchange(), self.fit_finish(), self.mae_local(),
+                                                       self.mae_exchange()))
+            return
         self._g1 = self.engine.capture(self.fit_local)
         self._g2 = self.engine.capture(lambda: (self.fit_finish(), self.mae_local()))
 
     def step(self):
-        if getattr(self, "_g1", None) is not None:
+        if getattr(self, "_g_all", None) is not None:
+            self._g_all.launch()
+        elif getattr(self, "_g1", None) is not None:
             self._g1.launch(); self.exchange(); self._g2.launch(); self.mae_exchange()
         else:
             self.fit_local(); self.exchange(); self.fit_finish(); self.mae_local(); self.mae_exchange()

@@ -101,3 +101,24 @@ def test_profile_labels_layout_info_and_block_cache(eng, ml100k):
     before = E.launch_count()
     m.refit(); eng.sync()
     assert E.launch_count() - before == 3
+
+
+def test_peer_exchange_single_rank_is_identity_and_graph_capturable(eng):
+    """world = 1 exercises the whole kernel path (publish, flag, wait, rank-ordered reduce, device-side epoch)."""
+    import torch
+    x = E.PeerExchange(eng, 1001, 0, 1, lambda b: [b])
+    with torch.cuda.stream(eng._keep):
+        buf = torch.arange(1001, dtype=torch.float64, device="cuda") * 0.25
+        ref = buf.clone()
+        for _ in range(3):                      # alternating parity buffers
+            x.allreduce_async(buf.data_ptr(), 1001)
+        eng.sync()
+        assert torch.equal(buf, ref) and not x.timed_out()
+        small = torch.tensor([3.5, 7.0], dtype=torch.float64, device="cuda")
+        g = eng.capture(lambda: (x.allreduce_async(buf.data_ptr(), 1001), x.allreduce_async(small.data_ptr(), 2)))
+        for _ in range(4):
+            g.launch()
+        eng.sync()
+        assert torch.equal(buf, ref) and small.tolist() == [3.5, 7.0] and not x.timed_out()
+        g.close()
+    x.close()
