@@ -258,7 +258,12 @@ def run_ours(args):
                 model.refit()
                 model.mae_async(T, out2.data_ptr())
             else:            # same number of exchanges on every rank
-                sb.fit_local(); sb.exchange(); sb.fit_finish(); sb.mae_local(); sb.mae_exchange()
+                sb.fit_local(); sb.exchange()
+                if sb.peer is not None and rank == 0 and _ == reps - 1:
+                    log(f"[rank 0] big exchange stamps (ns after start: published, barrier1, reduced, barrier2, done): {sb.peer.stamps()}")
+                sb.fit_finish(); sb.mae_local(); sb.mae_exchange()
+                if sb.peer is not None and rank == 0 and _ == reps - 1:
+                    log(f"[rank 0] small exchange stamps: {sb.peer.stamps()}")
             for name, ms in eng.profile_end():
                 per_kernel.setdefault(name, []).append(ms)
         per_kernel = {k: sum(v) / len(v) for k, v in per_kernel.items()}

@@ -155,6 +155,9 @@ MRS_API int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t ra
 MRS_API int32_t mrs_exchange_connect(mrs_exchange* x, const void* all_handles_world_x_64);
 MRS_API int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout, int64_t n_doubles);
 MRS_API int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out);
+/* diagnostics: %globaltimer (ns) of block 0 in the last exchange: [0] start, [1] published, [2] first barrier passed,
+ * [3] slice reduced, [4] second barrier passed (two-shot only), [5] done */
+MRS_API int32_t mrs_exchange_stamps(mrs_exchange* x, uint64_t* out8);
 MRS_API void mrs_exchange_destroy(mrs_exchange* x);
 
 MRS_API int32_t mrs_model_scalar(const mrs_model* m, int32_t vec_kind, double* out);

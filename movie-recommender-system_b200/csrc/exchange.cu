@@ -6,8 +6,11 @@
 // memory (NVLink store, release at system scope), (3) waits for the peers' flags, (4) reads all partial sums with
 // 128-bit peer loads and adds them in RANK ORDER, so every rank ends with bit-identical totals.  A 3.3 MB buffer is
 // latency bound: NCCL's all-reduce costs 30-40 us per call here, this kernel one peer round trip plus the reads.
-// Buffers are double-buffered by epoch parity, which removes the trailing barrier: a rank overwrites parity p again two
-// epochs later, and its peers enter the next epoch only after they finished reading.
+// Large buffers take the two-shot form so that the NVLink traffic per rank does not grow with the number of ranks: after
+// the first barrier every rank reduces only ITS slice (reading that slice from every peer) into a symmetric result
+// buffer, a second barrier follows, and every rank collects the reduced slices.  Small buffers ({sum |err|, n}) stay
+// one-shot (one barrier).  Buffers are double-buffered by epoch parity, which removes the trailing barrier: a rank
+// overwrites parity p again two epochs later, and its peers enter the next epoch only after they finished reading.
 //
 // The waits are bounded (about 2 s): a missing peer makes the kernel give up and set an error word instead of hanging.
 #include <algorithm>
@@ -20,12 +23,13 @@ struct mrs_exchange {
   mrs_engine* eng = nullptr;
   int32_t rank = 0, world = 1;
   int64_t n = 0;                 // capacity in doubles of one parity buffer
-  unsigned char* base = nullptr; // own symmetric allocation: [2][n] doubles | flags[world] u64 | error word
+  unsigned char* base = nullptr; // own symmetric allocation: publish [2][n] | result [2][n] doubles | flags [2][world] u64
   std::vector<void*> peer_base;  // mapped bases of all ranks (own = base)
   double** d_peer = nullptr;     // device array of the mapped bases
   unsigned long long* d_epoch = nullptr;  // number of completed exchanges (device side, so that launches can be graph-captured)
-  unsigned int* d_done = nullptr;  // [2] blocks-published / blocks-finished counters of this rank
+  unsigned int* d_done = nullptr;  // [3] blocks-published / blocks-reduced / blocks-finished counters of this rank
   int32_t* d_error = nullptr;
+  unsigned long long* d_stamps = nullptr;  // [8] globaltimer stamps of block 0 in the last exchange (diagnostics)
   bool connected = false;
 };
 
@@ -37,68 +41,131 @@ constexpr int kExThreads = 512;
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
+// barrier across the ranks, entered by thread 0 of every block: the last arriving block of this rank raises flag
+// `which` (0/1) in every rank's flag row, then every block waits until all ranks have raised theirs for this epoch
+__device__ __forceinline__ bool rank_barrier(double* const* __restrict__ peer, int32_t rank, int32_t world, int64_t cap, int which,
+                                             unsigned long long epoch, unsigned int* __restrict__ done, int32_t* __restrict__ error) {
+  if (atomicAdd(done, 1u) + 1u == gridDim.x) {
+    *done = 0;
+    __threadfence_system();
+    for (int p = 0; p < world; ++p) {
+      unsigned long long* flags = reinterpret_cast<unsigned long long*>(peer[p] + 4 * (size_t)cap) + (size_t)which * world;
+      st_release_sys(flags + rank, epoch);
+    }
+  }
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peer[rank] + 4 * (size_t)cap) + (size_t)which * world;
+  const long long t0 = clock64();
+  for (int p = 0; p < world; ++p) {
+    while (ld_acquire_sys(mine + p) < epoch) {
+      if (clock64() - t0 > 4000000000LL) { atomicExch(error, 1); return false; }  // ~2 s at 1.9 GHz: a peer is missing
+    }
+  }
+  return true;
+}
+
 // inout[0..n): this rank's partial sums on entry, the sum over all ranks (added in rank order) on exit
 __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* const* __restrict__ peer, int32_t rank, int32_t world, int64_t n,
-                                                                   int64_t cap, unsigned long long* __restrict__ epoch_done,
+                                                                   int64_t cap, int two_shot, unsigned long long* __restrict__ epoch_done,
                                                                    unsigned int* __restrict__ done, int32_t* __restrict__ error,
-                                                                   double* __restrict__ inout) {
+                                                                   unsigned long long* __restrict__ stamps, double* __restrict__ inout) {
   __shared__ bool ok;
+  const bool stamp = (blockIdx.x == 0 && threadIdx.x == 0);
+  if (stamp) stamps[0] = gtime();
   const unsigned long long epoch = *epoch_done + 1;  // stable for the whole kernel: only its last block advances it
   const int parity = (int)(epoch & 1);
-  double* mine = peer[rank] + (size_t)parity * cap;
-  // (1) publish
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mine[i] = inout[i];
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  double* pub = peer[rank] + (size_t)parity * cap;
+  // (1) publish (128-bit copies, 4 in flight per thread: the buffer is a few MB and latency bound)
+  {
+    const int64_t n2 = n >> 1;
+    const double2* src = reinterpret_cast<const double2*>(inout);
+    double2* dst = reinterpret_cast<double2*>(pub);
+    int64_t i = tid;
+    for (; i + 3 * nth < n2; i += 4 * nth) {
+      const double2 a = src[i], b = src[i + nth], c = src[i + 2 * nth], d = src[i + 3 * nth];
+      dst[i] = a; dst[i + nth] = b; dst[i + 2 * nth] = c; dst[i + 3 * nth] = d;
+    }
+    for (; i < n2; i += nth) dst[i] = src[i];
+    if ((n & 1) && tid == 0) pub[n - 1] = inout[n - 1];
+  }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // (2) the last publishing block of this rank raises the flag in every rank's flag row (own included)
-    if (atomicAdd(done, 1u) + 1u == gridDim.x) {
-      done[0] = 0;
-      __threadfence_system();
-      for (int p = 0; p < world; ++p) {
-        unsigned long long* flags = reinterpret_cast<unsigned long long*>(peer[p] + 2 * (size_t)cap);
-        st_release_sys(flags + rank, epoch);
-      }
-    }
-    // (3) wait for every rank's flag in OUR flag row
-    const unsigned long long* my_flags = reinterpret_cast<const unsigned long long*>(peer[rank] + 2 * (size_t)cap);
-    bool good = true;
-    const long long t0 = clock64();
-    for (int p = 0; p < world && good; ++p) {
-      while (ld_acquire_sys(my_flags + p) < epoch) {
-        if (clock64() - t0 > 4000000000LL) { good = false; atomicExch(error, 1); break; }  // ~2 s at 1.9 GHz
-      }
-    }
-    ok = good;
-  }
+  if (stamp) stamps[1] = gtime();
+  if (threadIdx.x == 0) ok = rank_barrier(peer, rank, world, cap, 0, epoch, done, error);  // (2) everybody has published
   __syncthreads();
-  if (ok) {
-    // (4) reduce in rank order (identical on every rank)
+  if (stamp) stamps[2] = gtime();
+  if (ok && !two_shot) {
+    // one-shot: every rank adds all partial sums, in rank order (identical everywhere); 2 x 128-bit peer loads per
+    // rank in flight per thread
     const int64_t n2 = n >> 1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = tid;
+    for (; i + nth < n2; i += 2 * nth) {
+      double2 a0 = make_double2(0.0, 0.0), a1 = a0;
+      for (int p = 0; p < world; ++p) {
+        const double2* src = reinterpret_cast<const double2*>(peer[p] + (size_t)parity * cap);
+        const double2 v0 = src[i], v1 = src[i + nth];
+        a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
+      }
+      reinterpret_cast<double2*>(inout)[i] = a0;
+      reinterpret_cast<double2*>(inout)[i + nth] = a1;
+    }
+    for (; i < n2; i += nth) {
+      double2 a0 = make_double2(0.0, 0.0);
+      for (int p = 0; p < world; ++p) {
+        const double2 v0 = reinterpret_cast<const double2*>(peer[p] + (size_t)parity * cap)[i];
+        a0.x += v0.x; a0.y += v0.y;
+      }
+      reinterpret_cast<double2*>(inout)[i] = a0;
+    }
+    if ((n & 1) && tid == 0) {
+      double a = 0.0;
+      for (int p = 0; p < world; ++p) a += (peer[p] + (size_t)parity * cap)[n - 1];
+      inout[n - 1] = a;
+    }
+  } else if (ok) {
+    // two-shot, n even: (3) reduce my slice in rank order into my result buffer ...
+    const int64_t n2 = n >> 1;
+    const int64_t lo = n2 * rank / world, hi = n2 * (rank + 1) / world;
+    double2* res = reinterpret_cast<double2*>(peer[rank] + (size_t)(2 + parity) * cap);
+    for (int64_t i = lo + tid; i < hi; i += nth) {
       double2 acc = make_double2(0.0, 0.0);
       for (int p = 0; p < world; ++p) {
         const double2 v = reinterpret_cast<const double2*>(peer[p] + (size_t)parity * cap)[i];
         acc.x += v.x;
         acc.y += v.y;
       }
-      reinterpret_cast<double2*>(inout)[i] = acc;
+      res[i] = acc;
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-      double a = 0.0;
-      for (int p = 0; p < world; ++p) a += (peer[p] + (size_t)parity * cap)[n - 1];
-      inout[n - 1] = a;
+    __threadfence_system();
+    __syncthreads();
+    if (stamp) stamps[3] = gtime();
+    if (threadIdx.x == 0) ok = rank_barrier(peer, rank, world, cap, 1, epoch, done + 1, error);  // (4) every slice is reduced
+    __syncthreads();
+    if (stamp) stamps[4] = gtime();
+    if (ok) {
+      // (5) ... and collect the reduced slices of all ranks
+      for (int p = 0; p < world; ++p) {
+        const int64_t plo = n2 * p / world, phi = n2 * (p + 1) / world;
+        const double2* src = reinterpret_cast<const double2*>(peer[p] + (size_t)(2 + parity) * cap);
+        for (int64_t i = plo + tid; i < phi; i += nth) reinterpret_cast<double2*>(inout)[i] = src[i];
+      }
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(done + 1, 1u) + 1u == gridDim.x) {  // last block out: this exchange is complete
-    done[1] = 0;
+  if (stamp) stamps[5] = gtime();
+  if (threadIdx.x == 0 && atomicAdd(done + 2, 1u) + 1u == gridDim.x) {  // last block out: this exchange is complete
+    done[2] = 0;
     *epoch_done = epoch;
   }
 }
@@ -118,17 +185,19 @@ extern "C" int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t
   mrs_exchange* x = new mrs_exchange();
   x->eng = e; x->rank = rank; x->world = world;
   x->n = (n_doubles + 1) & ~(int64_t)1;
-  const size_t bytes = 2 * (size_t)x->n * sizeof(double) + (size_t)world * sizeof(unsigned long long) + 64;
+  const size_t bytes = 4 * (size_t)x->n * sizeof(double) + 2 * (size_t)world * sizeof(unsigned long long) + 64;
   // IPC-shareable memory must come from cudaMalloc directly (not from the engine's block cache)
   cudaError_t ce = cudaMalloc((void**)&x->base, bytes);
   if (ce != cudaSuccess) { delete x; set_error("mrs_exchange_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(ce)); return MRS_ERR_NOMEM; }
   MRS_CUDA(cudaMemset(x->base, 0, bytes));
-  MRS_CUDA(cudaMalloc((void**)&x->d_done, 2 * sizeof(unsigned int)));
-  MRS_CUDA(cudaMemset(x->d_done, 0, 2 * sizeof(unsigned int)));
+  MRS_CUDA(cudaMalloc((void**)&x->d_done, 4 * sizeof(unsigned int)));
+  MRS_CUDA(cudaMemset(x->d_done, 0, 4 * sizeof(unsigned int)));
   MRS_CUDA(cudaMalloc((void**)&x->d_epoch, sizeof(unsigned long long)));
   MRS_CUDA(cudaMemset(x->d_epoch, 0, sizeof(unsigned long long)));
   MRS_CUDA(cudaMalloc((void**)&x->d_error, sizeof(int32_t)));
   MRS_CUDA(cudaMemset(x->d_error, 0, sizeof(int32_t)));
+  MRS_CUDA(cudaMalloc((void**)&x->d_stamps, 8 * sizeof(unsigned long long)));
+  MRS_CUDA(cudaMemset(x->d_stamps, 0, 8 * sizeof(unsigned long long)));
   MRS_CUDA(cudaMalloc((void**)&x->d_peer, sizeof(double*) * (size_t)world));
   cudaIpcMemHandle_t h;
   MRS_CUDA(cudaIpcGetMemHandle(&h, x->base));
@@ -165,8 +234,10 @@ extern "C" int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_in
   // every block waits on the flags: the grid must be co-resident (one CTA per SM at most)
   const int64_t work = (n_doubles + 1) / 2;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + kExThreads - 1) / kExThreads, (int64_t)x->eng->sm_count));
-  peer_allreduce_kernel<<<grid, kExThreads, 0, x->eng->stream>>>(x->d_peer, x->rank, x->world, n_doubles, x->n, x->d_epoch, x->d_done, x->d_error,
-                                                                 (double*)device_inout);
+  // two-shot (reduce my slice, barrier, collect) once the buffer is large enough to be bandwidth relevant
+  const int two_shot = (x->world > 2 && (n_doubles & 1) == 0 && n_doubles >= 16384) ? 1 : 0;
+  peer_allreduce_kernel<<<grid, kExThreads, 0, x->eng->stream>>>(x->d_peer, x->rank, x->world, n_doubles, x->n, two_shot, x->d_epoch, x->d_done,
+                                                                 x->d_error, x->d_stamps, (double*)device_inout);
   mark(x->eng, "peer_allreduce");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
@@ -180,6 +251,14 @@ extern "C" int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out) {
   return MRS_OK;
 }
 
+extern "C" int32_t mrs_exchange_stamps(mrs_exchange* x, uint64_t* out8) {
+  MRS_REQUIRE(x && out8, MRS_ERR_INVALID, "mrs_exchange_stamps: NULL argument");
+  use_engine(x->eng);
+  MRS_CUDA(cudaMemcpyAsync(out8, x->d_stamps, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, x->eng->stream));
+  MRS_CUDA(cudaStreamSynchronize(x->eng->stream));
+  return MRS_OK;
+}
+
 extern "C" void mrs_exchange_destroy(mrs_exchange* x) {
   if (!x) return;
   if (x->eng) { cudaSetDevice(x->eng->device); cudaStreamSynchronize(x->eng->stream); }
@@ -189,6 +268,7 @@ extern "C" void mrs_exchange_destroy(mrs_exchange* x) {
   if (x->d_done) cudaFree(x->d_done);
   if (x->d_epoch) cudaFree(x->d_epoch);
   if (x->d_error) cudaFree(x->d_error);
+  if (x->d_stamps) cudaFree(x->d_stamps);
   if (x->base) cudaFree(x->base);
   delete x;
 }
