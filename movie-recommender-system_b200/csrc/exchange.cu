@@ -52,26 +52,39 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// barrier across the ranks, entered by thread 0 of every block: the last arriving block of this rank raises flag
-// `which` (0/1) in every rank's flag row, then every block waits until all ranks have raised theirs for this epoch
+constexpr int kMaxWorld = 16;
+
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Barrier across the ranks, entered by ALL threads of every block.  The last arriving block of this rank makes this
+// rank's data visible (one system-scope fence) and then thread p raises flag `which` in rank p's flag row -- the `world`
+// NVLink stores go out together instead of one release-store after the other (8 ranks: 20 us -> a few us).  Then thread
+// p of every block polls rank p's flag in OUR row.  Returns false if a peer did not show up within ~2 s.
 __device__ __forceinline__ bool rank_barrier(double* const* __restrict__ peer, int32_t rank, int32_t world, int64_t cap, int which,
                                              unsigned long long epoch, unsigned int* __restrict__ done, int32_t* __restrict__ error) {
-  if (atomicAdd(done, 1u) + 1u == gridDim.x) {
-    *done = 0;
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const int last = (atomicAdd(done, 1u) + 1u == gridDim.x);
+    if (last) *done = 0;
+    s_last = last;
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < world) {
     __threadfence_system();
-    for (int p = 0; p < world; ++p) {
-      unsigned long long* flags = reinterpret_cast<unsigned long long*>(peer[p] + 4 * (size_t)cap) + (size_t)which * world;
-      st_release_sys(flags + rank, epoch);
+    unsigned long long* flags = reinterpret_cast<unsigned long long*>(peer[threadIdx.x] + 4 * (size_t)cap) + (size_t)which * world;
+    st_relaxed_sys(flags + rank, epoch);
+  }
+  int good = 1;
+  if ((int)threadIdx.x < world) {
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peer[rank] + 4 * (size_t)cap) + (size_t)which * world;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine + threadIdx.x) < epoch) {
+      if (clock64() - t0 > 4000000000LL) { atomicExch(error, 1); good = 0; break; }  // ~2 s at 1.9 GHz: a peer is missing
     }
   }
-  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peer[rank] + 4 * (size_t)cap) + (size_t)which * world;
-  const long long t0 = clock64();
-  for (int p = 0; p < world; ++p) {
-    while (ld_acquire_sys(mine + p) < epoch) {
-      if (clock64() - t0 > 4000000000LL) { atomicExch(error, 1); return false; }  // ~2 s at 1.9 GHz: a peer is missing
-    }
-  }
-  return true;
+  return __syncthreads_and(good) != 0;
 }
 
 // inout[0..n): this rank's partial sums on entry, the sum over all ranks (added in rank order) on exit
@@ -79,7 +92,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
                                                                    int64_t cap, int two_shot, unsigned long long* __restrict__ epoch_done,
                                                                    unsigned int* __restrict__ done, int32_t* __restrict__ error,
                                                                    unsigned long long* __restrict__ stamps, double* __restrict__ inout) {
-  __shared__ bool ok;
+  bool ok;
   const bool stamp = (blockIdx.x == 0 && threadIdx.x == 0);
   if (stamp) stamps[0] = gtime();
   const unsigned long long epoch = *epoch_done + 1;  // stable for the whole kernel: only its last block advances it
@@ -102,8 +115,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
   __threadfence_system();
   __syncthreads();
   if (stamp) stamps[1] = gtime();
-  if (threadIdx.x == 0) ok = rank_barrier(peer, rank, world, cap, 0, epoch, done, error);  // (2) everybody has published
-  __syncthreads();
+  ok = rank_barrier(peer, rank, world, cap, 0, epoch, done, error);  // (2) everybody has published
   if (stamp) stamps[2] = gtime();
   if (ok && !two_shot) {
     // one-shot: every rank adds all partial sums, in rank order (identical everywhere); 2 x 128-bit peer loads per
@@ -139,26 +151,42 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
     const int64_t lo = n2 * rank / world, hi = n2 * (rank + 1) / world;
     double2* res = reinterpret_cast<double2*>(peer[rank] + (size_t)(2 + parity) * cap);
     for (int64_t i = lo + tid; i < hi; i += nth) {
+      double2 v[kMaxWorld];
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p)  // all peer loads of the element go out together
+        if (p < world) v[p] = reinterpret_cast<const double2*>(peer[p] + (size_t)parity * cap)[i];
       double2 acc = make_double2(0.0, 0.0);
-      for (int p = 0; p < world; ++p) {
-        const double2 v = reinterpret_cast<const double2*>(peer[p] + (size_t)parity * cap)[i];
-        acc.x += v.x;
-        acc.y += v.y;
-      }
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p)
+        if (p < world) { acc.x += v[p].x; acc.y += v[p].y; }  // rank order
       res[i] = acc;
     }
     __threadfence_system();
     __syncthreads();
     if (stamp) stamps[3] = gtime();
-    if (threadIdx.x == 0) ok = rank_barrier(peer, rank, world, cap, 1, epoch, done + 1, error);  // (4) every slice is reduced
-    __syncthreads();
+    ok = rank_barrier(peer, rank, world, cap, 1, epoch, done + 1, error);  // (4) every slice is reduced
     if (stamp) stamps[4] = gtime();
     if (ok) {
       // (5) ... and collect the reduced slices of all ranks
-      for (int p = 0; p < world; ++p) {
-        const int64_t plo = n2 * p / world, phi = n2 * (p + 1) / world;
-        const double2* src = reinterpret_cast<const double2*>(peer[p] + (size_t)(2 + parity) * cap);
-        for (int64_t i = plo + tid; i < phi; i += nth) reinterpret_cast<double2*>(inout)[i] = src[i];
+      // element i lives in the result buffer of its owner; the owner is recovered from the slice bounds, so one
+      // flat loop keeps loads from all peers in flight
+      for (int64_t i0 = tid; i0 < n2; i0 += 4 * nth) {
+        double2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t i = i0 + k * nth;
+          if (i < n2) {
+            int p = (int)((i * world) / n2);                 // candidate owner, then fix the rounding of the bounds
+            while (p + 1 < world && i >= n2 * (p + 1) / world) ++p;
+            while (p > 0 && i < n2 * p / world) --p;
+            v[k] = reinterpret_cast<const double2*>(peer[p] + (size_t)(2 + parity) * cap)[i];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t i = i0 + k * nth;
+          if (i < n2) reinterpret_cast<double2*>(inout)[i] = v[k];
+        }
       }
     }
   }
@@ -178,8 +206,8 @@ using namespace mrs;
 // ---- C ABI (declared in include/mrs_b200.h)
 extern "C" int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t rank, int32_t world, void* ipc_handle_out64,
                                        mrs_exchange** out) {
-  MRS_REQUIRE(e && out && ipc_handle_out64 && n_doubles > 0 && world >= 1 && rank >= 0 && rank < world, MRS_ERR_INVALID,
-              "mrs_exchange_create: bad argument");
+  MRS_REQUIRE(e && out && ipc_handle_out64 && n_doubles > 0 && world >= 1 && world <= 16 && rank >= 0 && rank < world, MRS_ERR_INVALID,
+              "mrs_exchange_create: bad argument (1 <= world <= 16)");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   use_engine(e);
   mrs_exchange* x = new mrs_exchange();
