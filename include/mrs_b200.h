@@ -171,6 +171,12 @@ MRS_API int32_t mrs_model_vector(const mrs_model* m, int32_t vec_kind, double* v
  * getNeighbors / getSimilarity (P:596-649).  k <= 0: no neighbourhood restriction. ---- */
 MRS_API int32_t mrs_fit_similarity(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** out);
 MRS_API int32_t mrs_fit_similarity_async(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** inout);
+/* Row-block form (always the list path, any user count): neighbour lists are computed and kept only for the users with
+ * original id in [user_lo, user_hi) -- the rows one rank of a sharded run owns (BASELINE config 5; every rank holds the
+ * whole train set, so no exchange is needed before the rows).  Only the first min(k, users-1) neighbours of a user are
+ * kept (k > 0): mrs_sim_set_k accepts 0 < k' <= k, queries for users outside the range fail (mrs_predict / mrs_mae write
+ * NaN for them).  mrs_fit_similarity itself takes this path over all users above 16,384 users. */
+MRS_API int32_t mrs_fit_similarity_rows_async(mrs_model* m, int32_t sim_kind, int32_t k, int32_t user_lo, int32_t user_hi, mrs_sim** inout);
 /* change k without recomputing similarities (the sorted lists have the prefix property) */
 MRS_API int32_t mrs_sim_set_k(mrs_sim* s, int32_t k);
 MRS_API int32_t mrs_similarity(const mrs_sim* s, int32_t u, int32_t v, double* out);

@@ -137,6 +137,16 @@ struct mrs_ratings {
     int32_t* ell_col = nullptr;    // [slice_off[n_slices]*32] item id (0 for padding)
     int32_t* ell_src = nullptr;    // [same] position of the entry in the CSR arrays, -1 for padding
     int64_t ell_entries = 0;
+    bool ell_built = false;        // the ELL arrays are only built for the dense-matrix path
+    std::vector<int32_t> h_known;  // host copies used when a row range is laid out (knn_rows.cu)
+    std::vector<int32_t> h_order;  // compact indices sorted by row length, longest first
+    std::vector<int32_t> h_len;    // [n_known] row length
+    // ---- row-block path (knn_rows.cu): item-major arrays in compact user indices + per-column segment table
+    bool rows_built = false;
+    int32_t n_sub = 0;             // sub-ranges of kRowsSub compact indices (padded to a multiple of the warps per CTA)
+    int32_t* clen = nullptr;       // [n_known] row length of each compact index
+    int32_t* ccv = nullptr;        // [n] compact user index of each CSC entry
+    int32_t* seg = nullptr;        // [n_items * (n_sub+1)] first CSC entry of column i whose compact index is >= b * kRowsSub
   };
   mutable sim_layout sl;
   // ---- lazily built tiled item-major layout for the fit kernel (tiled.cu); half-star codes only
@@ -208,6 +218,15 @@ struct mrs_sim {
   double* mae_part = nullptr;
   int32_t mae_part_cap = 0;
   unsigned int* counter = nullptr;
+  // ---- row-block path (knn_rows.cu): no matrix; only the first k_fit neighbours of the users of a row range are kept
+  bool lists = false;
+  int32_t k_fit = 0;      // neighbours kept per user = min(k at fit time, n_known - 1)
+  int32_t row_lo = 0, row_hi = 0;  // compact indices [row_lo, row_hi) own lists (a rank's user shard)
+  int32_t* row_order = nullptr;    // [row_hi - row_lo] compact indices of the range, longest row first
+  double* cpre = nullptr;          // [n] r~ (cosine) of each CSC entry
+  double* Sbuf = nullptr;          // [batch_rows * ld] similarity rows of the batch in flight
+  int32_t batch_rows = 0;
+  int64_t ld = 0;
 };
 
 namespace mrs {
@@ -283,4 +302,13 @@ int32_t mae_personalized_async(const mrs_model* m, const mrs_sim* s, const mrs_r
 int32_t predict_personalized_async(const mrs_model* m, const mrs_sim* s, const int32_t* d_users, const int32_t* d_items,
                                    int64_t n, double* d_out, bool wsd_only);
 void free_sim_layout(const mrs_ratings* r);
+int32_t build_sim_layout(const mrs_ratings* R, bool with_ell);
+// knn_rows.cu
+int32_t rows_fit_async(mrs_model* m, mrs_sim* s, bool first);
+int32_t rows_alloc(mrs_model* m, mrs_sim* s, int32_t user_lo, int32_t user_hi);
+void rows_free(mrs_sim* s);
+void free_rows_layout(const mrs_ratings* r);
+int32_t mae_lists_async(const mrs_model* m, const mrs_sim* s, const mrs_ratings* test, double* d_out2);
+int32_t predict_lists_async(const mrs_model* m, const mrs_sim* s, const int32_t* d_users, const int32_t* d_items, int64_t n,
+                            double* d_out, bool wsd_only);
 }  // namespace mrs

@@ -56,52 +56,67 @@ __global__ void ell_fill_kernel(const int32_t* __restrict__ urow, const int32_t*
   }
 }
 
-int32_t build_sim_layout(const mrs_ratings* R) {
+}  // namespace
+
+int32_t build_sim_layout(const mrs_ratings* R, bool with_ell) {
   mrs_ratings::sim_layout& L = R->sl;
-  if (L.built) return MRS_OK;
   cudaStream_t st = R->eng->stream;
-  std::vector<int32_t> urow((size_t)R->n_users + 1);
-  MRS_CUDA(cudaMemcpyAsync(urow.data(), R->urow, sizeof(int32_t) * urow.size(), cudaMemcpyDeviceToHost, st));
-  MRS_CUDA(cudaStreamSynchronize(st));
-  std::vector<int32_t> known, cidx((size_t)R->n_users, -1);
-  for (int32_t u = 0; u < R->n_users; ++u)
-    if (urow[u + 1] > urow[u]) { cidx[u] = (int32_t)known.size(); known.push_back(u); }
-  const int32_t nk = (int32_t)known.size();
-  std::vector<int32_t> order(nk);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-    return urow[known[a] + 1] - urow[known[a]] > urow[known[b] + 1] - urow[known[b]];
-  });
-  const int32_t ns = (nk + 31) / 32;
-  std::vector<int32_t> perm((size_t)ns * 32, -1), soff((size_t)ns + 1, 0);
-  for (int32_t t = 0; t < nk; ++t) perm[t] = order[t];
-  for (int32_t s = 0; s < ns; ++s) {
-    const int32_t c = perm[(size_t)s * 32];
-    const int32_t w = urow[known[c] + 1] - urow[known[c]];  // longest row of the slice (rows sorted by length)
-    soff[s + 1] = soff[s] + w;
+  std::vector<int32_t> urow;
+  if (!L.built || (with_ell && !L.ell_built)) {
+    urow.resize((size_t)R->n_users + 1);
+    MRS_CUDA(cudaMemcpyAsync(urow.data(), R->urow, sizeof(int32_t) * urow.size(), cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
   }
-  L.n_known = nk;
-  L.n_slices = ns;
-  L.ell_entries = (int64_t)soff[ns] * 32;
-  MRS_TRY(dev_alloc(&L.known_user, (size_t)nk));
-  MRS_TRY(dev_alloc(&L.cidx, (size_t)R->n_users));
-  MRS_TRY(dev_alloc(&L.perm, perm.size()));
-  MRS_TRY(dev_alloc(&L.slice_off, soff.size()));
-  MRS_TRY(dev_alloc(&L.ell_col, (size_t)L.ell_entries));
-  MRS_TRY(dev_alloc(&L.ell_src, (size_t)L.ell_entries));
-  MRS_CUDA(cudaMemcpyAsync(L.known_user, known.data(), sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
-  MRS_CUDA(cudaMemcpyAsync(L.cidx, cidx.data(), sizeof(int32_t) * cidx.size(), cudaMemcpyHostToDevice, st));
-  MRS_CUDA(cudaMemcpyAsync(L.perm, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice, st));
-  MRS_CUDA(cudaMemcpyAsync(L.slice_off, soff.data(), sizeof(int32_t) * soff.size(), cudaMemcpyHostToDevice, st));
-  if (ns > 0) {
-    ell_fill_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(R->urow, R->ucol, L.known_user, L.perm, L.slice_off, ns, L.ell_col, L.ell_src);
-    count_launch();
+  if (!L.built) {
+    std::vector<int32_t>& known = L.h_known;
+    std::vector<int32_t> cidx((size_t)R->n_users, -1);
+    known.clear();
+    for (int32_t u = 0; u < R->n_users; ++u)
+      if (urow[u + 1] > urow[u]) { cidx[u] = (int32_t)known.size(); known.push_back(u); }
+    const int32_t nk = (int32_t)known.size();
+    L.h_len.resize((size_t)nk);
+    for (int32_t c = 0; c < nk; ++c) L.h_len[c] = urow[known[c] + 1] - urow[known[c]];
+    L.h_order.resize((size_t)nk);
+    std::iota(L.h_order.begin(), L.h_order.end(), 0);
+    std::stable_sort(L.h_order.begin(), L.h_order.end(), [&](int32_t a, int32_t b) { return L.h_len[a] > L.h_len[b]; });
+    L.n_known = nk;
+    L.n_slices = (nk + 31) / 32;
+    MRS_TRY(dev_alloc(&L.known_user, (size_t)nk));
+    MRS_TRY(dev_alloc(&L.cidx, (size_t)R->n_users));
+    MRS_CUDA(cudaMemcpyAsync(L.known_user, known.data(), sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
+    MRS_CUDA(cudaMemcpyAsync(L.cidx, cidx.data(), sizeof(int32_t) * cidx.size(), cudaMemcpyHostToDevice, st));
+    MRS_CUDA(cudaStreamSynchronize(st));  // cidx goes out of scope
+    L.built = true;
   }
-  MRS_CUDA(cudaGetLastError());
-  MRS_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
-  L.built = true;
+  if (with_ell && !L.ell_built) {
+    const int32_t nk = L.n_known, ns = L.n_slices;
+    const std::vector<int32_t>& known = L.h_known;
+    std::vector<int32_t> perm((size_t)ns * 32, -1), soff((size_t)ns + 1, 0);
+    for (int32_t t = 0; t < nk; ++t) perm[t] = L.h_order[t];
+    for (int32_t s = 0; s < ns; ++s) {
+      const int32_t c = perm[(size_t)s * 32];
+      const int32_t w = urow[known[c] + 1] - urow[known[c]];  // longest row of the slice (rows sorted by length)
+      soff[s + 1] = soff[s] + w;
+    }
+    L.ell_entries = (int64_t)soff[ns] * 32;
+    MRS_TRY(dev_alloc(&L.perm, perm.size()));
+    MRS_TRY(dev_alloc(&L.slice_off, soff.size()));
+    MRS_TRY(dev_alloc(&L.ell_col, (size_t)L.ell_entries));
+    MRS_TRY(dev_alloc(&L.ell_src, (size_t)L.ell_entries));
+    MRS_CUDA(cudaMemcpyAsync(L.perm, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice, st));
+    MRS_CUDA(cudaMemcpyAsync(L.slice_off, soff.data(), sizeof(int32_t) * soff.size(), cudaMemcpyHostToDevice, st));
+    if (ns > 0) {
+      ell_fill_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(R->urow, R->ucol, L.known_user, L.perm, L.slice_off, ns, L.ell_col, L.ell_src);
+      count_launch();
+    }
+    MRS_CUDA(cudaGetLastError());
+    MRS_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+    L.ell_built = true;
+  }
   return MRS_OK;
 }
+
+namespace {
 
 // ---------------- P1: deviations, squared norm, r~ (one warp per known user, canonical sequential order) -------------
 template <typename VT>
@@ -405,10 +420,11 @@ int32_t dispatch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
 void free_sim_layout(const mrs_ratings* r) {
   auto& L = r->sl;
   dev_free(L.known_user); dev_free(L.cidx); dev_free(L.perm); dev_free(L.slice_off); dev_free(L.ell_col); dev_free(L.ell_src);
+  free_rows_layout(r);
   L = mrs_ratings::sim_layout();
 }
 
-int32_t sim_fit_async(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout) {
+static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout, bool force_rows, int32_t user_lo, int32_t user_hi) {
   MRS_REQUIRE(m && inout, MRS_ERR_INVALID, "mrs_fit_similarity: NULL argument");
   MRS_REQUIRE(m->finished, MRS_ERR_INVALID, "mrs_fit_similarity: model not finished");
   MRS_REQUIRE(kind == MRS_SIM_UNIFORM || kind == MRS_SIM_COSINE || kind == MRS_SIM_JACCARD, MRS_ERR_INVALID,
@@ -419,45 +435,56 @@ int32_t sim_fit_async(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout) {
   mrs_engine* e = m->eng;
   cudaStream_t st = e->stream;
   use_engine(e);
-  MRS_TRY(build_sim_layout(R));
-  const auto& L = R->sl;
   const bool matrix = (kind != MRS_SIM_UNIFORM);
-  if (matrix) {
-    MRS_REQUIRE(L.n_known <= kMaxDenseUsers, MRS_ERR_UNSUPPORTED,
-                "mrs_fit_similarity: %d users exceed the dense-similarity path (max %d); the row-block streaming path is not built yet",
-                L.n_known, kMaxDenseUsers);
+  MRS_REQUIRE(!(force_rows && !matrix), MRS_ERR_INVALID, "mrs_fit_similarity_rows: the uniform similarity has no neighbour lists");
+  MRS_TRY(build_sim_layout(R, false));
+  const bool rows = matrix && (force_rows || R->sl.n_known > kMaxDenseUsers);
+  if (matrix && !rows) MRS_TRY(build_sim_layout(R, true));
+  const auto& L = R->sl;
+  if (rows) {
+    MRS_REQUIRE(k > 0, MRS_ERR_UNSUPPORTED,
+                "mrs_fit_similarity: with %d users only the first k neighbours of a user are kept (row-block path); k must be > 0",
+                L.n_known);
+  } else if (matrix) {
     MRS_REQUIRE((size_t)R->n_items * sizeof(double) <= (size_t)kSimMaxSmem, MRS_ERR_UNSUPPORTED,
                 "mrs_fit_similarity: item dimension %d does not fit the shared-memory staged similarity kernel", R->n_items);
   }
   mrs_sim* s = *inout;
-  if (s && (s->model != m || s->kind != kind)) {
-    set_error("mrs_fit_similarity_async: the handle passed for reuse belongs to another model or similarity kind");
+  if (s && (s->model != m || s->kind != kind || s->lists != rows)) {
+    set_error("mrs_fit_similarity_async: the handle passed for reuse belongs to another model, similarity kind or path");
     return MRS_ERR_INVALID;
   }
+  const bool first = !s;
   if (!s) {
     s = new mrs_sim();
     s->model = m;
     s->kind = kind;
     s->n_known = L.n_known;
     s->mae_part_cap = e->sm_count * 8;
+    s->lists = rows;
+    s->k = k;
     const size_t nk = (size_t)L.n_known;
     int32_t rc = MRS_OK;
     if (rc == MRS_OK) rc = dev_alloc(&s->udev, (size_t)R->n);
     if (rc == MRS_OK) rc = dev_alloc(&s->upre, (size_t)R->n);
     if (rc == MRS_OK) rc = dev_alloc(&s->unorm, nk);
-    if (rc == MRS_OK) rc = dev_alloc(&s->cdev, (size_t)R->n);
+    if (rc == MRS_OK && !rows) rc = dev_alloc(&s->cdev, (size_t)R->n);
     if (rc == MRS_OK) rc = dev_alloc(&s->mae_part, (size_t)s->mae_part_cap);
     if (rc == MRS_OK) rc = dev_alloc(&s->counter, 4);
     if (rc == MRS_OK && cudaMemsetAsync(s->counter, 0, 4 * sizeof(unsigned int), st) != cudaSuccess) rc = MRS_ERR_CUDA;
-    if (matrix) {
+    if (matrix && !rows) {
       if (rc == MRS_OK) rc = dev_alloc(&s->ell_val, (size_t)L.ell_entries);
       if (rc == MRS_OK) rc = dev_alloc(&s->S, nk * nk);
       if (rc == MRS_OK) rc = dev_alloc(&s->rank, nk * nk);
       if (rc == MRS_OK) rc = dev_alloc(&s->nbr_id, nk * (nk ? nk - 1 : 0));
       if (rc == MRS_OK) rc = dev_alloc(&s->nbr_sim, nk * (nk ? nk - 1 : 0));
     }
+    if (rc == MRS_OK && rows) rc = rows_alloc(m, s, user_lo, user_hi);
     if (rc != MRS_OK) { mrs_sim_destroy(s); return rc; }
     *inout = s;
+  } else if (rows) {
+    MRS_REQUIRE(k <= s->k_fit || s->k_fit >= s->n_known - 1, MRS_ERR_INVALID,
+                "mrs_fit_similarity_async: the handle keeps %d neighbours per user, k = %d does not fit", s->k_fit, k);
   }
   s->k = k;
   if (L.n_known == 0) return MRS_OK;
@@ -468,6 +495,10 @@ int32_t sim_fit_async(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout) {
   else
     dev_pre_kernel<double><<<(L.n_known + wpb - 1) / wpb, 256, 0, st>>>((const double*)R->uval, R->urow, L.known_user, L.n_known, m->uavg, s->udev, s->upre, s->unorm);
   mark(e, "dev_pre");
+  if (rows) {
+    MRS_CUDA(cudaGetLastError());
+    return rows_fit_async(m, s, first);
+  }
   // P2
   const int64_t work = std::max<int64_t>(R->n, matrix ? L.ell_entries : 0);
   const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)e->sm_count * 8));
@@ -491,9 +522,14 @@ int32_t sim_fit_async(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout) {
   return MRS_OK;
 }
 
+int32_t sim_fit_async(mrs_model* m, int32_t kind, int32_t k, mrs_sim** inout) {
+  return sim_fit_impl(m, kind, k, inout, false, 0, INT_MAX);
+}
+
 int32_t mae_personalized_async(const mrs_model* m, const mrs_sim* s, const mrs_ratings* T, double* d_out2) {
   MRS_REQUIRE(m && s && T && d_out2, MRS_ERR_INVALID, "mrs_mae: NULL argument");
   MRS_REQUIRE(s->model == m, MRS_ERR_INVALID, "mrs_mae: similarity handle belongs to another model");
+  if (s->lists) return mae_lists_async(m, s, T, d_out2);
   const mrs_ratings* R = m->train;
   const auto& L = R->sl;
   cudaStream_t st = m->eng->stream;
@@ -520,6 +556,7 @@ int32_t predict_personalized_async(const mrs_model* m, const mrs_sim* s, const i
   MRS_REQUIRE(m && s, MRS_ERR_INVALID, "mrs_predict: NULL argument");
   MRS_REQUIRE(s->model == m, MRS_ERR_INVALID, "mrs_predict: similarity handle belongs to another model");
   if (n == 0) return MRS_OK;
+  if (s->lists) return predict_lists_async(m, s, d_users, d_items, n, d_out, wsd_only);
   const mrs_ratings* R = m->train;
   const auto& L = R->sl;
   cudaStream_t st = m->eng->stream;
@@ -549,6 +586,10 @@ extern "C" int32_t mrs_fit_similarity_async(mrs_model* m, int32_t sim_kind, int3
   return sim_fit_async(m, sim_kind, k, inout);
 }
 
+extern "C" int32_t mrs_fit_similarity_rows_async(mrs_model* m, int32_t sim_kind, int32_t k, int32_t user_lo, int32_t user_hi, mrs_sim** inout) {
+  return sim_fit_impl(m, sim_kind, k, inout, true, user_lo, user_hi);
+}
+
 extern "C" int32_t mrs_fit_similarity(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** out) {
   MRS_REQUIRE(out, MRS_ERR_INVALID, "mrs_fit_similarity: NULL output");
   *out = nullptr;
@@ -565,6 +606,8 @@ extern "C" int32_t mrs_fit_similarity(mrs_model* m, int32_t sim_kind, int32_t k,
 
 extern "C" int32_t mrs_sim_set_k(mrs_sim* s, int32_t k) {
   MRS_REQUIRE(s, MRS_ERR_INVALID, "mrs_sim_set_k: NULL handle");
+  MRS_REQUIRE(!s->lists || (k > 0 && (k <= s->k_fit || s->k_fit >= s->n_known - 1)), MRS_ERR_UNSUPPORTED,
+              "mrs_sim_set_k: this handle keeps the first %d neighbours of each user; k = %d is outside (0, %d]", s->k_fit, k, s->k_fit);
   s->k = k;
   return MRS_OK;
 }
@@ -590,6 +633,7 @@ extern "C" void mrs_sim_destroy(mrs_sim* s) {
   if (s->model && s->model->eng) use_engine(s->model->eng);
   dev_free(s->udev); dev_free(s->upre); dev_free(s->unorm); dev_free(s->cdev); dev_free(s->ell_val); dev_free(s->S);
   dev_free(s->rank); dev_free(s->nbr_id); dev_free(s->nbr_sim); dev_free(s->mae_part); dev_free(s->counter);
+  rows_free(s);
   delete s;
 }
 
@@ -630,6 +674,20 @@ extern "C" int32_t mrs_similarity(const mrs_sim* s, int32_t u, int32_t v, double
     }
     return MRS_OK;
   }
+  if (s->lists) {  // s_k(u, v): the similarity if v is among the first k neighbours of u, else 0 (P:638-641)
+    MRS_REQUIRE(cu >= s->row_lo && cu < s->row_hi, MRS_ERR_INVALID, "mrs_similarity: user %d is outside the row range of this handle", u);
+    const int32_t kk = std::min(s->k, s->k_fit);
+    std::vector<int32_t> ids((size_t)std::max(kk, 1));
+    std::vector<double> sims((size_t)std::max(kk, 1));
+    const int64_t off = (int64_t)(cu - s->row_lo) * s->k_fit;
+    MRS_CUDA(cudaMemcpyAsync(ids.data(), s->nbr_id + off, sizeof(int32_t) * kk, cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaMemcpyAsync(sims.data(), s->nbr_sim + off, sizeof(double) * kk, cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    *out = 0.0;
+    for (int32_t j = 0; j < kk; ++j)
+      if (ids[(size_t)j] == v) { *out = sims[(size_t)j]; break; }
+    return MRS_OK;
+  }
   double val = 0.0;
   int32_t rk = 0;
   const int64_t off = (int64_t)cu * s->n_known + cv;
@@ -651,6 +709,18 @@ extern "C" int32_t mrs_neighbors(const mrs_sim* s, int32_t u, int32_t k, int32_t
   int32_t w = std::max(0, std::min(std::min(k, cand), cap));
   *n_out = w;
   if (w == 0) return MRS_OK;
+  if (s->lists && cu >= 0) {
+    MRS_REQUIRE(cu >= s->row_lo && cu < s->row_hi, MRS_ERR_INVALID, "mrs_neighbors: user %d is outside the row range of this handle", u);
+    MRS_REQUIRE(k <= s->k_fit || s->k_fit >= nk - 1, MRS_ERR_UNSUPPORTED,
+                "mrs_neighbors: this handle keeps the first %d neighbours of each user, %d were asked for", s->k_fit, k);
+    w = std::min(w, s->k_fit);
+    *n_out = w;
+    const int64_t off = (int64_t)(cu - s->row_lo) * s->k_fit;
+    if (ids_out) MRS_CUDA(cudaMemcpyAsync(ids_out, s->nbr_id + off, sizeof(int32_t) * w, cudaMemcpyDeviceToHost, st));
+    if (sims_out) MRS_CUDA(cudaMemcpyAsync(sims_out, s->nbr_sim + off, sizeof(double) * w, cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    return MRS_OK;
+  }
   if (s->kind != MRS_SIM_UNIFORM && cu >= 0) {
     const int64_t off = (int64_t)cu * (nk - 1);
     if (ids_out) MRS_CUDA(cudaMemcpyAsync(ids_out, s->nbr_id + off, sizeof(int32_t) * w, cudaMemcpyDeviceToHost, st));

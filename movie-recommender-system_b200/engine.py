@@ -26,7 +26,7 @@ EXPORTS = [
     "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
     "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_status", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
-    "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_sim_set_k",
+    "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
     "mrs_mae_async", "mrs_recommend",
 ]
@@ -101,6 +101,7 @@ def lib():
         "mrs_model_vector": (i32, [vp, i32, vp, vp, i64, P(i64)]),
         "mrs_fit_similarity": (i32, [vp, i32, i32, P(vp)]),
         "mrs_fit_similarity_async": (i32, [vp, i32, i32, P(vp)]),
+        "mrs_fit_similarity_rows_async": (i32, [vp, i32, i32, i32, i32, P(vp)]),
         "mrs_sim_set_k": (i32, [vp, i32]),
         "mrs_similarity": (i32, [vp, i32, i32, P(dbl)]),
         "mrs_neighbors": (i32, [vp, i32, i32, vp, vp, i32, P(i32)]),
@@ -339,8 +340,8 @@ class Model:
         """Enqueue predict+|err| reduction; {sum, count} (2 fp64) land at ``device_out_ptr``; no host sync."""
         _check(lib().mrs_mae_async(self._h, sim._h if sim is not None else None, int(kind), test._h, C.c_void_p(device_out_ptr)))
 
-    def similarity(self, kind=SIM_COSINE, k=0, sync=True):
-        return Sim(self, kind, k, sync=sync)
+    def similarity(self, kind=SIM_COSINE, k=0, sync=True, rows=None):
+        return Sim(self, kind, k, sync=sync, rows=rows)
 
     def recommend(self, user, n, kind=PRED_PERSONALIZED, sim=None):
         items = np.empty(max(n, 1), dtype=np.int32)
@@ -359,18 +360,26 @@ class Model:
 class Sim:
     """User-user similarity of a fitted model (uniform | cosine | jaccard), optionally restricted to k neighbours."""
 
-    def __init__(self, model, kind=SIM_COSINE, k=0, sync=True):
+    def __init__(self, model, kind=SIM_COSINE, k=0, sync=True, rows=None):
+        """``rows=(user_lo, user_hi)`` selects the row-block path: neighbour lists (first k) only for users with an id in
+        that range -- the rows a rank of a sharded run owns."""
         self.model, self.kind, self.k = model, int(kind), int(k)
+        self.rows = None if rows is None else (int(rows[0]), int(rows[1]))
         self._h = C.c_void_p()
-        if sync:
+        if sync and self.rows is None:
             _check(lib().mrs_fit_similarity(model._h, self.kind, self.k, C.byref(self._h)))
         else:
             self.refit()
+            if sync:
+                model.engine.sync()
 
     def refit(self, k=None):
         if k is not None:
             self.k = int(k)
-        _check(lib().mrs_fit_similarity_async(self.model._h, self.kind, self.k, C.byref(self._h)))
+        if self.rows is not None:
+            _check(lib().mrs_fit_similarity_rows_async(self.model._h, self.kind, self.k, self.rows[0], self.rows[1], C.byref(self._h)))
+        else:
+            _check(lib().mrs_fit_similarity_async(self.model._h, self.kind, self.k, C.byref(self._h)))
 
     def set_k(self, k):
         self.k = int(k)

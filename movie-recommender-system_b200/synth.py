@@ -115,9 +115,18 @@ def small(seed=7, n_users=60, n_items=90, n_ratings=1200, half_star=True):
     return {"train": train, "test": test, "all": (u, i, r), "n_users": n_users, "n_items": n_items}
 
 
+def mid(seed=11, n_users=20_000, n_items=3_000, n_ratings=600_000):
+    """More users than the dense-similarity path takes (16,384): exercises the row-block kNN path at a size the oracle
+    still answers per user in milliseconds."""
+    u, i, r, rng = _generate(n_users, np.arange(1, n_items + 1), n_ratings, half_star=True, seed=seed,
+                             min_per_user=8, sigma=1.0, zipf_a=1.0, zipf_c=20.0, max_frac=0.5)
+    train, test = _split(u, i, r, n_ratings // 5, rng)
+    return {"train": train, "test": test, "all": (u, i, r), "n_users": n_users, "n_items": n_items}
+
+
 def cached(name, **kw):
     """Generate (or load from a /tmp cache) one of the named sets; ml25m takes ~20 s to generate."""
-    fn = {"ml100k": ml100k, "ml25m": ml25m, "small": small}[name]
+    fn = {"ml100k": ml100k, "ml25m": ml25m, "small": small, "mid": mid}[name]
     tag = name + "".join(f"_{k}{v}" for k, v in sorted(kw.items()))
     path = os.path.join(os.environ.get("MRS_SYNTH_CACHE", "/tmp/mrs_b200_synth"), tag + f"_np{np.__version__}.npz")
     if os.path.exists(path):
