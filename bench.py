@@ -345,6 +345,11 @@ def run_ours(args):
         for h in hs:
             h.close()
 
+    knn25m = None
+    if not args.no_knn25m:
+        with torch.cuda.stream(stream):
+            knn25m = bench_knn25m(eng, stream, torch, dist, d, rank, world, dev, peer=not args.nccl)
+
     line = None
     if rank == 0:
         # ---- CPU baseline on this box's host cores (oracle port, single thread), bounded sample
@@ -375,6 +380,7 @@ def run_ours(args):
                                                  {"kind": "own NVLink peer-memory kernel", "timed_out": sb.peer.timed_out()}),
             "step_ms_min_max": [min(step_ms), max(step_ms)],
             "knn": knn,
+            "knn25m": knn25m,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -435,6 +441,62 @@ def bench_knn(eng, stream, torch):
             "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae)}
 
 
+def bench_knn25m(eng, stream, torch, dist, d, rank, world, dev, peer, k=300, reps=2):
+    """BASELINE config 5: kNN k=300 at ml-25m shape, similarity rows sharded over the ranks (train set replicated), fused
+    predict + MAE over each rank's test pairs, one 16-byte exchange.  Strong scaling: the job is fixed, N ranks split it."""
+    from mrs_b200 import sharded
+    tr, te = d["train"], d["test"]
+    sk = sharded.ShardedKnn(eng, tr, te, k=k, rank=rank, world=world, peer_exchange=peer)
+    sk.step()                                   # first use builds the layouts and fills the block cache
+    torch.cuda.synchronize(dev)
+    times, prof = [], {}
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.profile_begin()
+        a.record(stream)
+        sk.step()
+        b.record(stream)
+        torch.cuda.synchronize(dev)
+        prof = {}
+        for name, ms in eng.profile_end():
+            prof[name] = prof.get(name, 0.0) + ms
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    mae = sk.mae()
+    out = None
+    if rank == 0:
+        # neighbour lists of a few of this rank's users against the CPU oracle, at full size
+        from oracle import oracle as O
+        import numpy as np
+        t0 = time.perf_counter()
+        o = O.Oracle(*tr)
+        users = np.unique(tr[0][(tr[0] >= sk.user_lo) & (tr[0] < sk.user_hi)])
+        picks = np.random.default_rng(5).choice(users, 3, replace=False)
+        same = True
+        for u in picks:
+            ids, sims = sk.sim.neighbors(int(u), k)
+            oi, os_ = o.neighbors(int(u), k)
+            same &= ids.tolist() == oi.tolist() and sims.tolist() == os_.tolist()
+        ms = statistics.median(times)
+        out = {"metric": "knn_k300_ml25m_fit_predict_mae_s", "value": ms / 1000.0, "unit": "s", "n_gpus": world, "reps": reps,
+               "scaling": "strong", "mae": mae, "times_ms": times, "rows_rank0": [sk.user_lo, sk.user_hi],
+               "test_pairs_rank0": sk.n_test_local, "pairs_per_s": float(te[0].size) / (ms / 1000.0),
+               "rank0_kernel_ms": {a: round(b, 3) for a, b in prof.items()},
+               "exchange": "16 bytes {sum |err|, n}: " + ("own NVLink peer-memory kernel" if sk.peer is not None else
+                                                          ("nccl" if world > 1 else "none (1 rank)")),
+               "oracle_check": {"users": [int(u) for u in picks], "neighbour_lists_identical": bool(same),
+                                "seconds": time.perf_counter() - t0},
+               "note": "train set replicated on every rank (240 MB), no all-gather needed; similarity work = sum_i cnt_i^2 pair "
+                       "products, exact fp64 in the oracle's order"}
+    sk.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -442,6 +504,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nccl", action="store_true", help="N>1: use NCCL all-reduces instead of the library's peer-memory exchange kernel")
+    ap.add_argument("--no-knn25m", action="store_true", help="skip the kNN k=300 leg at ml-25m shape (BASELINE config 5)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.steps = max(args.steps, 1)

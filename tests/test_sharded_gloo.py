@@ -107,3 +107,52 @@ def test_two_rank_gloo_matches_single_process_oracle(ml100k):
         assert r[4] == pytest.approx(ref, rel=1e-9)                                  # same MAE on every rank
         assert r[5] == o.global_avg
         assert np.allclose(r[6], [o.item_avg_dev(i) for i in range(50)], rtol=1e-9, atol=1e-12)
+
+
+def _knn_worker(rank, world, port, q):
+    """Row-sharded kNN (BASELINE config 5): the train set is replicated, a rank evaluates the test pairs of its user range
+    (the rank-local kNN pass is the oracle here -- on a GPU it is ShardedKnn.fit/mae_local) and the ranks add {sum, n}."""
+    from oracle import oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d = synth.cached("ml100k")
+        tr, te = d["train"], tuple(x[:3000] for x in d["test"])
+        bounds = sharded.partition_rows(np.bincount(tr[0], minlength=int(tr[0].max()) + 1), world)
+        mte = sharded.shard_of(te[0], bounds, rank)
+        lte = tuple(x[mte] for x in te)
+        o = O.Oracle(*tr)
+        out2 = torch.tensor([o.mae(lte, kind=O.PERSONALIZED, simkind=O.SIM_COSINE, k=30) * lte[0].size, float(lte[0].size)],
+                            dtype=torch.float64)
+        sharded.all_reduce_sum(out2)
+        q.put((rank, bounds, int(mte.sum()), float(out2[0] / out2[1])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partition_balances_length_plus_constant():
+    counts = np.array([0, 100, 1, 1, 1, 1, 0, 50, 50, 2])
+    b = sharded.partition_rows(counts, 2)
+    assert b[0] == 0 and b[-1] == counts.size and 0 < b[1] < counts.size
+    w = counts + (counts > 0) * int(counts[counts > 0].mean())
+    assert abs(w[:b[1]].sum() - w[b[1]:].sum()) <= 2 * w.max()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_row_sharded_knn(ml100k):
+    from oracle import oracle as O
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_knn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=150) for _ in range(world))
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    te = tuple(x[:3000] for x in ml100k["test"])
+    ref = O.Oracle(*ml100k["train"]).mae(te, kind=O.PERSONALIZED, simkind=O.SIM_COSINE, k=30)
+    assert res[0][1] == res[1][1] and res[0][2] + res[1][2] == 3000
+    for r in res:
+        assert r[3] == pytest.approx(ref, rel=1e-9)
