@@ -201,7 +201,7 @@ class PeerExchange:
         """Nanosecond stamps of the last exchange, relative to its start: published, barrier 1, reduced, barrier 2, done."""
         o = (C.c_uint64 * 8)()
         _check(lib().mrs_exchange_stamps(self._h, o))
-        return [int(o[k]) - int(o[0]) if o[k] else None for k in range(1, 6)]
+        return [int(o[k]) - int(o[0]) if o[k] >= o[0] and o[k] else None for k in range(1, 6)]  # older = left by a previous call
 
     def timed_out(self):
         t = C.c_int32()
