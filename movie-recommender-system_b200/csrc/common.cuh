@@ -224,9 +224,6 @@ struct mrs_sim {
   int32_t row_lo = 0, row_hi = 0;  // compact indices [row_lo, row_hi) own lists (a rank's user shard)
   int32_t* row_order = nullptr;    // [row_hi - row_lo] compact indices of the range, longest row first
   double* cpre = nullptr;          // [n] r~ (cosine) of each CSC entry
-  double* Sbuf = nullptr;          // [batch_rows * ld] similarity rows of the batch in flight
-  int32_t batch_rows = 0;
-  int64_t ld = 0;
 };
 
 namespace mrs {

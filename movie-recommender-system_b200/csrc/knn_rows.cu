@@ -2,19 +2,21 @@
 // whose similarity matrix does not fit (ml-25m shape: 162,541 users -> 211 GB as fp64), and for a rank that owns only a
 // range of the rows (config 5: similarity row-blocks sharded across the GPUs of a box).
 //
-// Nothing n_known x n_known is ever held.  Rows are produced in batches, each row is reduced at once to its first
-// k neighbours in the order (similarity desc, user id asc) and only those lists are kept; prediction walks the list
-// of u and looks the item up in every neighbour's row.
+// Nothing n_known x n_known is ever held -- not even one row leaves the SM: a CTA produces the row of its user range by
+// range in shared memory, reduces it on the fly to the first k neighbours in the order (similarity desc, user id asc)
+// and writes only that list; prediction walks the list of u and looks the item up in every neighbour's row.
 //
 //   R1  similarity rows, ITEM-DRIVEN: the work is sum_i cnt_i^2 pair products (1.3e11 at ml-25m shape) instead of the
-//       n_users x nnz (3.3e12) of the dense-staged kernel in knn.cu.  A CTA owns (row user u, range of 16,384 compact user
-//       indices); each of its 32 warps owns 512 of them with private fp64 accumulators in shared memory.  The warp walks
+//       n_users x nnz (3.3e12) of the dense-staged kernel in knn.cu.  A CTA owns a row user u and visits the ranges of 16,384
+//       compact user indices one after the other; each of its 32 warps owns 512 of them with private fp64 accumulators.  The warp walks
 //       the items of u in ascending order and, for each, the slice of that item's column (users ascending) that falls into
 //       its 512 indices -- a per-column segment table gives the slice bounds.  acc[v] = acc[v] + r~(u,i) * r~(v,i) with
 //       non-fused, correctly rounded ops: for every (u, v) exactly the oracle's sequence (ascending item id over the
 //       intersection), so the similarity bits -- and with them the neighbour order -- are the oracle's.
-//   R2  selection: one CTA per row streams the row once, keeps candidates that beat the running k-th best (sim, id) in a
-//       shared-memory buffer and compacts it with a bitonic sort when it fills; exact, ties by ascending id.
+//   R2  selection, same CTA: after each range the 16,384 similarities pass a filter that keeps candidates beating the
+//       running k-th best (sim, id) in a shared-memory buffer, compacted by a bitonic sort when it fills; exact, ties by
+//       ascending id.  (A first version wrote the rows to HBM for a separate selection kernel: 2 x 211 GB of traffic at
+//       ml-25m shape that also evicted the hot columns from L2 -- 45 % hit rate in profiles/r01_ncu_full_raw_knnrows.csv.)
 //   R3  prediction / MAE from the lists: one warp per (u, i), lanes over the first k neighbours, binary search of i in the
 //       neighbour's row (items ascending).
 #include <algorithm>
@@ -93,97 +95,7 @@ __global__ void rows_cpre_kernel(const double* __restrict__ upre, const int32_t*
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += stride) cpre[p] = upre[csc_src[p]];
 }
 
-// ---------------- R1: similarity rows ---------------------------------------------------------------------------------
-template <int MODE>  // 1: cosine (P:424-426), 2: jaccard (P:454-458)
-__global__ void __launch_bounds__(kRowsWarps * 32, 1)
-    sim_rows_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol, const double* __restrict__ upre,
-                    const int32_t* __restrict__ known_user, const int32_t* __restrict__ clen, const int32_t* __restrict__ rows,
-                    const int32_t* __restrict__ seg, int32_t seg_stride, const int32_t* __restrict__ ccv,
-                    const double* __restrict__ cpre, int32_t n_known, double* __restrict__ Sbuf, int64_t ld) {
-  extern __shared__ __align__(16) double acc_all[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int32_t sub = blockIdx.x * kRowsWarps + w;
-  const int32_t base_cv = sub * kRowsSub;
-  double* acc = acc_all + w * kRowsSub;
-#pragma unroll
-  for (int x = 0; x < kRowsSub / 32; ++x) acc[x * 32 + lane] = 0.0;
-  __syncwarp();
-  const int32_t cu = rows[blockIdx.y];
-  const int32_t u = known_user[cu];
-  const int32_t b = urow[u], e = urow[u + 1];
-  if (base_cv < n_known) {
-    const int32_t* segp = seg + sub;
-    for (int32_t j0 = b; j0 < e; j0 += 32) {
-      const int32_t p = j0 + lane;
-      const bool valid = p < e;
-      const int32_t item = valid ? __ldg(ucol + p) : 0;
-      const double ru = (MODE == 1) ? (valid ? __ldg(upre + p) : 0.0) : 1.0;
-      const int64_t so = (int64_t)item * seg_stride;
-      const int32_t lo = valid ? __ldg(segp + so) : 0;
-      const int32_t hi = valid ? __ldg(segp + so + 1) : 0;
-      const int cnt = min(32, e - j0);
-      // stage d holds the first 32 entries of the slice of item (t0 + d), requested kRowsDepth items ahead of their use
-      int32_t s_lo[kRowsDepth], s_hi[kRowsDepth], s_cv[kRowsDepth];
-      double s_x[kRowsDepth];
-#pragma unroll
-      for (int d = 0; d < kRowsDepth; ++d) {
-        s_lo[d] = __shfl_sync(0xffffffffu, lo, d);
-        s_hi[d] = __shfl_sync(0xffffffffu, hi, d);
-        s_cv[d] = 0;
-        s_x[d] = 0.0;
-        const int32_t q = s_lo[d] + lane;
-        if (d < cnt && q < s_hi[d]) {
-          s_cv[d] = __ldg(ccv + q);
-          if (MODE == 1) s_x[d] = __ldg(cpre + q);
-        }
-      }
-      for (int t0 = 0; t0 < cnt; t0 += kRowsDepth) {
-#pragma unroll
-        for (int d = 0; d < kRowsDepth; ++d) {
-          const int t = t0 + d;
-          if (t < cnt) {  // warp-uniform
-            const double ru_t = __shfl_sync(0xffffffffu, ru, t);
-            const int32_t clo = s_lo[d], chi = s_hi[d];
-            const int32_t cv0 = s_cv[d];
-            const double x0 = s_x[d];
-            const int tn = t + kRowsDepth;
-            if (tn < cnt) {  // refill the stage
-              s_lo[d] = __shfl_sync(0xffffffffu, lo, tn);
-              s_hi[d] = __shfl_sync(0xffffffffu, hi, tn);
-              const int32_t q = s_lo[d] + lane;
-              if (q < s_hi[d]) {
-                s_cv[d] = __ldg(ccv + q);
-                if (MODE == 1) s_x[d] = __ldg(cpre + q);
-              }
-            }
-            if (clo + lane < chi) {
-              double* a = acc + (cv0 - base_cv);
-              *a = __dadd_rn(*a, (MODE == 1) ? __dmul_rn(ru_t, x0) : 1.0);  // ascending item id, no FMA
-            }
-            for (int32_t q = clo + 32 + lane; q < chi; q += 32) {  // slices longer than a warp (popular items)
-              double* a = acc + (__ldg(ccv + q) - base_cv);
-              *a = __dadd_rn(*a, (MODE == 1) ? __dmul_rn(ru_t, __ldg(cpre + q)) : 1.0);
-            }
-            __syncwarp();  // the next item may update the same user from another lane
-          }
-        }
-      }
-    }
-  }
-  double* out = Sbuf + (int64_t)blockIdx.y * ld;
-  const int32_t nu = (MODE == 2) ? (e - b) : 0;
-#pragma unroll
-  for (int x = 0; x < kRowsSub / 32; ++x) {
-    const int32_t cv = base_cv + x * 32 + lane;
-    if (cv < n_known) {
-      double s = acc[x * 32 + lane];
-      if (MODE == 2) s = s / (double)(nu + clen[cv] - (int32_t)s);  // P:458
-      out[cv] = s;
-    }
-  }
-}
-
-// ---------------- R2: first k of every row by (similarity desc, user id asc) -----------------------------------------
+// ---------------- R1 + R2: similarity row of one user, range by range, reduced on the fly to its first k neighbours -----
 __device__ void bitonic_sort_shared(double* key, int32_t* id, int32_t P) {
   for (int32_t size = 2; size <= P; size <<= 1) {
     for (int32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -202,60 +114,142 @@ __device__ void bitonic_sort_shared(double* key, int32_t* id, int32_t P) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) select_rows_kernel(const double* __restrict__ Sbuf, int64_t ld, const int32_t* __restrict__ rows,
-                                                          const int32_t* __restrict__ known_user, int32_t n_known, int32_t kk,
-                                                          int32_t row_lo, int32_t k_fit, int32_t* __restrict__ nbr_id,
-                                                          double* __restrict__ nbr_sim) {
-  extern __shared__ __align__(16) double c_key[];  // [kSelCap] keys, then [kSelCap] ids
-  int32_t* c_id = (int32_t*)(c_key + kSelCap);
+// One CTA per row user u.  For each range of 16,384 compact user indices: (R1) every warp accumulates its 512 similarities
+// in shared memory, (R2) the CTA passes the 16,384 values through the running top-k filter.  A row never leaves the SM:
+// only the k neighbours are written.
+template <int MODE>  // 1: cosine (P:424-426), 2: jaccard (P:454-458)
+__global__ void __launch_bounds__(kRowsWarps * 32, 1)
+    knn_rows_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol, const double* __restrict__ upre,
+                    const int32_t* __restrict__ known_user, const int32_t* __restrict__ clen, const int32_t* __restrict__ rows,
+                    const int32_t* __restrict__ seg, int32_t seg_stride, const int32_t* __restrict__ ccv,
+                    const double* __restrict__ cpre, int32_t n_known, int32_t n_ranges, int32_t kk, int32_t row_lo,
+                    int32_t* __restrict__ nbr_id, double* __restrict__ nbr_sim) {
+  extern __shared__ __align__(16) double acc_all[];             // [kRowsWarps * kRowsSub] accumulators
+  double* c_key = acc_all + kRowsWarps * kRowsSub;              // [kSelCap] candidate similarities
+  int32_t* c_id = (int32_t*)(c_key + kSelCap);                  // [kSelCap] candidate compact indices
   __shared__ int32_t count;
   __shared__ double tau_key;
   __shared__ int32_t tau_id;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* acc = acc_all + w * kRowsSub;
   const int32_t cu = rows[blockIdx.x];
-  const double* row = Sbuf + (int64_t)blockIdx.x * ld;
+  const int32_t u = known_user[cu];
+  const int32_t b = urow[u], e = urow[u + 1];
+  const int32_t nu = e - b;
   if (threadIdx.x == 0) { count = 0; tau_key = -INFINITY; tau_id = INT_MAX; }
-  __syncthreads();
-  for (int32_t tile0 = 0; tile0 < n_known; tile0 += kSelTile) {
-    const double tk = tau_key;
-    const int32_t ti = tau_id;
+
+  for (int32_t range = 0; range < n_ranges; ++range) {
+    const int32_t sub = range * kRowsWarps + w;
+    const int32_t base_cv = sub * kRowsSub;
 #pragma unroll
-    for (int r = 0; r < kSelTile / 1024; ++r) {
-      const int32_t x = tile0 + r * 1024 + threadIdx.x;
-      double s = 0.0;
-      bool ok = false;
-      if (x < n_known && x != cu) {  // P:608 allUsers - u
-        s = __ldcs(row + x);
-        ok = before(s, x, tk, ti);
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (m) {
-        int32_t pos = 0;
-        const int lane = threadIdx.x & 31;
-        if (lane == 0) pos = atomicAdd(&count, __popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-        if (ok) { c_key[pos] = s; c_id[pos] = x; }
+    for (int x = 0; x < kRowsSub / 32; ++x) acc[x * 32 + lane] = 0.0;
+    __syncwarp();
+    if (base_cv < n_known) {
+      const int32_t* segp = seg + sub;
+      for (int32_t j0 = b; j0 < e; j0 += 32) {
+        const int32_t p = j0 + lane;
+        const bool valid = p < e;
+        const int32_t item = valid ? __ldg(ucol + p) : 0;
+        const double ru = (MODE == 1) ? (valid ? __ldg(upre + p) : 0.0) : 1.0;
+        const int64_t so = (int64_t)item * seg_stride;
+        const int32_t lo = valid ? __ldg(segp + so) : 0;
+        const int32_t hi = valid ? __ldg(segp + so + 1) : 0;
+        const int cnt = min(32, e - j0);
+        // stage d holds the first 32 entries of the slice of item (t0 + d), requested kRowsDepth items ahead of their use
+        int32_t s_lo[kRowsDepth], s_hi[kRowsDepth], s_cv[kRowsDepth];
+        double s_x[kRowsDepth];
+#pragma unroll
+        for (int d = 0; d < kRowsDepth; ++d) {
+          s_lo[d] = __shfl_sync(0xffffffffu, lo, d);
+          s_hi[d] = __shfl_sync(0xffffffffu, hi, d);
+          s_cv[d] = 0;
+          s_x[d] = 0.0;
+          const int32_t q = s_lo[d] + lane;
+          if (d < cnt && q < s_hi[d]) {
+            s_cv[d] = __ldg(ccv + q);
+            if (MODE == 1) s_x[d] = __ldg(cpre + q);
+          }
+        }
+        for (int t0 = 0; t0 < cnt; t0 += kRowsDepth) {
+#pragma unroll
+          for (int d = 0; d < kRowsDepth; ++d) {
+            const int t = t0 + d;
+            if (t < cnt) {  // warp-uniform
+              const double ru_t = __shfl_sync(0xffffffffu, ru, t);
+              const int32_t clo = s_lo[d], chi = s_hi[d];
+              const int32_t cv0 = s_cv[d];
+              const double x0 = s_x[d];
+              const int tn = t + kRowsDepth;
+              if (tn < cnt) {  // refill the stage
+                s_lo[d] = __shfl_sync(0xffffffffu, lo, tn);
+                s_hi[d] = __shfl_sync(0xffffffffu, hi, tn);
+                const int32_t q = s_lo[d] + lane;
+                if (q < s_hi[d]) {
+                  s_cv[d] = __ldg(ccv + q);
+                  if (MODE == 1) s_x[d] = __ldg(cpre + q);
+                }
+              }
+              if (clo + lane < chi) {
+                double* a = acc + (cv0 - base_cv);
+                *a = __dadd_rn(*a, (MODE == 1) ? __dmul_rn(ru_t, x0) : 1.0);  // ascending item id, no FMA
+              }
+              for (int32_t q = clo + 32 + lane; q < chi; q += 32) {  // slices longer than a warp (popular items)
+                double* a = acc + (__ldg(ccv + q) - base_cv);
+                *a = __dadd_rn(*a, (MODE == 1) ? __dmul_rn(ru_t, __ldg(cpre + q)) : 1.0);
+              }
+              __syncwarp();  // the next item may update the same user from another lane
+            }
+          }
+        }
       }
     }
-    __syncthreads();
-    const int32_t c = count;
-    if (c > kSelCap - kSelTile) {  // compact: keep the first kk, raise the bar to the kk-th
-      int32_t P = 2;
-      while (P < c) P <<= 1;
-      for (int32_t x = c + threadIdx.x; x < P; x += blockDim.x) { c_key[x] = -INFINITY; c_id[x] = INT_MAX; }
-      bitonic_sort_shared(c_key, c_id, P);
-      if (threadIdx.x == 0) {
-        count = min(c, kk);
-        if (c >= kk) { tau_key = c_key[kk - 1]; tau_id = c_id[kk - 1]; }
+    __syncthreads();  // the range's 16,384 similarities are complete (and count / tau initialised before the first use)
+
+    // ---- R2: candidates that beat the running k-th best (sim, id) go to the buffer; a full buffer is sorted and cut to k
+    const int32_t range_base = range * kRowsWarps * kRowsSub;
+    for (int32_t tile0 = 0; tile0 < kRowsWarps * kRowsSub && range_base + tile0 < n_known; tile0 += kSelTile) {
+      const double tk = tau_key;
+      const int32_t ti = tau_id;
+#pragma unroll
+      for (int r = 0; r < kSelTile / 1024; ++r) {
+        const int32_t xl = tile0 + r * 1024 + threadIdx.x;
+        const int32_t x = range_base + xl;
+        double s = 0.0;
+        bool ok = false;
+        if (x < n_known && x != cu) {  // P:608 allUsers - u
+          s = acc_all[xl];
+          if (MODE == 2) s = s / (double)(nu + clen[x] - (int32_t)s);  // P:458
+          ok = before(s, x, tk, ti);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+          int32_t pos = 0;
+          if (lane == 0) pos = atomicAdd(&count, __popc(m));
+          pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+          if (ok) { c_key[pos] = s; c_id[pos] = x; }
+        }
       }
+      __syncthreads();
+      const int32_t c = count;
+      if (c > kSelCap - kSelTile) {  // compact: keep the first kk, raise the bar to the kk-th
+        int32_t P = 2;
+        while (P < c) P <<= 1;
+        for (int32_t x = c + threadIdx.x; x < P; x += blockDim.x) { c_key[x] = -INFINITY; c_id[x] = INT_MAX; }
+        bitonic_sort_shared(c_key, c_id, P);
+        if (threadIdx.x == 0) {
+          count = min(c, kk);
+          if (c >= kk) { tau_key = c_key[kk - 1]; tau_id = c_id[kk - 1]; }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   const int32_t c = count;
   int32_t P = 2;
   while (P < c) P <<= 1;
   for (int32_t x = c + threadIdx.x; x < P; x += blockDim.x) { c_key[x] = -INFINITY; c_id[x] = INT_MAX; }
   bitonic_sort_shared(c_key, c_id, P);
-  const int64_t off = (int64_t)(cu - row_lo) * k_fit;
+  const int64_t off = (int64_t)(cu - row_lo) * kk;
   for (int32_t j = threadIdx.x; j < kk; j += blockDim.x) {
     nbr_id[off + j] = known_user[c_id[j]];
     nbr_sim[off + j] = c_key[j];
@@ -372,8 +366,8 @@ void free_rows_layout(const mrs_ratings* r) {
 }
 
 void rows_free(mrs_sim* s) {
-  dev_free(s->row_order); dev_free(s->cpre); dev_free(s->Sbuf);  // the lists themselves are freed with the handle
-  s->row_order = nullptr; s->cpre = nullptr; s->Sbuf = nullptr;
+  dev_free(s->row_order); dev_free(s->cpre);  // the lists themselves are freed with the handle
+  s->row_order = nullptr; s->cpre = nullptr;
 }
 
 // allocate the buffers of a row range: users with original id in [user_lo, user_hi) own lists
@@ -391,12 +385,8 @@ int32_t rows_alloc(mrs_model* m, mrs_sim* s, int32_t user_lo, int32_t user_hi) {
   order.reserve((size_t)n_rows);
   for (int32_t c : L.h_order)
     if (c >= s->row_lo && c < s->row_hi) order.push_back(c);  // longest rows first: CTAs of a batch cost about the same
-  s->ld = ((int64_t)L.n_known + 15) & ~(int64_t)15;
-  const int sms = m->eng->sm_count;
-  s->batch_rows = std::max(1, std::min(n_rows, 4 * sms));
   MRS_TRY(dev_alloc(&s->row_order, (size_t)n_rows));
   MRS_TRY(dev_alloc(&s->cpre, (size_t)R->n));
-  MRS_TRY(dev_alloc(&s->Sbuf, (size_t)s->batch_rows * (size_t)s->ld));
   MRS_TRY(dev_alloc(&s->nbr_id, (size_t)n_rows * (size_t)std::max(s->k_fit, 1)));
   MRS_TRY(dev_alloc(&s->nbr_sim, (size_t)n_rows * (size_t)std::max(s->k_fit, 1)));
   if (n_rows > 0) {
@@ -417,26 +407,18 @@ int32_t rows_fit_async(mrs_model* m, mrs_sim* s, bool /*first*/) {
     rows_cpre_kernel<<<e->sm_count * 8, 256, 0, st>>>(s->upre, R->csc_src, R->n, s->cpre);
     mark(e, "rows_cpre");
   }
-  const size_t smem = (size_t)kRowsWarps * kRowsSub * sizeof(double);
-  MRS_CUDA(cudaFuncSetAttribute(sim_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MRS_CUDA(cudaFuncSetAttribute(sim_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t sel_smem = (size_t)kSelCap * (sizeof(double) + sizeof(int32_t));
-  MRS_CUDA(cudaFuncSetAttribute(select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  const size_t smem = (size_t)kRowsWarps * kRowsSub * sizeof(double) + (size_t)kSelCap * (sizeof(double) + sizeof(int32_t));
+  MRS_CUDA(cudaFuncSetAttribute(knn_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MRS_CUDA(cudaFuncSetAttribute(knn_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int32_t n_ranges = L.n_sub / kRowsWarps;
-  for (int32_t r0 = 0; r0 < n_rows; r0 += s->batch_rows) {
-    const int32_t nb = std::min(s->batch_rows, n_rows - r0);
-    const dim3 grid((unsigned)n_ranges, (unsigned)nb);
-    if (s->kind == MRS_SIM_COSINE)
-      sim_rows_kernel<1><<<grid, kRowsWarps * 32, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.clen, s->row_order + r0, L.seg,
-                                                             L.n_sub + 1, L.ccv, s->cpre, L.n_known, s->Sbuf, s->ld);
-    else
-      sim_rows_kernel<2><<<grid, kRowsWarps * 32, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.clen, s->row_order + r0, L.seg,
-                                                             L.n_sub + 1, L.ccv, s->cpre, L.n_known, s->Sbuf, s->ld);
-    mark(e, "sim_rows");
-    select_rows_kernel<<<nb, 1024, sel_smem, st>>>(s->Sbuf, s->ld, s->row_order + r0, L.known_user, L.n_known, s->k_fit, s->row_lo, s->k_fit,
-                                            s->nbr_id, s->nbr_sim);
-    mark(e, "select_rows");
-  }
+  // rows are listed longest first: the hardware hands the next CTA to the first SM that frees up (longest-processing-time order)
+  if (s->kind == MRS_SIM_COSINE)
+    knn_rows_kernel<1><<<n_rows, kRowsWarps * 32, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.clen, s->row_order, L.seg, L.n_sub + 1,
+                                                            L.ccv, s->cpre, L.n_known, n_ranges, s->k_fit, s->row_lo, s->nbr_id, s->nbr_sim);
+  else
+    knn_rows_kernel<2><<<n_rows, kRowsWarps * 32, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.clen, s->row_order, L.seg, L.n_sub + 1,
+                                                            L.ccv, s->cpre, L.n_known, n_ranges, s->k_fit, s->row_lo, s->nbr_id, s->nbr_sim);
+  mark(e, "knn_rows");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
 }
