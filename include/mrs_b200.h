@@ -39,6 +39,7 @@ typedef struct mrs_model mrs_model;
 typedef struct mrs_sim mrs_sim;
 typedef struct mrs_graph mrs_graph;
 typedef struct mrs_exchange mrs_exchange;
+typedef struct mrs_upload mrs_upload;     /* host -> device copies of one rating set in flight */
 
 typedef enum {
   MRS_OK = 0,
@@ -109,6 +110,16 @@ MRS_API int32_t mrs_profile_end(mrs_engine* e, char* names_out, int64_t names_ca
  * ranks of a sharded run pass the global values so that their exchange buffers line up. */
 MRS_API int32_t mrs_ratings_from_coo(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings,
                                      int64_t n, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
+/* Staged form of mrs_ratings_from_coo for callers that hand over several sets (train and test): mrs_upload_begin
+ * enqueues the host -> device copies on the engine's copy stream and returns at once (ids first, ratings last), so the
+ * copies of the second set run while the first one is being built; mrs_ratings_from_upload builds the set (it starts
+ * sorting as soon as the ids have arrived) and consumes the upload.  The host arrays must stay valid until
+ * mrs_ratings_from_upload (or mrs_upload_destroy) returns; they should be page-locked, otherwise the copies do not overlap.
+ * mrs_ratings_from_coo == mrs_upload_begin + mrs_ratings_from_upload. */
+MRS_API int32_t mrs_upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
+                                 mrs_upload** out);
+MRS_API int32_t mrs_ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
+MRS_API void mrs_upload_destroy(mrs_upload* up);
 /* Same parse rules as P:35-49: split on `sep`, trim, keep the row iff column 0 parses as an Int. */
 MRS_API int32_t mrs_ratings_from_file(mrs_engine* e, const char* path, const char* sep, mrs_ratings** out);
 /* value_kind: 0 = every rating is a multiple of 0.5 in [0,127.5] and is stored as a 1-byte code; 1 = fp64 values */

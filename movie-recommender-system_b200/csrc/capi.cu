@@ -124,6 +124,12 @@ extern "C" int32_t mrs_engine_create(int32_t device, void* cuda_stream, mrs_engi
     e->own_stream = true;
   }
   use_engine(e);
+  if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("mrs_engine_create: copy stream / event creation failed");
+    mrs_engine_destroy(e);
+    return MRS_ERR_CUDA;
+  }
   cudaError_t he = cudaMallocHost((void**)&e->h_pinned, 64 * sizeof(double));
   if (he != cudaSuccess) { set_error("cudaMallocHost failed: %s", cudaGetErrorString(he)); mrs_engine_destroy(e); return MRS_ERR_NOMEM; }
   *out = e;
@@ -134,6 +140,8 @@ extern "C" void mrs_engine_destroy(mrs_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  if (e->ev_order) cudaEventDestroy(e->ev_order);
   if (e->scratch) cudaFree(e->scratch);
   for (auto& kv : e->free_blocks) cudaFree(kv.second);
   e->free_blocks.clear();

@@ -82,6 +82,8 @@ struct mrs_engine {
   void* scratch = nullptr;  // reusable device scratch (CUB temp storage etc.)
   size_t scratch_bytes = 0;
   double* h_pinned = nullptr;  // small pinned staging area for scalar read-backs
+  cudaStream_t copy_stream = nullptr;  // host->device copies of staged uploads (mrs_upload_begin) run beside the kernels
+  cudaEvent_t ev_order = nullptr;      // orders the copy stream behind work already enqueued on `stream`
   // device block cache: buffers released by destroyed handles are kept (exact size match) and handed out again, so
   // rebuilding a rating set or a model does not go back to the driver (cudaMalloc/cudaFree of ~1 GB of layouts cost
   // 100+ ms per build).  Everything runs on one stream, so reuse is ordered.
@@ -92,6 +94,17 @@ struct mrs_engine {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
   std::vector<const char*> prof_names;
+};
+
+// host -> device copies of one rating set in flight on the engine's copy stream (mrs_upload_begin)
+struct mrs_upload {
+  mrs_engine* eng = nullptr;
+  int64_t n = 0;
+  int32_t* d_u = nullptr;
+  int32_t* d_i = nullptr;
+  double* d_r = nullptr;
+  cudaEvent_t ev_ids = nullptr;     // users and items have arrived
+  cudaEvent_t ev_values = nullptr;  // ratings have arrived
 };
 
 struct mrs_chunks {

@@ -17,31 +17,38 @@ namespace mrs {
 
 namespace {
 
-// one pass over the raw input: id ranges and whether every rating is a half-star code
-__global__ void scan_input_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ it,
-                                  const double* __restrict__ r, int64_t n, int32_t* __restrict__ stats) {
-  // stats: [0]=max user, [1]=max item, [2]=min id, [3]=number of ratings that are not k*0.5 in [0,127.5]
-  int32_t mu = -1, mi = -1, mn = 0x7fffffff, bad = 0;
+// passes over the raw input: id ranges (needed before the first sort) and whether every rating is a half-star code
+// (needed when the values are gathered); separate kernels because the ids arrive before the ratings (mrs_upload_begin)
+__global__ void scan_ids_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ it, int64_t n, int32_t* __restrict__ stats) {
+  // stats: [0]=max user, [1]=max item, [2]=min id
+  int32_t mu = -1, mi = -1, mn = 0x7fffffff;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     int32_t a = u[p], b = it[p];
     mu = max(mu, a);
     mi = max(mi, b);
     mn = min(mn, min(a, b));
-    double v = r[p] * 2.0;
-    if (!(v >= 0.0 && v <= 255.0 && v == floor(v))) bad++;
   }
   for (int o = 16; o > 0; o >>= 1) {
     mu = max(mu, __shfl_xor_sync(0xffffffffu, mu, o));
     mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
     mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    bad += __shfl_xor_sync(0xffffffffu, bad, o);
   }
   if ((threadIdx.x & 31) == 0) {
     atomicMax(&stats[0], mu);
     atomicMax(&stats[1], mi);
     atomicMin(&stats[2], mn);
-    if (bad) atomicAdd(&stats[3], bad);
   }
+}
+
+__global__ void scan_values_kernel(const double* __restrict__ r, int64_t n, int32_t* __restrict__ stats) {
+  // stats[3] = number of ratings that are not k*0.5 in [0,127.5]
+  int32_t bad = 0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    double v = r[p] * 2.0;
+    if (!(v >= 0.0 && v <= 255.0 && v == floor(v))) bad++;
+  }
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&stats[3], bad);
 }
 
 __global__ void make_keys_kernel(const int32_t* __restrict__ hi, const int32_t* __restrict__ lo, int64_t n,
@@ -52,23 +59,15 @@ __global__ void make_keys_kernel(const int32_t* __restrict__ hi, const int32_t* 
   }
 }
 
-// sorted (major<<32|minor) keys -> major array, minor array, gathered values, segment pointer, duplicate count
-template <typename VT, bool kEncode>
-__global__ void scatter_sorted_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ src, int64_t n,
-                                      int32_t n_seg, const void* __restrict__ values_in, int32_t* __restrict__ major_out,
-                                      int32_t* __restrict__ minor_out, VT* __restrict__ values_out,
-                                      int32_t* __restrict__ seg_ptr, int32_t* __restrict__ dup_count) {
+// sorted (major<<32|minor) keys -> major array, minor array, segment pointer, duplicate count (ids only: runs before
+// the ratings have arrived)
+__global__ void scatter_ids_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t n_seg, int32_t* __restrict__ major_out,
+                                   int32_t* __restrict__ minor_out, int32_t* __restrict__ seg_ptr, int32_t* __restrict__ dup_count) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     uint64_t k = keys[p];
     int32_t major = (int32_t)(k >> 32), minor = (int32_t)(k & 0xffffffffu);
     if (major_out) major_out[p] = major;
     minor_out[p] = minor;
-    if (kEncode) {
-      double v = ((const double*)values_in)[src[p]];
-      if (sizeof(VT) == 1) values_out[p] = (VT)(v * 2.0); else values_out[p] = (VT)v;
-    } else {
-      values_out[p] = ((const VT*)values_in)[src[p]];
-    }
     int32_t prev = -1;
     if (p > 0) {
       uint64_t kp = keys[p - 1];
@@ -78,6 +77,19 @@ __global__ void scatter_sorted_kernel(const uint64_t* __restrict__ keys, const i
     for (int32_t s = prev + 1; s <= major; ++s) seg_ptr[s] = (int32_t)p;
     if (p == n - 1)
       for (int32_t s = major + 1; s <= n_seg; ++s) seg_ptr[s] = (int32_t)n;
+  }
+}
+
+// values into sorted order: kEncode reads the raw fp64 ratings (and encodes half-star codes), else copies VT values
+template <typename VT, bool kEncode>
+__global__ void gather_sorted_kernel(const int32_t* __restrict__ src, int64_t n, const void* __restrict__ values_in, VT* __restrict__ values_out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    if (kEncode) {
+      double v = ((const double*)values_in)[src[p]];
+      if (sizeof(VT) == 1) values_out[p] = (VT)(v * 2.0); else values_out[p] = (VT)v;
+    } else {
+      values_out[p] = ((const VT*)values_in)[src[p]];
+    }
   }
 }
 
@@ -200,55 +212,69 @@ int32_t build_chunks(mrs_engine* e, const int32_t* seg_ptr, int32_t n_seg, int32
   return MRS_OK;
 }
 
-template <typename VT>
-int32_t build_sorted(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_t* d_i, const double* d_r, int32_t* d_dup) {
+struct sort_buffers {
+  uint64_t *k_in = nullptr, *k_out = nullptr;
+  int32_t *v_in = nullptr, *perm_u = nullptr;  // perm_u: raw position of every user-major entry (kept until the values arrive)
+  int32_t* v2_in = nullptr;
+};
+
+// Everything that needs the ids only -- both sorts, both index structures, the duplicate check -- so that it runs while the
+// ratings are still being copied.
+int32_t sort_ids(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_t* d_i, int32_t* d_dup, sort_buffers* B) {
   cudaStream_t st = e->stream;
   const int64_t n = R->n;
   const int block = 256;
   const int grid = grid_for(n, block, e->sm_count);
-  uint64_t *k_in = nullptr, *k_out = nullptr;
-  int32_t *v_in = nullptr, *v_out = nullptr;
-  MRS_TRY(dev_alloc(&k_in, (size_t)n));
-  MRS_TRY(dev_alloc(&k_out, (size_t)n));
-  MRS_TRY(dev_alloc(&v_in, (size_t)n));
-  MRS_TRY(dev_alloc(&v_out, (size_t)n));
-  VT *uval = nullptr, *ival = nullptr;
-  MRS_TRY(dev_alloc(&uval, (size_t)n + 32));  // +32: 128-bit loads may read past the last rating (masked)
-  MRS_TRY(dev_alloc(&ival, (size_t)n + 32));
-  R->uval = uval;
-  R->ival = ival;
+  MRS_TRY(dev_alloc(&B->k_in, (size_t)n));
+  MRS_TRY(dev_alloc(&B->k_out, (size_t)n));
+  MRS_TRY(dev_alloc(&B->v_in, (size_t)n));
+  MRS_TRY(dev_alloc(&B->perm_u, (size_t)n));
+  MRS_TRY(dev_alloc(&B->v2_in, (size_t)n));
   MRS_TRY(dev_alloc(&R->ucol, (size_t)n));
   MRS_TRY(dev_alloc(&R->coo_u, (size_t)n));
   MRS_TRY(dev_alloc(&R->irow, (size_t)n));
   MRS_TRY(dev_alloc(&R->csc_src, (size_t)n));
   MRS_TRY(dev_alloc(&R->urow, (size_t)R->n_users + 1));
   MRS_TRY(dev_alloc(&R->icolp, (size_t)R->n_items + 1));
-
   if (n == 0) {
     MRS_CUDA(cudaMemsetAsync(R->urow, 0, sizeof(int32_t) * ((size_t)R->n_users + 1), st));
     MRS_CUDA(cudaMemsetAsync(R->icolp, 0, sizeof(int32_t) * ((size_t)R->n_items + 1), st));
-  } else {
-    const int ubits = bits_for((uint32_t)(R->n_users - 1)), ibits = bits_for((uint32_t)(R->n_items - 1));
-    // ---- user-major: sort by (user, item)
-    make_keys_kernel<<<grid, block, 0, st>>>(d_u, d_i, n, k_in, v_in);
-    count_launch();
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ubits, st);
-    MRS_TRY(ensure_scratch(e, tmp));
-    cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ubits, st);
-    count_launch(4);
-    scatter_sorted_kernel<VT, true><<<grid, block, 0, st>>>(k_out, v_out, n, R->n_users, d_r, R->coo_u, R->ucol, uval, R->urow, d_dup);
-    count_launch();
-    // ---- item-major: sort by (item, user); payload = position in the user-major arrays
-    make_keys_kernel<<<grid, block, 0, st>>>(R->ucol, R->coo_u, n, k_in, v_in);
-    count_launch();
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ibits, st);
-    MRS_TRY(ensure_scratch(e, tmp));
-    cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32 + ibits, st);
-    count_launch(4);
-    scatter_sorted_kernel<VT, false><<<grid, block, 0, st>>>(k_out, v_out, n, R->n_items, uval, nullptr, R->irow, ival, R->icolp, d_dup);
-    count_launch();
-    MRS_CUDA(cudaMemcpyAsync(R->csc_src, v_out, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+    return MRS_OK;
+  }
+  const int ubits = bits_for((uint32_t)(R->n_users - 1)), ibits = bits_for((uint32_t)(R->n_items - 1));
+  // ---- user-major: sort by (user, item); payload = position in the raw input
+  make_keys_kernel<<<grid, block, 0, st>>>(d_u, d_i, n, B->k_in, B->v_in);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, 32 + ubits, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, 32 + ubits, st);
+  scatter_ids_kernel<<<grid, block, 0, st>>>(B->k_out, n, R->n_users, R->coo_u, R->ucol, R->urow, d_dup);
+  // ---- item-major: sort by (item, user); payload = position in the user-major arrays
+  make_keys_kernel<<<grid, block, 0, st>>>(R->ucol, R->coo_u, n, B->k_in, B->v2_in);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, B->k_in, B->k_out, B->v2_in, R->csc_src, (int)n, 0, 32 + ibits, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, B->k_in, B->k_out, B->v2_in, R->csc_src, (int)n, 0, 32 + ibits, st);
+  scatter_ids_kernel<<<grid, block, 0, st>>>(B->k_out, n, R->n_items, nullptr, R->irow, R->icolp, d_dup);
+  count_launch(12);
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+template <typename VT>
+int32_t finish_values(mrs_engine* e, mrs_ratings* R, const double* d_r, sort_buffers* B) {
+  cudaStream_t st = e->stream;
+  const int64_t n = R->n;
+  const int block = 256;
+  const int grid = grid_for(n, block, e->sm_count);
+  VT *uval = nullptr, *ival = nullptr;
+  MRS_TRY(dev_alloc(&uval, (size_t)n + 32));  // +32: 128-bit loads may read past the last rating (masked)
+  MRS_TRY(dev_alloc(&ival, (size_t)n + 32));
+  R->uval = uval;
+  R->ival = ival;
+  if (n) {
+    gather_sorted_kernel<VT, true><<<grid, block, 0, st>>>(B->perm_u, n, d_r, uval);
+    gather_sorted_kernel<VT, false><<<grid, block, 0, st>>>(R->csc_src, n, uval, ival);
+    count_launch(2);
     MRS_CUDA(cudaGetLastError());
   }
   if (sizeof(VT) == 1) MRS_TRY(build_padded_codes(e, R));
@@ -257,75 +283,147 @@ int32_t build_sorted(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const in
     MRS_TRY(build_chunks(e, R->icolp, R->n_items, kItemChunk, &R->ich));
   }
   MRS_CUDA(cudaStreamSynchronize(st));
-  dev_free(k_in); dev_free(k_out); dev_free(v_in); dev_free(v_out);
   return MRS_OK;
 }
 
 }  // namespace
 
-int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
-                      int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {
-  MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL engine or output");
+void free_upload(mrs_upload* up) {
+  if (!up) return;
+  use_engine(up->eng);
+  if (up->ev_values) cudaEventSynchronize(up->ev_values);  // the copies read host memory and write these buffers
+  dev_free(up->d_u); dev_free(up->d_i); dev_free(up->d_r);
+  if (up->ev_ids) cudaEventDestroy(up->ev_ids);
+  if (up->ev_values) cudaEventDestroy(up->ev_values);
+  delete up;
+}
+
+// Enqueue the three host -> device copies on the engine's copy stream and return at once.  The ids go first: the first
+// sort of the build needs only them and runs while the (twice as large) rating array is still on its way.
+int32_t upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n, mrs_upload** out) {
+  MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_upload_begin: NULL engine or output");
   MRS_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, MRS_ERR_UNSUPPORTED, "mrs_ratings_from_coo: n=%lld outside [0, 2^31)", (long long)n);
   MRS_REQUIRE(n == 0 || (users && items && ratings), MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL input array");
   use_engine(e);
+  mrs_upload* up = new mrs_upload();
+  up->eng = e;
+  up->n = n;
+  int32_t rc = dev_alloc(&up->d_u, (size_t)n);
+  if (rc == MRS_OK) rc = dev_alloc(&up->d_i, (size_t)n);
+  if (rc == MRS_OK) rc = dev_alloc(&up->d_r, (size_t)n);
+  cudaError_t ce = cudaSuccess;
+  if (rc == MRS_OK) ce = cudaEventCreateWithFlags(&up->ev_ids, cudaEventDisableTiming);
+  if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventCreateWithFlags(&up->ev_values, cudaEventDisableTiming);
+  // the staging buffers may be recycled blocks: stay behind whatever the compute stream still has queued on them
+  if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(e->ev_order, e->stream);
+  if (rc == MRS_OK && ce == cudaSuccess) ce = cudaStreamWaitEvent(e->copy_stream, e->ev_order, 0);
+  if (rc == MRS_OK && ce == cudaSuccess && n) {
+    ce = cudaMemcpyAsync(up->d_u, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->copy_stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(up->d_i, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->copy_stream);
+  }
+  if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(up->ev_ids, e->copy_stream);
+  if (rc == MRS_OK && ce == cudaSuccess && n) ce = cudaMemcpyAsync(up->d_r, ratings, sizeof(double) * n, cudaMemcpyHostToDevice, e->copy_stream);
+  if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(up->ev_values, e->copy_stream);
+  if (rc == MRS_OK && ce != cudaSuccess) { set_error("mrs_upload_begin: %s", cudaGetErrorString(ce)); rc = MRS_ERR_CUDA; }
+  if (rc != MRS_OK) { free_upload(up); return rc; }
+  *out = up;
+  return MRS_OK;
+}
+
+// Build the device-resident rating set from a staged upload (consumes it).
+int32_t ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {
+  MRS_REQUIRE(up && out, MRS_ERR_INVALID, "mrs_ratings_from_upload: NULL argument");
+  mrs_engine* e = up->eng;
+  use_engine(e);
   cudaStream_t st = e->stream;
-  int32_t *d_u = nullptr, *d_i = nullptr, *d_stats = nullptr;
-  double* d_r = nullptr;
-  MRS_TRY(dev_alloc(&d_u, (size_t)n));
-  MRS_TRY(dev_alloc(&d_i, (size_t)n));
-  MRS_TRY(dev_alloc(&d_r, (size_t)n));
-  MRS_TRY(dev_alloc(&d_stats, 8));
+  const int64_t n = up->n;
+  int32_t* d_stats = nullptr;
+  int32_t s = dev_alloc(&d_stats, 8);
+  if (s != MRS_OK) { free_upload(up); return s; }
   int32_t h_stats[5] = {-1, -1, 0x7fffffff, 0, 0};
-  MRS_CUDA(cudaMemcpyAsync(d_stats, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, st));
-  if (n) {
-    MRS_CUDA(cudaMemcpyAsync(d_u, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-    MRS_CUDA(cudaMemcpyAsync(d_i, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-    MRS_CUDA(cudaMemcpyAsync(d_r, ratings, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    scan_input_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(d_u, d_i, d_r, n, d_stats);
+  mrs_ratings* R = nullptr;
+  sort_buffers B;
+  auto fail = [&](int32_t code) {
+    dev_free(B.k_in); dev_free(B.k_out); dev_free(B.v_in); dev_free(B.perm_u); dev_free(B.v2_in);
+    dev_free(d_stats);
+    free_upload(up);
+    if (R) mrs_ratings_destroy(R);
+    return code;
+  };
+  cudaError_t ce = cudaMemcpyAsync(d_stats, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, up->ev_ids, 0);
+  if (ce == cudaSuccess && n) {
+    scan_ids_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_u, up->d_i, n, d_stats);
     count_launch();
   }
-  MRS_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
-  MRS_CUDA(cudaStreamSynchronize(st));
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_stats, d_stats, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { set_error("mrs_ratings_from_coo: %s", cudaGetErrorString(ce)); return fail(MRS_ERR_CUDA); }
   if (n && h_stats[2] < 0) {
-    dev_free(d_u); dev_free(d_i); dev_free(d_r); dev_free(d_stats);
     set_error("mrs_ratings_from_coo: negative user or item id (%d)", h_stats[2]);
-    return MRS_ERR_INVALID;
+    return fail(MRS_ERR_INVALID);
   }
-  mrs_ratings* R = new mrs_ratings();
+  R = new mrs_ratings();
   R->eng = e;
   R->n = n;
   R->n_users = std::max(n_users_dim, h_stats[0] + 1);
   R->n_items = std::max(n_items_dim, h_stats[1] + 1);
   if (R->n_users < 1) R->n_users = 1;
   if (R->n_items < 1) R->n_items = 1;
-  R->value_kind = (h_stats[3] == 0) ? kValueCode : kValueF64;
   int32_t* d_dup = d_stats + 4;
-  int32_t s = (R->value_kind == kValueCode) ? build_sorted<uint8_t>(e, R, d_u, d_i, d_r, d_dup)
-                                             : build_sorted<double>(e, R, d_u, d_i, d_r, d_dup);
+  s = sort_ids(e, R, up->d_u, up->d_i, d_dup, &B);  // enqueued before we wait for the ratings
+  if (s != MRS_OK) return fail(s);
+  ce = cudaStreamWaitEvent(st, up->ev_values, 0);
+  if (ce == cudaSuccess && n) {
+    scan_values_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_r, n, d_stats);
+    count_launch();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_stats + 3, d_stats + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { set_error("mrs_ratings_from_coo: %s", cudaGetErrorString(ce)); return fail(MRS_ERR_CUDA); }
+  R->value_kind = (h_stats[3] == 0) ? kValueCode : kValueF64;
+  s = (R->value_kind == kValueCode) ? finish_values<uint8_t>(e, R, up->d_r, &B) : finish_values<double>(e, R, up->d_r, &B);
   int32_t dup = 0;
   if (s == MRS_OK) {
-    cudaError_t ce = cudaMemcpy(&dup, d_dup, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    ce = cudaMemcpy(&dup, d_dup, sizeof(int32_t), cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(ce)); s = MRS_ERR_CUDA; }
   }
-  dev_free(d_u); dev_free(d_i); dev_free(d_r); dev_free(d_stats);
   if (s == MRS_OK && dup != 0) {
     // each duplicate pair is seen once in the CSR pass and once in the CSC pass
     set_error("mrs_ratings_from_coo: %d duplicate (user,item) pair(s); the reference keeps the last one (P:168), this engine rejects them", dup / 2);
     s = MRS_ERR_DUPLICATE;
   }
-  if (s != MRS_OK) {
-    mrs_ratings_destroy(R);
-    return s;
-  }
+  if (s != MRS_OK) return fail(s);
+  dev_free(B.k_in); dev_free(B.k_out); dev_free(B.v_in); dev_free(B.perm_u); dev_free(B.v2_in);
+  dev_free(d_stats);
+  free_upload(up);
   *out = R;
   return MRS_OK;
+}
+
+int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
+                      int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {
+  MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL engine or output");
+  mrs_upload* up = nullptr;
+  MRS_TRY(upload_begin(e, users, items, ratings, n, &up));
+  return ratings_from_upload(up, n_users_dim, n_items_dim, out);
 }
 
 }  // namespace mrs
 
 // ------------------------------------------------------------------ C ABI
 using namespace mrs;
+
+extern "C" int32_t mrs_upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
+                                    mrs_upload** out) {
+  return upload_begin(e, users, items, ratings, n, out);
+}
+
+extern "C" int32_t mrs_ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {
+  return ratings_from_upload(up, n_users_dim, n_items_dim, out);
+}
+
+extern "C" void mrs_upload_destroy(mrs_upload* up) { free_upload(up); }
 
 extern "C" int32_t mrs_ratings_from_coo(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings,
                                         int64_t n, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {

@@ -23,7 +23,7 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
-    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
+    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
     "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_status", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
@@ -78,6 +78,9 @@ def lib():
         "mrs_profile_begin": (i32, [vp]),
         "mrs_profile_end": (i32, [vp, C.c_char_p, i64, P(C.c_float), i32, P(i32)]),
         "mrs_ratings_from_coo": (i32, [vp, vp, vp, vp, i64, i32, i32, P(vp)]),
+        "mrs_upload_begin": (i32, [vp, vp, vp, vp, i64, P(vp)]),
+        "mrs_ratings_from_upload": (i32, [vp, i32, i32, P(vp)]),
+        "mrs_upload_destroy": (None, [vp]),
         "mrs_ratings_from_file": (i32, [vp, C.c_char_p, C.c_char_p, P(vp)]),
         "mrs_ratings_info": (i32, [vp, P(i64), P(i32), P(i32), P(i32)]),
         "mrs_ratings_bytes": (i32, [vp, P(i64)]),
@@ -175,6 +178,11 @@ class Engine:
     def ratings(self, users, items, ratings, n_users_dim=0, n_items_dim=0):
         return Ratings(self, users, items, ratings, n_users_dim, n_items_dim)
 
+    def upload(self, users, items, ratings):
+        """Start the host -> device copies of a rating set on the engine's copy stream and return at once; build the set
+        with ``Upload.ratings()``.  Lets the copies of a second set (test) run while the first (train) is being built."""
+        return Upload(self, users, items, ratings)
+
     def ratings_from_file(self, path, sep):
         return Ratings.from_file(self, path, sep)
 
@@ -227,6 +235,36 @@ class Graph:
         if getattr(self, "_h", None):
             lib().mrs_graph_destroy(self._h)
             self._h = None
+
+
+class Upload:
+    """A rating set on its way to the device (``mrs_upload_begin``); the host arrays are kept alive until it is consumed."""
+
+    def __init__(self, engine, users, items, ratings):
+        self.engine = engine
+        u = np.ascontiguousarray(users, dtype=np.int32)
+        i = np.ascontiguousarray(items, dtype=np.int32)
+        r = np.ascontiguousarray(ratings, dtype=np.float64)
+        if not (u.shape == i.shape == r.shape and u.ndim == 1):
+            raise ValueError("users, items, ratings must be 1-D arrays of equal length")
+        self._keep = (u, i, r)
+        self._h = C.c_void_p()
+        _check(lib().mrs_upload_begin(engine._h, _ptr(u), _ptr(i), _ptr(r), u.size, C.byref(self._h)))
+
+    def ratings(self, n_users_dim=0, n_items_dim=0):
+        h, self._h = self._h, None
+        out = C.c_void_p()
+        try:
+            _check(lib().mrs_ratings_from_upload(h, int(n_users_dim), int(n_items_dim), C.byref(out)))   # consumes the upload
+        finally:
+            self._keep = None
+        return Ratings(self.engine, None, None, None, _handle=out)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_upload_destroy(self._h)
+            self._h = None
+            self._keep = None
 
 
 class Ratings:

@@ -122,3 +122,28 @@ def test_peer_exchange_single_rank_is_identity_and_graph_capturable(eng):
         assert torch.equal(buf, ref) and small.tolist() == [3.5, 7.0] and not x.timed_out()
         g.close()
     x.close()
+
+
+def test_staged_upload_equals_direct_build(eng, ml100k):
+    """mrs_upload_begin + mrs_ratings_from_upload (copies on the copy stream, sort started when the ids are in) build the
+    same rating sets as mrs_ratings_from_coo; an upload that is never consumed can be dropped; bad input still fails loudly."""
+    import torch
+    tr, te = ml100k["train"], ml100k["test"]
+    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (*tr, *te)]
+    hu, hi, hr, tu, ti, tv = [p.numpy() for p in pin]
+    up_r, up_t = eng.upload(hu, hi, hr), eng.upload(tu, ti, tv)       # both in flight at once
+    R, T = up_r.ratings(), up_t.ratings()
+    R0, T0 = eng.ratings(*tr), eng.ratings(*te)
+    assert (R.n, R.n_users_dim, R.n_items_dim, R.value_kind) == (R0.n, R0.n_users_dim, R0.n_items_dim, R0.value_kind)
+    m, m0 = E.Model(eng, R), E.Model(eng, R0)
+    assert m.mae(T) == m0.mae(T0) == pytest.approx(O.Oracle(*tr).mae(te, kind=O.BASELINE), rel=1e-6)
+    assert np.array_equal(m.vector(E.USER_AVG)[0], m0.vector(E.USER_AVG)[0])
+    eng.upload(hu, hi, hr).close()                                    # dropped without building
+    bad = hu.copy(); bad[5] = -3
+    with pytest.raises(E.MrsError):
+        eng.upload(bad, hi, hr).ratings()
+    fr = tr[2] + 0.25                                                 # not half-star codes: the fp64 value path
+    Rf = eng.upload(tr[0], tr[1], fr).ratings()
+    assert Rf.value_kind == 1
+    for h in (m, m0, R, T, R0, T0, Rf):
+        h.close()

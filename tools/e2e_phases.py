@@ -24,3 +24,13 @@ for rep in range(3):
     print("rep", rep, "train build %.2f ms | test build %.2f | first fit (tiled layout + kernels) %.2f | first mae (mae layout + kernel) %.2f | d2h %.2f | total %.2f ms  mae=%.6f" % (
         *(1e3 * (t[k + 1] - t[k]) for k in range(5)), 1e3 * (t[-1] - t[0]), r[0] / r[1]))
     t0 = time.perf_counter(); m.close(); T.close(); R.close(); print("  destroy %.2f ms" % (1e3 * (time.perf_counter() - t0)))
+for rep in range(3):   # staged form: both uploads start at once (mrs_upload_begin), builds overlap the copies
+    t = [time.perf_counter()]
+    ur = eng.upload(hu, hi, hr); ut = eng.upload(tu, ti, tv); t.append(time.perf_counter())
+    R = ur.ratings(); t.append(time.perf_counter())
+    m = E.Model(eng, R, sync=False); t.append(time.perf_counter())
+    T = ut.ratings(); t.append(time.perf_counter())
+    m.mae_async(T, out.data_ptr()); r = out.cpu().numpy(); t.append(time.perf_counter())
+    print("staged rep", rep, "upload calls %.2f ms | train build %.2f | fit enqueue %.2f | test build %.2f | mae + d2h %.2f | total %.2f ms  mae=%.6f" % (
+        *(1e3 * (t[k + 1] - t[k]) for k in range(5)), 1e3 * (t[-1] - t[0]), r[0] / r[1]))
+    m.close(); T.close(); R.close()
