@@ -289,6 +289,69 @@ __global__ void __launch_bounds__(512) sort_rank_kernel(const double* __restrict
   if (threadIdx.x == 0) rank[(int64_t)cu * n_known + cu] = INT_MAX;  // s_k(u,u) = 0 (A.5)
 }
 
+// Same result for P <= 2048 with two elements per thread held in registers: compare-exchange partners at element
+// distance 1 live in the same thread, at distance 2..32 in the same warp (shuffles), only distance >= 64 goes through
+// shared memory -- 10 of the 55 stages of a 1024-element network need a barrier instead of all of them.
+template <int P>
+__global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __restrict__ S, const int32_t* __restrict__ known_user,
+                                                             int32_t n_known, int32_t* __restrict__ rank, int32_t* __restrict__ nbr_id,
+                                                             double* __restrict__ nbr_sim) {
+  __shared__ double sk[P];
+  __shared__ int32_t si[P];
+  const int32_t cu = blockIdx.x;
+  const int32_t e0 = 2 * threadIdx.x, e1 = e0 + 1;
+  const bool c0 = (e0 < n_known && e0 != cu), c1 = (e1 < n_known && e1 != cu);  // P:608 allUsers - u
+  double k0 = c0 ? S[(int64_t)cu * n_known + e0] : -INFINITY, k1 = c1 ? S[(int64_t)cu * n_known + e1] : -INFINITY;
+  int32_t i0 = c0 ? e0 : INT_MAX, i1 = c1 ? e1 : INT_MAX;
+#pragma unroll 1
+  for (int32_t size = 2; size <= P; size <<= 1) {
+    const bool up = ((e0 & size) == 0);
+#pragma unroll 1
+    for (int32_t stride = size >> 1; stride >= 64; stride >>= 1) {
+      sk[e0] = k0; si[e0] = i0; sk[e1] = k1; si[e1] = i1;
+      __syncthreads();
+      const double pk0 = sk[e0 ^ stride], pk1 = sk[e1 ^ stride];
+      const int32_t pi0 = si[e0 ^ stride], pi1 = si[e1 ^ stride];
+      __syncthreads();
+      const bool keep_first = (((e0 & stride) == 0) == up);
+      const bool b0 = before(pk0, pi0, k0, i0), b1 = before(pk1, pi1, k1, i1);
+      const bool a0 = before(k0, i0, pk0, pi0), a1 = before(k1, i1, pk1, pi1);
+      if (keep_first ? b0 : a0) { k0 = pk0; i0 = pi0; }
+      if (keep_first ? b1 : a1) { k1 = pk1; i1 = pi1; }
+    }
+#pragma unroll
+    for (int32_t stride = 32; stride >= 2; stride >>= 1) {
+      if (stride < size) {
+        const int m = stride >> 1;
+        const double pk0 = __shfl_xor_sync(0xffffffffu, k0, m), pk1 = __shfl_xor_sync(0xffffffffu, k1, m);
+        const int32_t pi0 = __shfl_xor_sync(0xffffffffu, i0, m), pi1 = __shfl_xor_sync(0xffffffffu, i1, m);
+        const bool keep_first = (((e0 & stride) == 0) == up);
+        const bool b0 = before(pk0, pi0, k0, i0), b1 = before(pk1, pi1, k1, i1);
+        const bool a0 = before(k0, i0, pk0, pi0), a1 = before(k1, i1, pk1, pi1);
+        if (keep_first ? b0 : a0) { k0 = pk0; i0 = pi0; }
+        if (keep_first ? b1 : a1) { k1 = pk1; i1 = pi1; }
+      }
+    }
+    // distance 1: both elements are this thread's
+    if (up ? before(k1, i1, k0, i0) : before(k0, i0, k1, i1)) {
+      const double tk = k0; k0 = k1; k1 = tk;
+      const int32_t ti = i0; i0 = i1; i1 = ti;
+    }
+  }
+  const int32_t nn = n_known - 1;
+  if (e0 < nn) {
+    nbr_id[(int64_t)cu * nn + e0] = known_user[i0];
+    nbr_sim[(int64_t)cu * nn + e0] = k0;
+    rank[(int64_t)cu * n_known + i0] = e0;
+  }
+  if (e1 < nn) {
+    nbr_id[(int64_t)cu * nn + e1] = known_user[i1];
+    nbr_sim[(int64_t)cu * nn + e1] = k1;
+    rank[(int64_t)cu * n_known + i1] = e1;
+  }
+  if (threadIdx.x == 0) rank[(int64_t)cu * n_known + cu] = INT_MAX;  // s_k(u,u) = 0 (A.5)
+}
+
 // ---------------- P5: weighted-sum deviation + prediction (+ |error| reduction), one warp per (u,i) ----------------
 // SIMMODE 0: uniform (s == 1, P:400); 1: matrix, no neighbourhood; 2: matrix restricted to the first k neighbours of u
 template <int SIMMODE, bool WSD = false>
@@ -514,9 +577,17 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
   // P4
   int32_t P = 2;
   while (P < L.n_known) P <<= 1;
-  const size_t smem = (size_t)P * (sizeof(double) + sizeof(int32_t));
-  MRS_CUDA(cudaFuncSetAttribute(sort_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sort_rank_kernel<<<L.n_known, 512, smem, st>>>(s->S, L.known_user, L.n_known, P, s->rank, s->nbr_id, s->nbr_sim);
+  if (P <= 512) {
+    sort_rank_reg_kernel<512><<<L.n_known, 256, 0, st>>>(s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim);
+  } else if (P == 1024) {
+    sort_rank_reg_kernel<1024><<<L.n_known, 512, 0, st>>>(s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim);
+  } else if (P == 2048) {
+    sort_rank_reg_kernel<2048><<<L.n_known, 1024, 0, st>>>(s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim);
+  } else {
+    const size_t smem = (size_t)P * (sizeof(double) + sizeof(int32_t));
+    MRS_CUDA(cudaFuncSetAttribute(sort_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_rank_kernel<<<L.n_known, 512, smem, st>>>(s->S, L.known_user, L.n_known, P, s->rank, s->nbr_id, s->nbr_sim);
+  }
   mark(e, "sort_rank");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

@@ -192,3 +192,24 @@ def test_answer_documents_have_the_reference_schema(eng, ml100k, tmp_path):
     assert list(r) == ["Meta", "R.1", "R.2"] and len(r["R.2"]) == 3 and all(len(x) == 3 for x in r["R.2"])
     assert all(x[0] not in (1, 3) for x in r["R.2"])                                          # rated items are never recommended
     json.dumps([b, d, p, k, r])
+
+
+@pytest.mark.parametrize("n_users", [300, 1500, 3000])
+def test_sort_kernels_at_other_sizes(eng, n_users):
+    """The neighbour sort has a register/shuffle form for up to 2,048 users (512-, 1,024-, 2,048-element networks) and a
+    shared-memory form above: every one must give the oracle's lists."""
+    from mrs_b200 import synth
+    d = synth.small(seed=n_users, n_users=n_users, n_items=400, n_ratings=n_users * 25)
+    tr = d["train"]
+    R = eng.ratings(*tr)
+    m = E.Model(eng, R)
+    o = O.Oracle(*tr)
+    s = m.similarity(E.SIM_COSINE, 0)
+    users = np.unique(tr[0])
+    for u in users[:: max(1, users.size // 25)]:
+        k = int(users.size)
+        ids, sims = s.neighbors(int(u), k)
+        oi, os_ = o.neighbors(int(u), k)
+        assert ids.tolist() == oi.tolist() and sims.tolist() == os_.tolist()
+    for h in (s, m, R):
+        h.close()
