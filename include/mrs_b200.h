@@ -165,6 +165,10 @@ MRS_API void mrs_model_destroy(mrs_model* m);
 MRS_API int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t rank, int32_t world, void* ipc_handle_out64, mrs_exchange** out);
 MRS_API int32_t mrs_exchange_connect(mrs_exchange* x, const void* all_handles_world_x_64);
 MRS_API int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout, int64_t n_doubles);
+/* Same over the positions device_idx[0..n_idx) of `device_inout` only (int32, on the device, identical on every rank): the
+ * other positions neither travel nor change.  The exchange buffer of a model is indexed by item id; with sparse ids most of
+ * its slots are zero on every rank (72 % at ml-25m shape), and the slots in use are known once the rating sets are loaded. */
+MRS_API int32_t mrs_exchange_allreduce_indexed_async(mrs_exchange* x, void* device_inout, const int32_t* device_idx, int64_t n_idx);
 MRS_API int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out);
 /* diagnostics: %globaltimer (ns) of block 0 in the last exchange: [0] start, [1] published, [2] first barrier passed,
  * [3] slice reduced, [4] second barrier passed (two-shot only), [5] done */

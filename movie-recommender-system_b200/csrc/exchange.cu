@@ -68,6 +68,7 @@ __device__ __forceinline__ bool rank_barrier(double* const* __restrict__ peer, i
   if (threadIdx.x == 0) {
     const int last = (atomicAdd(done, 1u) + 1u == gridDim.x);
     if (last) *done = 0;
+    __threadfence();  // the other blocks' data (fenced before their arrival) is ordered before what follows
     s_last = last;
   }
   __syncthreads();
@@ -87,11 +88,25 @@ __device__ __forceinline__ bool rank_barrier(double* const* __restrict__ peer, i
   return __syncthreads_and(good) != 0;
 }
 
+// result pair i of the compact array -> its place in the caller's buffer
+__device__ __forceinline__ void put2(double* __restrict__ inout, const int32_t* __restrict__ idx, int64_t i, double2 v) {
+  if (idx) {
+    inout[__ldg(idx + 2 * i)] = v.x;
+    inout[__ldg(idx + 2 * i + 1)] = v.y;
+  } else {
+    reinterpret_cast<double2*>(inout)[i] = v;
+  }
+}
+
 // inout[0..n): this rank's partial sums on entry, the sum over all ranks (added in rank order) on exit
 __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* const* __restrict__ peer, int32_t rank, int32_t world, int64_t n,
                                                                    int64_t cap, int two_shot, unsigned long long* __restrict__ epoch_done,
                                                                    unsigned int* __restrict__ done, int32_t* __restrict__ error,
-                                                                   unsigned long long* __restrict__ stamps, double* __restrict__ inout) {
+                                                                   unsigned long long* __restrict__ stamps, double* __restrict__ inout,
+                                                                   const int32_t* __restrict__ idx) {
+  // idx != nullptr: the exchange covers the n positions idx[0..n) of `inout` only (the slots that can be non-zero on some
+  // rank -- 28 % of the exchange buffer at ml-25m shape, whose item ids are sparse); everything below works on the compact
+  // array, only the first read and the last write go through the index list
   bool ok;
   const bool stamp = (blockIdx.x == 0 && threadIdx.x == 0);
   if (stamp) stamps[0] = gtime();
@@ -100,7 +115,9 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   double* pub = peer[rank] + (size_t)parity * cap;
   // (1) publish (128-bit copies, 4 in flight per thread: the buffer is a few MB and latency bound)
-  {
+  if (idx) {
+    for (int64_t j = tid; j < n; j += nth) pub[j] = inout[__ldg(idx + j)];
+  } else {
     const int64_t n2 = n >> 1;
     const double2* src = reinterpret_cast<const double2*>(inout);
     double2* dst = reinterpret_cast<double2*>(pub);
@@ -112,7 +129,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
     for (; i < n2; i += nth) dst[i] = src[i];
     if ((n & 1) && tid == 0) pub[n - 1] = inout[n - 1];
   }
-  __threadfence_system();
+  __threadfence();  // device scope: the barrier's last block makes everything visible system-wide before it raises the flags
   __syncthreads();
   if (stamp) stamps[1] = gtime();
   ok = rank_barrier(peer, rank, world, cap, 0, epoch, done, error);  // (2) everybody has published
@@ -129,8 +146,8 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
         const double2 v0 = src[i], v1 = src[i + nth];
         a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
       }
-      reinterpret_cast<double2*>(inout)[i] = a0;
-      reinterpret_cast<double2*>(inout)[i + nth] = a1;
+      put2(inout, idx, i, a0);
+      put2(inout, idx, i + nth, a1);
     }
     for (; i < n2; i += nth) {
       double2 a0 = make_double2(0.0, 0.0);
@@ -138,12 +155,12 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
         const double2 v0 = reinterpret_cast<const double2*>(peer[p] + (size_t)parity * cap)[i];
         a0.x += v0.x; a0.y += v0.y;
       }
-      reinterpret_cast<double2*>(inout)[i] = a0;
+      put2(inout, idx, i, a0);
     }
     if ((n & 1) && tid == 0) {
       double a = 0.0;
       for (int p = 0; p < world; ++p) a += (peer[p] + (size_t)parity * cap)[n - 1];
-      inout[n - 1] = a;
+      inout[idx ? idx[n - 1] : n - 1] = a;
     }
   } else if (ok) {
     // two-shot, n even: (3) reduce my slice in rank order into my result buffer ...
@@ -161,7 +178,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
         if (p < world) { acc.x += v[p].x; acc.y += v[p].y; }  // rank order
       res[i] = acc;
     }
-    __threadfence_system();
+    __threadfence();
     __syncthreads();
     if (stamp) stamps[3] = gtime();
     ok = rank_barrier(peer, rank, world, cap, 1, epoch, done + 1, error);  // (4) every slice is reduced
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int64_t i = i0 + k * nth;
-          if (i < n2) reinterpret_cast<double2*>(inout)[i] = v[k];
+          if (i < n2) put2(inout, idx, i, v[k]);
         }
       }
     }
@@ -252,7 +269,18 @@ extern "C" int32_t mrs_exchange_connect(mrs_exchange* x, const void* all_handles
   return MRS_OK;
 }
 
+static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_doubles, const int32_t* device_idx);
+
 extern "C" int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout, int64_t n_doubles) {
+  return allreduce_impl(x, device_inout, n_doubles, nullptr);
+}
+
+extern "C" int32_t mrs_exchange_allreduce_indexed_async(mrs_exchange* x, void* device_inout, const int32_t* device_idx, int64_t n_idx) {
+  MRS_REQUIRE(device_idx, MRS_ERR_INVALID, "mrs_exchange_allreduce_indexed_async: NULL index list");
+  return allreduce_impl(x, device_inout, n_idx, device_idx);
+}
+
+static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_doubles, const int32_t* device_idx) {
   MRS_REQUIRE(x && device_inout, MRS_ERR_INVALID, "mrs_exchange_allreduce_async: NULL argument");
   MRS_REQUIRE(x->connected, MRS_ERR_INVALID, "mrs_exchange_allreduce_async: call mrs_exchange_connect first");
   MRS_REQUIRE(n_doubles > 0 && n_doubles <= x->n, MRS_ERR_INVALID, "mrs_exchange_allreduce_async: %lld doubles exceed the capacity %lld",
@@ -263,9 +291,11 @@ extern "C" int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_in
   const int64_t work = (n_doubles + 1) / 2;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + kExThreads - 1) / kExThreads, (int64_t)x->eng->sm_count));
   // two-shot (reduce my slice, barrier, collect) once the buffer is large enough to be bandwidth relevant
-  const int two_shot = (x->world > 2 && (n_doubles & 1) == 0 && n_doubles >= 16384) ? 1 : 0;
+  // (its second barrier, fence and phase cost about 12 us, i.e. about 10 MB of NVLink time: below that every rank simply
+  // reads all the peers' buffers)
+  const int two_shot = (x->world > 2 && (n_doubles & 1) == 0 && (int64_t)(x->world - 1) * n_doubles * 8 > (int64_t)12 << 20) ? 1 : 0;
   peer_allreduce_kernel<<<grid, kExThreads, 0, x->eng->stream>>>(x->d_peer, x->rank, x->world, n_doubles, x->n, two_shot, x->d_epoch, x->d_done,
-                                                                 x->d_error, x->d_stamps, (double*)device_inout);
+                                                                 x->d_error, x->d_stamps, (double*)device_inout, device_idx);
   mark(x->eng, "peer_allreduce");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
     "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
-    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_status", "mrs_exchange_stamps", "mrs_exchange_destroy",
+    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_exchange_status", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
@@ -96,6 +96,7 @@ def lib():
         "mrs_exchange_create": (i32, [vp, i64, i32, i32, vp, P(vp)]),
         "mrs_exchange_connect": (i32, [vp, vp]),
         "mrs_exchange_allreduce_async": (i32, [vp, vp, i64]),
+        "mrs_exchange_allreduce_indexed_async": (i32, [vp, vp, vp, i64]),
         "mrs_exchange_status": (i32, [vp, P(i32)]),
         "mrs_exchange_stamps": (i32, [vp, P(C.c_uint64)]),
         "mrs_exchange_destroy": (None, [vp]),
@@ -204,6 +205,10 @@ class PeerExchange:
 
     def allreduce_async(self, device_ptr, n_doubles):
         _check(lib().mrs_exchange_allreduce_async(self._h, C.c_void_p(int(device_ptr)), int(n_doubles)))
+
+    def allreduce_indexed_async(self, device_ptr, device_idx_ptr, n_idx):
+        """Sum only the positions ``idx[0..n_idx)`` (int32 on the device, identical on every rank) of the buffer."""
+        _check(lib().mrs_exchange_allreduce_indexed_async(self._h, C.c_void_p(int(device_ptr)), C.c_void_p(int(device_idx_ptr)), int(n_idx)))
 
     def stamps(self):
         """Nanosecond stamps of the last exchange, relative to its start: published, barrier 1, reduced, barrier 2, done."""

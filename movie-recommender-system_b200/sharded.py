@@ -114,6 +114,25 @@ class ShardedBaseline:
                     dist.all_gather_object(out, b, group=group)
                     return out
                 self.peer = E.PeerExchange(engine, max(int(self.xbuf.numel()), 2), rank, world, gather)
+                self.xidx = self._slots_in_use(dist, item_averages)
+
+    def _slots_in_use(self, dist, item_averages):
+        """Positions of the exchange buffer that are non-zero on SOME rank: the slots of the items that occur in some rank's
+        train shard (+ the two global sums).  Known once the shards are loaded; only these travel in each exchange."""
+        torch = self.torch
+        n_items = int(self.train.n_items_dim)
+        self.fit_local()                                   # leaves this rank's per-item counts in xbuf[I:2I]
+        torch.cuda.synchronize(self.device)
+        used = (self.xbuf[n_items:2 * n_items] > 0).to(torch.int32)
+        dist.all_reduce(used, op=dist.ReduceOp.MAX, group=self.group)      # set-up time only
+        known = torch.nonzero(used, as_tuple=False).flatten().to(torch.int32)
+        parts = [known, known + n_items, torch.tensor([2 * n_items, 2 * n_items + 1], dtype=torch.int32, device=self.device)]
+        if item_averages:
+            parts.append(known + (2 * n_items + 2))
+        idx = torch.cat(parts)
+        if idx.numel() % 2:                                # the two-shot form works on pairs: repeat a slot (harmless)
+            idx = torch.cat([idx, idx[-1:]])
+        return idx.contiguous()
 
     # ---- the five pieces of a step (all asynchronous on the engine's stream)
     def fit_local(self):
@@ -121,7 +140,7 @@ class ShardedBaseline:
 
     def exchange(self):                                # THE collective of the fit (P:267-268, P:247)
         if self.peer is not None:
-            self.peer.allreduce_async(self.xbuf.data_ptr(), self.xbuf.numel())
+            self.peer.allreduce_indexed_async(self.xbuf.data_ptr(), self.xidx.data_ptr(), self.xidx.numel())
         else:
             all_reduce_sum(self.xbuf, self.group)
 

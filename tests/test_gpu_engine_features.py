@@ -121,6 +121,12 @@ def test_peer_exchange_single_rank_is_identity_and_graph_capturable(eng):
         eng.sync()
         assert torch.equal(buf, ref) and small.tolist() == [3.5, 7.0] and not x.timed_out()
         g.close()
+        # indexed form: only the listed slots take part (odd and even counts, one-shot sizes)
+        for idx_list in ([5, 17, 900], [0, 2, 4, 1000]):
+            idx = torch.tensor(idx_list, dtype=torch.int32, device="cuda")
+            x.allreduce_indexed_async(buf.data_ptr(), idx.data_ptr(), idx.numel())
+            eng.sync()
+            assert torch.equal(buf, ref) and not x.timed_out()
     x.close()
 
 
