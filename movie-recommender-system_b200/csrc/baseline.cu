@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256) item_partial_kernel(const int32_t* __rest
 __global__ void __launch_bounds__(256) item_finalize_kernel(const double* __restrict__ xbuf, int32_t n_items,
                                                            double* __restrict__ idevavg, double* __restrict__ iavg,
                                                            double* __restrict__ gavg) {
+  pdl_trigger();  // the MAE pass may set up its rings while this runs
+  pdl_wait();     // xbuf is complete (local finalisation or the cross-rank exchange)
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     const double gs = xbuf[2 * (size_t)n_items], gc = xbuf[2 * (size_t)n_items + 1];
@@ -464,7 +466,8 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
 
 int32_t fit_finish(mrs_model* m) {
   MRS_REQUIRE(m, MRS_ERR_INVALID, "mrs_fit_finish: NULL model");
-  item_finalize_kernel<<<(m->n_items + 255) / 256, 256, 0, m->eng->stream>>>(m->xbuf, m->n_items, m->idevavg, m->iavg, m->gavg);
+  MRS_CUDA(launch_pdl(item_finalize_kernel, dim3((m->n_items + 255) / 256), dim3(256), 0, m->eng->stream, m->xbuf, m->n_items, m->idevavg,
+                      m->iavg, m->gavg));
   mark(m->eng, "item_finalize");
   MRS_CUDA(cudaGetLastError());
   m->finished = true;

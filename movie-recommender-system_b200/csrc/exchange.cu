@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
   // idx != nullptr: the exchange covers the n positions idx[0..n) of `inout` only (the slots that can be non-zero on some
   // rank -- 28 % of the exchange buffer at ml-25m shape, whose item ids are sparse); everything below works on the compact
   // array, only the first read and the last write go through the index list
+  pdl_trigger();  // the kernel behind this one may be scheduled as SMs free up (it waits for our completion itself)
+  pdl_wait();     // `inout` is complete
   bool ok;
   const bool stamp = (blockIdx.x == 0 && threadIdx.x == 0);
   if (stamp) stamps[0] = gtime();
@@ -294,8 +296,8 @@ static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_dou
   // (its second barrier, fence and phase cost about 12 us, i.e. about 10 MB of NVLink time: below that every rank simply
   // reads all the peers' buffers)
   const int two_shot = (x->world > 2 && (n_doubles & 1) == 0 && (int64_t)(x->world - 1) * n_doubles * 8 > (int64_t)12 << 20) ? 1 : 0;
-  peer_allreduce_kernel<<<grid, kExThreads, 0, x->eng->stream>>>(x->d_peer, x->rank, x->world, n_doubles, x->n, two_shot, x->d_epoch, x->d_done,
-                                                                 x->d_error, x->d_stamps, (double*)device_inout, device_idx);
+  MRS_CUDA(launch_pdl(peer_allreduce_kernel, dim3(grid), dim3(kExThreads), 0, x->eng->stream, x->d_peer, x->rank, x->world, n_doubles, x->n,
+                      two_shot, x->d_epoch, x->d_done, x->d_error, x->d_stamps, (double*)device_inout, device_idx));
   mark(x->eng, "peer_allreduce");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
