@@ -122,6 +122,12 @@ MRS_API int32_t mrs_ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int
 MRS_API void mrs_upload_destroy(mrs_upload* up);
 /* Same parse rules as P:35-49: split on `sep`, trim, keep the row iff column 0 parses as an Int. */
 MRS_API int32_t mrs_ratings_from_file(mrs_engine* e, const char* path, const char* sep, mrs_ratings** out);
+/* The same on `nbytes` of text in host memory (what a JVM caller holds after reading a file or an HDFS block).  The text is
+ * copied to the device and parsed there, one thread per line; only ratings written in another form than
+ * [sign]digits[.digits] with at most 15 digits (exponents, hex, NaN ...) send the text through the host parser instead.
+ * `sep` is a literal string of at most 8 bytes (the reference passes it to String.split, i.e. as a regex: "\t", ",", "::"
+ * mean the same either way). */
+MRS_API int32_t mrs_ratings_from_text(mrs_engine* e, const char* text, int64_t nbytes, const char* sep, mrs_ratings** out);
 /* value_kind: 0 = every rating is a multiple of 0.5 in [0,127.5] and is stored as a 1-byte code; 1 = fp64 values */
 MRS_API int32_t mrs_ratings_info(const mrs_ratings* r, int64_t* n, int32_t* n_users_dim, int32_t* n_items_dim, int32_t* value_kind);
 /* bytes of device memory the hot kernels read per pass over this set: [0] user-major payload, [1] item-major payload,

@@ -430,8 +430,13 @@ extern "C" int32_t mrs_ratings_from_coo(mrs_engine* e, const int32_t* users, con
   return build_ratings(e, users, items, ratings, n, n_users_dim, n_items_dim, out);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Text loader: `load` (P:35-49) = textFile -> split(sep) -> trim -> keep the row iff column 0 is an Int.
+// The text is parsed ON THE DEVICE (one thread per line); the host parser below states the same rules and is used only
+// when a rating is written in a form the device parser does not take (exponent, hex, NaN, more than 15 digits).
+
 // Java semantics of Integer.parseInt after trim (P:27-33 toInt): optional sign, then decimal digits only.
-static bool parse_java_int(const char* b, const char* e, int32_t* out) {
+__host__ __device__ static bool parse_java_int(const char* b, const char* e, int32_t* out) {
   while (b < e && (unsigned char)*b <= ' ') ++b;  // String.trim strips chars <= U+0020
   while (e > b && (unsigned char)e[-1] <= ' ') --e;
   if (b == e) return false;
@@ -450,6 +455,243 @@ static bool parse_java_int(const char* b, const char* e, int32_t* out) {
   return true;
 }
 
+// first three columns of a line split on the literal separator; returns the number of columns found (1..3, 4 = more)
+__host__ __device__ static int split3(const char* p, const char* le, const char* sep, int seplen, const char** c, const char** ce) {
+  c[0] = p; c[1] = c[2] = nullptr;
+  ce[0] = ce[1] = ce[2] = le;
+  int nc = 1;
+  const char* q = p;
+  while (nc < 4) {
+    const char* hit = nullptr;
+    for (const char* t = q; t + seplen <= le; ++t) {
+      bool eq = true;
+      for (int k = 0; k < seplen; ++k)
+        if (t[k] != sep[k]) { eq = false; break; }
+      if (eq) { hit = t; break; }
+    }
+    if (!hit) break;
+    ce[nc - 1] = hit;
+    if (nc < 3) c[nc] = hit + seplen;
+    q = hit + seplen;
+    ++nc;
+  }
+  return nc;
+}
+
+namespace mrs {
+namespace {
+
+constexpr int kMaxSep = 8;
+struct sep_arg { char s[kMaxSep]; int len; };
+
+struct is_newline {
+  const char* text;
+  __device__ bool operator()(int32_t p) const { return text[p] == '\n'; }
+};
+
+// [sign] digits [. digits], at most 15 significant digits: mantissa and power of ten are exact doubles, one correctly
+// rounded division gives the correctly rounded value (what Double.parseDouble returns).  0 = parsed, 2 = another form.
+__device__ int parse_plain_decimal(const char* b, const char* e, double* out) {
+  while (b < e && (unsigned char)*b <= ' ') ++b;
+  while (e > b && (unsigned char)e[-1] <= ' ') --e;
+  if (b == e) return 2;
+  bool neg = false;
+  if (*b == '-' || *b == '+') { neg = (*b == '-'); ++b; }
+  unsigned long long mant = 0;
+  int nd = 0, frac = 0;
+  bool digit = false, dot = false;
+  for (; b < e; ++b) {
+    const char ch = *b;
+    if (ch >= '0' && ch <= '9') {
+      digit = true;
+      if (nd > 15) return 2;
+      mant = mant * 10ull + (unsigned)(ch - '0');
+      if (mant) ++nd;
+      if (dot) ++frac;
+    } else if (ch == '.' && !dot) {
+      dot = true;
+    } else {
+      return 2;
+    }
+  }
+  if (!digit || nd > 15 || frac > 22) return 2;
+  double p10 = 1.0;
+  for (int k = 0; k < frac; ++k) p10 *= 10.0;  // exact up to 1e22
+  const double v = __ddiv_rn((double)mant, p10);
+  *out = neg ? -v : v;
+  return 0;
+}
+
+// status[0] = first line (0-based) with a malformed row, status[1] = number of ratings in another number form
+__global__ void parse_lines_kernel(const char* __restrict__ text, const int32_t* __restrict__ nl_pos, int32_t n_lines, sep_arg sep,
+                                   int32_t* __restrict__ us, int32_t* __restrict__ is, double* __restrict__ rs,
+                                   unsigned char* __restrict__ keep, int32_t* __restrict__ status) {
+  const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_lines) return;
+  const char* p = text + (l ? nl_pos[l - 1] + 1 : 0);
+  const char* le = text + nl_pos[l];
+  if (le > p && le[-1] == '\r') --le;  // textFile strips \r\n as well as \n
+  const char *c[3], *ce[3];
+  const int nc = split3(p, le, sep.s, sep.len, c, ce);
+  int32_t uu = 0, ii = 0;
+  double rr = 0.0;
+  unsigned char k = 0;
+  if (parse_java_int(c[0], ce[0], &uu)) {  // P:40: rows whose column 0 is not an Int are dropped (header skip)
+    if (nc < 3 || !parse_java_int(c[1], ce[1], &ii)) {
+      atomicMin(status, l);                // the reference throws at P:41
+    } else if (parse_plain_decimal(c[2], ce[2], &rr) != 0) {
+      atomicAdd(status + 1, 1);
+    } else {
+      k = 1;
+    }
+  }
+  us[l] = uu; is[l] = ii; rs[l] = rr; keep[l] = k;
+}
+
+// the same rules on the host (strtod takes every number form); returns the 1-based line of the first malformed row or 0
+int64_t parse_text_host(const char* text, size_t len, const char* sep, std::vector<int32_t>& us, std::vector<int32_t>& is,
+                        std::vector<double>& rs, bool* bad_number) {
+  const int seplen = (int)strlen(sep);
+  const char* p = text;
+  const char* end = text + len;
+  int64_t lineno = 0;
+  *bad_number = false;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    if (!nl) nl = end;
+    const char* le = nl;
+    if (le > p && le[-1] == '\r') --le;
+    ++lineno;
+    const char *c[3], *ce[3];
+    const int nc = split3(p, le, sep, seplen, c, ce);
+    int32_t uu = 0, ii = 0;
+    if (parse_java_int(c[0], ce[0], &uu)) {
+      if (nc < 3 || !parse_java_int(c[1], ce[1], &ii)) return lineno;
+      std::string tok(c[2], ce[2]);
+      char* endp = nullptr;
+      double rr = strtod(tok.c_str(), &endp);
+      while (endp && *endp && (unsigned char)*endp <= ' ') ++endp;
+      if (endp == tok.c_str() || (endp && *endp)) { *bad_number = true; return lineno; }
+      us.push_back(uu); is.push_back(ii); rs.push_back(rr);
+    }
+    p = nl + 1;
+  }
+  return 0;
+}
+
+// text (host memory, not retained) -> rating set
+int32_t ratings_from_text(mrs_engine* e, const char* text, int64_t nbytes, const char* sep, const char* what, mrs_ratings** out) {
+  MRS_REQUIRE(e && sep && out && sep[0] && (text || nbytes == 0), MRS_ERR_INVALID, "mrs_ratings_from_text: NULL/empty argument");
+  const size_t seplen = strlen(sep);
+  MRS_REQUIRE(seplen <= (size_t)kMaxSep, MRS_ERR_UNSUPPORTED, "mrs_ratings_from_text: separator longer than %d bytes", kMaxSep);
+  MRS_REQUIRE(nbytes >= 0 && nbytes < (int64_t)0x7ffffff0, MRS_ERR_UNSUPPORTED, "mrs_ratings_from_text: %lld bytes outside [0, 2^31)", (long long)nbytes);
+  use_engine(e);
+  cudaStream_t st = e->stream;
+  const int32_t n = (int32_t)nbytes + 1;  // + a final '\n' so that the last line is terminated
+  char* d_text = nullptr;
+  int32_t *d_nl = nullptr, *d_num = nullptr, *d_status = nullptr, *l_u = nullptr, *l_i = nullptr;
+  double* l_r = nullptr;
+  unsigned char* d_keep = nullptr;
+  mrs_upload* up = nullptr;
+  auto cleanup = [&]() {
+    dev_free(d_text); dev_free(d_nl); dev_free(d_num); dev_free(d_status); dev_free(l_u); dev_free(l_i); dev_free(l_r); dev_free(d_keep);
+  };
+#define MRS_TEXT_TRY(expr)                                                      \
+  do {                                                                          \
+    int32_t s__ = (expr);                                                       \
+    if (s__ != MRS_OK) { cleanup(); if (up) free_upload(up); return s__; }      \
+  } while (0)
+#define MRS_TEXT_CUDA(expr)                                                                             \
+  do {                                                                                                  \
+    cudaError_t c__ = (expr);                                                                           \
+    if (c__ != cudaSuccess) {                                                                           \
+      set_error("mrs_ratings_from_text: %s", cudaGetErrorString(c__));                                  \
+      cleanup(); if (up) free_upload(up);                                                               \
+      return MRS_ERR_CUDA;                                                                              \
+    }                                                                                                   \
+  } while (0)
+  MRS_TEXT_TRY(dev_alloc(&d_text, (size_t)n));
+  MRS_TEXT_TRY(dev_alloc(&d_num, 4));
+  MRS_TEXT_TRY(dev_alloc(&d_status, 4));
+  if (nbytes) MRS_TEXT_CUDA(cudaMemcpyAsync(d_text, text, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+  MRS_TEXT_CUDA(cudaMemsetAsync(d_text + nbytes, '\n', 1, st));
+  // ---- line ends
+  cub::CountingInputIterator<int32_t> pos(0);
+  size_t tmp = 0;
+  MRS_TEXT_TRY(dev_alloc(&d_nl, (size_t)n));  // upper bound: every byte a newline
+  cub::DeviceSelect::If(nullptr, tmp, pos, d_nl, d_num, n, is_newline{d_text}, st);
+  MRS_TEXT_TRY(ensure_scratch(e, tmp));
+  cub::DeviceSelect::If(e->scratch, tmp, pos, d_nl, d_num, n, is_newline{d_text}, st);
+  count_launch(2);
+  int32_t n_lines = 0;
+  MRS_TEXT_CUDA(cudaMemcpyAsync(&n_lines, d_num, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_TEXT_CUDA(cudaStreamSynchronize(st));
+  // ---- one thread per line
+  MRS_TEXT_TRY(dev_alloc(&l_u, (size_t)n_lines));
+  MRS_TEXT_TRY(dev_alloc(&l_i, (size_t)n_lines));
+  MRS_TEXT_TRY(dev_alloc(&l_r, (size_t)n_lines));
+  MRS_TEXT_TRY(dev_alloc(&d_keep, (size_t)n_lines));
+  int32_t h_status[2] = {0x7fffffff, 0};
+  MRS_TEXT_CUDA(cudaMemcpyAsync(d_status, h_status, sizeof(h_status), cudaMemcpyHostToDevice, st));
+  sep_arg sa;
+  memset(&sa, 0, sizeof(sa));
+  memcpy(sa.s, sep, seplen);
+  sa.len = (int)seplen;
+  parse_lines_kernel<<<(n_lines + 255) / 256, 256, 0, st>>>(d_text, d_nl, n_lines, sa, l_u, l_i, l_r, d_keep, d_status);
+  count_launch();
+  MRS_TEXT_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+  MRS_TEXT_CUDA(cudaStreamSynchronize(st));
+  if (h_status[0] != 0x7fffffff) {
+    cleanup();
+    set_error("mrs_ratings_from_file: %s:%lld: malformed row (the reference throws at predictions.scala:41)", what, (long long)h_status[0] + 1);
+    return MRS_ERR_IO;
+  }
+  if (h_status[1] != 0) {  // some rating is not a plain decimal: the host parser (strtod) decides
+    cleanup();
+    std::vector<int32_t> us, is;
+    std::vector<double> rs;
+    bool bad_number = false;
+    const int64_t bad = parse_text_host(text, (size_t)nbytes, sep, us, is, rs, &bad_number);
+    if (bad) {
+      set_error(bad_number ? "mrs_ratings_from_file: %s:%lld: rating is not a number"
+                           : "mrs_ratings_from_file: %s:%lld: malformed row (the reference throws at predictions.scala:41)", what, (long long)bad);
+      return MRS_ERR_IO;
+    }
+    return build_ratings(e, us.data(), is.data(), rs.data(), (int64_t)us.size(), 0, 0, out);
+  }
+  // ---- kept rows, compacted straight into the staging buffers of the build
+  up = new mrs_upload();
+  up->eng = e;
+  MRS_TEXT_TRY(dev_alloc(&up->d_u, (size_t)n_lines));
+  MRS_TEXT_TRY(dev_alloc(&up->d_i, (size_t)n_lines));
+  MRS_TEXT_TRY(dev_alloc(&up->d_r, (size_t)n_lines));
+  MRS_TEXT_CUDA(cudaEventCreateWithFlags(&up->ev_ids, cudaEventDisableTiming));
+  MRS_TEXT_CUDA(cudaEventCreateWithFlags(&up->ev_values, cudaEventDisableTiming));
+  cub::DeviceSelect::Flagged(nullptr, tmp, l_r, d_keep, up->d_r, d_num, n_lines, st);
+  MRS_TEXT_TRY(ensure_scratch(e, tmp));
+  cub::DeviceSelect::Flagged(e->scratch, tmp, l_u, d_keep, up->d_u, d_num, n_lines, st);
+  cub::DeviceSelect::Flagged(e->scratch, tmp, l_i, d_keep, up->d_i, d_num, n_lines, st);
+  cub::DeviceSelect::Flagged(e->scratch, tmp, l_r, d_keep, up->d_r, d_num, n_lines, st);
+  count_launch(6);
+  int32_t kept = 0;
+  MRS_TEXT_CUDA(cudaMemcpyAsync(&kept, d_num, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_TEXT_CUDA(cudaEventRecord(up->ev_ids, st));
+  MRS_TEXT_CUDA(cudaEventRecord(up->ev_values, st));
+  MRS_TEXT_CUDA(cudaStreamSynchronize(st));
+  up->n = kept;
+  cleanup();
+#undef MRS_TEXT_TRY
+#undef MRS_TEXT_CUDA
+  return ratings_from_upload(up, 0, 0, out);
+}
+
+}  // namespace
+}  // namespace mrs
+
+extern "C" int32_t mrs_ratings_from_text(mrs_engine* e, const char* text, int64_t nbytes, const char* sep, mrs_ratings** out) {
+  return ratings_from_text(e, text, nbytes, sep, "<text>", out);
+}
+
 extern "C" int32_t mrs_ratings_from_file(mrs_engine* e, const char* path, const char* sep, mrs_ratings** out) {
   MRS_REQUIRE(e && path && sep && out && sep[0], MRS_ERR_INVALID, "mrs_ratings_from_file: NULL/empty argument");
   FILE* f = fopen(path, "rb");
@@ -459,60 +701,12 @@ extern "C" int32_t mrs_ratings_from_file(mrs_engine* e, const char* path, const 
     fseek(f, 0, SEEK_END);
     long sz = ftell(f);
     fseek(f, 0, SEEK_SET);
-    buf.resize((size_t)std::max(0L, sz) + 1);
-    size_t got = fread(buf.data(), 1, (size_t)std::max(0L, sz), f);
-    buf.resize(got + 1);
-    buf[got] = '\n';
+    buf.resize((size_t)std::max(0L, sz));
+    size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+    buf.resize(got);
     fclose(f);
   }
-  const size_t seplen = strlen(sep);
-  std::vector<int32_t> us, is;
-  std::vector<double> rs;
-  const char* p = buf.data();
-  const char* end = buf.data() + buf.size();
-  int64_t lineno = 0;
-  while (p < end) {
-    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-    if (!nl) nl = end;
-    const char* le = nl;
-    if (le > p && le[-1] == '\r') --le;  // textFile strips \r\n as well as \n
-    ++lineno;
-    {
-      // split(sep): first three columns
-      const char* c[4] = {p, nullptr, nullptr, nullptr};
-      const char* ce[4] = {le, le, le, le};
-      int nc = 1;
-      const char* q = p;
-      while (nc < 4) {
-        const char* hit = nullptr;
-        for (const char* t = q; t + seplen <= le; ++t)
-          if (memcmp(t, sep, seplen) == 0) { hit = t; break; }
-        if (!hit) break;
-        ce[nc - 1] = hit;
-        c[nc] = hit + seplen;
-        q = hit + seplen;
-        ++nc;
-      }
-      int32_t uu = 0, ii = 0;
-      if (parse_java_int(c[0], ce[0], &uu)) {  // P:40: rows whose column 0 is not an Int are dropped (header skip)
-        if (nc < 3 || !parse_java_int(c[1], ce[1], &ii)) {
-          set_error("mrs_ratings_from_file: %s:%lld: malformed row (the reference throws at predictions.scala:41)", path, (long long)lineno);
-          return MRS_ERR_IO;
-        }
-        std::string tok(c[2], ce[2]);
-        char* endp = nullptr;
-        double rr = strtod(tok.c_str(), &endp);
-        while (endp && *endp && (unsigned char)*endp <= ' ') ++endp;
-        if (endp == tok.c_str() || (endp && *endp)) {
-          set_error("mrs_ratings_from_file: %s:%lld: rating is not a number", path, (long long)lineno);
-          return MRS_ERR_IO;
-        }
-        us.push_back(uu); is.push_back(ii); rs.push_back(rr);
-      }
-    }
-    p = nl + 1;
-  }
-  return build_ratings(e, us.data(), is.data(), rs.data(), (int64_t)us.size(), 0, 0, out);
+  return ratings_from_text(e, buf.data(), (int64_t)buf.size(), sep, path, out);
 }
 
 extern "C" int32_t mrs_ratings_info(const mrs_ratings* r, int64_t* n, int32_t* n_users_dim, int32_t* n_items_dim, int32_t* value_kind) {

@@ -23,7 +23,7 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
-    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
+    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
     "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_exchange_status", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
@@ -82,6 +82,7 @@ def lib():
         "mrs_ratings_from_upload": (i32, [vp, i32, i32, P(vp)]),
         "mrs_upload_destroy": (None, [vp]),
         "mrs_ratings_from_file": (i32, [vp, C.c_char_p, C.c_char_p, P(vp)]),
+        "mrs_ratings_from_text": (i32, [vp, C.c_char_p, i64, C.c_char_p, P(vp)]),
         "mrs_ratings_info": (i32, [vp, P(i64), P(i32), P(i32), P(i32)]),
         "mrs_ratings_bytes": (i32, [vp, P(i64)]),
         "mrs_ratings_layout_info": (i32, [vp, P(i64)]),
@@ -183,6 +184,9 @@ class Engine:
         """Start the host -> device copies of a rating set on the engine's copy stream and return at once; build the set
         with ``Upload.ratings()``.  Lets the copies of a second set (test) run while the first (train) is being built."""
         return Upload(self, users, items, ratings)
+
+    def ratings_from_text(self, text, sep):
+        return Ratings.from_text(self, text, sep)
 
     def ratings_from_file(self, path, sep):
         return Ratings.from_file(self, path, sep)
@@ -296,6 +300,14 @@ class Ratings:
     def from_file(cls, engine, path, sep):
         h = C.c_void_p()
         _check(lib().mrs_ratings_from_file(engine._h, os.fsencode(path), sep.encode(), C.byref(h)))
+        return cls(engine, None, None, None, _handle=h)
+
+    @classmethod
+    def from_text(cls, engine, text, sep):
+        """Parse ``text`` (bytes) on the device with the rules of the reference's ``load`` (P:35-49)."""
+        data = bytes(text)
+        h = C.c_void_p()
+        _check(lib().mrs_ratings_from_text(engine._h, data, len(data), sep.encode(), C.byref(h)))
         return cls(engine, None, None, None, _handle=h)
 
     def bytes(self):

@@ -194,3 +194,34 @@ def test_ml25m_shape_full_size(eng):
     assert float((idv * cnt_i).sum()) == pytest.approx(float(dev.sum()), rel=1e-9, abs=1e-6)
     p = m.predict(te[0][:200000], te[1][:200000], E.PRED_BASELINE)
     assert p.min() >= 0.5 - 1e-9 and p.max() <= 5.0 + 1e-9
+
+
+def test_device_text_parser_follows_the_reference_rules(eng):
+    """`load` (P:35-49): split on the separator, trim every column, keep the row iff column 0 is an Int; column 1 must be
+    an Int and column 2 a Double.  Parsed on the device; odd number forms go through the host parser with the same result."""
+    def parse(text, sep):
+        R = eng.ratings_from_text(text, sep)
+        m = E.Model(eng, R)
+        n = R.n
+        ua, uc = m.vector(E.USER_AVG)
+        ia, ic = m.vector(E.ITEM_AVG)
+        out = (n, {u: ua[u] for u in np.flatnonzero(uc)}, {i: ia[i] for i in np.flatnonzero(ic)})
+        m.close(); R.close()
+        return out
+
+    plain = b"userId::movieId::rating::ts\n 1 :: 10 :: 4.5 ::99\n2::10::3\n\n+3::11::0.5::x::y\r\nabc::1::1\n2::11:: 5.0\n7::12::.5\n7::13::2."
+    n, ua, ia = parse(plain, "::")
+    assert n == 6                                                       # header, blank line and the `abc` row are dropped
+    assert ua == {1: 4.5, 2: 4.0, 3: 0.5, 7: 1.25} and ia == {10: 3.75, 11: 2.75, 12: 0.5, 13: 2.0}
+    odd = plain + b"\n9::14::1e0\n9::15::0x1p1\n"                      # exponent / hex forms: host parser, same rows plus two
+    n2, ua2, ia2 = parse(odd, "::")
+    assert n2 == 8 and ua2[9] == 1.5 and ia2[15] == 2.0 and {k: v for k, v in ua2.items() if k != 9} == ua
+    assert parse(b"1\t2\t3.25\n", "\t")[0] == 1 and eng.ratings_from_text(b"", ",").n == 0
+    assert parse(b"1,2,0.1\n1,3,0.7\n", ",")[1] == {1: (0.1 + 0.7) / 2}                                    # correctly rounded
+    assert parse(b"1,2,0.1\n1,3,0.30000000000000004\n", ",")[1] == {1: (0.1 + 0.30000000000000004) / 2}   # 17 digits: host parser
+    for bad in (b"1,2\n", b"1,x,3\n", b"5,6,7\n1,2,\n", b"1,2,abc\n"):
+        with pytest.raises(E.MrsError) as ei:
+            eng.ratings_from_text(bad, ",")
+        assert ei.value.status == -5
+    with pytest.raises(E.MrsError):
+        eng.ratings_from_text(b"-1,2,3\n", ",")                        # negative id: rejected by the build, as from arrays
