@@ -140,7 +140,15 @@ __global__ void __launch_bounds__(256) dev_pre_kernel(const VT* __restrict__ uva
     }
     const double d2 = __dmul_rn(d, d);  // math.pow(y, 2), P:474
     const int cnt = min(32, e - base);
-    for (int j = 0; j < cnt; ++j) ss = __dadd_rn(ss, __shfl_sync(0xffffffffu, d2, j));  // ascending item id
+    if (cnt == 32) {  // full chunk: the 32 broadcasts are independent and go out together, only the additions form a chain
+      double t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = __shfl_sync(0xffffffffu, d2, j);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ss = __dadd_rn(ss, t[j]);  // ascending item id
+    } else {
+      for (int j = 0; j < cnt; ++j) ss = __dadd_rn(ss, __shfl_sync(0xffffffffu, d2, j));  // ascending item id
+    }
   }
   const double w = __dsqrt_rn(ss);
   if (lane == 0) unorm[c] = w;
@@ -313,11 +321,11 @@ __global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __re
       const double pk0 = sk[e0 ^ stride], pk1 = sk[e1 ^ stride];
       const int32_t pi0 = si[e0 ^ stride], pi1 = si[e1 ^ stride];
       __syncthreads();
+      // (similarity, id) pairs are distinct, so "partner after mine" is the negation of "partner before mine"; the only
+      // equal pairs are padding slots, and swapping two of those changes nothing
       const bool keep_first = (((e0 & stride) == 0) == up);
-      const bool b0 = before(pk0, pi0, k0, i0), b1 = before(pk1, pi1, k1, i1);
-      const bool a0 = before(k0, i0, pk0, pi0), a1 = before(k1, i1, pk1, pi1);
-      if (keep_first ? b0 : a0) { k0 = pk0; i0 = pi0; }
-      if (keep_first ? b1 : a1) { k1 = pk1; i1 = pi1; }
+      if (before(pk0, pi0, k0, i0) == keep_first) { k0 = pk0; i0 = pi0; }
+      if (before(pk1, pi1, k1, i1) == keep_first) { k1 = pk1; i1 = pi1; }
     }
 #pragma unroll
     for (int32_t stride = 32; stride >= 2; stride >>= 1) {
@@ -326,10 +334,8 @@ __global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __re
         const double pk0 = __shfl_xor_sync(0xffffffffu, k0, m), pk1 = __shfl_xor_sync(0xffffffffu, k1, m);
         const int32_t pi0 = __shfl_xor_sync(0xffffffffu, i0, m), pi1 = __shfl_xor_sync(0xffffffffu, i1, m);
         const bool keep_first = (((e0 & stride) == 0) == up);
-        const bool b0 = before(pk0, pi0, k0, i0), b1 = before(pk1, pi1, k1, i1);
-        const bool a0 = before(k0, i0, pk0, pi0), a1 = before(k1, i1, pk1, pi1);
-        if (keep_first ? b0 : a0) { k0 = pk0; i0 = pi0; }
-        if (keep_first ? b1 : a1) { k1 = pk1; i1 = pi1; }
+        if (before(pk0, pi0, k0, i0) == keep_first) { k0 = pk0; i0 = pi0; }
+        if (before(pk1, pi1, k1, i1) == keep_first) { k1 = pk1; i1 = pi1; }
       }
     }
     // distance 1: both elements are this thread's
