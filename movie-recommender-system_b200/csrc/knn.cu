@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(256) dev_pre_kernel(const VT* __restrict__ uva
                                                      const int32_t* __restrict__ known_user, int32_t n_known,
                                                      const double* __restrict__ uavg, double* __restrict__ udev,
                                                      double* __restrict__ upre, double* __restrict__ unorm) {
+  pdl_trigger();  // every kernel of the kNN closure is launched with programmatic dependent launch: its launch latency
+  pdl_wait();     // overlaps the tail of its predecessor (7 kernels of 7-100 us each); its inputs are complete from here on
   const int lane = threadIdx.x & 31;
   const int32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= n_known) return;
@@ -160,6 +162,8 @@ template <int MODE>  // 0: deviations only (uniform); 1: cosine; 2: jaccard
 __global__ void gather_values_kernel(const double* __restrict__ udev, const double* __restrict__ upre,
                                      const int32_t* __restrict__ csc_src, int64_t n, const int32_t* __restrict__ ell_src,
                                      int64_t ell_entries, double* __restrict__ cdev, double* __restrict__ ell_val) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += stride) cdev[p] = udev[csc_src[p]];
   if (MODE != 0) {
@@ -186,7 +190,9 @@ __global__ void __launch_bounds__(kSimThreads) similarity_kernel(const int32_t* 
   constexpr int kStride = (UB >= 4) ? UB + 2 : UB;
   extern __shared__ __align__(16) double su[];
   const int32_t cu0 = blockIdx.x * UB;
-  for (int32_t x = threadIdx.x; x < n_items * kStride; x += blockDim.x) su[x] = 0.0;
+  pdl_trigger();
+  for (int32_t x = threadIdx.x; x < n_items * kStride; x += blockDim.x) su[x] = 0.0;  // overlaps the previous kernel
+  pdl_wait();
   __syncthreads();
 #pragma unroll
   for (int t = 0; t < UB; ++t) {
@@ -280,6 +286,8 @@ __global__ void __launch_bounds__(512) sort_rank_kernel(const double* __restrict
                                                        int32_t* __restrict__ nbr_id, double* __restrict__ nbr_sim) {
   extern __shared__ double sh_key[];
   int32_t* sh_id = (int32_t*)(sh_key + P);
+  pdl_trigger();
+  pdl_wait();
   const int32_t cu = blockIdx.x;
   for (int32_t x = threadIdx.x; x < P; x += blockDim.x) {
     const bool cand = (x < n_known && x != cu);  // P:608 allUsers - u
@@ -306,6 +314,8 @@ __global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __re
                                                              double* __restrict__ nbr_sim) {
   __shared__ double sk[P];
   __shared__ int32_t si[P];
+  pdl_trigger();
+  pdl_wait();
   const int32_t cu = blockIdx.x;
   const int32_t e0 = 2 * threadIdx.x, e1 = e0 + 1;
   const bool c0 = (e0 < n_known && e0 != cu), c1 = (e1 < n_known && e1 != cu);  // P:608 allUsers - u
@@ -406,6 +416,8 @@ __global__ void __launch_bounds__(256) pers_mae_kernel(const int32_t* __restrict
                                                       unsigned int* __restrict__ counter, double* __restrict__ out2) {
   __shared__ double sh[8];
   __shared__ bool is_last;
+  pdl_trigger();
+  pdl_wait();
   const double gavg = gavg_p[0];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   double acc = 0.0;  // identical in every lane of the warp
@@ -467,8 +479,8 @@ int32_t launch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
   const size_t smem = (size_t)R->n_items * ((UB >= 4) ? UB + 2 : UB) * sizeof(double);
   MRS_CUDA(cudaFuncSetAttribute(similarity_kernel<UB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (L.n_known + UB - 1) / UB;
-  similarity_kernel<UB, MODE><<<grid, kSimThreads, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.n_known, R->n_items, L.perm,
-                                                       L.slice_off, L.n_slices, L.ell_col, s->ell_val, s->S);
+  MRS_CUDA(launch_pdl(similarity_kernel<UB, MODE>, dim3(grid), dim3(kSimThreads), smem, st, R->urow, R->ucol, s->upre, L.known_user, L.n_known,
+                      R->n_items, L.perm, L.slice_off, L.n_slices, L.ell_col, s->ell_val, s->S));
   mark(R->eng, "similarity");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
@@ -560,9 +572,11 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
   // P1
   const int wpb = 8;
   if (R->value_kind == kValueCode)
-    dev_pre_kernel<uint8_t><<<(L.n_known + wpb - 1) / wpb, 256, 0, st>>>((const uint8_t*)R->uval, R->urow, L.known_user, L.n_known, m->uavg, s->udev, s->upre, s->unorm);
+    MRS_CUDA(launch_pdl(dev_pre_kernel<uint8_t>, dim3((L.n_known + wpb - 1) / wpb), dim3(256), 0, st, (const uint8_t*)R->uval, R->urow, L.known_user,
+                        L.n_known, m->uavg, s->udev, s->upre, s->unorm));
   else
-    dev_pre_kernel<double><<<(L.n_known + wpb - 1) / wpb, 256, 0, st>>>((const double*)R->uval, R->urow, L.known_user, L.n_known, m->uavg, s->udev, s->upre, s->unorm);
+    MRS_CUDA(launch_pdl(dev_pre_kernel<double>, dim3((L.n_known + wpb - 1) / wpb), dim3(256), 0, st, (const double*)R->uval, R->urow, L.known_user,
+                        L.n_known, m->uavg, s->udev, s->upre, s->unorm));
   mark(e, "dev_pre");
   if (rows) {
     MRS_CUDA(cudaGetLastError());
@@ -571,9 +585,9 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
   // P2
   const int64_t work = std::max<int64_t>(R->n, matrix ? L.ell_entries : 0);
   const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)e->sm_count * 8));
-  if (kind == MRS_SIM_UNIFORM) gather_values_kernel<0><<<g2, 256, 0, st>>>(s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val);
-  else if (kind == MRS_SIM_COSINE) gather_values_kernel<1><<<g2, 256, 0, st>>>(s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val);
-  else gather_values_kernel<2><<<g2, 256, 0, st>>>(s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val);
+  if (kind == MRS_SIM_UNIFORM) MRS_CUDA(launch_pdl(gather_values_kernel<0>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val));
+  else if (kind == MRS_SIM_COSINE) MRS_CUDA(launch_pdl(gather_values_kernel<1>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val));
+  else MRS_CUDA(launch_pdl(gather_values_kernel<2>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val));
   mark(e, "gather_values");
   MRS_CUDA(cudaGetLastError());
   if (!matrix) return MRS_OK;
@@ -584,15 +598,15 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
   int32_t P = 2;
   while (P < L.n_known) P <<= 1;
   if (P <= 512) {
-    sort_rank_reg_kernel<512><<<L.n_known, 256, 0, st>>>(s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim);
+    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<512>, dim3(L.n_known), dim3(256), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim));
   } else if (P == 1024) {
-    sort_rank_reg_kernel<1024><<<L.n_known, 512, 0, st>>>(s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim);
+    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<1024>, dim3(L.n_known), dim3(512), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim));
   } else if (P == 2048) {
-    sort_rank_reg_kernel<2048><<<L.n_known, 1024, 0, st>>>(s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim);
+    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<2048>, dim3(L.n_known), dim3(1024), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim));
   } else {
     const size_t smem = (size_t)P * (sizeof(double) + sizeof(int32_t));
     MRS_CUDA(cudaFuncSetAttribute(sort_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sort_rank_kernel<<<L.n_known, 512, smem, st>>>(s->S, L.known_user, L.n_known, P, s->rank, s->nbr_id, s->nbr_sim);
+    MRS_CUDA(launch_pdl(sort_rank_kernel, dim3(L.n_known), dim3(512), smem, st, s->S, L.known_user, L.n_known, P, s->rank, s->nbr_id, s->nbr_sim));
   }
   mark(e, "sort_rank");
   MRS_CUDA(cudaGetLastError());
@@ -613,10 +627,10 @@ int32_t mae_personalized_async(const mrs_model* m, const mrs_sim* s, const mrs_r
   const int wpb = 8;
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>((T->n + wpb - 1) / wpb, (int64_t)s->mae_part_cap));
   const int mode = sim_mode(s);
-#define MRS_PERS_MAE(VT, MODE)                                                                                              \
-  pers_mae_kernel<VT, MODE><<<grid, 256, 0, st>>>(T->coo_u, T->ucol, (const VT*)T->uval, T->n, m->n_users, m->n_items, m->uavg, \
-                                                  m->gavg, R->icolp, R->irow, s->cdev, L.cidx, s->S, s->rank, L.n_known, s->k,  \
-                                                  s->mae_part, s->counter, d_out2)
+#define MRS_PERS_MAE(VT, MODE)                                                                                                   \
+  MRS_CUDA(launch_pdl(pers_mae_kernel<VT, MODE>, dim3(grid), dim3(256), 0, st, T->coo_u, T->ucol, (const VT*)T->uval, T->n, m->n_users,   \
+                      m->n_items, m->uavg, m->gavg, R->icolp, R->irow, s->cdev, L.cidx, s->S, s->rank, L.n_known, s->k, s->mae_part, \
+                      s->counter, d_out2))
   if (T->value_kind == kValueCode) {
     if (mode == 0) MRS_PERS_MAE(uint8_t, 0); else if (mode == 1) MRS_PERS_MAE(uint8_t, 1); else MRS_PERS_MAE(uint8_t, 2);
   } else {
