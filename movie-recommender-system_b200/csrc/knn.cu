@@ -175,7 +175,7 @@ __global__ void gather_values_kernel(const double* __restrict__ udev, const doub
 }
 
 // ---------------- P3: user-user similarity, shared-memory-staged SpGEMM --------------------------------------------
-constexpr int kSimThreads = 1024;  // 32 warps: about one slice per warp at ml-100k shape (943 users = 30 slices)
+constexpr int kSimThreads = 512;  // 16 warps with up to 128 registers each (see the slice loop)
 template <int UB, int MODE>  // MODE 1: cosine (P:424-426), 2: jaccard (P:454-458)
 __global__ void __launch_bounds__(kSimThreads) similarity_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol,
                                                         const double* __restrict__ upre, const int32_t* __restrict__ known_user,
@@ -204,7 +204,16 @@ __global__ void __launch_bounds__(kSimThreads) similarity_kernel(const int32_t* 
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  for (int32_t slice = threadIdx.x >> 5; slice < n_slices; slice += (blockDim.x >> 5)) {
+  // Slices are sorted by width (the 32 longest rows first: ~750 items against ~20 for the last slice) and the sum of one
+  // (u, v) pair is a serial chain over the slice's rows, so the kernel lasts as long as the warp that owns the widest slice
+  // (capture r01_ncu_full_raw_knn_final.csv: 18 % of the warp slots active, the critical warps waiting on the column loads
+  // of every batch and on each row's shared-memory loads in turn).  Hence: 16 warps with up to 128 registers each; slices
+  // dealt out in a snake so every warp gets wide and narrow ones; the next batch of (column, value) pairs is requested while
+  // the current one is accumulated; the shared-memory loads of four rows go out together before their products are added.
+  const int32_t nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5;
+  for (int32_t round = 0; round * nwarps < n_slices; ++round) {
+    const int32_t slice = round * nwarps + ((round & 1) ? nwarps - 1 - wid : wid);
+    if (slice >= n_slices) continue;
     const int32_t cv = perm[slice * 32 + lane];
     const int32_t base = slice_off[slice], width = slice_off[slice + 1] - base;
     double acc[UB];
@@ -212,28 +221,48 @@ __global__ void __launch_bounds__(kSimThreads) similarity_kernel(const int32_t* 
     for (int t = 0; t < UB; ++t) acc[t] = 0.0;
     const int32_t* colp = ell_col + ((int64_t)base << 5) + lane;
     const double* valp = ell_val + ((int64_t)base << 5) + lane;
-    constexpr int kB = 8;  // rows of the slice requested before the first use (the row walk is a serial chain otherwise)
+    constexpr int kB = 8;   // rows per batch of global loads
+    constexpr int kH = 4;   // rows whose shared-memory loads are issued together
+    int32_t ncol[kB];
+    double nval[kB];
+#pragma unroll
+    for (int q = 0; q < kB; ++q) {
+      const bool in = q < width;
+      ncol[q] = in ? __ldg(colp + ((int64_t)q << 5)) : 0;
+      nval[q] = in ? __ldg(valp + ((int64_t)q << 5)) : 0.0;  // padding: +/-0 products leave the sums unchanged
+    }
     for (int32_t j0 = 0; j0 < width; j0 += kB) {
       int32_t col[kB];
       double val[kB];
 #pragma unroll
-      for (int k = 0; k < kB; ++k) {
-        const bool in = j0 + k < width;
-        col[k] = in ? __ldg(colp + ((int64_t)(j0 + k) << 5)) : 0;
-        val[k] = in ? __ldg(valp + ((int64_t)(j0 + k) << 5)) : 0.0;  // padding: +/-0 products leave the sums unchanged
+      for (int q = 0; q < kB; ++q) { col[q] = ncol[q]; val[q] = nval[q]; }
+#pragma unroll
+      for (int q = 0; q < kB; ++q) {
+        const bool in = j0 + kB + q < width;
+        ncol[q] = in ? __ldg(colp + ((int64_t)(j0 + kB + q) << 5)) : 0;
+        nval[q] = in ? __ldg(valp + ((int64_t)(j0 + kB + q) << 5)) : 0.0;
       }
 #pragma unroll
-      for (int k = 0; k < kB; ++k) {
-        const double* row = su + col[k] * kStride;
+      for (int h = 0; h < kB; h += kH) {
         if (UB >= 2) {
+          double2 v[kH][UB >= 2 ? UB / 2 : 1];
 #pragma unroll
-          for (int t = 0; t < UB; t += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(row + t);
-            acc[t] = __dadd_rn(acc[t], __dmul_rn(v.x, val[k]));  // ascending item id, no FMA
-            acc[t + (UB >= 2 ? 1 : 0)] = __dadd_rn(acc[t + (UB >= 2 ? 1 : 0)], __dmul_rn(v.y, val[k]));
+          for (int q = 0; q < kH; ++q) {
+            const double* row = su + col[h + q] * kStride;
+#pragma unroll
+            for (int t = 0; t < UB; t += 2) v[q][t / 2] = *reinterpret_cast<const double2*>(row + t);
+          }
+#pragma unroll
+          for (int q = 0; q < kH; ++q) {
+#pragma unroll
+            for (int t = 0; t < UB; t += 2) {
+              acc[t] = __dadd_rn(acc[t], __dmul_rn(v[q][t / 2].x, val[h + q]));  // ascending item id, no FMA
+              acc[t + (UB >= 2 ? 1 : 0)] = __dadd_rn(acc[t + (UB >= 2 ? 1 : 0)], __dmul_rn(v[q][t / 2].y, val[h + q]));
+            }
           }
         } else {
-          acc[0] = __dadd_rn(acc[0], __dmul_rn(row[0], val[k]));
+#pragma unroll
+          for (int q = 0; q < kH; ++q) acc[0] = __dadd_rn(acc[0], __dmul_rn(su[col[h + q] * kStride], val[h + q]));
         }
       }
     }
