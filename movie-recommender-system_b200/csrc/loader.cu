@@ -93,10 +93,6 @@ __global__ void gather_sorted_kernel(const int32_t* __restrict__ src, int64_t n,
   }
 }
 
-__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
 __global__ void chunk_count_kernel(const int32_t* __restrict__ seg_ptr, int32_t n_seg, int32_t chunk, int32_t* __restrict__ counts) {
   int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n_seg) {
