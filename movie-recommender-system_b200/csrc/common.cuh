@@ -173,6 +173,8 @@ struct mrs_ratings {
     int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
     int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
     int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
+    int2* warp_part = nullptr;         // [n_tiles * part_ctas * 32] slices [x, y) of every warp of the item pass (static: the
+    int32_t part_ctas = 0;             //  cost-balanced partition depends on the layout and the CTAs per tile only)
   };
   mutable tiled_layout tl;
   // ---- lazily built item-tiled layout for the fused predict + |error| kernel (mae_tiled.cu); half-star codes only

@@ -191,9 +191,26 @@ __device__ __forceinline__ void hand_over(int32_t item, double acc, uint32_t csu
   }
 }
 
+// slices [x, y) of every warp of the item pass: an equal share of its tile's cost, rounded to whole slices
+__global__ void __launch_bounds__(kTiledThreads) item_partition_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ tile_slice_ptr,
+                                                                      int32_t ctas_per_tile, int2* __restrict__ warp_part) {
+  if ((threadIdx.x & 31) != 0) return;
+  const int32_t tile = blockIdx.x / ctas_per_tile, share = blockIdx.x % ctas_per_tile;
+  constexpr int32_t wpb = kTiledThreads >> 5;
+  const int32_t wid = threadIdx.x >> 5;
+  const int32_t ts0 = tile_slice_ptr[tile], ts1 = tile_slice_ptr[tile + 1];
+  const int32_t ra = __ldg(slice_off + ts0), rb = __ldg(slice_off + ts1);
+  const int32_t nw = ctas_per_tile * wpb, w = share * wpb + wid;
+  const int64_t total_cost = (int64_t)(rb - ra) + (int64_t)kSliceCost * (ts1 - ts0);
+  const int32_t c_lo = (int32_t)((total_cost * w) / nw), c_hi = (int32_t)((total_cost * (w + 1)) / nw);
+  const int32_t cur = lower_bound_cost(slice_off, ts0, ts1, ra, c_lo);   // slices whose cost prefix lies in [c_lo, c_hi)
+  const int32_t s_hi = lower_bound_cost(slice_off, ts0, ts1, ra, c_hi);
+  warp_part[(size_t)blockIdx.x * wpb + wid] = make_int2(cur, s_hi);
+}
+
 template <bool WITH_SUM>
 __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint32_t* __restrict__ entry, const int32_t* __restrict__ slice_off,
-                                                                     const int32_t* __restrict__ tile_slice_ptr, int32_t ctas_per_tile,
+                                                                     const int2* __restrict__ warp_part, int32_t ctas_per_tile,
                                                                      const uint32_t* __restrict__ usum, const int32_t* __restrict__ urow,
                                                                      int32_t n_users, const int32_t* __restrict__ slot_item,
                                                                      double* __restrict__ uavg, long long* __restrict__ xdev_fix,
@@ -217,13 +234,11 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
 
   // ---- this warp's slices: an equal share of the tile's cost, rounded to whole slices
   // (cost of a slice = its rows + kSliceCost for handing over 32 unit sums; the tail of a tile is made of 1-2 row slices)
-  const int32_t ts0 = tile_slice_ptr[tile], ts1 = tile_slice_ptr[tile + 1];
-  const int32_t ra = __ldg(slice_off + ts0), rb = __ldg(slice_off + ts1);
-  const int32_t nw = ctas_per_tile * wpb, w = share * wpb + wid;
-  const int64_t total_cost = (int64_t)(rb - ra) + (int64_t)kSliceCost * (ts1 - ts0);
-  const int32_t c_lo = (int32_t)((total_cost * w) / nw), c_hi = (int32_t)((total_cost * (w + 1)) / nw);
-  int32_t cur = lower_bound_cost(slice_off, ts0, ts1, ra, c_lo);   // slices whose cost prefix lies in [c_lo, c_hi)
-  const int32_t s_hi = lower_bound_cost(slice_off, ts0, ts1, ra, c_hi);
+  // (the partition is static: item_partition_kernel ran the two binary searches per warp once, when the layout was built --
+  // 28 dependent loads that used to open every pass)
+  const int2 part = __ldg(warp_part + (size_t)blockIdx.x * wpb + wid);
+  int32_t cur = part.x;
+  const int32_t s_hi = part.y;
   const int32_t r0 = (cur < s_hi) ? __ldg(slice_off + cur) : 0;
   const int32_t r_end = (cur < s_hi) ? __ldg(slice_off + s_hi) : 0;
   const int32_t n_chunks = (r_end - r0 + kRows - 1) / kRows;
@@ -350,7 +365,7 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
 
 void free_tiled_layout(const mrs_ratings* R) {
   auto& T = R->tl;
-  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.slot_item);
+  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.slot_item); dev_free(T.warp_part);
   T = mrs_ratings::tiled_layout();
 }
 
@@ -481,11 +496,21 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
   // one CTA of 1024 threads per SM; every tile gets the same number of CTAs and the grid never exceeds one wave
   const int32_t ctas_per_tile = std::max(1, e->sm_count / T.n_tiles);
   const dim3 grid2(T.n_tiles * ctas_per_tile), block2(kTiledThreads);
+  if (T.part_ctas != ctas_per_tile) {  // first pass on this engine (or another SM count): lay the static partition down
+    auto& TL = R->tl;
+    dev_free(TL.warp_part);
+    TL.warp_part = nullptr;
+    MRS_TRY(dev_alloc(&TL.warp_part, (size_t)grid2.x * (kTiledThreads / 32)));
+    item_partition_kernel<<<grid2, block2, 0, st>>>(T.slice_off, T.tile_slice_ptr, ctas_per_tile, TL.warp_part);
+    count_launch();
+    MRS_CUDA(cudaGetLastError());
+    TL.part_ctas = ctas_per_tile;
+  }
   if (m->want_item_avg)
-    MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.tile_slice_ptr, ctas_per_tile, m->usum, R->urow,
+    MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow,
                         R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
   else
-    MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.tile_slice_ptr, ctas_per_tile, m->usum, R->urow,
+    MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow,
                         R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
   mark(e, "item_tiled");
   MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
