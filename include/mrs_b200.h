@@ -167,7 +167,9 @@ MRS_API void mrs_model_destroy(mrs_model* m);
  * mrs_exchange_allreduce_async then sums `n_doubles` fp64 values in place across the ranks IN RANK ORDER (bit-identical
  * result everywhere) with one kernel: publish, flag the peers, wait, 128-bit peer loads.  Replaces the NCCL all-reduce of
  * the exchange buffer (P:267-268, P:247) and of {sum |err|, n}; can be captured in a CUDA graph.  Every rank must issue
- * the same sequence of calls.  A peer that never arrives makes the kernel give up after ~2 s: mrs_exchange_status. */
+ * the same sequence of calls.  A peer that never arrives makes the kernel give up after ~2 s (mrs_exchange_set_timeout_ms):
+ * it then overwrites the caller's buffer with NaN (nothing downstream can pass for a result) and sets an error word that
+ * mrs_exchange_status reads; once the host has seen it the handle refuses further exchanges (MRS_ERR_CUDA). */
 MRS_API int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t rank, int32_t world, void* ipc_handle_out64, mrs_exchange** out);
 MRS_API int32_t mrs_exchange_connect(mrs_exchange* x, const void* all_handles_world_x_64);
 MRS_API int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout, int64_t n_doubles);
@@ -176,6 +178,7 @@ MRS_API int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout
  * its slots are zero on every rank (72 % at ml-25m shape), and the slots in use are known once the rating sets are loaded. */
 MRS_API int32_t mrs_exchange_allreduce_indexed_async(mrs_exchange* x, void* device_inout, const int32_t* device_idx, int64_t n_idx);
 MRS_API int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out);
+MRS_API int32_t mrs_exchange_set_timeout_ms(mrs_exchange* x, int64_t milliseconds);
 /* diagnostics: %globaltimer (ns) of block 0 in the last exchange: [0] start, [1] published, [2] first barrier passed,
  * [3] slice reduced, [4] second barrier passed (two-shot only), [5] done */
 MRS_API int32_t mrs_exchange_stamps(mrs_exchange* x, uint64_t* out8);

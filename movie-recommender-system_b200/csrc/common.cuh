@@ -90,6 +90,9 @@ struct mrs_engine {
   std::unordered_multimap<size_t, void*> free_blocks;
   std::unordered_map<void*, size_t> live_blocks;
   size_t cached_bytes = 0;
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remembered per engine, not per process
+  // (bit 0: item pass kernels, bit 1: test pass kernel)
+  uint32_t smem_attr_done = 0;
   // diagnostics: event after every launch while profiling (mrs_profile_begin/end)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;

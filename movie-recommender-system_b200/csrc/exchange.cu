@@ -31,6 +31,8 @@ struct mrs_exchange {
   int32_t* d_error = nullptr;
   unsigned long long* d_stamps = nullptr;  // [8] globaltimer stamps of block 0 in the last exchange (diagnostics)
   bool connected = false;
+  bool failed = false;           // a timed-out exchange was observed by the host: the handle refuses further exchanges
+  long long timeout_cycles = 4000000000LL;  // bound of every flag wait (~2 s at 1.9 GHz); mrs_exchange_set_timeout_ms
 };
 
 namespace mrs {
@@ -63,7 +65,8 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned l
 // NVLink stores go out together instead of one release-store after the other (8 ranks: 20 us -> a few us).  Then thread
 // p of every block polls rank p's flag in OUR row.  Returns false if a peer did not show up within ~2 s.
 __device__ __forceinline__ bool rank_barrier(double* const* __restrict__ peer, int32_t rank, int32_t world, int64_t cap, int which,
-                                             unsigned long long epoch, unsigned int* __restrict__ done, int32_t* __restrict__ error) {
+                                             unsigned long long epoch, unsigned int* __restrict__ done, int32_t* __restrict__ error,
+                                             long long timeout_cycles) {
   __shared__ int s_last;
   if (threadIdx.x == 0) {
     const int last = (atomicAdd(done, 1u) + 1u == gridDim.x);
@@ -82,7 +85,7 @@ __device__ __forceinline__ bool rank_barrier(double* const* __restrict__ peer, i
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peer[rank] + 4 * (size_t)cap) + (size_t)which * world;
     const long long t0 = clock64();
     while (ld_acquire_sys(mine + threadIdx.x) < epoch) {
-      if (clock64() - t0 > 4000000000LL) { atomicExch(error, 1); good = 0; break; }  // ~2 s at 1.9 GHz: a peer is missing
+      if (clock64() - t0 > timeout_cycles) { atomicExch(error, 1); good = 0; break; }  // a peer is missing
     }
   }
   return __syncthreads_and(good) != 0;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
                                                                    int64_t cap, int two_shot, unsigned long long* __restrict__ epoch_done,
                                                                    unsigned int* __restrict__ done, int32_t* __restrict__ error,
                                                                    unsigned long long* __restrict__ stamps, double* __restrict__ inout,
-                                                                   const int32_t* __restrict__ idx) {
+                                                                   const int32_t* __restrict__ idx, long long timeout_cycles) {
   // idx != nullptr: the exchange covers the n positions idx[0..n) of `inout` only (the slots that can be non-zero on some
   // rank -- 28 % of the exchange buffer at ml-25m shape, whose item ids are sparse); everything below works on the compact
   // array, only the first read and the last write go through the index list
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
   __threadfence();  // device scope: the barrier's last block makes everything visible system-wide before it raises the flags
   __syncthreads();
   if (stamp) stamps[1] = gtime();
-  ok = rank_barrier(peer, rank, world, cap, 0, epoch, done, error);  // (2) everybody has published
+  ok = rank_barrier(peer, rank, world, cap, 0, epoch, done, error, timeout_cycles);  // (2) everybody has published
   if (stamp) stamps[2] = gtime();
   if (ok && !two_shot) {
     // one-shot: every rank adds all partial sums, in rank order (identical everywhere); 2 x 128-bit peer loads per
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
     __threadfence();
     __syncthreads();
     if (stamp) stamps[3] = gtime();
-    ok = rank_barrier(peer, rank, world, cap, 1, epoch, done + 1, error);  // (4) every slice is reduced
+    ok = rank_barrier(peer, rank, world, cap, 1, epoch, done + 1, error, timeout_cycles);  // (4) every slice is reduced
     if (stamp) stamps[4] = gtime();
     if (ok) {
       // (5) ... and collect the reduced slices of all ranks
@@ -211,8 +214,13 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
   }
   __syncthreads();
   if (stamp) stamps[5] = gtime();
+  // A peer that never showed up (error word set by whichever block gave up): the sums are incomplete.  Poison the
+  // caller's buffer so that nothing downstream can pass for a result (the MAE becomes NaN), whatever this block saw.
+  if (*reinterpret_cast<volatile int32_t*>(error) != 0)
+    for (int64_t j = tid; j < n; j += nth) inout[idx ? __ldg(idx + j) : j] = nan("");
   if (threadIdx.x == 0 && atomicAdd(done + 2, 1u) + 1u == gridDim.x) {  // last block out: this exchange is complete
     done[2] = 0;
+    done[1] = 0;  // blocks that gave up in the first barrier never entered the second one: re-arm it
     *epoch_done = epoch;
   }
 }
@@ -288,6 +296,8 @@ static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_dou
   MRS_REQUIRE(n_doubles > 0 && n_doubles <= x->n, MRS_ERR_INVALID, "mrs_exchange_allreduce_async: %lld doubles exceed the capacity %lld",
               (long long)n_doubles, (long long)x->n);
   MRS_REQUIRE(((uintptr_t)device_inout & 15) == 0, MRS_ERR_INVALID, "mrs_exchange_allreduce_async: buffer must be 16-byte aligned");
+  MRS_REQUIRE(!x->failed, MRS_ERR_CUDA, "mrs_exchange_allreduce_async: an earlier exchange on this handle timed out (a peer was missing); "
+              "its results were poisoned with NaN and the handle is dead -- destroy it and create a new one");
   use_engine(x->eng);
   // every block waits on the flags: the grid must be co-resident (one CTA per SM at most)
   const int64_t work = (n_doubles + 1) / 2;
@@ -297,7 +307,7 @@ static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_dou
   // reads all the peers' buffers)
   const int two_shot = (x->world > 2 && (n_doubles & 1) == 0 && (int64_t)(x->world - 1) * n_doubles * 8 > (int64_t)12 << 20) ? 1 : 0;
   MRS_CUDA(launch_pdl(peer_allreduce_kernel, dim3(grid), dim3(kExThreads), 0, x->eng->stream, x->d_peer, x->rank, x->world, n_doubles, x->n,
-                      two_shot, x->d_epoch, x->d_done, x->d_error, x->d_stamps, (double*)device_inout, device_idx));
+                      two_shot, x->d_epoch, x->d_done, x->d_error, x->d_stamps, (double*)device_inout, device_idx, x->timeout_cycles));
   mark(x->eng, "peer_allreduce");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
@@ -308,6 +318,13 @@ extern "C" int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out) {
   use_engine(x->eng);
   MRS_CUDA(cudaMemcpyAsync(timed_out, x->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, x->eng->stream));
   MRS_CUDA(cudaStreamSynchronize(x->eng->stream));
+  if (*timed_out) x->failed = true;  // sticky: see allreduce_impl
+  return MRS_OK;
+}
+
+extern "C" int32_t mrs_exchange_set_timeout_ms(mrs_exchange* x, int64_t milliseconds) {
+  MRS_REQUIRE(x && milliseconds > 0, MRS_ERR_INVALID, "mrs_exchange_set_timeout_ms: bad argument");
+  x->timeout_cycles = (long long)milliseconds * 2000000LL;  // clock64 ticks at <= 2 GHz: the bound is at least `milliseconds`
   return MRS_OK;
 }
 

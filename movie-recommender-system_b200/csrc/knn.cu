@@ -290,6 +290,11 @@ __global__ void __launch_bounds__(kSimThreads) similarity_kernel(const int32_t* 
 __device__ __forceinline__ bool before(double ka, int32_t ia, double kb, int32_t ib) {
   return (ka > kb) || (ka == kb && ia < ib);
 }
+// A NaN similarity (a user whose average is exactly 1.0 has scale 0 below it: deviation -inf, r~ NaN, like the JVM) is not
+// ordered by `before`; the sorting networks need a total order or they duplicate / drop elements and padding ids
+// (INT_MAX) reach the output.  NaN keys therefore rank as -inf (last, ties by id); the reference's sortWith has no
+// defined result for them either.
+__device__ __forceinline__ double sort_key(double s) { return s != s ? -INFINITY : s; }
 
 // in-shared-memory bitonic sort of P (power of two) (key,id) pairs into `before` order
 __device__ void bitonic_sort_shared(double* key, int32_t* id, int32_t P) {
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(512) sort_rank_kernel(const double* __restrict
   const int32_t cu = blockIdx.x;
   for (int32_t x = threadIdx.x; x < P; x += blockDim.x) {
     const bool cand = (x < n_known && x != cu);  // P:608 allUsers - u
-    sh_key[x] = cand ? S[(int64_t)cu * n_known + x] : -INFINITY;
+    sh_key[x] = cand ? sort_key(S[(int64_t)cu * n_known + x]) : -INFINITY;
     sh_id[x] = cand ? x : INT_MAX;
   }
   bitonic_sort_shared(sh_key, sh_id, P);
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __re
   const int32_t cu = blockIdx.x;
   const int32_t e0 = 2 * threadIdx.x, e1 = e0 + 1;
   const bool c0 = (e0 < n_known && e0 != cu), c1 = (e1 < n_known && e1 != cu);  // P:608 allUsers - u
-  double k0 = c0 ? S[(int64_t)cu * n_known + e0] : -INFINITY, k1 = c1 ? S[(int64_t)cu * n_known + e1] : -INFINITY;
+  double k0 = c0 ? sort_key(S[(int64_t)cu * n_known + e0]) : -INFINITY, k1 = c1 ? sort_key(S[(int64_t)cu * n_known + e1]) : -INFINITY;
   int32_t i0 = c0 ? e0 : INT_MAX, i1 = c1 ? e1 : INT_MAX;
 #pragma unroll 1
   for (int32_t size = 2; size <= P; size <<= 1) {

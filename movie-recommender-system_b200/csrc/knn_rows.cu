@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1)
         if (x < n_known && x != cu) {  // P:608 allUsers - u
           s = acc_all[xl];
           if (MODE == 2) s = s / (double)(nu + clen[x] - (int32_t)s);  // P:458
+          if (s != s) s = -INFINITY;  // NaN has no place in the (sim desc, id asc) order: it ranks last (see knn.cu sort_key)
           ok = before(s, x, tk, ti);
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);

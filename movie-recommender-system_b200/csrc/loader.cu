@@ -41,11 +41,12 @@ __global__ void scan_ids_kernel(const int32_t* __restrict__ u, const int32_t* __
 }
 
 __global__ void scan_values_kernel(const double* __restrict__ r, int64_t n, int32_t* __restrict__ stats) {
-  // stats[3] = number of ratings that are not k*0.5 in [0,127.5]
+  // stats[3] = number of ratings that are not k*0.5 in [0,127]: code 0xFF is the padding mark of the item-tiled test
+  // layout (mae_tiled.cu), so a rating of 127.5 sends the set to the fp64-valued kernels instead of being dropped
   int32_t bad = 0;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     double v = r[p] * 2.0;
-    if (!(v >= 0.0 && v <= 255.0 && v == floor(v))) bad++;
+    if (!(v >= 0.0 && v <= 254.0 && v == floor(v))) bad++;
   }
   for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&stats[3], bad);

@@ -234,10 +234,9 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
   MRS_TRY(build_mae_layout(T));
   const auto& L = T->ml;
   mrs_engine* e = m->eng;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(e->smem_attr_done & 2u)) {
     MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
-    attr_set = true;
+    e->smem_attr_done |= 2u;
   }
   const int32_t ctas_per_tile = std::max(1, e->sm_count / L.n_tiles);
   const int32_t grid = L.n_tiles * ctas_per_tile;

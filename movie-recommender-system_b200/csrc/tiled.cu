@@ -487,15 +487,15 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
 int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused) {
   const auto& T = R->tl;
   cudaStream_t st = e->stream;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(e->smem_attr_done & 1u)) {
     MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
     MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
-    attr_set = true;
+    e->smem_attr_done |= 1u;
   }
   // one CTA of 1024 threads per SM; every tile gets the same number of CTAs and the grid never exceeds one wave
   const int32_t ctas_per_tile = std::max(1, e->sm_count / T.n_tiles);
   const dim3 grid2(T.n_tiles * ctas_per_tile), block2(kTiledThreads);
+  bool part_fresh = false;
   if (T.part_ctas != ctas_per_tile) {  // first pass on this engine (or another SM count): lay the static partition down
     auto& TL = R->tl;
     dev_free(TL.warp_part);
@@ -505,13 +505,23 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
     count_launch();
     MRS_CUDA(cudaGetLastError());
     TL.part_ctas = ctas_per_tile;
+    part_fresh = true;
   }
+  // The item pass reads warp_part in its prologue, BEFORE griddepcontrol.wait: in the pass that has just written the table
+  // it is launched as a plain stream-ordered kernel (a programmatic dependent may run ahead of its predecessor's writes).
+  auto launch_item = [&](auto kernel) -> cudaError_t {
+    if (part_fresh) {
+      kernel<<<grid2, block2, kTiledSmem, st>>>(T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow, R->n_users, T.slot_item, m->uavg,
+                                                 m->xdev_fix, m->xcode_sum);
+      return cudaGetLastError();
+    }
+    return launch_pdl(kernel, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow, R->n_users, T.slot_item,
+                      m->uavg, m->xdev_fix, m->xcode_sum);
+  };
   if (m->want_item_avg)
-    MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow,
-                        R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
+    MRS_CUDA(launch_item(item_tiled_kernel<true>));
   else
-    MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow,
-                        R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
+    MRS_CUDA(launch_item(item_tiled_kernel<false>));
   mark(e, "item_tiled");
   MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
                       m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg));

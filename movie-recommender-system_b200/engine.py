@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
     "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
-    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_exchange_status", "mrs_exchange_stamps", "mrs_exchange_destroy",
+    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
@@ -99,6 +99,7 @@ def lib():
         "mrs_exchange_allreduce_async": (i32, [vp, vp, i64]),
         "mrs_exchange_allreduce_indexed_async": (i32, [vp, vp, vp, i64]),
         "mrs_exchange_status": (i32, [vp, P(i32)]),
+        "mrs_exchange_set_timeout_ms": (i32, [vp, i64]),
         "mrs_exchange_stamps": (i32, [vp, P(C.c_uint64)]),
         "mrs_exchange_destroy": (None, [vp]),
         "mrs_model_scalar": (i32, [vp, i32, P(dbl)]),
@@ -221,9 +222,19 @@ class PeerExchange:
         return [int(o[k]) - int(o[0]) if o[k] >= o[0] and o[k] else None for k in range(1, 6)]  # older = left by a previous call
 
     def timed_out(self):
+        """True if a peer never arrived in some exchange since creation (synchronises the stream).  The kernel has then
+        overwritten the exchanged buffer with NaN, and the handle refuses further exchanges."""
         t = C.c_int32()
         _check(lib().mrs_exchange_status(self._h, C.byref(t)))
         return bool(t.value)
+
+    def check(self):
+        """Raise if an exchange timed out (call where the host synchronises anyway: after reading a result)."""
+        if self.timed_out():
+            raise MrsError(-2, "peer-memory exchange timed out: a rank did not arrive; results are NaN and the handle is dead")
+
+    def set_timeout_ms(self, ms):
+        _check(lib().mrs_exchange_set_timeout_ms(self._h, int(ms)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -183,10 +183,20 @@ class ShardedBaseline:
     def mae_async(self):
         self.mae_local(); self.mae_exchange()
 
+    def check(self):
+        """Raise if a peer-memory exchange of this pass timed out (host sync).  Call it wherever a result is read."""
+        if self.peer is not None:
+            self.peer.check()
+
+    def result(self):
+        """{sum |err|, n} of the last step as an MAE (host sync); raises if an exchange timed out."""
+        r = self.out2.cpu().numpy()
+        self.check()
+        return float(r[0] / r[1])
+
     def mae(self):
         self.mae_async()
-        r = self.out2.cpu().numpy()
-        return float(r[0] / r[1])
+        return self.result()
 
 
 class ShardedKnn:
@@ -252,6 +262,8 @@ class ShardedKnn:
 
     def mae(self):
         r = self.out2.cpu().numpy()
+        if self.peer is not None:
+            self.peer.check()
         return float(r[0] / r[1])
 
     def close(self):
