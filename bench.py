@@ -95,17 +95,48 @@ def load_workload(rank):
     return d
 
 
+def host_threads():
+    """Host threads this process may use (torch.distributed.run exports OMP_NUM_THREADS=1: the CPU arms pass their
+    thread count explicitly to the oracle's `num_threads` clauses instead of trusting the OpenMP default)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def rank_workload(d, rank, world):
+    """(train, test, n_users_dim, n_items_dim) of one rank of the headline (weak-scaling) workload: at N > 1 every rank
+    holds one ml-25m-shaped shard of DISTINCT users with its own item popularity (synth.weak_shard), laid out on the
+    global id space so that the per-item exchange buffers of all ranks line up."""
+    if world == 1:
+        return d["train"], d["test"], 0, 0
+    from mrs_b200 import synth
+    s = synth.weak_shard(d, rank)
+    return s["train"], s["test"], world * s["user_stride"] + 1, s["max_item_id"] + 1
+
+
+def whole_workload(d, world):
+    """The union of all ranks' shards: what a CPU reference has to process for the same total work."""
+    if world == 1:
+        return d["train"], d["test"]
+    from mrs_b200 import synth
+    u = synth.weak_union(d, world)
+    return u["train"], u["test"]
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
-    """The reference's CPU algorithm (oracle port of the Spark twin, partitions = host threads) on the same workload."""
+    """The reference's CPU algorithm (oracle port of the Spark twin, partitions = host threads) on the same TOTAL workload
+    as our arm at this N: the union of the N ranks' shards, all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus, 1)
     d = load_workload(0)
-    tr, te = d["train"], d["test"]
+    tr, te = whole_workload(d, world)
     n = tr[0].size + te[0].size
-    threads = oracle.max_threads()
+    threads = host_threads()
     for _ in range(max(args.warmup, 0)):
         oracle.spark_baseline_mae(tr, te, nthreads=threads)
     times = []
@@ -120,9 +151,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": value / PUBLISHED_RATINGS_PER_S, "dtype": "f64", "data": "synthetic ml-25m shape (seed 449)",
-        "config": workload_config(d, 1),
+        "config": workload_config(d, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "whole workload per step (fit on 20,000,076 train + MAE on 5,000,019 test), arrays already parsed"},
+                         "sample": f"whole workload per step: the union of the {world} rank shard(s) (fit on {tr[0].size:,} train + MAE on "
+                                   f"{te[0].size:,} test ratings), arrays already parsed"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mae": mae,
         "note": "the Scala/Spark reference cannot run here (no JVM); this is oracle/mrs_oracle.c orc_baseline_mae_spark, "
@@ -141,7 +173,9 @@ def workload_config(d, world):
         "layout": "train: user-major codes padded to 16 B vectors (1 B/rating + 4 B/vector), user-tiled item-major sliced-ELL "
                   "(4 B/rating: valid|code|16-bit local user); test: item-tiled, one packed 8-byte word per rating (int32 user | 16-bit local item | code)",
         "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
-        "parallelism": f"user-sharded x{world}, one all-reduce of the per-item exchange buffer (own NVLink peer-memory kernel)" if world > 1 else "single GPU",
+        "parallelism": (f"user-sharded x{world}: every rank holds one ml-25m-shaped shard of distinct users with its own item "
+                        "popularity (synth.weak_shard); one all-reduce of the per-item exchange buffer (own NVLink peer-memory kernel)")
+                       if world > 1 else "single GPU",
     }
 
 
@@ -167,14 +201,13 @@ def run_ours(args):
             os.environ.pop("NCCL_DEBUG")   # keeps NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     d = load_workload(rank)
-    tr, te = d["train"], d["test"]
+    tr, te, nu_dim, ni_dim = rank_workload(d, rank, world)   # N > 1: a distinct shard per rank, on the global id space
     n_step = int(tr[0].size + te[0].size)
 
     stream = torch.cuda.Stream(device=dev)
     eng = E.Engine(local_rank, stream=stream.cuda_stream)
-    # global table sizes so that every rank's exchange buffer lines up (here all shards have the same shape)
-    R = eng.ratings(*tr)
-    T = eng.ratings(*te)
+    R = eng.ratings(*tr, nu_dim, ni_dim)
+    T = eng.ratings(*te, nu_dim, ni_dim)
     model = E.Model(eng, R) if world == 1 else None
     # the timed closure is baselinePredictorSpark + MeanAbsoluteErrorSpark: it never forms per-item rating averages
     # (P:362-391), so that optional part of the fit is switched off (it costs about 8 % of the item pass)
@@ -312,16 +345,18 @@ def run_ours(args):
     def e2e_step():
         up_r = eng.upload(hu, hi, hr)    # both sets start travelling at once on the engine's copy stream ...
         up_t = eng.upload(tu, ti, tv)
-        R2 = up_r.ratings()              # ... the train set is sorted while its ratings and the test set are still in flight
+        R2 = up_r.ratings(nu_dim, ni_dim)  # ... the train set is sorted while its ratings and the test set are still in flight
         if world == 1:
             m2 = E.Model(eng, R2, sync=False)
-            T2 = up_t.ratings()
+            T2 = up_t.ratings(nu_dim, ni_dim)
             m2.mae_async(T2, out2.data_ptr())
             r = out2.cpu().numpy()       # D2H read of the result
             handles = (m2, T2, R2)
         else:
-            T2 = up_t.ratings()
-            s2 = sharded.ShardedBaseline(eng, R2, T2)   # NCCL here: the peer buffers belong to the long-lived pass above
+            T2 = up_t.ratings(nu_dim, ni_dim)
+            # the exchange object (IPC-mapped peer buffers) is long-lived and shared with the pass above; the rating sets
+            # are new every step, so the whole exchange buffer travels (no set-up collective for the slots in use)
+            s2 = sharded.ShardedBaseline(eng, R2, T2, peer=sb.peer, indexed=False)
             s2.fit()
             s2.mae_async()
             r = s2.out2.cpu().numpy()
@@ -353,16 +388,44 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             knn25m = bench_knn25m(eng, stream, torch, dist, d, rank, world, dev, peer=not args.nccl)
 
+    strong = None
+    if world > 1 and not args.no_strong:
+        with torch.cuda.stream(stream):
+            strong = bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, peer=not args.nccl)
+
     line = None
     if rank == 0:
-        # ---- CPU baseline on this box's host cores (oracle port, single thread), bounded sample
         import oracle
-        t0 = time.perf_counter()
-        cpu_mae, _ = oracle.spark_baseline_mae(tr, te, nthreads=1)
-        cpu_s = time.perf_counter() - t0
-        cpu = {"value": n_step / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "whole workload once (fit on 20,000,076 train + MAE on 5,000,019 test), arrays already parsed",
-               "seconds": cpu_s, "mae": cpu_mae, "host_cores_available": os.cpu_count()}
+        if world == 1:
+            # ---- CPU baseline on this box's host cores: the oracle's Spark-twin port with 1, 4 and all host threads
+            # (the local[1] / local[4] / local[N] stand-ins of BASELINE.md section 3), 3 measurements each, mean and
+            # population sigma like the reference's own statistics (P:18-25)
+            by_threads = {}
+            cpu_mae = None
+            for j in sorted({1, min(4, host_threads()), host_threads()}):
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    cpu_mae, _g = oracle.spark_baseline_mae(tr, te, nthreads=j)
+                    ts.append(time.perf_counter() - t0)
+                mean_s = sum(ts) / len(ts)
+                by_threads[str(j)] = {"ratings_per_s": n_step / mean_s, "mean_ms": 1000.0 * mean_s,
+                                      "stddev_ms": 1000.0 * (sum((t - mean_s) ** 2 for t in ts) / len(ts)) ** 0.5, "runs": len(ts)}
+            top = str(host_threads())
+            cpu = {"value": by_threads[top]["ratings_per_s"], "unit": UNIT, "cores": host_threads(), "kind": "port",
+                   "sample": "whole workload (fit on 20,000,076 train + MAE on 5,000,019 test), arrays already parsed; 3 runs per thread count",
+                   "by_threads": by_threads, "mae": cpu_mae, "host_cores_available": os.cpu_count()}
+        else:
+            # N > 1: no CPU baseline line (rank 0 at N=1 only), but the parity check needs the oracle's MAE of the UNION of
+            # all ranks' shards -- distinct data per rank, so an exchange that did nothing cannot match it
+            wtr, wte = whole_workload(d, world)
+            t0 = time.perf_counter()
+            cpu_mae, _g = oracle.spark_baseline_mae(wtr, wte, nthreads=host_threads())
+            cpu = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                   "sample": f"parity only: oracle MAE of the union of the {world} shards ({wtr[0].size + wte[0].size:,} ratings) "
+                             f"in {time.perf_counter() - t0:.2f} s; the timed CPU baseline is reported at N=1 and by --impl reference",
+                   "mae": cpu_mae}
+            del wtr, wte
         knn = bench_knn(eng, stream, torch) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -383,6 +446,7 @@ def run_ours(args):
             "exchange": None if sb is None else ("nccl" if sb.peer is None else
                                                  {"kind": "own NVLink peer-memory kernel", "timed_out": sb.peer.timed_out()}),
             "step_ms_min_max": [min(step_ms), max(step_ms)],
+            "strong_scaling": strong,
             "knn": knn,
             "knn25m": knn25m,
         }
@@ -393,6 +457,74 @@ def run_ours(args):
         dist.destroy_process_group()
     sys.stdout.flush()
     return 0
+
+
+def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, peer):
+    """BASELINE config 4 as worded: ONE ml-25m-shaped set, its users partitioned over the ranks
+    (distributed/DistributedBaseline.scala:30-47 with --master local[N]; reduceByKey/collect of P:267-268 = the exchange).
+    A rank holds the train rows and the test pairs of its user range (sharded.partition_users / shard_of), the tables are
+    laid out on the global id space.  Strong scaling: the job is fixed, N ranks split it.  Parity: the MAE against the
+    oracle and the per-item average deviations against a single-GPU fit of the whole set on rank 0."""
+    import numpy as np
+    from mrs_b200 import engine as E, sharded
+    tr, te = d["train"], d["test"]
+    nu_dim = int(max(tr[0].max(), te[0].max())) + 1
+    ni_dim = int(max(tr[1].max(), te[1].max())) + 1
+    bounds = sharded.partition_users(np.bincount(tr[0], minlength=nu_dim), world)
+    mtr, mte = sharded.shard_of(tr[0], bounds, rank), sharded.shard_of(te[0], bounds, rank)
+    R = eng.ratings(tr[0][mtr], tr[1][mtr], tr[2][mtr], nu_dim, ni_dim)
+    T = eng.ratings(te[0][mte], te[1][mte], te[2][mte], nu_dim, ni_dim)
+    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=peer)
+    sb.step()
+    torch.cuda.synchronize(dev)
+    if not args.no_graph:
+        sb.capture()
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        sb.step()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record(stream)
+        sb.step()
+        b.record(stream)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms = float(tot.item()) / args.steps
+    mae = sb.result()
+    n_total = int(tr[0].size + te[0].size)
+    out = None
+    idev = sb.model.vector(E.ITEM_AVG_DEV)[0]
+    if rank == 0:
+        import oracle
+        ref_mae, _g = oracle.spark_baseline_mae(tr, te, nthreads=host_threads())
+        R1 = eng.ratings(*tr, nu_dim, ni_dim)
+        m1 = E.Model(eng, R1)
+        idev1 = m1.vector(E.ITEM_AVG_DEV)[0]
+        tol = 1e-6 * np.maximum(np.abs(idev1), 1e-12)
+        worst = float(np.max(np.abs(idev - idev1) / np.maximum(np.abs(idev1), 1e-12)))
+        out = {"metric": METRIC, "value": n_total / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "ms_per_step": ms,
+               "scaling": "strong", "steps": args.steps,
+               "workload": "ONE synthetic ml-25m-shaped set (20,000,076 train / 5,000,019 test), users partitioned over the ranks "
+                           "(sharded.partition_users: contiguous id ranges balanced by rating count)",
+               "user_bounds": [int(b) for b in bounds], "train_ratings_rank0": int(mtr.sum()), "test_ratings_rank0": int(mte.sum()),
+               "mae": mae, "oracle_mae": ref_mae, "mae_matches_cpu_port": bool(abs(mae - ref_mae) <= 1e-6 * abs(ref_mae)),
+               "item_avg_dev_matches_single_gpu_fit": bool(np.all(np.abs(idev - idev1) <= tol)), "item_avg_dev_worst_rel": worst,
+               "exchange": "nccl" if sb.peer is None else "own NVLink peer-memory kernel"}
+        m1.close(); R1.close()
+    torch.cuda.synchronize(dev)
+    dist.barrier()                 # nobody may still be reading our symmetric buffers when they are unmapped
+    for g in ("_g_all", "_g1", "_g2"):
+        if getattr(sb, g, None) is not None:
+            getattr(sb, g).close()
+    sb.close(close_peer=True)
+    for h in (T, R):
+        h.close()
+    return out
 
 
 def bench_knn(eng, stream, torch):
@@ -521,6 +653,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nccl", action="store_true", help="N>1: use NCCL all-reduces instead of the library's peer-memory exchange kernel")
     ap.add_argument("--no-knn25m", action="store_true", help="skip the kNN k=300 leg at ml-25m shape (BASELINE config 5)")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling leg (ONE ml-25m set user-sharded over the ranks)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.steps = max(args.steps, 1)

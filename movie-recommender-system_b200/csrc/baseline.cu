@@ -21,6 +21,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+__global__ void fill_f64_kernel(double* __restrict__ p, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // ---- K1: per-user chunk sums of ratings (user-major values only: 1 B/rating for half-star codes)
 template <typename VT>
 __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restrict__ uval, const int32_t* __restrict__ urow,
@@ -440,7 +444,15 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
     }
     if (s == MRS_OK) s = dev_alloc(&m->upart, (size_t)R->uch.n_chunks);
     // padded to whole user tiles: the tiled kernel stages a tile's averages with one 64 KB bulk copy
-    if (s == MRS_OK) s = dev_alloc(&m->uavg, ((size_t)R->n_users + kTileUsers - 1) / kTileUsers * kTileUsers + kTileUsers);
+    const size_t uavg_len = ((size_t)R->n_users + kTileUsers - 1) / kTileUsers * kTileUsers + kTileUsers;
+    if (s == MRS_OK) s = dev_alloc(&m->uavg, uavg_len);
+    if (s == MRS_OK && codes) {
+      // the item pass writes the averages of the tiles that have ratings; user tiles without any (the id range of another
+      // rank in a sharded run) keep this "no ratings" mark (P:222 getOrElse(user, -1.0)) for the life of the model
+      fill_f64_kernel<<<std::max(1, std::min((int)((uavg_len + 255) / 256), e->sm_count * 8)), 256, 0, e->stream>>>(m->uavg, (int64_t)uavg_len, -1.0);
+      count_launch();
+      if (cudaGetLastError() != cudaSuccess) s = MRS_ERR_CUDA;
+    }
     if (s == MRS_OK) s = dev_alloc(&m->ipart, 2 * (size_t)R->ich.n_chunks);
     if (s == MRS_OK) s = dev_alloc(&m->xbuf, 3 * (size_t)R->n_items + 2);
     if (s == MRS_OK) s = dev_alloc(&m->idevavg, (size_t)R->n_items);

@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" surface declared in include/mrs_b200.h (engine, model queries, fit / MAE /
 // predict wrappers).  Kernels live in loader.cu, baseline.cu and knn.cu.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -86,6 +87,49 @@ int32_t ensure_scratch(mrs_engine* e, size_t bytes) {
   }
   e->scratch_bytes = want;
   return MRS_OK;
+}
+
+std::vector<int3> deal_ctas(const std::vector<int64_t>& tile_cost, int32_t n_ctas) {
+  const int32_t nt = (int32_t)tile_cost.size();
+  int64_t total = 0;
+  int32_t busy = 0;
+  for (int64_t c : tile_cost) { total += c; busy += c > 0; }
+  std::vector<int3> desc;
+  if (total == 0 || n_ctas <= 0) return desc;
+  std::vector<int32_t> share((size_t)nt, 0);
+  if (busy >= n_ctas) {  // more busy tiles than CTAs: one CTA per busy tile (the grid is then larger than one wave)
+    for (int32_t t = 0; t < nt; ++t) share[(size_t)t] = tile_cost[(size_t)t] > 0 ? 1 : 0;
+  } else {
+    // one CTA per busy tile, the rest by largest remainder of the exact proportional share
+    std::vector<double> want((size_t)nt, 0.0);
+    int32_t given = 0;
+    for (int32_t t = 0; t < nt; ++t)
+      if (tile_cost[(size_t)t] > 0) {
+        want[(size_t)t] = (double)tile_cost[(size_t)t] * (double)n_ctas / (double)total;
+        share[(size_t)t] = std::max<int32_t>(1, (int32_t)want[(size_t)t]);
+        given += share[(size_t)t];
+      }
+    while (given < n_ctas) {  // hand the remaining CTAs to the tiles with the most cost per CTA
+      int32_t best = -1;
+      double worst = -1.0;
+      for (int32_t t = 0; t < nt; ++t)
+        if (share[(size_t)t] > 0 && (double)tile_cost[(size_t)t] / share[(size_t)t] > worst) { worst = (double)tile_cost[(size_t)t] / share[(size_t)t]; best = t; }
+      ++share[(size_t)best];
+      ++given;
+    }
+    while (given > n_ctas) {  // (the floor of one CTA per busy tile can overshoot): take from the tiles with the least cost per CTA
+      int32_t best = -1;
+      double least = 1e300;
+      for (int32_t t = 0; t < nt; ++t)
+        if (share[(size_t)t] > 1 && (double)tile_cost[(size_t)t] / (share[(size_t)t] - 1) < least) { least = (double)tile_cost[(size_t)t] / (share[(size_t)t] - 1); best = t; }
+      if (best < 0) break;
+      --share[(size_t)best];
+      --given;
+    }
+  }
+  for (int32_t t = 0; t < nt; ++t)
+    for (int32_t k = 0; k < share[(size_t)t]; ++k) desc.push_back(make_int3(t, k, share[(size_t)t]));
+  return desc;
 }
 
 }  // namespace mrs

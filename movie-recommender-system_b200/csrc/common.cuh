@@ -176,8 +176,12 @@ struct mrs_ratings {
     int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
     int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
     int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
-    int2* warp_part = nullptr;         // [n_tiles * part_ctas * 32] slices [x, y) of every warp of the item pass (static: the
-    int32_t part_ctas = 0;             //  cost-balanced partition depends on the layout and the CTAs per tile only)
+    // static work partition of the item pass (depends on the layout and the SM count only; laid down with the layout):
+    // CTA b works on tile cta_desc[b].x as share .y of .z -- CTAs are dealt out to the tiles in proportion to their
+    // cost, tiles without ratings (a rank of a sharded run owns a user range) get none
+    int32_t n_ctas = 0;
+    int3* cta_desc = nullptr;          // [n_ctas]
+    int2* warp_part = nullptr;         // [n_ctas * 32] slices [x, y) of every warp
   };
   mutable tiled_layout tl;
   // ---- lazily built item-tiled layout for the fused predict + |error| kernel (mae_tiled.cu); half-star codes only
@@ -187,6 +191,8 @@ struct mrs_ratings {
     int64_t n_rows = 0;         // 32-entry rows incl. padding (every tile starts at a row boundary)
     uint2* entry = nullptr;     // [n_rows*32] .x = user id, .y = local item | code << 16 (code 0xFF = padding)
     int32_t* tile_row_ptr = nullptr;  // [n_tiles+1] first row of every tile
+    int32_t n_ctas = 0;         // CTAs dealt out to the item tiles in proportion to their rows (see tiled_layout)
+    int3* cta_desc = nullptr;   // [n_ctas] (tile, share, shares of the tile)
   };
   mutable mae_layout ml;
 };
@@ -293,6 +299,9 @@ inline void dev_free(void* p) {
 // loader.cu
 int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
                       int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
+// Deal `n_ctas` CTAs out to tiles in proportion to their cost (largest remainder; every tile with cost > 0 gets at least
+// one as long as there are enough CTAs): desc[b] = (tile, share, shares of that tile), tiles ascending.
+std::vector<int3> deal_ctas(const std::vector<int64_t>& tile_cost, int32_t n_ctas);
 // tiled.cu
 constexpr int kTileUsers = 8192;  // users per tile: 64 KB of fp64 averages in shared memory
 constexpr int kUnitLen = 64;      // (tile,item) segments are cut into units of at most this many entries

@@ -64,7 +64,7 @@ constexpr size_t kMaeSmem = (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 3
 
 // one CTA = (item tile, share of the tile's rows); 32 warps, one CTA per SM
 __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const uint2* __restrict__ entry, const int32_t* __restrict__ tile_row_ptr,
-                                                                          int32_t ctas_per_tile, int32_t n_users, int32_t n_items,
+                                                                          const int3* __restrict__ cta_desc, int32_t n_users, int32_t n_items,
                                                                           const double* __restrict__ uavg, const double* __restrict__ idevavg,
                                                                           const double* __restrict__ gavg_p, double n_total,
                                                                           double* __restrict__ part, unsigned int* __restrict__ counter,
@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 32) * kMaeStages * kMaeRows * 256);
   __shared__ double sh[kMaeThreads / 32];
   __shared__ bool is_last;
-  const int32_t tile = blockIdx.x / ctas_per_tile, share = blockIdx.x % ctas_per_tile;
+  const int3 cd = cta_desc[blockIdx.x];
+  const int32_t tile = cd.x, share = cd.y, ctas_per_tile = cd.z;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int32_t wpb = kMaeThreads >> 5;
   uint64_t* bar = s_bar + wid * kMaeStages;
@@ -184,7 +185,7 @@ int grid_for(int64_t n, int block, int sm_count) {
 
 void free_mae_layout(const mrs_ratings* T) {
   auto& L = T->ml;
-  dev_free(L.entry); dev_free(L.tile_row_ptr);
+  dev_free(L.entry); dev_free(L.tile_row_ptr); dev_free(L.cta_desc);
   L = mrs_ratings::mae_layout();
 }
 
@@ -224,6 +225,15 @@ int32_t build_mae_layout(const mrs_ratings* T) {
   mae_scatter_kernel<<<grid, 256, 0, st>>>(k_out, perm, tile_ptr, L.tile_row_ptr, T->coo_u, T->ucol, (const uint8_t*)T->uval, n, L.entry);
   count_launch(6);
   MRS_CUDA(cudaGetLastError());
+  {  // CTAs of the test pass, dealt out to the item tiles in proportion to their rows
+    std::vector<int64_t> cost((size_t)NT);
+    for (int32_t t = 0; t < NT; ++t) cost[(size_t)t] = h_rows[(size_t)t + 1] - h_rows[(size_t)t];
+    const std::vector<int3> desc = deal_ctas(cost, e->sm_count);
+    L.n_ctas = (int32_t)desc.size();
+    MRS_TRY(dev_alloc(&L.cta_desc, std::max<size_t>(1, desc.size())));
+    MRS_CUDA(cudaMemcpyAsync(L.cta_desc, desc.data(), sizeof(int3) * desc.size(), cudaMemcpyHostToDevice, st));
+    MRS_CUDA(cudaStreamSynchronize(st));  // `desc` must outlive the copy
+  }
   MRS_CUDA(cudaStreamSynchronize(st));
   dev_free(k_in); dev_free(k_out); dev_free(p_in); dev_free(perm); dev_free(tile_ptr);
   L.built = true;
@@ -238,11 +248,10 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
     MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
     e->smem_attr_done |= 2u;
   }
-  const int32_t ctas_per_tile = std::max(1, e->sm_count / L.n_tiles);
-  const int32_t grid = L.n_tiles * ctas_per_tile;
-  MRS_REQUIRE(grid <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set needs %d CTAs, more than the %d partial slots of the model", grid,
+  const int32_t grid = L.n_ctas;
+  MRS_REQUIRE(grid > 0 && grid <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set needs %d CTAs, more than the %d partial slots of the model", grid,
               m->mae_part_cap);
-  MRS_CUDA(launch_pdl(predict_mae_tiled_kernel, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, ctas_per_tile, m->n_users,
+  MRS_CUDA(launch_pdl(predict_mae_tiled_kernel, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
                       m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2));
   mark(e, "predict_mae_tiled");
   MRS_CUDA(cudaGetLastError());

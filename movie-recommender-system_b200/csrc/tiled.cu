@@ -193,9 +193,10 @@ __device__ __forceinline__ void hand_over(int32_t item, double acc, uint32_t csu
 
 // slices [x, y) of every warp of the item pass: an equal share of its tile's cost, rounded to whole slices
 __global__ void __launch_bounds__(kTiledThreads) item_partition_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ tile_slice_ptr,
-                                                                      int32_t ctas_per_tile, int2* __restrict__ warp_part) {
+                                                                      const int3* __restrict__ cta_desc, int2* __restrict__ warp_part) {
   if ((threadIdx.x & 31) != 0) return;
-  const int32_t tile = blockIdx.x / ctas_per_tile, share = blockIdx.x % ctas_per_tile;
+  const int3 cd = cta_desc[blockIdx.x];
+  const int32_t tile = cd.x, share = cd.y, ctas_per_tile = cd.z;
   constexpr int32_t wpb = kTiledThreads >> 5;
   const int32_t wid = threadIdx.x >> 5;
   const int32_t ts0 = tile_slice_ptr[tile], ts1 = tile_slice_ptr[tile + 1];
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kTiledThreads) item_partition_kernel(const int
 
 template <bool WITH_SUM>
 __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint32_t* __restrict__ entry, const int32_t* __restrict__ slice_off,
-                                                                     const int2* __restrict__ warp_part, int32_t ctas_per_tile,
+                                                                     const int2* __restrict__ warp_part, const int3* __restrict__ cta_desc,
                                                                      const uint32_t* __restrict__ usum, const int32_t* __restrict__ urow,
                                                                      int32_t n_users, const int32_t* __restrict__ slot_item,
                                                                      double* __restrict__ uavg, long long* __restrict__ xdev_fix,
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
   uint2* s_sc = reinterpret_cast<uint2*>(smem_raw);                                       // [kTileUsers] (code sum, count)
   uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTileUsers * 8);      // [warps][kStages][kRows*32]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128);
-  const int32_t tile = blockIdx.x / ctas_per_tile, share = blockIdx.x % ctas_per_tile;
+  const int3 cd = cta_desc[blockIdx.x];
+  const int32_t tile = cd.x, share = cd.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int32_t wpb = kTiledThreads >> 5;
   uint64_t* bar = s_bar + wid * kStages;           // this warp's stage barriers
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
 
 void free_tiled_layout(const mrs_ratings* R) {
   auto& T = R->tl;
-  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.slot_item); dev_free(T.warp_part);
+  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.slot_item); dev_free(T.warp_part); dev_free(T.cta_desc);
   T = mrs_ratings::tiled_layout();
 }
 
@@ -472,7 +474,29 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   MRS_TRY(dev_alloc(&T.slot_item, (size_t)NS * 32));
   MRS_CUDA(cudaMemsetAsync(T.slot_item, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
   slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, T.slot_item);
-  count_launch(20);
+  // ---- static work partition of the item pass: CTAs dealt out to the tiles by cost, then slices to the warps of each CTA.
+  // Laid down here, behind the layout's final synchronisation: the item pass reads warp_part in its prologue, before
+  // griddepcontrol.wait, so the table must never be written by a kernel of the pass itself.
+  {
+    std::vector<int32_t> h_slice_off((size_t)NS + 1);
+    MRS_CUDA(cudaMemcpyAsync(h_slice_off.data(), T.slice_off, sizeof(int32_t) * ((size_t)NS + 1), cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    std::vector<int64_t> cost((size_t)NT, 0);
+    for (int32_t t = 0; t < NT; ++t) {
+      const int32_t s0 = h_tile_slice[t], s1 = h_tile_slice[t + 1];
+      cost[(size_t)t] = (int64_t)(h_slice_off[(size_t)s1] - h_slice_off[(size_t)s0]) + (int64_t)kSliceCost * (s1 - s0);
+    }
+    const std::vector<int3> desc = deal_ctas(cost, e->sm_count);
+    T.n_ctas = (int32_t)desc.size();
+    MRS_TRY(dev_alloc(&T.cta_desc, std::max<size_t>(1, desc.size())));
+    MRS_TRY(dev_alloc(&T.warp_part, std::max<size_t>(1, desc.size()) * (kTiledThreads / 32)));
+    if (T.n_ctas > 0) {
+      MRS_CUDA(cudaMemcpyAsync(T.cta_desc, desc.data(), sizeof(int3) * desc.size(), cudaMemcpyHostToDevice, st));
+      item_partition_kernel<<<T.n_ctas, kTiledThreads, 0, st>>>(T.slice_off, T.tile_slice_ptr, T.cta_desc, T.warp_part);
+      MRS_CUDA(cudaStreamSynchronize(st));  // `desc` (pageable host memory) must outlive the copy
+    }
+  }
+  count_launch(21);
   MRS_CUDA(cudaGetLastError());
   MRS_CUDA(cudaStreamSynchronize(st));
   for (void* p : {(void*)tk_in, (void*)tk_out, (void*)pos_in, (void*)perm, (void*)item_of, (void*)head, (void*)seg_start, (void*)flag,
@@ -492,36 +516,16 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
     MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
     e->smem_attr_done |= 1u;
   }
-  // one CTA of 1024 threads per SM; every tile gets the same number of CTAs and the grid never exceeds one wave
-  const int32_t ctas_per_tile = std::max(1, e->sm_count / T.n_tiles);
-  const dim3 grid2(T.n_tiles * ctas_per_tile), block2(kTiledThreads);
-  bool part_fresh = false;
-  if (T.part_ctas != ctas_per_tile) {  // first pass on this engine (or another SM count): lay the static partition down
-    auto& TL = R->tl;
-    dev_free(TL.warp_part);
-    TL.warp_part = nullptr;
-    MRS_TRY(dev_alloc(&TL.warp_part, (size_t)grid2.x * (kTiledThreads / 32)));
-    item_partition_kernel<<<grid2, block2, 0, st>>>(T.slice_off, T.tile_slice_ptr, ctas_per_tile, TL.warp_part);
-    count_launch();
-    MRS_CUDA(cudaGetLastError());
-    TL.part_ctas = ctas_per_tile;
-    part_fresh = true;
+  // one CTA of 1024 threads per SM: the grid (T.n_ctas <= SM count unless there are more busy tiles than SMs) is one wave
+  const dim3 grid2(T.n_ctas), block2(kTiledThreads);
+  if (T.n_ctas > 0) {
+    if (m->want_item_avg)
+      MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
+                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
+    else
+      MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
+                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum));
   }
-  // The item pass reads warp_part in its prologue, BEFORE griddepcontrol.wait: in the pass that has just written the table
-  // it is launched as a plain stream-ordered kernel (a programmatic dependent may run ahead of its predecessor's writes).
-  auto launch_item = [&](auto kernel) -> cudaError_t {
-    if (part_fresh) {
-      kernel<<<grid2, block2, kTiledSmem, st>>>(T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow, R->n_users, T.slot_item, m->uavg,
-                                                 m->xdev_fix, m->xcode_sum);
-      return cudaGetLastError();
-    }
-    return launch_pdl(kernel, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, ctas_per_tile, m->usum, R->urow, R->n_users, T.slot_item,
-                      m->uavg, m->xdev_fix, m->xcode_sum);
-  };
-  if (m->want_item_avg)
-    MRS_CUDA(launch_item(item_tiled_kernel<true>));
-  else
-    MRS_CUDA(launch_item(item_tiled_kernel<false>));
   mark(e, "item_tiled");
   MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
                       m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg));

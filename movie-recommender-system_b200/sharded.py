@@ -89,7 +89,11 @@ class ShardedBaseline:
 
     `engine` must have been created on the CUDA stream the collectives run on (``torch.cuda.current_stream()``)."""
 
-    def __init__(self, engine, train, test, group=None, item_averages=False, peer_exchange=False):
+    def __init__(self, engine, train, test, group=None, item_averages=False, peer_exchange=False, peer=None, indexed=True):
+        """``peer_exchange``: create the library's peer-memory exchange object for the two all-reduces (else NCCL through
+        torch.distributed).  ``peer``: an existing PeerExchange to reuse instead (its buffers are long-lived IPC mappings;
+        a pass that is rebuilt every step, like the end-to-end arm of bench.py, must not create one per step);
+        ``indexed=False`` then exchanges the whole buffer, so no set-up collective is needed for the new rating sets."""
         import torch
         from . import engine as E
         self.E, self.torch, self.group = E, torch, group
@@ -103,8 +107,12 @@ class ShardedBaseline:
             self.xbuf = self.xbuf[:mandatory_size(train.n_items_dim)]
         self.out2 = torch.zeros(2, dtype=torch.float64, device=self.device)
         # peer_exchange: the two all-reduces run as the library's own NVLink peer-memory kernel instead of NCCL
-        self.peer = None
-        if peer_exchange:
+        self.peer = peer
+        self.xidx = None
+        if peer is not None and indexed:
+            import torch.distributed as dist
+            self.xidx = self._slots_in_use(dist, item_averages)
+        if peer_exchange and peer is None:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
                 world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -139,8 +147,10 @@ class ShardedBaseline:
         self.E._check(self.E.lib().mrs_fit_local(self.engine._h, self.train._h, self.E.C.byref(self.model._h)))
 
     def exchange(self):                                # THE collective of the fit (P:267-268, P:247)
-        if self.peer is not None:
+        if self.peer is not None and self.xidx is not None:
             self.peer.allreduce_indexed_async(self.xbuf.data_ptr(), self.xidx.data_ptr(), self.xidx.numel())
+        elif self.peer is not None:
+            self.peer.allreduce_async(self.xbuf.data_ptr(), self.xbuf.numel())
         else:
             all_reduce_sum(self.xbuf, self.group)
 
@@ -182,6 +192,15 @@ class ShardedBaseline:
 
     def mae_async(self):
         self.mae_local(); self.mae_exchange()
+
+    def close(self, close_peer=False):
+        """Release the model (and, if asked, the exchange object -- only the pass that created it should)."""
+        if self.model is not None:
+            self.model.close()
+            self.model = None
+        if close_peer and self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def check(self):
         """Raise if a peer-memory exchange of this pass timed out (host sync).  Call it wherever a result is read."""

@@ -124,6 +124,36 @@ def mid(seed=11, n_users=20_000, n_items=3_000, n_ratings=600_000):
     return {"train": train, "test": test, "all": (u, i, r), "n_users": n_users, "n_items": n_items}
 
 
+def weak_shard(d, rank, stride=None):
+    """Rank ``rank``'s shard of a weak-scaling workload built from one generated set ``d``: the same shape on every
+    rank but DISTINCT data -- users are moved to the id range of the rank (``u + rank * stride``, ``stride`` = number
+    of users of ``d``) and the items are rotated through the set's item ids by a rank-specific offset, so which items
+    are popular differs from rank to rank.  The union over the ranks is a valid rating set (unique pairs) whose
+    per-item sums differ from every single shard's: a run whose cross-rank exchange does nothing cannot reproduce
+    the union's item deviations or MAE.  Rank 0's shard is ``d`` itself."""
+    stride = int(d["n_users"]) if stride is None else int(stride)
+    ids = np.unique(d["all"][1])
+    off = (int(rank) * 7919) % ids.size
+
+    def move(t):
+        u, i, r = t
+        if rank == 0:
+            return u, i, r
+        idx = np.searchsorted(ids, i)
+        idx += off
+        idx %= ids.size
+        return (u + np.int32(rank * stride)).astype(np.int32), ids[idx].astype(np.int32), r
+    return {"train": move(d["train"]), "test": move(d["test"]), "n_users": d["n_users"], "n_items": d["n_items"],
+            "user_stride": stride, "max_item_id": int(ids[-1])}
+
+
+def weak_union(d, world):
+    """Concatenation of all ranks' weak_shard()s: the set a CPU reference must process for the same total work."""
+    parts = [weak_shard(d, r) for r in range(world)]
+    cat = lambda k, j: np.concatenate([p[k][j] for p in parts])
+    return {"train": tuple(cat("train", j) for j in range(3)), "test": tuple(cat("test", j) for j in range(3))}
+
+
 def cached(name, **kw):
     """Generate (or load from a /tmp cache) one of the named sets; ml25m takes ~20 s to generate."""
     fn = {"ml100k": ml100k, "ml25m": ml25m, "small": small, "mid": mid}[name]
