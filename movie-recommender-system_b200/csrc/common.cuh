@@ -165,23 +165,37 @@ struct mrs_ratings {
     int32_t* seg = nullptr;        // [n_items * (n_sub+1)] first CSC entry of column i whose compact index is >= b * kRowsSub
   };
   mutable sim_layout sl;
-  // ---- lazily built tiled item-major layout for the fit kernel (tiled.cu); half-star codes only
+  // ---- lazily built layout of the item pass of the fit (itempass.cu); half-star codes only.
+  // The train entries are split by item popularity into two user-tiled sliced-ELL structures (see itempass.cu):
+  //   popular items: tiles of kPopTileUsers users, 16-bit entries = index into the tile's (user, code) deviation table
+  //   rare items:    tiles of kRareTileUsers users, 32-bit entries = code | slot of the user's (code sum, count) pair
+  struct ell_part {
+    int32_t tile_users = 0;
+    int32_t n_tiles = 0, n_units = 0, n_slices = 0;
+    int64_t n_rows = 0;                // 128-byte rows (32 lanes x one 32-bit word)
+    int64_t n_entries = 0;             // ratings held by this part
+    uint32_t* entry = nullptr;         // [n_rows * 32] words
+    int32_t* slice_off = nullptr;      // [n_slices+1] first row of each slice
+    int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
+    std::vector<int32_t> h_slice_off;  // host copies for the static work partition
+    std::vector<int32_t> h_tile_slice; // [n_tiles+1]
+  };
   struct tiled_layout {
     bool built = false;
-    int32_t n_tiles = 0;
-    int32_t n_units = 0;
-    int32_t n_slices = 0;
-    int64_t n_slots = 0;               // 32 * (rows of all slices)
-    uint32_t* entry = nullptr;         // [n_slots] bit31 valid | code << 16 | user id local to the tile
-    int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
-    int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
-    int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
-    // static work partition of the item pass (depends on the layout and the SM count only; laid down with the layout):
-    // CTA b works on tile cta_desc[b].x as share .y of .z -- CTAs are dealt out to the tiles in proportion to their
-    // cost, tiles without ratings (a rank of a sharded run owns a user range) get none
+    ell_part pop, rare;
+    int32_t code_min = 0, n_codes = 0; // columns of the popular part's deviation table: codes code_min .. code_min+n_codes-1
+    int32_t pop_threshold = 0;         // items with at least this many ratings are "popular" (INT_MAX: no popular part)
+    // static work partition of the pass (depends on the layout and the SM count only; laid down with the layout):
+    // CTA b works on tile cta_desc[b].x (popular tiles first, then the rare ones) as share .y of .z; CTAs are dealt out
+    // in proportion to the tiles' cost, tiles without ratings (another rank's user range in a sharded run) get none
     int32_t n_ctas = 0;
     int3* cta_desc = nullptr;          // [n_ctas]
-    int2* warp_part = nullptr;         // [n_ctas * 32] slices [x, y) of every warp
+    int2* warp_part = nullptr;         // [n_ctas * 32] slices [x, y) of every warp, in the slice numbering of its part
+    // per-item rating sums (P:134), only when item averages are wanted: the item-major codes padded to 16-byte vectors
+    // of ONE item each, summed by the same kernel as the per-user sums (K1)
+    uint8_t* ival16 = nullptr;
+    int32_t* vec_col = nullptr;
+    int32_t n_ivec = 0;
   };
   mutable tiled_layout tl;
   // ---- lazily built item-tiled layout for the fused predict + |error| kernel (mae_tiled.cu); half-star codes only
@@ -205,7 +219,7 @@ struct mrs_model {
   unsigned long long* k1_part = nullptr;  // [1] sum of all half-star codes (integer atomics in K1, re-armed by K2b)
   int32_t k1_blocks = 0;
   long long* xdev_fix = nullptr;            // [n_items] per-item deviation sums in units of 2^-40 (exact integer accumulation)
-  unsigned long long* xcode_sum = nullptr;  // [n_items] per-item sums of half-star codes
+  uint32_t* xcode_sum = nullptr;            // [n_items] per-item sums of half-star codes (only filled when item averages are wanted)
   bool want_item_avg = true;                // also accumulate per-item rating sums during the fit (P:134; not needed by P:362)
   double* upart = nullptr;      // [uch.n_chunks] chunk partial sums of ratings (fp64-value path)
   double* uavg = nullptr;       // [n_users]  average, -1.0 for unknown users (the reference's own sentinel, P:222)
@@ -302,13 +316,20 @@ int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items,
 // Deal `n_ctas` CTAs out to tiles in proportion to their cost (largest remainder; every tile with cost > 0 gets at least
 // one as long as there are enough CTAs): desc[b] = (tile, share, shares of that tile), tiles ascending.
 std::vector<int3> deal_ctas(const std::vector<int64_t>& tile_cost, int32_t n_ctas);
-// tiled.cu
-constexpr int kTileUsers = 8192;  // users per tile: 64 KB of fp64 averages in shared memory
-constexpr int kUnitLen = 64;      // (tile,item) segments are cut into units of at most this many entries
-constexpr int kUnitBits = 7;      // bits of (kUnitLen - len) in the unit sort key
+// itempass.cu
+constexpr int kTileUsers = 8192;      // padding granule of the per-user tables
+constexpr int kPopTileUsers = 2048;   // users per tile of the popular part: 2048 x 10 codes x 8 B = 160 KB of deviations in shared memory
+constexpr int kRareTileUsers = 16384; // users per tile of the rare part: 128 KB of (code sum, count) pairs in shared memory
+constexpr int kMaxCodes = 10;         // columns of the deviation table (half-star data: 0.5 .. 5.0)
+constexpr int kUnitLen = 64;          // (tile,item) segments are cut into units of at most this many entries
+constexpr int kUnitBits = 7;          // bits of (kUnitLen - len) in the unit sort key
 int32_t build_tiled_layout(const mrs_ratings* R);
 void free_tiled_layout(const mrs_ratings* R);
+int32_t build_item_vectors(const mrs_ratings* R);
 int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize);
+// baseline.cu: K1 on any padded code-vector array (per-user sums; per-item sums when item averages are wanted)
+int32_t launch_code_sums(mrs_engine* e, const uint8_t* val16, const int32_t* vec_seg, int32_t n_vec, uint32_t* seg_sum,
+                         unsigned long long* total_or_null, const char* label);
 // mae_tiled.cu
 constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item deviations in shared memory
 int32_t build_mae_layout(const mrs_ratings* T);
