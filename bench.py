@@ -21,6 +21,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+FLUSH_MODE = ["write+read"]
 METRIC = "ml25m_baseline_mae_pass_ratings_per_s"
 UNIT = "ratings/s"
 # distributed-25m-4.json:16-21, 66,147.47 ms for ~25,000,095 ratings on Spark local[4]
@@ -172,7 +173,8 @@ def workload_config(d, world):
         "users_per_gpu": int(d["n_users"]), "items": int(d["n_items"]),
         "layout": "train: user-major codes padded to 16 B vectors (1 B/rating + 4 B/vector), user-tiled item-major sliced-ELL "
                   "(4 B/rating: valid|code|16-bit local user); test: item-tiled, one packed 8-byte word per rating (int32 user | 16-bit local item | code)",
-        "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
+        "l2": "flushed between timed iterations, outside the event pair: 256 MiB write" +
+              (" + 256 MiB read of a second buffer (cold and clean L2: no dirty-line write-backs inside the timed region)" if FLUSH_MODE[0] != "write" else ""),
         "parallelism": (f"user-sharded x{world}: every rank holds one ml-25m-shaped shard of distinct users with its own item "
                         "popularity (synth.weak_shard); one all-reduce of the per-item exchange buffer (own NVLink peer-memory kernel)")
                        if world > 1 else "single GPU",
@@ -215,7 +217,22 @@ def run_ours(args):
         model.set_item_averages(False)
         model.refit()
     bytes_r, bytes_t = R.bytes(), T.bytes()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    class _Flush:
+        """L2 flush between timed iterations, outside the event pairs: a 256 MiB write (twice the 126 MB L2) followed, unless
+        --flush write, by a 256 MiB read of a second buffer.  The write alone leaves the L2 full of DIRTY lines, whose
+        write-backs then compete with the timed kernels' reads for HBM; the read evicts them, so the timed region starts
+        from a cold AND clean L2 (none of the workload's data is resident either way)."""
+
+        def __init__(self):
+            self.a = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            self.b = torch.zeros(256 << 20, dtype=torch.uint8, device=dev) if args.flush != "write" else None
+            self.sink = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def zero_(self):
+            self.a.zero_()
+            if self.b is not None:
+                self.sink += self.b.view(torch.int64).sum()
+    flush = _Flush()
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
     from mrs_b200 import sharded
@@ -653,10 +670,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nccl", action="store_true", help="N>1: use NCCL all-reduces instead of the library's peer-memory exchange kernel")
     ap.add_argument("--no-knn25m", action="store_true", help="skip the kNN k=300 leg at ml-25m shape (BASELINE config 5)")
+    ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
+                    help="L2 flush between timed iterations: 256 MiB write, or write followed by a 256 MiB read (cold and clean L2)")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling leg (ONE ml-25m set user-sharded over the ranks)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.steps = max(args.steps, 1)
+    FLUSH_MODE[0] = args.flush
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

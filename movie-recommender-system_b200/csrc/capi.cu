@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -174,6 +175,10 @@ extern "C" int32_t mrs_engine_create(int32_t device, void* cuda_stream, mrs_engi
     mrs_engine_destroy(e);
     return MRS_ERR_CUDA;
   }
+  if (getenv("MRS_TIMELINE") && atoi(getenv("MRS_TIMELINE"))) {  // diagnostics: per-kernel start/end stamps of a pass
+    if (cudaMalloc((void**)&e->d_timeline, 32 * sizeof(unsigned long long)) != cudaSuccess) e->d_timeline = nullptr;
+    if (e->d_timeline) cudaMemset(e->d_timeline, 0, 32 * sizeof(unsigned long long));
+  }
   cudaError_t he = cudaMallocHost((void**)&e->h_pinned, 64 * sizeof(double));
   if (he != cudaSuccess) { set_error("cudaMallocHost failed: %s", cudaGetErrorString(he)); mrs_engine_destroy(e); return MRS_ERR_NOMEM; }
   *out = e;
@@ -187,12 +192,26 @@ extern "C" void mrs_engine_destroy(mrs_engine* e) {
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->ev_order) cudaEventDestroy(e->ev_order);
   if (e->scratch) cudaFree(e->scratch);
+  if (e->d_timeline) cudaFree(e->d_timeline);
   for (auto& kv : e->free_blocks) cudaFree(kv.second);
   e->free_blocks.clear();
   if (tls_engine == e) tls_engine = nullptr;
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
+}
+
+// diagnostics: copy out and re-arm the timeline of the engine (MRS_TIMELINE=1): out[2k] earliest start, out[2k+1] latest end
+// of kernel k (0 user sums, 1 user tables, 2 item pass, 3 item finalize, 4 test pass, 5 item sums), %globaltimer ns
+extern "C" int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32) {
+  MRS_REQUIRE(e && out32, MRS_ERR_INVALID, "mrs_debug_timeline: NULL argument");
+  MRS_REQUIRE(e->d_timeline, MRS_ERR_INVALID, "mrs_debug_timeline: the engine was created without MRS_TIMELINE=1");
+  MRS_CUDA(cudaStreamSynchronize(e->stream));
+  MRS_CUDA(cudaMemcpy(out32, e->d_timeline, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  uint64_t init[32];
+  for (int k = 0; k < 32; ++k) init[k] = (k & 1) ? 0ull : ~0ull;
+  MRS_CUDA(cudaMemcpy(e->d_timeline, init, sizeof(init), cudaMemcpyHostToDevice));
+  return MRS_OK;
 }
 
 extern "C" int32_t mrs_engine_sync(mrs_engine* e) {
@@ -319,7 +338,7 @@ extern "C" int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, in
 extern "C" void mrs_model_destroy(mrs_model* m) {
   if (!m) return;
   if (m->eng) use_engine(m->eng);
-  dev_free(m->uinv_hi); dev_free(m->uinv_lo);
+  dev_free(m->uinv_hi); dev_free(m->uinv_lo); dev_free(m->pop_img); dev_free(m->rare_img);
   dev_free(m->usum); dev_free(m->k1_part); dev_free(m->xdev_fix); dev_free(m->xcode_sum);
   dev_free(m->upart); dev_free(m->uavg); dev_free(m->ipart); dev_free(m->xbuf); dev_free(m->idevavg); dev_free(m->iavg);
   dev_free(m->gavg); dev_free(m->mae_part); dev_free(m->counters);

@@ -57,6 +57,19 @@ __host__ __device__ inline double decode_value(double v) { return v; }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// diagnostics (MRS_TIMELINE=1): slot 2k = earliest start, 2k+1 = latest end of kernel k of a pass, in %globaltimer ns
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long* tl, int k) {
+  if (tl && threadIdx.x == 0) atomicMin(tl + 2 * k, gtimer_ns());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl, int k) {
+  if (tl && threadIdx.x == 0) atomicMax(tl + 2 * k + 1, gtimer_ns());
+}
+
 // P:57-61 -- strict comparisons, equality -> 1
 __host__ __device__ inline double scale_fn(double x, double y) {
   if (x > y) return 5.0 - y;
@@ -91,8 +104,9 @@ struct mrs_engine {
   std::unordered_map<void*, size_t> live_blocks;
   size_t cached_bytes = 0;
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remembered per engine, not per process
-  // (bit 0: item pass kernels, bit 1: test pass kernel)
+  // (bit 0: item pass kernels, bit 1: test pass kernel, bits 4..: carve-out preference of the small kernels)
   uint32_t smem_attr_done = 0;
+  unsigned long long* d_timeline = nullptr;  // [32] diagnostics, allocated when MRS_TIMELINE=1 (mrs_debug_timeline)
   // diagnostics: event after every launch while profiling (mrs_profile_begin/end)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -185,12 +199,15 @@ struct mrs_ratings {
     ell_part pop, rare;
     int32_t code_min = 0, n_codes = 0; // columns of the popular part's deviation table: codes code_min .. code_min+n_codes-1
     int32_t pop_threshold = 0;         // items with at least this many ratings are "popular" (INT_MAX: no popular part)
-    // static work partition of the pass (depends on the layout and the SM count only; laid down with the layout):
-    // CTA b works on tile cta_desc[b].x (popular tiles first, then the rare ones) as share .y of .z; CTAs are dealt out
-    // in proportion to the tiles' cost, tiles without ratings (another rank's user range in a sharded run) get none
-    int32_t n_ctas = 0;
-    int3* cta_desc = nullptr;          // [n_ctas]
-    int2* warp_part = nullptr;         // [n_ctas * 32] slices [x, y) of every warp, in the slice numbering of its part
+    int32_t user_lo = 0, user_hi = 0;  // ids of the first user with ratings and one past the last (a rank of a sharded run owns a range)
+    // static work partition of the pass (depends on the layout and the SM count only; laid down with the layout): every
+    // CTA gets an equal share of the cost of BOTH parts, as a list of segments -- runs of slices of one tile (the table
+    // in shared memory belongs to a tile): seg[k].x = tile (bit 30: rare part), seg[k].y = first of the segment's 32
+    // per-warp slice ranges in warp_part.  Tiles without ratings (another rank's users in a sharded run) cost nothing.
+    int32_t n_ctas = 0, n_segs = 0;
+    int32_t* cta_seg_ptr = nullptr;    // [n_ctas+1]
+    int2* seg = nullptr;               // [n_segs]
+    int2* warp_part = nullptr;         // [n_segs * 32] slices [x, y) of every warp, in the slice numbering of its part
     // per-item rating sums (P:134), only when item averages are wanted: the item-major codes padded to 16-byte vectors
     // of ONE item each, summed by the same kernel as the per-user sums (K1)
     uint8_t* ival16 = nullptr;
@@ -223,8 +240,12 @@ struct mrs_model {
   bool want_item_avg = true;                // also accumulate per-item rating sums during the fit (P:134; not needed by P:362)
   double* upart = nullptr;      // [uch.n_chunks] chunk partial sums of ratings (fp64-value path)
   double* uavg = nullptr;       // [n_users]  average, -1.0 for unknown users (the reference's own sentinel, P:222)
-  double* uinv_hi = nullptr;    // [n_users]  1 / (5 - avg)   (code path: reciprocal of scale() for ratings above the average)
-  double* uinv_lo = nullptr;    // [n_users]  1 / (avg - 1)   (                              ... below the average)
+  // code path: shared-memory images of the item pass' per-tile tables, written by K1b (user_table_kernel) and pulled
+  // into shared memory with one bulk copy per (CTA, segment):
+  double* pop_img = nullptr;    // [pop tiles][n_codes * kPopTileUsers + 2]  dev[code][user] of every popular-part tile (+ zero slot)
+  uint2* rare_img = nullptr;    // [rare tiles][kRareTileUsers + 2]          (code sum, count) of every rare-part tile (+ dummy user)
+  double* uinv_hi = nullptr;    // (unused)
+  double* uinv_lo = nullptr;    // (unused)
   double* ipart = nullptr;      // [2 * ich.n_chunks] chunk partials: deviations | ratings
   double* xbuf = nullptr;       // [3*n_items + 2] exchange buffer: devsum | count | gsum gcount | ratesum
   double* idevavg = nullptr;    // [n_items]  0.0 for unknown items (P:197)
@@ -265,6 +286,7 @@ struct mrs_sim {
 };
 
 namespace mrs {
+extern long long* g_pass_dbg;  // diagnostics buffer (MRS_PASS_DEBUG)
 extern thread_local mrs_engine* tls_engine;  // engine whose block cache serves dev_alloc / dev_free on this thread
 inline void use_engine(const mrs_engine* e) {
   cudaSetDevice(e->device);
@@ -300,6 +322,16 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// Every kernel of a pass asks for the same shared-memory carve-out (the maximum, which the item pass and the test pass
+// need): kernels with different carve-outs cannot share an SM, so a small kernel between two big ones would otherwise
+// force two reconfigurations of every SM and defeat programmatic dependent launch.  `bit` remembers per engine that the
+// attribute has been set for this kernel on this device.
+template <typename K>
+inline void prefer_max_smem(mrs_engine* e, K kernel, uint32_t bit) {
+  if (e->smem_attr_done & bit) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e->smem_attr_done |= bit;
+}
 template <typename T>
 int32_t dev_alloc(T** p, size_t count) {
   if (count == 0) count = 1;
@@ -326,6 +358,7 @@ constexpr int kUnitBits = 7;          // bits of (kUnitLen - len) in the unit so
 int32_t build_tiled_layout(const mrs_ratings* R);
 void free_tiled_layout(const mrs_ratings* R);
 int32_t build_item_vectors(const mrs_ratings* R);
+int32_t alloc_table_images(mrs_engine* e, const mrs_ratings* R, mrs_model* m, size_t uavg_len);
 int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize);
 // baseline.cu: K1 on any padded code-vector array (per-user sums; per-item sums when item averages are wanted)
 int32_t launch_code_sums(mrs_engine* e, const uint8_t* val16, const int32_t* vec_seg, int32_t n_vec, uint32_t* seg_sum,

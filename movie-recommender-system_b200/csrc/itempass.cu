@@ -43,6 +43,11 @@ int grid_for(int64_t n, int block, int sm_count) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + block - 1) / block, (int64_t)sm_count * 16));
 }
 
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------------ layout kernels
 // item of every CSC position (binary search in the column pointer)
 __global__ void item_of_kernel(const int32_t* __restrict__ icolp, int32_t n_items, int64_t n, int32_t* __restrict__ item_of) {
@@ -197,9 +202,108 @@ __global__ void entry_fill_rare_kernel(const int32_t* __restrict__ unit_begin, c
 }
 
 __global__ void slot_item_kernel(const int32_t* __restrict__ unit_slot, const int32_t* __restrict__ unit_item, int32_t n_units,
-                                 int32_t* __restrict__ slot_item) {
+                                 int32_t* __restrict__ slot_item, int32_t* __restrict__ slot_unit) {
   const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id < n_units) slot_item[unit_slot[id]] = unit_item[id];
+  if (id < n_units) {
+    slot_item[unit_slot[id]] = unit_item[id];
+    slot_unit[unit_slot[id]] = id;
+  }
+}
+
+// Entry placement that avoids shared-memory bank conflicts in the pass.  The pass gathers one 8-byte table slot per
+// entry; a 64-bit shared-memory load is served 16 lanes at a time and conflict free only if those 16 lanes hit 16
+// different 8-byte bank pairs -- for both tables the bank pair is (user id & 15).  With entries in (item, user) order the
+// keys of a row are random: 3.2 wavefronts per half warp instead of 1 (ncu, round 2: 2.7 M of 4.7 M shared-memory
+// wavefronts of the pass were conflicts).  The order of the entries INSIDE a unit is free (it only fixes the summation
+// order), so one warp per slice deals them out position by position: every lane offers an entry whose key is still free
+// in its half warp at this position (lowest lane wins a contested key, the others offer another key in the next round);
+// a lane that has no such entry leaves the position to padding if it still has slack, else takes a conflict.
+template <bool POP>
+__global__ void __launch_bounds__(128) entry_fill_ordered_kernel(const int32_t* __restrict__ slot_unit, const int32_t* __restrict__ unit_begin,
+                                                                const int32_t* __restrict__ unit_len, const int32_t* __restrict__ unit_tile,
+                                                                int32_t n_slices, const int32_t* __restrict__ perm,
+                                                                const int32_t* __restrict__ irow, const uint8_t* __restrict__ ival,
+                                                                const int32_t* __restrict__ slice_off, int32_t code_min,
+                                                                uint32_t* __restrict__ entry) {
+  __shared__ uint32_t s_ent[4][32 * kUnitLen];   // entries of the lane's unit, grouped by key
+  __shared__ uint8_t s_next[4][32][16];          // next unplaced entry of every key group
+  __shared__ uint8_t s_end[4][32][16];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int32_t slice = blockIdx.x * 4 + w;
+  if (slice >= n_slices) return;
+  constexpr int32_t TU = POP ? kPopTileUsers : kRareTileUsers;
+  const int32_t id = slot_unit[slice * 32 + lane];
+  const int32_t len = id >= 0 ? unit_len[id] : 0;
+  const int32_t b = id >= 0 ? unit_begin[id] : 0;
+  const int32_t ubase = id >= 0 ? unit_tile[id] * TU : 0;
+  uint32_t* ent = s_ent[w] + lane * kUnitLen;
+  uint8_t* nxt = s_next[w][lane];
+  uint8_t* end = s_end[w][lane];
+  // counting sort of the unit's entries by key
+  int32_t cnt[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cnt[k] = 0;
+  for (int32_t j = 0; j < len; ++j) {
+    const int32_t key = (irow[perm[b + j]] - ubase) & 15;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cnt[k] += (key == k);
+  }
+  uint32_t avail = 0;
+  {
+    int32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      nxt[k] = (uint8_t)run;
+      run += cnt[k];
+      end[k] = (uint8_t)run;
+      if (cnt[k]) avail |= 1u << k;
+    }
+  }
+  for (int32_t j = 0; j < len; ++j) {
+    const int32_t p = perm[b + j];
+    const int32_t x = irow[p] - ubase;
+    const uint32_t e = POP ? (uint32_t)(((int32_t)ival[p] - code_min) * kPopTileUsers + x) : (((uint32_t)ival[p] << 20) | ((uint32_t)x << 3));
+    ent[nxt[x & 15]++] = e;
+  }
+  {  // rewind the group cursors
+    int32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { nxt[k] = (uint8_t)run; run += cnt[k]; }
+  }
+  __syncwarp();
+  const int64_t row0 = slice_off[slice];
+  const int32_t n_pos = (slice_off[slice + 1] - slice_off[slice]) * (POP ? 2 : 1);
+  const int half = lane >> 4;
+  int32_t remaining = len;
+  uint16_t* entry16 = reinterpret_cast<uint16_t*>(entry);
+  for (int32_t pos = 0; pos < n_pos; ++pos) {
+    uint32_t taken = 0;
+    int32_t mine = -1;
+    const bool need = remaining > 0;
+    const int rot = (lane + pos) & 15;
+    while (true) {
+      const uint32_t cand = (need && mine < 0) ? (avail & ~taken) : 0u;
+      int32_t prop = -1;
+      if (cand) {
+        const uint32_t r = ((cand >> rot) | (cand << (16 - rot))) & 0xffffu;
+        prop = (__ffs(r) - 1 + rot) & 15;
+      }
+      if (!__any_sync(0xffffffffu, prop >= 0)) break;
+      const uint32_t same = __match_any_sync(0xffffffffu, prop >= 0 ? (prop | (half << 4)) : (64 + lane));
+      const bool win = prop >= 0 && (__ffs(same) - 1 == lane);
+      if (win) mine = prop;
+      const uint32_t won = __reduce_or_sync(0xffffffffu, win ? (1u << (prop + 16 * half)) : 0u);
+      taken |= (won >> (16 * half)) & 0xffffu;
+    }
+    if (need && mine < 0 && remaining >= n_pos - pos) mine = __ffs(avail) - 1;  // no slack left: take a conflict
+    if (mine >= 0) {
+      const uint32_t e = ent[nxt[mine]++];
+      if (nxt[mine] == end[mine]) avail &= ~(1u << mine);
+      --remaining;
+      if (POP) entry16[((((row0 + (pos >> 1)) << 5) + lane) << 1) + (pos & 1)] = (uint16_t)e;
+      else entry[((row0 + pos) << 5) + lane] = e;
+    }
+  }
 }
 
 // item-major codes padded to 16-byte vectors of one item each (for the per-item rating sums): one warp per item
@@ -225,26 +329,34 @@ constexpr int kRows = 8;     // 128-byte rows per ring stage (1 KB)
 constexpr int kStages = 2;   // ring depth per warp
 constexpr double kFixScale = 1099511627776.0;  // 2^40
 // shared memory: table (the larger of the two parts' tables + one dummy slot) | rings | barriers
-constexpr size_t kPopTableBytes = ((size_t)kPopTileUsers * kMaxCodes + 1) * 8;
-constexpr size_t kRareTableBytes = ((size_t)kRareTileUsers + 1) * 8;
+constexpr size_t kPopTableBytes = ((size_t)kPopTileUsers * kMaxCodes + 2) * 8;   // + zero slot for padding entries (+1: bulk copies move 16-byte units)
+constexpr size_t kRareTableBytes = ((size_t)kRareTileUsers + 2) * 8;             // + dummy user of padding entries
 constexpr size_t kTableBytes = ((kPopTableBytes > kRareTableBytes ? kPopTableBytes : kRareTableBytes) + 127) / 128 * 128;
 constexpr size_t kRingBytes = (size_t)kPassWarps * kStages * kRows * 128;
-constexpr size_t kPassSmem = kTableBytes + kRingBytes + (size_t)kPassWarps * kStages * 8;
+constexpr size_t kPassSmem = kTableBytes + kRingBytes + (size_t)kPassWarps * kStages * 8 + 16;
 static_assert(kPassSmem <= 232448, "item pass: shared memory budget of one CTA");
+
+// One segment of a CTA's work: a run of slices of ONE tile of one part (the table in shared memory belongs to a tile)
+// (int2: x = tile of the part, bit 30 set = rare part; y = first of the 32 per-warp slice ranges of the segment in warp_part)
+struct PassSeg {
+  int32_t tile;
+  int32_t wp;
+};
+static_assert(sizeof(PassSeg) == sizeof(int2), "PassSeg is stored as int2");
 
 struct PassArgs {
   const uint32_t *entry_pop, *entry_rare;
   const int32_t *slice_off_pop, *slice_off_rare;
   const int32_t *slot_item_pop, *slot_item_rare;
-  const int2* warp_part;
-  const int3* cta_desc;
-  int32_t n_pop_tiles;
-  int32_t code_min, n_codes;
-  const uint32_t* usum;
-  const int32_t* urow;
-  int32_t n_users;
-  double* uavg;
+  const int32_t* cta_seg_ptr;    // [n_ctas+1] segments of every CTA
+  const PassSeg* seg;
+  const int2* warp_part;         // [n_segments * 32] slices [x, y) of every warp, in the slice numbering of the part
+  int32_t n_codes;
+  const double* pop_img;         // table images written by K1b
+  const uint2* rare_img;
   long long* xdev_fix;
+  unsigned long long* tl;        // diagnostics (MRS_TIMELINE=1)
+  long long* dbg;                // diagnostics (MRS_PASS_DEBUG=1): 16 clock64 stamps per CTA, else NULL
 };
 
 // full-precision reciprocal of a double that holds an integer of at most 20 significant bits: the hardware seed reads
@@ -278,206 +390,253 @@ __device__ __forceinline__ void hand_over(int32_t item, double acc, long long* _
   if (item >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(xdev_fix + item), (unsigned long long)__double2ll_rn(acc * kFixScale));
 }
 
+// state of a warp's slice walk inside a segment
+struct Walk {
+  int32_t cur, s_hi, end1, end2, item1, item2;
+};
+
+__device__ __forceinline__ void walk_begin(Walk& wk, const int2 wp, const int32_t* __restrict__ slice_off, const int32_t* __restrict__ slot_item,
+                                           int lane) {
+  wk.cur = wp.x; wk.s_hi = wp.y;
+  wk.end1 = (wk.cur < wk.s_hi) ? __ldg(slice_off + wk.cur + 1) : 0x7fffffff;        // end row of the current slice
+  wk.end2 = (wk.cur + 1 < wk.s_hi) ? __ldg(slice_off + wk.cur + 2) : 0x7fffffff;    // ... of the next one (prefetched)
+  wk.item1 = (wk.cur < wk.s_hi) ? __ldg(slot_item + wk.cur * 32 + lane) : -1;       // item of this lane's unit in the current slice
+  wk.item2 = (wk.cur + 1 < wk.s_hi) ? __ldg(slot_item + (wk.cur + 1) * 32 + lane) : -1;
+}
+// the slice ended with the previous row: hand this lane's unit sum over and move to the next slice
+__device__ __forceinline__ void walk_next(Walk& wk, double& acc, const int32_t* __restrict__ slice_off, const int32_t* __restrict__ slot_item,
+                                          int lane, long long* __restrict__ xdev_fix) {
+  hand_over(wk.item1, acc, xdev_fix);
+  acc = 0.0;
+  ++wk.cur;
+  wk.end1 = wk.end2; wk.item1 = wk.item2;
+  wk.end2 = (wk.cur + 1 < wk.s_hi) ? __ldg(slice_off + wk.cur + 2) : 0x7fffffff;
+  wk.item2 = (wk.cur + 1 < wk.s_hi) ? __ldg(slot_item + (wk.cur + 1) * 32 + lane) : -1;
+}
+
+__device__ __forceinline__ void ring_request(uint32_t* ring, uint64_t* bar, const uint32_t* __restrict__ entry, int32_t cc, int32_t rr, int32_t r_end) {
+  const int st = cc % kStages;
+  const uint32_t bytes = (uint32_t)min(kRows, r_end - rr) * 128u;
+  tma::mbar_arrive_expect_tx(bar + st, bytes);
+  tma::bulk_g2s(ring + st * kRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
+}
+
 __global__ void __launch_bounds__(kPassThreads, 1) item_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* s_tab = reinterpret_cast<double*>(smem_raw);                       // popular: dev[user][code]; rare: (S, c) pairs
+  double* s_tab = reinterpret_cast<double*>(smem_raw);                       // popular: dev[code][user]; rare: (S, c) pairs
   uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw + kTableBytes);    // [warps][kStages][kRows*32]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + kTableBytes + kRingBytes);
-  const int3 cd = a.cta_desc[blockIdx.x];
-  const bool is_pop = cd.x < a.n_pop_tiles;
-  const int32_t tile = is_pop ? cd.x : cd.x - a.n_pop_tiles;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  tl_begin(a.tl, 2);
   uint64_t* bar = s_bar + wid * kStages;
+  uint64_t* tabbar = s_bar + kPassWarps * kStages;   // completion of the table's bulk copy
   uint32_t* ring = s_ring + (size_t)wid * kStages * kRows * 32;
-  const uint32_t* __restrict__ entry = is_pop ? a.entry_pop : a.entry_rare;
-  const int32_t* __restrict__ slice_off = is_pop ? a.slice_off_pop : a.slice_off_rare;
-  const int32_t* __restrict__ slot_item = is_pop ? a.slot_item_pop : a.slot_item_rare;
-
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < kStages; ++st) tma::mbar_init(bar + st, 1);
+    if (wid == 0) tma::mbar_init(tabbar, 1);
     tma::fence_barrier_init();
   }
-  __syncwarp();
+  __syncthreads();
+  const int32_t seg_lo = __ldg(a.cta_seg_ptr + blockIdx.x), seg_hi = __ldg(a.cta_seg_ptr + blockIdx.x + 1);
+  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  int dbg_n = 0;
+#define MRS_STAMP() do { if (dbg && threadIdx.x == 0 && dbg_n < 13) dbg[dbg_n++] = clock64(); } while (0)
+  MRS_STAMP();
+  if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[13] = (long long)t; }
+  int32_t cc = 0;  // chunks this warp has consumed so far (ring stage and barrier phase follow from it)
 
-  // ---- this warp's slices (static partition) and the first ring stages: everything here reads the layout only, so it
-  // overlaps the tail of K1 (programmatic dependent launch)
-  const int2 wp = __ldg(a.warp_part + (size_t)blockIdx.x * kPassWarps + wid);
-  int32_t cur = wp.x;
-  const int32_t s_hi = wp.y;
-  const int32_t r0 = (cur < s_hi) ? __ldg(slice_off + cur) : 0;
-  const int32_t r_end = (cur < s_hi) ? __ldg(slice_off + s_hi) : 0;
-  const int32_t n_chunks = (r_end - r0 + kRows - 1) / kRows;
-  if (lane == 0) {
-#pragma unroll
-    for (int st = 0; st < kStages; ++st) {
-      if (st < n_chunks) {
-        const int32_t rr = r0 + st * kRows;
-        const uint32_t bytes = (uint32_t)min(kRows, r_end - rr) * 128u;
-        tma::mbar_arrive_expect_tx(bar + st, bytes);
-        tma::bulk_g2s(ring + st * kRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
-      }
-    }
-  }
-  int32_t end1 = (cur < s_hi) ? __ldg(slice_off + cur + 1) : 0x7fffffff;        // end row of the current slice
-  int32_t end2 = (cur + 1 < s_hi) ? __ldg(slice_off + cur + 2) : 0x7fffffff;    // ... of the next one (prefetched)
-  int32_t item1 = (cur < s_hi) ? __ldg(slot_item + cur * 32 + lane) : -1;       // item of this lane's unit in the current slice
-  int32_t item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
-
-  pdl_trigger();  // K2b may be scheduled as SMs free up
-  pdl_wait();     // K1's per-user code sums are complete from here on
-
-  // ---- per-user averages (P:113 / P:274): every CTA writes an equal share of the user table (exact sum, one correctly
-  // rounded division, P:18; -1.0 = no ratings, the reference's own sentinel P:222)
+  // the rows of the first segment start travelling before K1 has finished (they only depend on the layout)
+  PassSeg sg = (seg_lo < seg_hi) ? a.seg[seg_lo] : PassSeg{0, 0};
+  int2 wp = (seg_lo < seg_hi) ? __ldg(a.warp_part + sg.wp + wid) : make_int2(0, 0);
   {
-    const int32_t per = (a.n_users + gridDim.x - 1) / gridDim.x;
-    const int32_t u_lo = blockIdx.x * per, u_hi = min(a.n_users, u_lo + per);
-    for (int32_t u = u_lo + threadIdx.x; u < u_hi; u += kPassThreads) {
-      const uint32_t S = __ldg(a.usum + u);
-      const uint32_t cnt = (uint32_t)(__ldg(a.urow + u + 1) - __ldg(a.urow + u));
-      a.uavg[u] = cnt ? (0.5 * (double)S) / (double)cnt : -1.0;
+    const bool rare = (sg.tile >> 30) & 1;
+    const uint32_t* entry = rare ? a.entry_rare : a.entry_pop;
+    const int32_t* slice_off = rare ? a.slice_off_rare : a.slice_off_pop;
+    if (wp.x < wp.y && lane == 0) {
+      const int32_t r0 = __ldg(slice_off + wp.x), r_end = __ldg(slice_off + wp.y);
+#pragma unroll
+      for (int k = 0; k < kStages; ++k)
+        if (r0 + k * kRows < r_end) ring_request(ring, bar, entry, k, r0 + k * kRows, r_end);
     }
   }
-
-  double acc = 0.0;
-  if (is_pop) {
-    // ---- deviation table of the tile: dev[j][x] for code code_min + j and user u0 + x.  One thread per user: the two
-    // reciprocals of its scale() values once, then one multiplication per code; consecutive threads write consecutive
-    // slots of a column (no bank conflicts)
-    const int32_t u0 = tile * kPopTileUsers;
-    const int32_t nc = a.n_codes;
-    const int32_t n_slots = kPopTileUsers * nc;
-#pragma unroll
-    for (int32_t x = threadIdx.x; x < kPopTileUsers; x += kPassThreads) {
-      const int32_t u = u0 + x;
-      const bool in = u < a.n_users;
-      const int32_t S = in ? (int32_t)__ldg(a.usum + u) : 0;
-      const int32_t cnt = in ? __ldg(a.urow + u + 1) - __ldg(a.urow + u) : 0;
-      const double inv_hi = rcp_small_int(int_to_double(10 * cnt - S));  // 1 / (5 - avg) up to the common factor 2c
-      const double inv_lo = rcp_small_int(int_to_double(S - 2 * cnt));   // 1 / (avg - 1)
-      for (int32_t j = 0; j < nc; ++j) {
-        const int32_t N = cnt * (a.code_min + j) - S;
-        double dev = int_to_double(N) * (N > 0 ? inv_hi : inv_lo);
-        if (N == 0 || cnt == 0) dev = 0.0;  // r == avg: the reference's 0/1 (also keeps 0 * inf out when avg is exactly 1 or 5)
-        s_tab[j * kPopTileUsers + x] = dev;
-      }
+  // ... and the rows of the later segments are asked into the L2 now: a warp's ring holds 2 KB, far too little to cover
+  // HBM latency at the rate the rows are consumed (stamps, round 2: 1.5 us per 1 KB chunk), but its whole run of a
+  // segment is contiguous and only a few KB -- one bulk prefetch per (warp, segment), in flight while K1 finishes and
+  // the first table is built
+  if (lane == 0) {
+    for (int32_t si = seg_lo; si < seg_hi; ++si) {
+      const PassSeg s2 = a.seg[si];
+      const int2 w2 = __ldg(a.warp_part + s2.wp + wid);
+      if (w2.x >= w2.y) continue;
+      const bool rare = (s2.tile >> 30) & 1;
+      const int32_t* so = rare ? a.slice_off_rare : a.slice_off_pop;
+      const int32_t ra = __ldg(so + w2.x), rb = __ldg(so + w2.y);
+      const int32_t skip = (si == seg_lo) ? kStages * kRows : 0;  // (already requested into shared memory)
+      if (rb - ra > skip) tma::prefetch_l2((rare ? a.entry_rare : a.entry_pop) + ((int64_t)(ra + skip) << 5), (uint32_t)(rb - ra - skip) * 128u);
     }
-    if (threadIdx.x == 0) s_tab[n_slots] = 0.0;  // padding entries point here
-    __syncthreads();
+  }
+  pdl_trigger();  // K2b may be scheduled as SMs free up
+  pdl_wait();     // K1b's table images are complete from here on
+  MRS_STAMP();
+  MRS_STAMP();
+  for (int32_t si = seg_lo; si < seg_hi; ++si) {
+    if (si > seg_lo) {
+      sg = a.seg[si];
+      wp = __ldg(a.warp_part + sg.wp + wid);
+      __syncthreads();  // every warp is done with the previous segment's table
+    }
+    const bool rare = (sg.tile >> 30) & 1;
+    const int32_t tile = sg.tile & 0x3fffffff;
+    const uint32_t* __restrict__ entry = rare ? a.entry_rare : a.entry_pop;
+    const int32_t* __restrict__ slice_off = rare ? a.slice_off_rare : a.slice_off_pop;
+    const int32_t* __restrict__ slot_item = rare ? a.slot_item_rare : a.slot_item_pop;
+    const int32_t r0 = (wp.x < wp.y) ? __ldg(slice_off + wp.x) : 0;
+    const int32_t r_end = (wp.x < wp.y) ? __ldg(slice_off + wp.y) : 0;
+    const int32_t n_chunks = (r_end - r0 + kRows - 1) / kRows;
+    if (si > seg_lo && lane == 0) {  // (the first segment's rows were requested in the prologue)
+#pragma unroll
+      for (int k = 0; k < kStages; ++k)
+        if (k < n_chunks) ring_request(ring, bar, entry, cc + k, r0 + k * kRows, r_end);
+    }
+    Walk wk;
+    walk_begin(wk, wp, slice_off, slot_item, lane);
+    double acc = 0.0;
 
-    for (int32_t c = 0; c < n_chunks; ++c) {
-      const int st = c % kStages;
-      const int32_t r = r0 + c * kRows;
-      const int32_t nrows = min(kRows, r_end - r);
-      tma::mbar_wait(bar + st, (uint32_t)(c / kStages) & 1u);
-      const uint32_t* rp = ring + st * kRows * 32 + lane;  // conflict free: lane l reads word l of a row
+    // ---- the tile's table: one image written by K1b, pulled into shared memory by bulk copies (4 in flight)
+    {
+      const uint32_t bytes = rare ? (uint32_t)kRareTableBytes : (uint32_t)((size_t)kPopTileUsers * a.n_codes + 2) * 8u;
+      if (threadIdx.x == 0) {
+        const unsigned char* img = rare ? reinterpret_cast<const unsigned char*>(a.rare_img) + (size_t)tile * kRareTableBytes
+                                        : reinterpret_cast<const unsigned char*>(a.pop_img) + (size_t)tile * bytes;
+        tma::mbar_arrive_expect_tx(tabbar, bytes);
+        const uint32_t piece = ((bytes / 4) + 15u) & ~15u;
+        for (uint32_t off = 0; off < bytes; off += piece) tma::bulk_g2s(smem_raw + off, img + off, min(piece, bytes - off), tabbar);
+      }
+      tma::mbar_wait(tabbar, (uint32_t)(si - seg_lo) & 1u);
+    }
+    MRS_STAMP();
+
+    if (!rare) {
+      const int32_t n_slots = kPopTileUsers * a.n_codes;
       const uint32_t pad = (uint32_t)n_slots | ((uint32_t)n_slots << 16);
-      uint32_t w[kRows];
-      if (nrows == kRows) {
+      for (int32_t c = 0; c < n_chunks; ++c, ++cc) {
+        const int st = cc % kStages;
+        const int32_t r = r0 + c * kRows;
+        const int32_t nrows = min(kRows, r_end - r);
+        tma::mbar_wait(bar + st, (uint32_t)(cc / kStages) & 1u);
+        const uint32_t* rp = ring + st * kRows * 32 + lane;  // conflict free: lane l reads word l of a row
+        uint32_t w[kRows];
+        if (nrows == kRows) {
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) w[k] = rp[k * 32];
-      } else {
+          for (int k = 0; k < kRows; ++k) w[k] = rp[k * 32];
+        } else {
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) w[k] = (k < nrows) ? rp[k * 32] : pad;
-      }
-      __syncwarp();
-      if (lane == 0 && c + kStages < n_chunks) {  // the stage is free again: request the chunk kStages ahead
-        const int32_t rr = r + kStages * kRows;
-        const uint32_t bytes = (uint32_t)min(kRows, r_end - rr) * 128u;
-        tma::mbar_arrive_expect_tx(bar + st, bytes);
-        tma::bulk_g2s(ring + st * kRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
-      }
-#pragma unroll
-      for (int h = 0; h < kRows; h += 4) {
-        double d0[4], d1[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // all gathers of the half stage go out together
-          d0[k] = *reinterpret_cast<const double*>(smem_raw + ((w[h + k] << 3) & 0x7fff8u));
-          d1[k] = *reinterpret_cast<const double*>(smem_raw + ((w[h + k] >> 13) & 0x7fff8u));
+          for (int k = 0; k < kRows; ++k) w[k] = (k < nrows) ? rp[k * 32] : pad;
         }
+        __syncwarp();
+        if (lane == 0 && c + kStages < n_chunks)  // the stage is free again: request the chunk kStages ahead
+          ring_request(ring, bar, entry, cc + kStages, r + kStages * kRows, r_end);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // ordered accumulation + slice boundaries (warp-uniform branch)
-          if (r + h + k == end1) {     // the slice ended with the previous row: hand this lane's unit sum over
-            hand_over(item1, acc, a.xdev_fix);
-            acc = 0.0;
-            ++cur;
-            end1 = end2; item1 = item2;
-            end2 = (cur + 1 < s_hi) ? __ldg(slice_off + cur + 2) : 0x7fffffff;
-            item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
+        for (int h = 0; h < kRows; h += 4) {
+          double d0[4], d1[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // all gathers of the half stage go out together
+            d0[k] = *reinterpret_cast<const double*>(smem_raw + ((w[h + k] << 3) & 0x7fff8u));
+            d1[k] = *reinterpret_cast<const double*>(smem_raw + ((w[h + k] >> 13) & 0x7fff8u));
           }
-          acc += d0[k];
-          acc += d1[k];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // ordered accumulation + slice boundaries (warp-uniform branch)
+            if (r + h + k == wk.end1) walk_next(wk, acc, slice_off, slot_item, lane, a.xdev_fix);
+            acc += d0[k];
+            acc += d1[k];
+          }
         }
       }
-    }
-  } else {
-    // ---- (code sum, count) of the tile's users; slot kRareTileUsers is the dummy user of padding entries: S = 0, c = 1
-    // gives N = 0 for code 0, i.e. a deviation of exactly 0
-    uint2* s_sc = reinterpret_cast<uint2*>(s_tab);
-    const int32_t u0 = tile * kRareTileUsers;
-    constexpr int kPer = kRareTileUsers / kPassThreads;
-#pragma unroll
-    for (int k0 = 0; k0 < kPer; k0 += 8) {  // 8 users per thread at a time: their 24 loads go out together
-      uint32_t S[8];
-      int32_t b0[8], b1[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int32_t u = u0 + (k0 + k) * kPassThreads + threadIdx.x;
-        const bool in = u < a.n_users;
-        S[k] = in ? __ldg(a.usum + u) : 0u;
-        b0[k] = in ? __ldg(a.urow + u) : 0;
-        b1[k] = in ? __ldg(a.urow + u + 1) : 0;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s_sc[(k0 + k) * kPassThreads + threadIdx.x] = make_uint2(S[k], (uint32_t)(b1[k] - b0[k]));
-    }
-    if (threadIdx.x == 0) s_sc[kRareTileUsers] = make_uint2(0u, 1u);
-    __syncthreads();
-    const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_tab);
-    constexpr uint32_t kPadEntry = (uint32_t)kRareTileUsers << 3;
+    } else {
+      constexpr uint32_t kPadEntry = (uint32_t)kRareTileUsers << 3;
 
-    for (int32_t c = 0; c < n_chunks; ++c) {
-      const int st = c % kStages;
-      const int32_t r = r0 + c * kRows;
-      const int32_t nrows = min(kRows, r_end - r);
-      tma::mbar_wait(bar + st, (uint32_t)(c / kStages) & 1u);
-      const uint32_t* rp = ring + st * kRows * 32 + lane;
-      uint32_t ev[kRows];
-      if (nrows == kRows) {
+      for (int32_t c = 0; c < n_chunks; ++c, ++cc) {
+        const int st = cc % kStages;
+        const int32_t r = r0 + c * kRows;
+        const int32_t nrows = min(kRows, r_end - r);
+        tma::mbar_wait(bar + st, (uint32_t)(cc / kStages) & 1u);
+        const uint32_t* rp = ring + st * kRows * 32 + lane;
+        uint32_t ev[kRows];
+        if (nrows == kRows) {
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) ev[k] = rp[k * 32];
-      } else {
+          for (int k = 0; k < kRows; ++k) ev[k] = rp[k * 32];
+        } else {
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : kPadEntry;
-      }
-      __syncwarp();
-      if (lane == 0 && c + kStages < n_chunks) {
-        const int32_t rr = r + kStages * kRows;
-        const uint32_t bytes = (uint32_t)min(kRows, r_end - rr) * 128u;
-        tma::mbar_arrive_expect_tx(bar + st, bytes);
-        tma::bulk_g2s(ring + st * kRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
-      }
-      double dv[kRows];
-#pragma unroll
-      for (int k = 0; k < kRows; ++k) {  // heavy part: no branches, 8 independent chains
-        const uint2 sc = *reinterpret_cast<const uint2*>(tab + (ev[k] & 0xffff8u));
-        dv[k] = dev_from_counts(sc.x, sc.y, ev[k] >> 20);
-      }
-#pragma unroll
-      for (int k = 0; k < kRows; ++k) {
-        if (r + k == end1) {
-          hand_over(item1, acc, a.xdev_fix);
-          acc = 0.0;
-          ++cur;
-          end1 = end2; item1 = item2;
-          end2 = (cur + 1 < s_hi) ? __ldg(slice_off + cur + 2) : 0x7fffffff;
-          item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
+          for (int k = 0; k < kRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : kPadEntry;
         }
-        acc += dv[k];
+        __syncwarp();
+        if (lane == 0 && c + kStages < n_chunks) ring_request(ring, bar, entry, cc + kStages, r + kStages * kRows, r_end);
+        double dv[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {  // heavy part: no branches, 8 independent chains
+          const uint2 sc = *reinterpret_cast<const uint2*>(smem_raw + (ev[k] & 0xffff8u));
+          dv[k] = dev_from_counts(sc.x, sc.y, ev[k] >> 20);
+        }
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          if (r + k == wk.end1) walk_next(wk, acc, slice_off, slot_item, lane, a.xdev_fix);
+          acc += dv[k];
+        }
       }
+    }
+    if (wk.cur < wk.s_hi) hand_over(wk.item1, acc, a.xdev_fix);  // last slice of the range
+    MRS_STAMP();  // (warp 0's own end of the segment)
+  }
+  if (a.tl) { __syncthreads(); tl_end(a.tl, 2); }
+  if (dbg) {
+    __syncthreads();
+    MRS_STAMP();
+    if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[14] = (long long)t; dbg[15] = dbg_n; }
+  }
+#undef MRS_STAMP
+}
+
+// K1b: per user, everything the item pass and the test pass need from K1's code sums: the average (P:113 / P:274: exact
+// sum, one correctly rounded division, P:18; -1.0 = no ratings, the reference's own sentinel P:222), the (code sum, count)
+// pair in the rare-part table image and the column of deviations dev[code] in the popular-part table image (two
+// reciprocals per user, one multiplication per code).  The images have the shared-memory layout of the item pass, so a
+// CTA of the pass pulls a tile's table in with one bulk copy instead of building it (stamps, round 2: building cost
+// 3-5 us per CTA and segment, a third of the pass).
+__global__ void __launch_bounds__(256) user_table_kernel(uint32_t* __restrict__ usum, const int32_t* __restrict__ urow, int32_t u_lo,
+                                                        int32_t u_hi, int32_t code_min, int32_t nc, double* __restrict__ uavg,
+                                                        double* __restrict__ pop_img, uint2* __restrict__ rare_img,
+                                                        unsigned long long* __restrict__ tl) {
+  tl_begin(tl, 1);
+  pdl_trigger();
+  pdl_wait();  // K1's sums are complete
+  const int32_t u = u_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= u_hi) { tl_end(tl, 1); return; }
+  const int32_t S = (int32_t)usum[u];
+  usum[u] = 0;  // re-armed for K1's integer atomics of the next pass (no memset node in front of every pass)
+  const int32_t cnt = __ldg(urow + u + 1) - __ldg(urow + u);
+  uavg[u] = cnt ? (0.5 * (double)S) / (double)cnt : -1.0;
+  rare_img[(size_t)(u / kRareTileUsers) * (kRareTileUsers + 2) + (u % kRareTileUsers)] = make_uint2((uint32_t)S, (uint32_t)cnt);
+  if (pop_img) {
+    double* col = pop_img + (size_t)(u / kPopTileUsers) * ((size_t)kPopTileUsers * nc + 2) + (u % kPopTileUsers);
+    const double inv_hi = rcp_small_int(int_to_double(10 * cnt - S));  // 1 / (5 - avg) up to the common factor 2c
+    const double inv_lo = rcp_small_int(int_to_double(S - 2 * cnt));   // 1 / (avg - 1)
+    for (int32_t j = 0; j < nc; ++j) {
+      const int32_t N = cnt * (code_min + j) - S;
+      double dev = int_to_double(N) * (N > 0 ? inv_hi : inv_lo);
+      if (N == 0 || cnt == 0) dev = 0.0;  // r == avg: the reference's 0/1 (also keeps 0 * inf out when avg is exactly 1 or 5)
+      col[(size_t)j * kPopTileUsers] = dev;
     }
   }
-  if (cur < s_hi) hand_over(item1, acc, a.xdev_fix);  // last slice of the range
+  tl_end(tl, 1);
+}
+
+// one-time initialisation of a model's table images: zeros, the dummy user (S = 0, c = 1: deviation 0 for code 0) of every
+// rare tile, and "no ratings" for every user average (users outside [user_lo, user_hi) never get anything else)
+__global__ void table_init_kernel(uint2* __restrict__ rare_img, int32_t n_rare_tiles, double* __restrict__ uavg, int64_t n_uavg) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_rare_tiles) rare_img[(size_t)i * (kRareTileUsers + 2) + kRareTileUsers] = make_uint2(0u, 1u);
+  for (int64_t k = i; k < n_uavg; k += (int64_t)gridDim.x * blockDim.x) uavg[k] = -1.0;
 }
 
 // K2b: per item, integer accumulators -> exchange buffer (and re-arm them for the next pass); optionally finish the fit
@@ -485,7 +644,9 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
                                                                  const int32_t* __restrict__ icolp, int32_t n_items,
                                                                  unsigned long long* __restrict__ k1_part, double n_total,
                                                                  double* __restrict__ xbuf, int fused, double* __restrict__ idevavg,
-                                                                 double* __restrict__ iavg, double* __restrict__ gavg) {
+                                                                 double* __restrict__ iavg, double* __restrict__ gavg,
+                                                                 unsigned long long* __restrict__ tl) {
+  tl_begin(tl, 3);
   pdl_trigger();
   pdl_wait();  // the accumulators are complete once the item pass has finished
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -496,7 +657,7 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
     if (fused) gavg[0] = n_total > 0.0 ? gs / n_total : 0.0;
   }
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
+  if (i >= n_items) { tl_end(tl, 3); return; }
   const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
   const double rs = 0.5 * (double)xcode_sum[i];
   xdev_fix[i] = 0;
@@ -509,6 +670,7 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
     idevavg[i] = cnt > 0.0 ? ds / cnt : 0.0;
     iavg[i] = cnt > 0.0 ? rs / cnt : nan("");
   }
+  tl_end(tl, 3);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -621,29 +783,35 @@ int32_t build_part(const mrs_ratings* R, const PartTemps& tmp_in, int32_t want, 
   P.n_rows = P.h_slice_off[(size_t)NS];
   MRS_TRY(dev_alloc(&P.entry, (size_t)P.n_rows * 32 + 32));
   fill_u32_kernel<<<grid_for(P.n_rows * 32, block, e->sm_count), block, 0, st>>>(P.entry, P.n_rows * 32, pad_word);
-  if (pop)
-    entry_fill_pop_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, P.slice_off,
-                                                  code_min, n_codes, reinterpret_cast<uint16_t*>(P.entry));
-  else
-    entry_fill_rare_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, P.slice_off,
-                                                   P.entry);
-  // ---- item of every slot (empty slots: -1)
+  // ---- item and unit of every slot (empty slots: -1)
+  int32_t* slot_unit = nullptr;
   MRS_TRY(dev_alloc(&P.slot_item, (size_t)NS * 32));
+  MRS_TRY(dev_alloc(&slot_unit, (size_t)NS * 32));
   MRS_CUDA(cudaMemsetAsync(P.slot_item, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
-  slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, P.slot_item);
+  MRS_CUDA(cudaMemsetAsync(slot_unit, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
+  slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, P.slot_item, slot_unit);
+  if (env_int("MRS_NO_REORDER", 0)) {  // entries in (item, user) order: the A/B switch for the bank-conflict-aware placement
+    if (pop)
+      entry_fill_pop_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival,
+                                                    P.slice_off, code_min, n_codes, reinterpret_cast<uint16_t*>(P.entry));
+    else
+      entry_fill_rare_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival,
+                                                     P.slice_off, P.entry);
+  } else if (pop) {
+    entry_fill_ordered_kernel<true><<<(NS + 3) / 4, 128, 0, st>>>(slot_unit, unit_begin, unit_len, unit_tile, NS, perm, R->irow, (const uint8_t*)R->ival,
+                                                                 P.slice_off, code_min, P.entry);
+  } else {
+    entry_fill_ordered_kernel<false><<<(NS + 3) / 4, 128, 0, st>>>(slot_unit, unit_begin, unit_len, unit_tile, NS, perm, R->irow, (const uint8_t*)R->ival,
+                                                                  P.slice_off, code_min, P.entry);
+  }
   count_launch(18);
   MRS_CUDA(cudaGetLastError());
   MRS_CUDA(cudaStreamSynchronize(st));
   for (void* p : {(void*)tk_in, (void*)tk_out, (void*)pos_in, (void*)perm, (void*)head, (void*)seg_start, (void*)flag, (void*)uid,
                   (void*)unit_begin, (void*)unit_item, (void*)unit_tile, (void*)unit_len, (void*)ids, (void*)sorted_id, (void*)skey,
-                  (void*)skey_out, (void*)tile_first, (void*)unit_slot, (void*)slice_rows, (void*)d_tile_unit_ptr, (void*)d_tile_slice})
+                  (void*)skey_out, (void*)tile_first, (void*)unit_slot, (void*)slice_rows, (void*)d_tile_unit_ptr, (void*)d_tile_slice, (void*)slot_unit})
     dev_free(p);
   return MRS_OK;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
 }
 
 // first slice s in [lo, hi) whose cost prefix (rows before it + slice_cost * slices before it) is >= v
@@ -659,10 +827,12 @@ int32_t lower_bound_cost(const std::vector<int32_t>& slice_off, int32_t lo, int3
 
 }  // namespace
 
+long long* g_pass_dbg = nullptr;
+
 void free_tiled_layout(const mrs_ratings* R) {
   auto& T = R->tl;
   free_part(T.pop); free_part(T.rare);
-  dev_free(T.cta_desc); dev_free(T.warp_part); dev_free(T.ival16); dev_free(T.vec_col);
+  dev_free(T.cta_seg_ptr); dev_free(T.seg); dev_free(T.warp_part); dev_free(T.ival16); dev_free(T.vec_col);
   T = mrs_ratings::tiled_layout();
 }
 
@@ -691,6 +861,12 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
     MRS_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
     MRS_CUDA(cudaStreamSynchronize(st));
   }
+  if (n > 0) {  // the sorted COO starts with the first user that has ratings and ends with the last
+    MRS_CUDA(cudaMemcpyAsync(&T.user_lo, R->coo_u, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaMemcpyAsync(&T.user_hi, R->coo_u + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    T.user_hi += 1;
+  }
   T.code_min = (n > 0) ? h_stats[0] : 0;
   T.n_codes = (n > 0) ? h_stats[1] - h_stats[0] + 1 : 1;
   // popular = long enough (tile, item) runs with tiles of kPopTileUsers users: about 6 ratings per tile on average.
@@ -709,42 +885,93 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   MRS_TRY(build_part(R, tmp, 0, kRareTileUsers, n - (int64_t)h_pop, T.code_min, T.n_codes, T.rare));
   dev_free(tmp.item_of); dev_free(tmp.pop_flag); dev_free(d_stats); dev_free(d_count);
 
-  // ---- static work partition: CTAs dealt out to the tiles of both parts by cost, then slices to the warps of each CTA.
-  // Cost model (issue slots, from the SASS): a popular row (64 ratings) ~ 14 instructions per lane, a rare row (32
-  // ratings) ~ 34, handing a slice over ~ 40 (the atomics occupy the load/store unit for about that long).
-  const int w_pop_row = env_int("MRS_W_POP_ROW", 14), w_rare_row = env_int("MRS_W_RARE_ROW", 34), w_slice = env_int("MRS_W_SLICE", 40);
-  const int32_t pop_slice_cost = std::max(1, w_slice / w_pop_row), rare_slice_cost = std::max(1, w_slice / w_rare_row);
-  const int32_t NTP = T.pop.n_tiles, NTR = T.rare.n_tiles;
-  std::vector<int64_t> cost((size_t)NTP + NTR, 0);
-  auto tile_cost = [](const mrs_ratings::ell_part& P, int32_t t, int w_row, int32_t slice_cost) -> int64_t {
-    if (P.n_slices == 0) return 0;
-    const int32_t s0 = P.h_tile_slice[(size_t)t], s1 = P.h_tile_slice[(size_t)t + 1];
-    return ((int64_t)(P.h_slice_off[(size_t)s1] - P.h_slice_off[(size_t)s0]) + (int64_t)slice_cost * (s1 - s0)) * w_row;
-  };
-  for (int32_t t = 0; t < NTP; ++t) cost[(size_t)t] = tile_cost(T.pop, t, w_pop_row, pop_slice_cost);
-  for (int32_t t = 0; t < NTR; ++t) cost[(size_t)NTP + t] = tile_cost(T.rare, t, w_rare_row, rare_slice_cost);
-  const std::vector<int3> desc = deal_ctas(cost, e->sm_count);
-  T.n_ctas = (int32_t)desc.size();
-  std::vector<int2> wpart(std::max<size_t>(1, desc.size()) * kPassWarps, make_int2(0, 0));
-  for (size_t b = 0; b < desc.size(); ++b) {
-    const bool pop = desc[b].x < NTP;
-    const mrs_ratings::ell_part& P = pop ? T.pop : T.rare;
-    const int32_t t = pop ? desc[b].x : desc[b].x - NTP;
-    const int32_t slice_cost = pop ? pop_slice_cost : rare_slice_cost;
-    const int32_t ts0 = P.h_tile_slice[(size_t)t], ts1 = P.h_tile_slice[(size_t)t + 1];
-    const int64_t total = (int64_t)(P.h_slice_off[(size_t)ts1] - P.h_slice_off[(size_t)ts0]) + (int64_t)slice_cost * (ts1 - ts0);
-    const int64_t nw = (int64_t)desc[b].z * kPassWarps;
-    for (int w = 0; w < kPassWarps; ++w) {
-      const int64_t gw = (int64_t)desc[b].y * kPassWarps + w;
-      const int32_t lo = lower_bound_cost(P.h_slice_off, ts0, ts1, slice_cost, total * gw / nw);
-      const int32_t hi = lower_bound_cost(P.h_slice_off, ts0, ts1, slice_cost, total * (gw + 1) / nw);
-      wpart[b * kPassWarps + w] = make_int2(lo, hi);
+  // ---- static work partition.  The slices of both parts form one sequence (popular tiles, then rare tiles); every CTA
+  // takes a contiguous run of it, cut into segments at tile boundaries (the table in shared memory belongs to a tile),
+  // each segment split over the 32 warps.  Cost of a run, in units of one 128-byte row (7 ns per CTA for both kinds of
+  // rows -- stamps, round 2): rows + slice_cost per slice (handing a slice over) + table_cost per segment (pulling a
+  // tile's table into shared memory: ~3 us).  The runs are made equal in cost by bisection on the cost per CTA, so most
+  // CTAs work on ONE tile and load one table.
+  const int32_t n_ctas = (n > 0) ? e->sm_count : 0;
+  const int32_t slice_cost[2] = {std::max(1, env_int("MRS_POP_SLICE_COST", 3)), std::max(1, env_int("MRS_RARE_SLICE_COST", 2))};
+  const int64_t table_cost = env_int("MRS_TABLE_COST", 400);
+  std::vector<std::vector<int2>> cta_segs((size_t)std::max(n_ctas, 1));  // per CTA: (tile | kind, first slice); end slices in a parallel vector
+  std::vector<std::vector<int32_t>> cta_seg_end((size_t)std::max(n_ctas, 1));
+  if (n_ctas > 0) {
+    struct Piece { int part, tile, s0, s1; };   // the non-empty tiles in sequence order
+    std::vector<Piece> pieces;
+    for (int part = 0; part < 2; ++part) {
+      const mrs_ratings::ell_part& P = part == 0 ? T.pop : T.rare;
+      for (int32_t t = 0; t < P.n_tiles && P.n_slices > 0; ++t)
+        if (P.h_tile_slice[(size_t)t + 1] > P.h_tile_slice[(size_t)t]) pieces.push_back({part, t, P.h_tile_slice[(size_t)t], P.h_tile_slice[(size_t)t + 1]});
     }
+    auto slice_c = [&](const Piece& pc, int32_t s_) -> int64_t {
+      const mrs_ratings::ell_part& P = pc.part == 0 ? T.pop : T.rare;
+      return (int64_t)(P.h_slice_off[(size_t)s_ + 1] - P.h_slice_off[(size_t)s_]) + slice_cost[pc.part];
+    };
+    // greedy sweep for a cost cap: returns the number of CTAs used (and the cuts when `emit`)
+    auto sweep = [&](int64_t cap, bool emit) -> int64_t {
+      int64_t used = 0, acc = 0;
+      bool open = false;
+      for (const Piece& pc : pieces) {
+        int32_t s0 = pc.s0;
+        while (s0 < pc.s1) {
+          if (!open) { ++used; acc = 0; open = true; }
+          acc += table_cost;
+          int32_t s1 = s0;
+          while (s1 < pc.s1 && (acc + slice_c(pc, s1) <= cap || s1 == s0)) { acc += slice_c(pc, s1); ++s1; }
+          if (emit) {
+            const size_t b_ = (size_t)std::min<int64_t>(used - 1, n_ctas - 1);
+            cta_segs[b_].push_back(make_int2(pc.tile | (pc.part << 30), s0));
+            cta_seg_end[b_].push_back(s1);
+          }
+          if (s1 < pc.s1) open = false;                                  // the cap was reached inside the tile: next CTA
+          else if (acc + table_cost + table_cost / 2 > cap) open = false;  // not worth opening another tile for a sliver
+          s0 = s1;
+        }
+      }
+      return used;
+    };
+    int64_t lo = 1, hi = 0;
+    for (const Piece& pc : pieces) {
+      const mrs_ratings::ell_part& P = pc.part == 0 ? T.pop : T.rare;
+      hi += (int64_t)(P.h_slice_off[(size_t)pc.s1] - P.h_slice_off[(size_t)pc.s0]) + (int64_t)slice_cost[pc.part] * (pc.s1 - pc.s0) + table_cost;
+    }
+    hi = std::max<int64_t>(hi, 2);
+    while (lo < hi) {  // smallest cap that needs at most n_ctas CTAs
+      const int64_t mid = (lo + hi) / 2;
+      if (sweep(mid, false) <= n_ctas) hi = mid; else lo = mid + 1;
+    }
+    sweep(lo, true);
   }
-  MRS_TRY(dev_alloc(&T.cta_desc, std::max<size_t>(1, desc.size())));
-  MRS_TRY(dev_alloc(&T.warp_part, wpart.size()));
-  if (!desc.empty()) MRS_CUDA(cudaMemcpyAsync(T.cta_desc, desc.data(), sizeof(int3) * desc.size(), cudaMemcpyHostToDevice, st));
-  MRS_CUDA(cudaMemcpyAsync(T.warp_part, wpart.data(), sizeof(int2) * wpart.size(), cudaMemcpyHostToDevice, st));
+  std::vector<int32_t> seg_ptr((size_t)n_ctas + 1, 0);
+  std::vector<int2> segs, wpart;
+  for (int32_t b_ = 0; b_ < n_ctas; ++b_) {
+    for (size_t k = 0; k < cta_segs[(size_t)b_].size(); ++k) {
+      const int2 sgm = cta_segs[(size_t)b_][k];
+      const int part = (sgm.x >> 30) & 1;
+      const mrs_ratings::ell_part& P = part == 0 ? T.pop : T.rare;
+      const int32_t sc = slice_cost[part];
+      const int32_t s0 = sgm.y, s1 = cta_seg_end[(size_t)b_][k];
+      const int64_t total = (int64_t)(P.h_slice_off[(size_t)s1] - P.h_slice_off[(size_t)s0]) + (int64_t)sc * (s1 - s0);
+      segs.push_back(make_int2(sgm.x, (int32_t)wpart.size()));
+      for (int w = 0; w < kPassWarps; ++w) {
+        const int32_t lo = lower_bound_cost(P.h_slice_off, s0, s1, sc, total * w / kPassWarps);
+        const int32_t hi = lower_bound_cost(P.h_slice_off, s0, s1, sc, total * (w + 1) / kPassWarps);
+        wpart.push_back(make_int2(lo, hi));
+      }
+    }
+    seg_ptr[(size_t)b_ + 1] = (int32_t)segs.size();
+  }
+  T.n_ctas = n_ctas;
+  T.n_segs = (int32_t)segs.size();
+  MRS_TRY(dev_alloc(&T.cta_seg_ptr, seg_ptr.size()));
+  MRS_TRY(dev_alloc(&T.seg, std::max<size_t>(1, segs.size())));
+  MRS_TRY(dev_alloc(&T.warp_part, std::max<size_t>(1, wpart.size())));
+  MRS_CUDA(cudaMemcpyAsync(T.cta_seg_ptr, seg_ptr.data(), sizeof(int32_t) * seg_ptr.size(), cudaMemcpyHostToDevice, st));
+  if (!segs.empty()) {
+    MRS_CUDA(cudaMemcpyAsync(T.seg, segs.data(), sizeof(int2) * segs.size(), cudaMemcpyHostToDevice, st));
+    MRS_CUDA(cudaMemcpyAsync(T.warp_part, wpart.data(), sizeof(int2) * wpart.size(), cudaMemcpyHostToDevice, st));
+  }
   MRS_CUDA(cudaStreamSynchronize(st));  // the host vectors must outlive the copies; the pass reads the tables in its prologue
   T.built = true;
   return MRS_OK;
@@ -781,6 +1008,22 @@ int32_t build_item_vectors(const mrs_ratings* R) {
   return MRS_OK;
 }
 
+// table images of a new model (sizes follow the layout) and their one-time initialisation
+int32_t alloc_table_images(mrs_engine* e, const mrs_ratings* R, mrs_model* m, size_t uavg_len) {
+  const auto& T = R->tl;
+  const size_t pop_doubles = (size_t)std::max(T.pop.n_tiles, 1) * ((size_t)kPopTileUsers * T.n_codes + 2);
+  const size_t rare_pairs = (size_t)std::max(T.rare.n_tiles, 1) * (kRareTileUsers + 2);
+  MRS_TRY(dev_alloc(&m->pop_img, pop_doubles));
+  MRS_TRY(dev_alloc(&m->rare_img, rare_pairs));
+  MRS_CUDA(cudaMemsetAsync(m->pop_img, 0, pop_doubles * sizeof(double), e->stream));
+  MRS_CUDA(cudaMemsetAsync(m->rare_img, 0, rare_pairs * sizeof(uint2), e->stream));
+  table_init_kernel<<<std::max(1, std::min((int)((uavg_len + 255) / 256), e->sm_count * 8)), 256, 0, e->stream>>>(m->rare_img, T.rare.n_tiles, m->uavg,
+                                                                                                            (int64_t)uavg_len);
+  count_launch();
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
 int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused) {
   const auto& T = R->tl;
   cudaStream_t st = e->stream;
@@ -788,24 +1031,48 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
     MRS_CUDA(cudaFuncSetAttribute(item_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassSmem));
     e->smem_attr_done |= 1u;
   }
+  prefer_max_smem(e, user_table_kernel, 1u << 7);
+  prefer_max_smem(e, item_tiled_finalize_kernel, 1u << 8);
+  if (T.user_hi > T.user_lo) {  // K1b: averages + the table images of the tiles that have ratings
+    MRS_CUDA(launch_pdl(user_table_kernel, dim3((T.user_hi - T.user_lo + 255) / 256), dim3(256), 0, st, m->usum, R->urow, T.user_lo, T.user_hi,
+                        T.code_min, T.n_codes, m->uavg, T.pop.n_slices > 0 ? m->pop_img : (double*)nullptr, m->rare_img, e->d_timeline));
+    mark(e, "user_tables");
+  }
   if (T.n_ctas > 0) {
     PassArgs a;
     a.entry_pop = T.pop.entry; a.entry_rare = T.rare.entry;
     a.slice_off_pop = T.pop.slice_off; a.slice_off_rare = T.rare.slice_off;
     a.slot_item_pop = T.pop.slot_item; a.slot_item_rare = T.rare.slot_item;
-    a.warp_part = T.warp_part; a.cta_desc = T.cta_desc;
-    a.n_pop_tiles = T.pop.n_tiles;
-    a.code_min = T.code_min; a.n_codes = T.n_codes;
-    a.usum = m->usum; a.urow = R->urow; a.n_users = R->n_users; a.uavg = m->uavg; a.xdev_fix = m->xdev_fix;
+    a.cta_seg_ptr = T.cta_seg_ptr; a.seg = reinterpret_cast<const PassSeg*>(T.seg); a.warp_part = T.warp_part;
+    a.n_codes = T.n_codes;
+    a.pop_img = m->pop_img; a.rare_img = m->rare_img; a.xdev_fix = m->xdev_fix;
+    a.dbg = nullptr;
+    a.tl = e->d_timeline;
+    static long long* g_dbg = nullptr;  // diagnostics only (tools/pass_stamps.py): one buffer per process
+    if (env_int("MRS_PASS_DEBUG", 0) == 1) {
+      if (!g_dbg) MRS_CUDA(cudaMalloc((void**)&g_dbg, sizeof(long long) * 16 * 1024));
+      MRS_CUDA(cudaMemsetAsync(g_dbg, 0, sizeof(long long) * 16 * 1024, st));
+      a.dbg = g_dbg;
+      g_pass_dbg = g_dbg;
+    }
     // one CTA of 1024 threads per SM: the grid (T.n_ctas <= SM count unless there are more busy tiles than SMs) is one wave
     MRS_CUDA(launch_pdl(item_pass_kernel, dim3(T.n_ctas), dim3(kPassThreads), kPassSmem, st, a));
     mark(e, "item_tiled");
   }
   MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
-                      m->k1_part, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg));
+                      m->k1_part, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg, e->d_timeline));
   mark(e, "item_tiled_finalize");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
 }
 
 }  // namespace mrs
+
+// diagnostics: clock64 stamps of the last item pass launched with MRS_PASS_DEBUG=1 (16 per CTA; [15] = number of stamps)
+extern "C" int32_t mrs_debug_pass_stamps(int64_t* out, int32_t n_ctas) {
+  MRS_REQUIRE(out && n_ctas > 0 && n_ctas <= 1024, MRS_ERR_INVALID, "mrs_debug_pass_stamps: bad argument");
+  MRS_REQUIRE(mrs::g_pass_dbg, MRS_ERR_INVALID, "mrs_debug_pass_stamps: no pass has run with MRS_PASS_DEBUG=1");
+  MRS_CUDA(cudaDeviceSynchronize());
+  MRS_CUDA(cudaMemcpy(out, mrs::g_pass_dbg, sizeof(int64_t) * 16 * (size_t)n_ctas, cudaMemcpyDeviceToHost));
+  return MRS_OK;
+}
