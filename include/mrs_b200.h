@@ -87,6 +87,10 @@ MRS_API int64_t mrs_launch_count(void);
 MRS_API int32_t mrs_engine_create(int32_t device, void* cuda_stream, mrs_engine** out);
 MRS_API void mrs_engine_destroy(mrs_engine* e);
 MRS_API int32_t mrs_engine_sync(mrs_engine* e);
+/* diagnostics: an engine created with MRS_TIMELINE=1 in the environment records, per kernel k of the baseline pass (0 user
+ * sums, 1 item pass, 2 item finalize, 3 test pass), the earliest block start out32[2k] and the latest block end out32[2k+1]
+ * in %globaltimer nanoseconds; the call synchronises, copies them out and re-arms the slots (tools/timeline.py) */
+MRS_API int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32);
 
 /* CUDA-graph capture of any sequence of the asynchronous entry points (mrs_fit_async, mrs_fit_local, mrs_fit_finish,
  * mrs_fit_similarity_async, mrs_mae_async) on this engine's stream: the kernels of a pass take tens of microseconds, so
@@ -138,13 +142,6 @@ MRS_API int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* bytes3);
  * item-tiled test layout; [7] 16-code vectors of the padded user-major code array */
 MRS_API int32_t mrs_ratings_layout_info(const mrs_ratings* r, int64_t* out8);
 MRS_API void mrs_ratings_destroy(mrs_ratings* r);
-/* diagnostics: with MRS_PASS_DEBUG=1 in the environment the item pass of the fit records 16 clock64 stamps per CTA (start,
- * dependency wait passed, averages written, then per segment: table built, warp 0 done; last: all warps done; [15] = count) */
-MRS_API int32_t mrs_debug_pass_stamps(int64_t* out, int32_t n_ctas);
-/* diagnostics: engines created with MRS_TIMELINE=1 record, per kernel k of the baseline pass (0 user sums, 1 user tables,
- * 2 item pass, 3 item finalize, 4 test pass, 5 item sums), the earliest block start out32[2k] and the latest block end
- * out32[2k+1] in %globaltimer nanoseconds; the call synchronises, copies them out and re-arms the slots */
-MRS_API int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32);
 
 /* ---- fit: replaces the eager part of computePrediction (P:205-214) / baselinePredictorSpark (P:362-368)
  * and of computeAvgRating/computeUserAvg/computeItemAvg/computeItemAvgDev ---- */

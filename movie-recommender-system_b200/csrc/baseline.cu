@@ -57,9 +57,9 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
 // atomicAdd per (warp, user).  Integer sums are exact: the result does not depend on the order of the atomics.
 __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
                                                       uint32_t* __restrict__ usum, unsigned long long* __restrict__ gsum_codes,
-                                                      unsigned long long* __restrict__ tl, int tl_k) {
+                                                      unsigned long long* __restrict__ tl) {
   __shared__ uint32_t sh[8];
-  tl_begin(tl, tl_k);
+  tl_begin(tl, 0);
   pdl_trigger();  // the item pass may start its prologue (ring prefetch) while this kernel runs
   const int lane = threadIdx.x & 31;
   constexpr int V = 2;  // vectors per thread (both loads are issued before the first use)
@@ -94,9 +94,9 @@ __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict
   if (threadIdx.x == 0) {
     unsigned long long a = 0;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += sh[k];
-    if (gsum_codes) atomicAdd(gsum_codes, a);  // integer: exact, order independent
+    atomicAdd(gsum_codes, a);  // integer: exact, order independent
   }
-  tl_end(tl, tl_k);
+  tl_end(tl, 0);
 }
 
 // ---- K1b: per-user average (-1.0 sentinel for users without ratings) + global rating sum / count
@@ -351,34 +351,14 @@ inline int chunk_grid(int32_t n_chunks, int sm_count) {
   return std::max(1, std::min(g, sm_count * 8));
 }
 
-// code path: K1 (user code sums) [-> item code sums, only when item averages are wanted] -> K2 item pass (forms the user
-// averages on the way) -> K2b finalize.  K1 and the item sums are plain stream-ordered launches; K2 and K2b are
-// programmatic dependents of the kernel right before them (their prologues overlap its tail).
+// code path: K1 (user code sums) -> K2 tiled item pass (forms the user averages on the way) -> K2b finalize
 int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused) {
-  // (usum is zero on entry: cleared when the model is created, re-armed by K1b after every pass)
-  MRS_TRY(launch_code_sums(e, R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, "user_sum"));
-  if (m->want_item_avg) {  // P:134: per-item rating sums with the same kernel on the item-major code vectors
-    MRS_TRY(build_item_vectors(R));
-    MRS_TRY(launch_code_sums(e, R->tl.ival16, R->tl.vec_col, R->tl.n_ivec, m->xcode_sum, nullptr, "item_sum"));
-  }
+  MRS_CUDA(cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream));
+  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, e->d_timeline);
+  mark(e, "user_sum");
+  MRS_CUDA(cudaGetLastError());
   return launch_item_tiled(e, R, m, fused);
 }
-
-}  // namespace
-
-int32_t launch_code_sums(mrs_engine* e, const uint8_t* val16, const int32_t* vec_seg, int32_t n_vec, uint32_t* seg_sum,
-                         unsigned long long* total_or_null, const char* label) {
-  if (n_vec <= 0) return MRS_OK;
-  prefer_max_smem(e, user_sum_kernel, 1u << 4);
-  user_sum_kernel<<<(n_vec + 511) / 512, 256, 0, e->stream>>>(val16, vec_seg, n_vec, seg_sum, total_or_null, e->d_timeline, total_or_null ? 0 : 5);
-  mark(e, label);
-  MRS_CUDA(cudaGetLastError());
-  return MRS_OK;
-}
-
-namespace {
-
-int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused);
 
 template <typename VT>
 int32_t launch_fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model* m) {
@@ -458,25 +438,27 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
     int32_t s = MRS_OK;
     if (codes) {
       if (s == MRS_OK) s = dev_alloc(&m->usum, (size_t)R->n_users);
-      if (s == MRS_OK && cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
       if (s == MRS_OK) s = dev_alloc(&m->k1_part, 1);
       if (s == MRS_OK && cudaMemsetAsync(m->k1_part, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
       if (s == MRS_OK) s = dev_alloc(&m->xdev_fix, (size_t)R->n_items);
       if (s == MRS_OK) s = dev_alloc(&m->xcode_sum, (size_t)R->n_items);
       if (s == MRS_OK && cudaMemsetAsync(m->xdev_fix, 0, sizeof(long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
-      if (s == MRS_OK && cudaMemsetAsync(m->xcode_sum, 0, sizeof(uint32_t) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+      if (s == MRS_OK && cudaMemsetAsync(m->xcode_sum, 0, sizeof(unsigned long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
     }
     if (s == MRS_OK) s = dev_alloc(&m->upart, (size_t)R->uch.n_chunks);
     // padded to whole user tiles: the tiled kernel stages a tile's averages with one 64 KB bulk copy
     const size_t uavg_len = ((size_t)R->n_users + kTileUsers - 1) / kTileUsers * kTileUsers + kTileUsers;
     if (s == MRS_OK) s = dev_alloc(&m->uavg, uavg_len);
-    if (s == MRS_OK && codes) s = alloc_table_images(e, R, m, uavg_len);
+    if (s == MRS_OK && codes) {
+      // the item pass writes the averages of the tiles that have ratings; user tiles without any (the id range of another
+      // rank in a sharded run) keep this "no ratings" mark (P:222 getOrElse(user, -1.0)) for the life of the model
+      fill_f64_kernel<<<std::max(1, std::min((int)((uavg_len + 255) / 256), e->sm_count * 8)), 256, 0, e->stream>>>(m->uavg, (int64_t)uavg_len, -1.0);
+      count_launch();
+      if (cudaGetLastError() != cudaSuccess) s = MRS_ERR_CUDA;
+    }
     if (s == MRS_OK) s = dev_alloc(&m->ipart, 2 * (size_t)R->ich.n_chunks);
     if (s == MRS_OK) s = dev_alloc(&m->xbuf, 3 * (size_t)R->n_items + 2);
-    // padded to whole item tiles with zeros: the test pass pulls a tile's 8,192 deviations in with one bulk copy
-    const size_t idev_len = ((size_t)R->n_items + kMaeTileItems - 1) / kMaeTileItems * kMaeTileItems;
-    if (s == MRS_OK) s = dev_alloc(&m->idevavg, idev_len);
-    if (s == MRS_OK && cudaMemsetAsync(m->idevavg, 0, sizeof(double) * idev_len, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+    if (s == MRS_OK) s = dev_alloc(&m->idevavg, (size_t)R->n_items);
     if (s == MRS_OK) s = dev_alloc(&m->iavg, (size_t)R->n_items);
     if (s == MRS_OK) s = dev_alloc(&m->gavg, 1);
     if (s == MRS_OK) s = dev_alloc(&m->mae_part, (size_t)m->mae_part_cap);
@@ -499,7 +481,6 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
 
 int32_t fit_finish(mrs_model* m) {
   MRS_REQUIRE(m, MRS_ERR_INVALID, "mrs_fit_finish: NULL model");
-  prefer_max_smem(m->eng, item_finalize_kernel, 1u << 5);
   MRS_CUDA(launch_pdl(item_finalize_kernel, dim3((m->n_items + 255) / 256), dim3(256), 0, m->eng->stream, m->xbuf, m->n_items, m->idevavg,
                       m->iavg, m->gavg));
   mark(m->eng, "item_finalize");

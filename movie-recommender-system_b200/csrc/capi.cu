@@ -201,8 +201,6 @@ extern "C" void mrs_engine_destroy(mrs_engine* e) {
   delete e;
 }
 
-// diagnostics: copy out and re-arm the timeline of the engine (MRS_TIMELINE=1): out[2k] earliest start, out[2k+1] latest end
-// of kernel k (0 user sums, 1 user tables, 2 item pass, 3 item finalize, 4 test pass, 5 item sums), %globaltimer ns
 extern "C" int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32) {
   MRS_REQUIRE(e && out32, MRS_ERR_INVALID, "mrs_debug_timeline: NULL argument");
   MRS_REQUIRE(e->d_timeline, MRS_ERR_INVALID, "mrs_debug_timeline: the engine was created without MRS_TIMELINE=1");
@@ -338,7 +336,7 @@ extern "C" int32_t mrs_model_exchange_buffer(mrs_model* m, void** device_ptr, in
 extern "C" void mrs_model_destroy(mrs_model* m) {
   if (!m) return;
   if (m->eng) use_engine(m->eng);
-  dev_free(m->uinv_hi); dev_free(m->uinv_lo); dev_free(m->pop_img); dev_free(m->rare_img);
+  dev_free(m->uinv_hi); dev_free(m->uinv_lo);
   dev_free(m->usum); dev_free(m->k1_part); dev_free(m->xdev_fix); dev_free(m->xcode_sum);
   dev_free(m->upart); dev_free(m->uavg); dev_free(m->ipart); dev_free(m->xbuf); dev_free(m->idevavg); dev_free(m->iavg);
   dev_free(m->gavg); dev_free(m->mae_part); dev_free(m->counters);

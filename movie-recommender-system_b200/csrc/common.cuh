@@ -57,7 +57,7 @@ __host__ __device__ inline double decode_value(double v) { return v; }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// diagnostics (MRS_TIMELINE=1): slot 2k = earliest start, 2k+1 = latest end of kernel k of a pass, in %globaltimer ns
+// diagnostics (MRS_TIMELINE=1): slot 2k = earliest block start, 2k+1 = latest block end of kernel k of a pass, %globaltimer ns
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -104,7 +104,7 @@ struct mrs_engine {
   std::unordered_map<void*, size_t> live_blocks;
   size_t cached_bytes = 0;
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remembered per engine, not per process
-  // (bit 0: item pass kernels, bit 1: test pass kernel, bits 4..: carve-out preference of the small kernels)
+  // (bit 0: item pass kernels, bit 1: test pass kernel)
   uint32_t smem_attr_done = 0;
   unsigned long long* d_timeline = nullptr;  // [32] diagnostics, allocated when MRS_TIMELINE=1 (mrs_debug_timeline)
   // diagnostics: event after every launch while profiling (mrs_profile_begin/end)
@@ -179,40 +179,23 @@ struct mrs_ratings {
     int32_t* seg = nullptr;        // [n_items * (n_sub+1)] first CSC entry of column i whose compact index is >= b * kRowsSub
   };
   mutable sim_layout sl;
-  // ---- lazily built layout of the item pass of the fit (itempass.cu); half-star codes only.
-  // The train entries are split by item popularity into two user-tiled sliced-ELL structures (see itempass.cu):
-  //   popular items: tiles of kPopTileUsers users, 16-bit entries = index into the tile's (user, code) deviation table
-  //   rare items:    tiles of kRareTileUsers users, 32-bit entries = code | slot of the user's (code sum, count) pair
-  struct ell_part {
-    int32_t tile_users = 0;
-    int32_t n_tiles = 0, n_units = 0, n_slices = 0;
-    int64_t n_rows = 0;                // 128-byte rows (32 lanes x one 32-bit word)
-    int64_t n_entries = 0;             // ratings held by this part
-    uint32_t* entry = nullptr;         // [n_rows * 32] words
-    int32_t* slice_off = nullptr;      // [n_slices+1] first row of each slice
-    int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
-    std::vector<int32_t> h_slice_off;  // host copies for the static work partition
-    std::vector<int32_t> h_tile_slice; // [n_tiles+1]
-  };
+  // ---- lazily built tiled item-major layout for the fit kernel (tiled.cu); half-star codes only
   struct tiled_layout {
     bool built = false;
-    ell_part pop, rare;
-    int32_t code_min = 0, n_codes = 0; // columns of the popular part's deviation table: codes code_min .. code_min+n_codes-1
-    int32_t pop_threshold = 0;         // items with at least this many ratings are "popular" (INT_MAX: no popular part)
-    int32_t user_lo = 0, user_hi = 0;  // ids of the first user with ratings and one past the last (a rank of a sharded run owns a range)
-    // static work partition of the pass (depends on the layout and the SM count only; laid down with the layout): every
-    // CTA gets an equal share of the cost of BOTH parts, as a list of segments -- runs of slices of one tile (the table
-    // in shared memory belongs to a tile): seg[k].x = tile (bit 30: rare part), seg[k].y = first of the segment's 32
-    // per-warp slice ranges in warp_part.  Tiles without ratings (another rank's users in a sharded run) cost nothing.
-    int32_t n_ctas = 0, n_segs = 0;
-    int32_t* cta_seg_ptr = nullptr;    // [n_ctas+1]
-    int2* seg = nullptr;               // [n_segs]
-    int2* warp_part = nullptr;         // [n_segs * 32] slices [x, y) of every warp, in the slice numbering of its part
-    // per-item rating sums (P:134), only when item averages are wanted: the item-major codes padded to 16-byte vectors
-    // of ONE item each, summed by the same kernel as the per-user sums (K1)
-    uint8_t* ival16 = nullptr;
-    int32_t* vec_col = nullptr;
-    int32_t n_ivec = 0;
+    int32_t n_tiles = 0;
+    int32_t n_units = 0;
+    int32_t n_slices = 0;
+    int64_t n_slots = 0;               // 32 * (rows of all slices)
+    uint32_t* entry = nullptr;         // [n_slots] bit31 valid | code << 16 | user id local to the tile
+    int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
+    int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
+    int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
+    // static work partition of the item pass (depends on the layout and the SM count only; laid down with the layout):
+    // CTA b works on tile cta_desc[b].x as share .y of .z -- CTAs are dealt out to the tiles in proportion to their
+    // cost, tiles without ratings (a rank of a sharded run owns a user range) get none
+    int32_t n_ctas = 0;
+    int3* cta_desc = nullptr;          // [n_ctas]
+    int2* warp_part = nullptr;         // [n_ctas * 32] slices [x, y) of every warp
   };
   mutable tiled_layout tl;
   // ---- lazily built item-tiled layout for the fused predict + |error| kernel (mae_tiled.cu); half-star codes only
@@ -236,16 +219,12 @@ struct mrs_model {
   unsigned long long* k1_part = nullptr;  // [1] sum of all half-star codes (integer atomics in K1, re-armed by K2b)
   int32_t k1_blocks = 0;
   long long* xdev_fix = nullptr;            // [n_items] per-item deviation sums in units of 2^-40 (exact integer accumulation)
-  uint32_t* xcode_sum = nullptr;            // [n_items] per-item sums of half-star codes (only filled when item averages are wanted)
+  unsigned long long* xcode_sum = nullptr;  // [n_items] per-item sums of half-star codes
   bool want_item_avg = true;                // also accumulate per-item rating sums during the fit (P:134; not needed by P:362)
   double* upart = nullptr;      // [uch.n_chunks] chunk partial sums of ratings (fp64-value path)
   double* uavg = nullptr;       // [n_users]  average, -1.0 for unknown users (the reference's own sentinel, P:222)
-  // code path: shared-memory images of the item pass' per-tile tables, written by K1b (user_table_kernel) and pulled
-  // into shared memory with one bulk copy per (CTA, segment):
-  double* pop_img = nullptr;    // [pop tiles][n_codes * kPopTileUsers + 2]  dev[code][user] of every popular-part tile (+ zero slot)
-  uint2* rare_img = nullptr;    // [rare tiles][kRareTileUsers + 2]          (code sum, count) of every rare-part tile (+ dummy user)
-  double* uinv_hi = nullptr;    // (unused)
-  double* uinv_lo = nullptr;    // (unused)
+  double* uinv_hi = nullptr;    // [n_users]  1 / (5 - avg)   (code path: reciprocal of scale() for ratings above the average)
+  double* uinv_lo = nullptr;    // [n_users]  1 / (avg - 1)   (                              ... below the average)
   double* ipart = nullptr;      // [2 * ich.n_chunks] chunk partials: deviations | ratings
   double* xbuf = nullptr;       // [3*n_items + 2] exchange buffer: devsum | count | gsum gcount | ratesum
   double* idevavg = nullptr;    // [n_items]  0.0 for unknown items (P:197)
@@ -286,7 +265,6 @@ struct mrs_sim {
 };
 
 namespace mrs {
-extern long long* g_pass_dbg;  // diagnostics buffer (MRS_PASS_DEBUG)
 extern thread_local mrs_engine* tls_engine;  // engine whose block cache serves dev_alloc / dev_free on this thread
 inline void use_engine(const mrs_engine* e) {
   cudaSetDevice(e->device);
@@ -322,16 +300,6 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-// Every kernel of a pass asks for the same shared-memory carve-out (the maximum, which the item pass and the test pass
-// need): kernels with different carve-outs cannot share an SM, so a small kernel between two big ones would otherwise
-// force two reconfigurations of every SM and defeat programmatic dependent launch.  `bit` remembers per engine that the
-// attribute has been set for this kernel on this device.
-template <typename K>
-inline void prefer_max_smem(mrs_engine* e, K kernel, uint32_t bit) {
-  if (e->smem_attr_done & bit) return;
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  e->smem_attr_done |= bit;
-}
 template <typename T>
 int32_t dev_alloc(T** p, size_t count) {
   if (count == 0) count = 1;
@@ -348,21 +316,13 @@ int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items,
 // Deal `n_ctas` CTAs out to tiles in proportion to their cost (largest remainder; every tile with cost > 0 gets at least
 // one as long as there are enough CTAs): desc[b] = (tile, share, shares of that tile), tiles ascending.
 std::vector<int3> deal_ctas(const std::vector<int64_t>& tile_cost, int32_t n_ctas);
-// itempass.cu
-constexpr int kTileUsers = 8192;      // padding granule of the per-user tables
-constexpr int kPopTileUsers = 2048;   // users per tile of the popular part: 2048 x 10 codes x 8 B = 160 KB of deviations in shared memory
-constexpr int kRareTileUsers = 16384; // users per tile of the rare part: 128 KB of (code sum, count) pairs in shared memory
-constexpr int kMaxCodes = 10;         // columns of the deviation table (half-star data: 0.5 .. 5.0)
-constexpr int kUnitLen = 64;          // (tile,item) segments are cut into units of at most this many entries
-constexpr int kUnitBits = 7;          // bits of (kUnitLen - len) in the unit sort key
+// tiled.cu
+constexpr int kTileUsers = 8192;  // users per tile: 64 KB of fp64 averages in shared memory
+constexpr int kUnitLen = 64;      // (tile,item) segments are cut into units of at most this many entries
+constexpr int kUnitBits = 7;      // bits of (kUnitLen - len) in the unit sort key
 int32_t build_tiled_layout(const mrs_ratings* R);
 void free_tiled_layout(const mrs_ratings* R);
-int32_t build_item_vectors(const mrs_ratings* R);
-int32_t alloc_table_images(mrs_engine* e, const mrs_ratings* R, mrs_model* m, size_t uavg_len);
 int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize);
-// baseline.cu: K1 on any padded code-vector array (per-user sums; per-item sums when item averages are wanted)
-int32_t launch_code_sums(mrs_engine* e, const uint8_t* val16, const int32_t* vec_seg, int32_t n_vec, uint32_t* seg_sum,
-                         unsigned long long* total_or_null, const char* label);
 // mae_tiled.cu
 constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item deviations in shared memory
 int32_t build_mae_layout(const mrs_ratings* T);

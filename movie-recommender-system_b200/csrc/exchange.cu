@@ -306,7 +306,6 @@ static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_dou
   // (its second barrier, fence and phase cost about 12 us, i.e. about 10 MB of NVLink time: below that every rank simply
   // reads all the peers' buffers)
   const int two_shot = (x->world > 2 && (n_doubles & 1) == 0 && (int64_t)(x->world - 1) * n_doubles * 8 > (int64_t)12 << 20) ? 1 : 0;
-  prefer_max_smem(x->eng, peer_allreduce_kernel, 1u << 6);
   MRS_CUDA(launch_pdl(peer_allreduce_kernel, dim3(grid), dim3(kExThreads), 0, x->eng->stream, x->d_peer, x->rank, x->world, n_doubles, x->n,
                       two_shot, x->d_epoch, x->d_done, x->d_error, x->d_stamps, (double*)device_inout, device_idx, x->timeout_cycles));
   mark(x->eng, "peer_allreduce");

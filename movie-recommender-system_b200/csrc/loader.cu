@@ -722,15 +722,14 @@ extern "C" int32_t mrs_ratings_bytes(const mrs_ratings* r, int64_t* b) {
   b[1] = r->n * (4 + vs);    // item-major pass: user id + value
   b[2] = r->n * (8 + vs);    // sorted COO pass: user id + item id + value
   if (r->uval16) b[0] = (int64_t)r->n_vec * 20;  // padded codes (16 per vector) + one user id per vector
-  if (r->tl.built) b[1] = r->tl.pop.n_entries * 2 + r->tl.rare.n_entries * 4;  // item pass: 16-bit entries of popular items, 32-bit entries of rare ones (padding not counted)
+  if (r->tl.built) b[1] = r->n * 4;              // tiled item-major layout: one packed 32-bit word per rating (padding not counted)
   if (r->ml.built) b[2] = r->n * 8;              // item-tiled test layout: one packed 8-byte word per rating (padding not counted)
   return MRS_OK;
 }
 
 extern "C" int32_t mrs_ratings_layout_info(const mrs_ratings* r, int64_t* o) {
   MRS_REQUIRE(r && o, MRS_ERR_INVALID, "mrs_ratings_layout_info: NULL argument");
-  o[0] = r->tl.pop.n_tiles + r->tl.rare.n_tiles; o[1] = r->tl.pop.n_units + r->tl.rare.n_units;
-  o[2] = r->tl.pop.n_slices + r->tl.rare.n_slices; o[3] = (r->tl.pop.n_rows + r->tl.rare.n_rows) * 32;
+  o[0] = r->tl.n_tiles; o[1] = r->tl.n_units; o[2] = r->tl.n_slices; o[3] = r->tl.n_slots;
   o[4] = r->ml.n_tiles; o[5] = r->ml.n_rows; o[6] = r->ml.n_rows * 32; o[7] = r->n_vec;
   return MRS_OK;
 }

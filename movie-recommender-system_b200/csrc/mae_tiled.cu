@@ -10,7 +10,6 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
-#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -61,7 +60,7 @@ __global__ void mae_scatter_kernel(const uint16_t* __restrict__ key, const int32
 constexpr int kMaeThreads = 1024;
 constexpr int kMaeRows = 8;    // rows (32 entries of 8 bytes = 256 B) per ring stage: 2 KB
 constexpr int kMaeStages = 2;
-constexpr size_t kMaeSmem = (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 32) * kMaeStages * kMaeRows * 256 + (size_t)(kMaeThreads / 32) * kMaeStages * 8 + 16;
+constexpr size_t kMaeSmem = (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 32) * kMaeStages * kMaeRows * 256 + (size_t)(kMaeThreads / 32) * kMaeStages * 8;
 
 // one CTA = (item tile, share of the tile's rows); 32 warps, one CTA per SM
 __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const uint2* __restrict__ entry, const int32_t* __restrict__ tile_row_ptr,
@@ -69,13 +68,8 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
                                                                           const double* __restrict__ uavg, const double* __restrict__ idevavg,
                                                                           const double* __restrict__ gavg_p, double n_total,
                                                                           double* __restrict__ part, unsigned int* __restrict__ counter,
-                                                                          double* __restrict__ out2, unsigned long long* __restrict__ tl,
-                                                                          long long* __restrict__ dbg_all) {
-  tl_begin(tl, 4);
-  long long* dbg = dbg_all ? dbg_all + (size_t)blockIdx.x * 16 : nullptr;
-  int dbg_n = 0;
-#define MRS_STAMP() do { if (dbg && threadIdx.x == 0 && dbg_n < 13) dbg[dbg_n++] = clock64(); } while (0)
-  MRS_STAMP();
+                                                                          double* __restrict__ out2, unsigned long long* __restrict__ tl) {
+  tl_begin(tl, 3);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_dev = reinterpret_cast<double*>(smem_raw);                                     // [kMaeTileItems]
   uint2* s_ring = reinterpret_cast<uint2*>(smem_raw + (size_t)kMaeTileItems * 8);          // [warps][stages][rows*32]
@@ -88,14 +82,12 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
   constexpr int32_t wpb = kMaeThreads >> 5;
   uint64_t* bar = s_bar + wid * kMaeStages;
   uint2* ring = s_ring + (size_t)wid * kMaeStages * kMaeRows * 32;
-  uint64_t* tabbar = s_bar + wpb * kMaeStages;   // completion of the bulk copy of the tile's item deviations
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < kMaeStages; ++st) tma::mbar_init(bar + st, 1);
-    if (wid == 0) tma::mbar_init(tabbar, 1);
     tma::fence_barrier_init();
   }
-  __syncthreads();
+  __syncwarp();
   // ---- this warp's rows: an equal share of the tile's rows
   const int32_t ra = tile_row_ptr[tile], rb = tile_row_ptr[tile + 1];
   const int32_t nw = ctas_per_tile * wpb, w = share * wpb + wid;
@@ -113,30 +105,16 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
       }
     }
   }
-  // ---- while the fit is still running: ask the L2 for the rest of this warp's rows (a warp's ring holds 4 KB and its whole
-  // run is only a few chunks: without this every chunk waits for HBM) and for this CTA's share of the user averages
-  // (gathered per entry below; a prefetch is only a hint to the L2, the point of coherence, so it is safe while the
-  // averages are still being written)
-  if (lane == 0 && r_end - r0 > kMaeStages * kMaeRows)
-    tma::prefetch_l2(entry + ((int64_t)(r0 + kMaeStages * kMaeRows) << 5), (uint32_t)(r_end - r0 - kMaeStages * kMaeRows) * 256u);
-  {
-    const int64_t total = ((int64_t)n_users * 8 + 15) & ~(int64_t)15;
-    const int64_t per = ((total + gridDim.x - 1) / gridDim.x + 15) & ~(int64_t)15;
-    const int64_t lo = (int64_t)blockIdx.x * per + (int64_t)wid * 16384;   // 16 KB pieces, one per warp
-    const int64_t hi = min(total, (int64_t)(blockIdx.x + 1) * per);
-    if (lane == 0 && lo < hi) tma::prefetch_l2(reinterpret_cast<const unsigned char*>(uavg) + lo, (uint32_t)min((int64_t)16384, hi - lo));
-  }
-  // ---- the tile's item deviations (unknown item -> 0.0, P:226-227): one bulk copy of 64 KB (the table is padded to whole
-  // tiles with zeros)
-  pdl_wait();  // barriers, partition, prefetches and the first ring stages overlapped the end of the fit; its outputs are complete from here on
-  MRS_STAMP();
-  if (threadIdx.x == 0) {
-    tma::mbar_arrive_expect_tx(tabbar, (uint32_t)kMaeTileItems * 8u);
-    tma::bulk_g2s(s_dev, idevavg + (size_t)tile * kMaeTileItems, (uint32_t)kMaeTileItems * 8u, tabbar);
+  // ---- the tile's item deviations (unknown item -> 0.0, P:226-227)
+  pdl_wait();  // barriers, partition and the first ring stages overlapped the end of the fit; its outputs are complete from here on
+  const int32_t i0 = tile * kMaeTileItems;
+#pragma unroll 4
+  for (int32_t x = threadIdx.x; x < kMaeTileItems; x += kMaeThreads) {
+    const int32_t i = i0 + x;
+    s_dev[x] = (i < n_items) ? __ldg(idevavg + i) : 0.0;
   }
   const double gavg = gavg_p[0];
-  tma::mbar_wait(tabbar, 0u);
-  MRS_STAMP();
+  __syncthreads();
 
   double acc = 0.0;
   for (int32_t c = 0; c < n_chunks; ++c) {
@@ -170,11 +148,9 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
       acc += (code != 0xffu) ? err : 0.0;                           // 0xFF = padding slot
     }
   }
-  MRS_STAMP();
   acc = warp_sum(acc);
   if (lane == 0) sh[wid] = acc;
   __syncthreads();
-  MRS_STAMP();
   if (threadIdx.x < 32) {
     double t = (threadIdx.x < wpb) ? sh[threadIdx.x] : 0.0;
     t = warp_sum(t);
@@ -200,10 +176,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
       *counter = 0;
     }
   }
-  MRS_STAMP();
-  if (dbg && threadIdx.x == 0) dbg[15] = dbg_n;
-#undef MRS_STAMP
-  tl_end(tl, 4);
+  tl_end(tl, 3);
 }
 
 int grid_for(int64_t n, int block, int sm_count) {
@@ -278,19 +251,10 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
     e->smem_attr_done |= 2u;
   }
   const int32_t grid = L.n_ctas;
-  long long* mae_dbg = nullptr;
-  {
-    const char* v = getenv("MRS_PASS_DEBUG");
-    if (v && atoi(v) == 2) {  // diagnostics: the test pass records the per-CTA stamps instead of the item pass
-      if (!g_pass_dbg) MRS_CUDA(cudaMalloc((void**)&g_pass_dbg, sizeof(long long) * 16 * 1024));
-      MRS_CUDA(cudaMemsetAsync(g_pass_dbg, 0, sizeof(long long) * 16 * 1024, e->stream));
-      mae_dbg = g_pass_dbg;
-    }
-  }
   MRS_REQUIRE(grid > 0 && grid <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set needs %d CTAs, more than the %d partial slots of the model", grid,
               m->mae_part_cap);
   MRS_CUDA(launch_pdl(predict_mae_tiled_kernel, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
-                      m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, mae_dbg));
+                      m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline));
   mark(e, "predict_mae_tiled");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

@@ -1,0 +1,542 @@
+// tiled.cu -- the item-deviation pass of the fit (P:155-186 / P:316-343) on a layout made for B200:
+//
+//   * users are cut into tiles of kTileUsers; a CTA stages the tile's fp64 user averages in shared memory
+//     (64 KB), so the 20 M random 8-byte gathers of the pass hit shared-memory banks instead of L2 sectors
+//     (capture A: 640 MB of L2 sector traffic, L1 hit rate 11 %);
+//   * inside a tile the entries are item-major; every (tile, item) segment is cut into units of <= kUnitLen
+//     entries, units are sorted by length and packed 32 to a "slice" in sliced-ELL order (entry j of lane l at
+//     row j, column l), so a warp streams a slice with one coalesced 128-byte load per row and every lane
+//     accumulates ITS unit sequentially: no cross-lane reduction, no atomics, a fixed summation order;
+//   * an entry is 4 bytes: valid bit | half-star code | 16-bit user id local to the tile.
+//
+// The finalisation kernel adds the units of an item in (tile, sub-chunk) order, so the pass is bit-reproducible.
+// Deviation = (r - avg) * (1 / scale): the two possible reciprocals of a user, 1/(5-avg) and 1/(avg-1), are computed
+// once per user with a correctly rounded division (user_avg_kernel) and staged in shared memory next to the average,
+// so the inner loop has no division.  d * fl(1/s) differs from the reference's fl(d / s) by <= 1 ulp -- far inside
+// the 1e-6 parity bound; the kNN path, whose neighbour ranking needs the exact bits, computes its own deviations
+// with a true division (knn.cu).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace mrs {
+namespace {
+
+struct MaxOp {
+  __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+
+// item of every CSC position (binary search in the column pointer) and its tile; the sort key is the tile only,
+// the radix sort is stable so (item, user) order survives inside a tile
+__global__ void tile_keys_kernel(const int32_t* __restrict__ irow, const int32_t* __restrict__ icolp, int32_t n_items, int64_t n,
+                                 uint16_t* __restrict__ tile_key, int32_t* __restrict__ pos, int32_t* __restrict__ item_of) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    int32_t lo = 0, hi = n_items;  // largest i with icolp[i] <= p
+    while (hi - lo > 1) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (icolp[mid] <= (int32_t)p) lo = mid; else hi = mid;
+    }
+    item_of[p] = lo;
+    tile_key[p] = (uint16_t)(irow[p] / kTileUsers);
+    pos[p] = (int32_t)p;
+  }
+}
+
+// q = position in (tile, item, user) order.  head_pos[q] = q at the first entry of a (tile,item) segment, else 0
+__global__ void seg_head_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ item_of, const int32_t* __restrict__ irow,
+                                int64_t n, int32_t* __restrict__ head_pos) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    bool head = (q == 0);
+    if (!head) {
+      const int32_t p = perm[q], pp = perm[q - 1];
+      head = (item_of[p] != item_of[pp]) || (irow[p] / kTileUsers != irow[pp] / kTileUsers);
+    }
+    head_pos[q] = head ? (int32_t)q : 0;
+  }
+}
+
+__global__ void unit_flag_kernel(const int32_t* __restrict__ seg_start, int64_t n, int32_t* __restrict__ flag) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    flag[q] = ((q - seg_start[q]) % kUnitLen == 0) ? 1 : 0;
+}
+
+__global__ void unit_scatter_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ uid, const int32_t* __restrict__ perm,
+                                    const int32_t* __restrict__ item_of, const int32_t* __restrict__ irow, int64_t n,
+                                    int32_t* __restrict__ unit_begin, int32_t* __restrict__ unit_item, int32_t* __restrict__ unit_tile) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    if (flag[q]) {
+      const int32_t id = uid[q], p = perm[q];
+      unit_begin[id] = (int32_t)q;
+      unit_item[id] = item_of[p];
+      unit_tile[id] = irow[p] / kTileUsers;
+    }
+  }
+}
+
+// length of each unit, its (tile, kUnitLen - len) sort key and the first unit of every tile (unit ids ascend with the tile)
+__global__ void unit_len_kernel(const int32_t* __restrict__ unit_begin, const int32_t* __restrict__ unit_tile, int32_t n_units, int64_t n,
+                                int32_t* __restrict__ unit_len, uint32_t* __restrict__ sort_key, int32_t* __restrict__ ids,
+                                int32_t* __restrict__ tile_first) {
+  const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_units) return;
+  const int32_t b = unit_begin[id];
+  const int32_t e = (id + 1 < n_units) ? unit_begin[id + 1] : (int32_t)n;
+  const int32_t len = e - b;
+  unit_len[id] = len;
+  sort_key[id] = ((uint32_t)unit_tile[id] << kUnitBits) | (uint32_t)(kUnitLen - len);
+  ids[id] = id;
+  if (id == 0 || unit_tile[id - 1] != unit_tile[id]) tile_first[unit_tile[id]] = id;
+}
+
+// sorted index j -> slot (slice*32 + lane); lane 0 of a slice holds its longest unit
+__global__ void slot_assign_kernel(const int32_t* __restrict__ sorted_id, const int32_t* __restrict__ unit_tile,
+                                   const int32_t* __restrict__ unit_len, const int32_t* __restrict__ tile_unit_ptr,
+                                   const int32_t* __restrict__ tile_slice_ptr, int32_t n_units, int32_t* __restrict__ unit_slot,
+                                   int32_t* __restrict__ slice_width) {
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_units) return;
+  const int32_t id = sorted_id[j];
+  const int32_t t = unit_tile[id];
+  const int32_t r = j - tile_unit_ptr[t];
+  const int32_t slice = tile_slice_ptr[t] + (r >> 5), lane = r & 31;
+  unit_slot[id] = slice * 32 + lane;
+  if (lane == 0) slice_width[slice] = unit_len[id];
+}
+
+__global__ void entry_fill_kernel(const int32_t* __restrict__ unit_begin, const int32_t* __restrict__ unit_len,
+                                  const int32_t* __restrict__ unit_slot, const int32_t* __restrict__ unit_tile, int32_t n_units,
+                                  const int32_t* __restrict__ perm, const int32_t* __restrict__ irow, const uint8_t* __restrict__ ival,
+                                  const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry) {
+  const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_units) return;
+  const int32_t b = unit_begin[id], len = unit_len[id], slot = unit_slot[id];
+  const int32_t slice = slot >> 5, lane = slot & 31;
+  const int64_t row0 = slice_off[slice];
+  const int32_t ubase = unit_tile[id] * kTileUsers;
+  for (int32_t j = 0; j < len; ++j) {
+    const int32_t p = perm[b + j];
+    entry[((row0 + j) << 5) + lane] = 0x80000000u | ((uint32_t)ival[p] << 16) | (uint32_t)(irow[p] - ubase);
+  }
+}
+
+__global__ void slot_item_kernel(const int32_t* __restrict__ unit_slot, const int32_t* __restrict__ unit_item, int32_t n_units,
+                                 int32_t* __restrict__ slot_item) {
+  const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < n_units) slot_item[unit_slot[id]] = unit_item[id];
+}
+
+int grid_for(int64_t n, int block, int sm_count) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + block - 1) / block, (int64_t)sm_count * 16));
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// full-precision reciprocal without the IEEE division sequence: hardware seed + 2 Newton steps (4 DFMA)
+__device__ __forceinline__ double fast_rcp(double s) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+  r = fma(r, fma(-s, r, 1.0), r);
+  r = fma(r, fma(-s, r, 1.0), r);
+  return r;
+}
+
+// K2: one CTA = (tile, share of the tile's work), 32 warps, one CTA per SM.
+// Shared memory: (code sum, rating count) of the tile's users (64 KB, code sums from K1) + a private ring of
+// kStages x kRows 128-byte rows per warp filled by 1-D bulk asynchronous copies (TMA) and signalled through mbarriers:
+// ~100 KB of entries are in flight per SM without costing registers.  Slices of a tile are contiguous in memory, so a
+// warp that owns a contiguous range of slices streams one contiguous run of rows; slice boundaries only decide when a
+// lane's unit sum is handed over.  Unit sums are fp64 (fixed order inside the unit); they are combined across units
+// with integer atomics on a 2^-40 grid, which is exact, so the item sums do not depend on the order of arrival.
+constexpr int kTiledThreads = 1024;
+constexpr int kRows = 8;    // rows per ring stage (1 KB)
+constexpr int kStages = 4;  // ring depth per warp
+constexpr int kSliceCost = 3;
+constexpr double kFixScale = 1099511627776.0;  // 2^40
+constexpr size_t kTiledSmem = (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128 + (size_t)(kTiledThreads / 32 * kStages) * 8;
+
+// first slice s in [lo, hi) whose cost prefix (rows before it + kSliceCost * slices before it) is >= v
+__device__ __forceinline__ int32_t lower_bound_cost(const int32_t* __restrict__ slice_off, int32_t lo, int32_t hi, int32_t row_base, int32_t v) {
+  const int32_t s0 = lo;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (__ldg(slice_off + mid) - row_base + kSliceCost * (mid - s0) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Deviation of one entry in exact integer form; branch free so that the rows of a batch overlap in the pipeline.
+// With r = code/2 and avg = S/(2c) (S = the user's code sum, c = its rating count):
+//     r - avg = (c*code - S)/(2c),   5 - avg = (10c - S)/(2c),   avg - 1 = (S - 2c)/(2c)
+// so (r - avg)/scale(r, avg) (P:57-61, P:167) = N/D with N = c*code - S and D = 10c - S (N > 0) or S - 2c (N < 0):
+// two small integers, ONE rounding (the reference rounds the average, the difference and the quotient: <= 2 ulp apart).
+// r > avg <=> N > 0 exactly (|avg - r| >= 1/(2c) whenever they differ, far above an ulp), so the branch is the reference's.
+__device__ __forceinline__ double tiled_dev(uint32_t e, const uint2* __restrict__ s_sc) {
+  const uint32_t code = (e >> 16) & 0xffu;              // 0 for padding
+  const uint2 sc = s_sc[e & 0xffffu];                   // .x = S, .y = c
+  const int32_t N = (int32_t)(sc.y * code) - (int32_t)sc.x;
+  const int32_t D = N > 0 ? (int32_t)(10u * sc.y) - (int32_t)sc.x : (int32_t)sc.x - (int32_t)(2u * sc.y);
+  const double dev = (double)N * fast_rcp((double)D);
+  return (N != 0 && (int32_t)e < 0) ? dev : 0.0;        // r == avg -> 0/1 = 0; padding (valid bit clear) contributes nothing
+}
+
+template <bool WITH_SUM>
+__device__ __forceinline__ void hand_over(int32_t item, double acc, uint32_t csum, long long* __restrict__ xdev_fix,
+                                          unsigned long long* __restrict__ xcode_sum) {
+  if (item >= 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(xdev_fix + item), (unsigned long long)__double2ll_rn(acc * kFixScale));
+    if (WITH_SUM) atomicAdd(xcode_sum + item, (unsigned long long)csum);
+  }
+}
+
+// slices [x, y) of every warp of the item pass: an equal share of its tile's cost, rounded to whole slices
+__global__ void __launch_bounds__(kTiledThreads) item_partition_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ tile_slice_ptr,
+                                                                      const int3* __restrict__ cta_desc, int2* __restrict__ warp_part) {
+  if ((threadIdx.x & 31) != 0) return;
+  const int3 cd = cta_desc[blockIdx.x];
+  const int32_t tile = cd.x, share = cd.y, ctas_per_tile = cd.z;
+  constexpr int32_t wpb = kTiledThreads >> 5;
+  const int32_t wid = threadIdx.x >> 5;
+  const int32_t ts0 = tile_slice_ptr[tile], ts1 = tile_slice_ptr[tile + 1];
+  const int32_t ra = __ldg(slice_off + ts0), rb = __ldg(slice_off + ts1);
+  const int32_t nw = ctas_per_tile * wpb, w = share * wpb + wid;
+  const int64_t total_cost = (int64_t)(rb - ra) + (int64_t)kSliceCost * (ts1 - ts0);
+  const int32_t c_lo = (int32_t)((total_cost * w) / nw), c_hi = (int32_t)((total_cost * (w + 1)) / nw);
+  const int32_t cur = lower_bound_cost(slice_off, ts0, ts1, ra, c_lo);   // slices whose cost prefix lies in [c_lo, c_hi)
+  const int32_t s_hi = lower_bound_cost(slice_off, ts0, ts1, ra, c_hi);
+  warp_part[(size_t)blockIdx.x * wpb + wid] = make_int2(cur, s_hi);
+}
+
+template <bool WITH_SUM>
+__global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint32_t* __restrict__ entry, const int32_t* __restrict__ slice_off,
+                                                                     const int2* __restrict__ warp_part, const int3* __restrict__ cta_desc,
+                                                                     const uint32_t* __restrict__ usum, const int32_t* __restrict__ urow,
+                                                                     int32_t n_users, const int32_t* __restrict__ slot_item,
+                                                                     double* __restrict__ uavg, long long* __restrict__ xdev_fix,
+                                                                     unsigned long long* __restrict__ xcode_sum, unsigned long long* __restrict__ tl) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  tl_begin(tl, 1);
+  uint2* s_sc = reinterpret_cast<uint2*>(smem_raw);                                       // [kTileUsers] (code sum, count)
+  uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTileUsers * 8);      // [warps][kStages][kRows*32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128);
+  const int3 cd = cta_desc[blockIdx.x];
+  const int32_t tile = cd.x, share = cd.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int32_t wpb = kTiledThreads >> 5;
+  uint64_t* bar = s_bar + wid * kStages;           // this warp's stage barriers
+  uint32_t* ring = s_ring + (size_t)wid * kStages * kRows * 32;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) tma::mbar_init(bar + st, 1);
+    tma::fence_barrier_init();
+  }
+  __syncwarp();
+
+  // ---- this warp's slices: an equal share of the tile's cost, rounded to whole slices
+  // (cost of a slice = its rows + kSliceCost for handing over 32 unit sums; the tail of a tile is made of 1-2 row slices)
+  // (the partition is static: item_partition_kernel ran the two binary searches per warp once, when the layout was built --
+  // 28 dependent loads that used to open every pass)
+  const int2 part = __ldg(warp_part + (size_t)blockIdx.x * wpb + wid);
+  int32_t cur = part.x;
+  const int32_t s_hi = part.y;
+  const int32_t r0 = (cur < s_hi) ? __ldg(slice_off + cur) : 0;
+  const int32_t r_end = (cur < s_hi) ? __ldg(slice_off + s_hi) : 0;
+  const int32_t n_chunks = (r_end - r0 + kRows - 1) / kRows;
+  if (lane == 0) {  // the first kStages chunks go out before the averages are formed
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) {
+      if (st < n_chunks) {
+        const int32_t rr = r0 + st * kRows;
+        const uint32_t bytes = (uint32_t)min(kRows, r_end - rr) * 128u;
+        tma::mbar_arrive_expect_tx(bar + st, bytes);
+        tma::bulk_g2s(ring + st * kRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
+      }
+    }
+  }
+  int32_t end1 = (cur < s_hi) ? __ldg(slice_off + cur + 1) : 0x7fffffff;        // end row of the current slice
+  int32_t end2 = (cur + 1 < s_hi) ? __ldg(slice_off + cur + 2) : 0x7fffffff;    // ... of the next one (prefetched)
+  int32_t item1 = (cur < s_hi) ? __ldg(slot_item + cur * 32 + lane) : -1;       // item of this lane's unit in the current slice
+  int32_t item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
+
+  // ---- the tile's users: (code sum from K1, rating count); the first CTA of the tile also publishes the averages
+  pdl_trigger();  // K2b may be scheduled as SMs free up
+  pdl_wait();     // everything above (barriers, partition, first ring stages) overlapped K1; usum is complete from here on
+  {
+    const int32_t u0 = tile * kTileUsers;
+    constexpr int kPer = kTileUsers / kTiledThreads;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int32_t x = k * kTiledThreads + threadIdx.x;
+      const int32_t u = u0 + x;
+      const bool in = u < n_users;
+      const uint32_t S = in ? __ldg(usum + u) : 0u;
+      const uint32_t cnt = in ? (uint32_t)(__ldg(urow + u + 1) - __ldg(urow + u)) : 0u;
+      s_sc[x] = make_uint2(S, cnt);
+      if (share == 0 && in)  // exact sum, one correctly rounded division (P:18); -1.0: no ratings (the reference's sentinel, P:222)
+        uavg[u] = cnt ? (0.5 * (double)S) / (double)cnt : -1.0;
+    }
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+  uint32_t csum = 0;
+  for (int32_t c = 0; c < n_chunks; ++c) {
+    const int st = c % kStages;
+    const int32_t r = r0 + c * kRows;
+    const int32_t nrows = min(kRows, r_end - r);
+    tma::mbar_wait(bar + st, (uint32_t)(c / kStages) & 1u);
+    const uint32_t* rp = ring + st * kRows * 32 + lane;  // conflict free: lane l reads word l of a row
+    const bool plain = (nrows == kRows) && (end1 > r) && (end1 >= r + kRows);  // whole chunk inside the current slice
+    uint32_t ev[kRows];
+    if (plain) {
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) ev[k] = rp[k * 32];
+    } else {
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : 0u;
+    }
+    __syncwarp();
+    if (lane == 0 && c + kStages < n_chunks) {  // the stage is free again: request the chunk kStages ahead
+      const int32_t rr = r + kStages * kRows;
+      const uint32_t bytes = (uint32_t)min(kRows, r_end - rr) * 128u;
+      tma::mbar_arrive_expect_tx(bar + st, bytes);
+      tma::bulk_g2s(ring + st * kRows * 32, entry + ((int64_t)rr << 5), bytes, bar + st);
+    }
+    double dv[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) dv[k] = tiled_dev(ev[k], s_sc);  // heavy part: no branches, 8 independent chains
+    if (plain) {
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        acc += dv[k];
+        if (WITH_SUM) csum += (ev[k] >> 16) & 0xffu;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {  // ordered accumulation + slice boundaries (warp-uniform branch)
+        if (r + k == end1) {             // the slice ended with the previous row: hand this lane's unit sum over
+          hand_over<WITH_SUM>(item1, acc, csum, xdev_fix, xcode_sum);
+          acc = 0.0; csum = 0;
+          ++cur;
+          end1 = end2; item1 = item2;
+          end2 = (cur + 1 < s_hi) ? __ldg(slice_off + cur + 2) : 0x7fffffff;
+          item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
+        }
+        acc += dv[k];
+        if (WITH_SUM) csum += (ev[k] >> 16) & 0xffu;
+      }
+    }
+  }
+  if (cur < s_hi) hand_over<WITH_SUM>(item1, acc, csum, xdev_fix, xcode_sum);  // last slice of the range
+  if (tl) { __syncthreads(); tl_end(tl, 1); }
+}
+
+// K2b: per item, integer accumulators -> exchange buffer (and re-arm them for the next pass); optionally finish the fit
+__global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __restrict__ xdev_fix, unsigned long long* __restrict__ xcode_sum,
+                                                                 const int32_t* __restrict__ icolp, int32_t n_items,
+                                                                 unsigned long long* __restrict__ k1_part, int32_t n_k1, double n_total,
+                                                                 double* __restrict__ xbuf, int fused, double* __restrict__ idevavg,
+                                                                 double* __restrict__ iavg, double* __restrict__ gavg,
+                                                                 unsigned long long* __restrict__ tl) {
+  tl_begin(tl, 2);
+  pdl_trigger();
+  pdl_wait();  // the accumulators are complete once the item pass has finished
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
+    k1_part[0] = 0;                              // re-arm for the next pass
+    xbuf[2 * (size_t)n_items] = gs;
+    xbuf[2 * (size_t)n_items + 1] = n_total;
+    if (fused) gavg[0] = n_total > 0.0 ? gs / n_total : 0.0;
+  }
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) { tl_end(tl, 2); return; }
+  const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
+  const double rs = 0.5 * (double)xcode_sum[i];
+  xdev_fix[i] = 0;
+  xcode_sum[i] = 0;
+  const double cnt = (double)(icolp[i + 1] - icolp[i]);
+  xbuf[i] = ds;
+  xbuf[(size_t)n_items + i] = cnt;
+  xbuf[2 * (size_t)n_items + 2 + i] = rs;
+  if (fused) {
+    idevavg[i] = cnt > 0.0 ? ds / cnt : 0.0;
+    iavg[i] = cnt > 0.0 ? rs / cnt : nan("");
+  }
+  tl_end(tl, 2);
+}
+
+}  // namespace
+
+void free_tiled_layout(const mrs_ratings* R) {
+  auto& T = R->tl;
+  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.slot_item); dev_free(T.warp_part); dev_free(T.cta_desc);
+  T = mrs_ratings::tiled_layout();
+}
+
+int32_t build_tiled_layout(const mrs_ratings* R) {
+  auto& T = R->tl;
+  if (T.built) return MRS_OK;
+  MRS_REQUIRE(R->value_kind == kValueCode, MRS_ERR_INVALID, "tiled layout needs half-star codes");
+  mrs_engine* e = R->eng;
+  cudaStream_t st = e->stream;
+  const int64_t n = R->n;
+  const int32_t NI = R->n_items;
+  const int32_t NT = (R->n_users + kTileUsers - 1) / kTileUsers;
+  MRS_REQUIRE(NT < 65536, MRS_ERR_UNSUPPORTED, "too many user tiles (%d)", NT);
+  T.n_tiles = NT;
+  const int block = 256;
+  const int grid = grid_for(n, block, e->sm_count);
+  std::vector<int32_t> h_tile_slice((size_t)NT + 1, 0);
+  MRS_TRY(dev_alloc(&T.tile_slice_ptr, (size_t)NT + 1));
+  if (n == 0) {
+    MRS_CUDA(cudaMemsetAsync(T.tile_slice_ptr, 0, sizeof(int32_t) * ((size_t)NT + 1), st));
+    MRS_TRY(dev_alloc(&T.slice_off, 1));
+    MRS_CUDA(cudaMemsetAsync(T.slice_off, 0, sizeof(int32_t), st));
+    MRS_TRY(dev_alloc(&T.entry, 1));
+    MRS_TRY(dev_alloc(&T.slot_item, 1));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    T.built = true;
+    return MRS_OK;
+  }
+  // ---- (tile, item, user) order: stable radix sort of the CSC positions on the tile id only
+  uint16_t *tk_in = nullptr, *tk_out = nullptr;
+  int32_t *pos_in = nullptr, *perm = nullptr, *item_of = nullptr, *head = nullptr, *seg_start = nullptr, *flag = nullptr, *uid = nullptr;
+  MRS_TRY(dev_alloc(&tk_in, (size_t)n)); MRS_TRY(dev_alloc(&tk_out, (size_t)n));
+  MRS_TRY(dev_alloc(&pos_in, (size_t)n)); MRS_TRY(dev_alloc(&perm, (size_t)n));
+  MRS_TRY(dev_alloc(&item_of, (size_t)n)); MRS_TRY(dev_alloc(&head, (size_t)n));
+  MRS_TRY(dev_alloc(&seg_start, (size_t)n)); MRS_TRY(dev_alloc(&flag, (size_t)n)); MRS_TRY(dev_alloc(&uid, (size_t)n + 1));
+  tile_keys_kernel<<<grid, block, 0, st>>>(R->irow, R->icolp, NI, n, tk_in, pos_in, item_of);
+  int tbits = 1;
+  while ((1 << tbits) < NT) ++tbits;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, tk_in, tk_out, pos_in, perm, (int)n, 0, tbits, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, tk_in, tk_out, pos_in, perm, (int)n, 0, tbits, st);
+  // ---- units
+  seg_head_kernel<<<grid, block, 0, st>>>(perm, item_of, R->irow, n, head);
+  cub::DeviceScan::InclusiveScan(nullptr, tmp, head, seg_start, MaxOp(), (int)n, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceScan::InclusiveScan(e->scratch, tmp, head, seg_start, MaxOp(), (int)n, st);
+  unit_flag_kernel<<<grid, block, 0, st>>>(seg_start, n, flag);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, flag, uid, (int)n, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceScan::ExclusiveSum(e->scratch, tmp, flag, uid, (int)n, st);
+  int32_t last_uid = 0, last_flag = 0;
+  MRS_CUDA(cudaMemcpyAsync(&last_uid, uid + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaMemcpyAsync(&last_flag, flag + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  const int32_t NUN = last_uid + last_flag;
+  T.n_units = NUN;
+  int32_t *unit_begin = nullptr, *unit_item = nullptr, *unit_tile = nullptr, *unit_len = nullptr, *ids = nullptr, *sorted_id = nullptr;
+  int32_t *tile_count = nullptr, *unit_slot = nullptr, *slice_width = nullptr, *d_tile_unit_ptr = nullptr;
+  uint32_t *skey = nullptr, *skey_out = nullptr;
+  MRS_TRY(dev_alloc(&unit_begin, (size_t)NUN)); MRS_TRY(dev_alloc(&unit_item, (size_t)NUN)); MRS_TRY(dev_alloc(&unit_tile, (size_t)NUN));
+  MRS_TRY(dev_alloc(&unit_len, (size_t)NUN)); MRS_TRY(dev_alloc(&ids, (size_t)NUN)); MRS_TRY(dev_alloc(&sorted_id, (size_t)NUN));
+  MRS_TRY(dev_alloc(&skey, (size_t)NUN)); MRS_TRY(dev_alloc(&skey_out, (size_t)NUN));
+  MRS_TRY(dev_alloc(&tile_count, (size_t)NT + 1)); MRS_TRY(dev_alloc(&unit_slot, (size_t)NUN));
+  MRS_TRY(dev_alloc(&d_tile_unit_ptr, (size_t)NT + 1));
+  MRS_CUDA(cudaMemsetAsync(tile_count, 0xff, sizeof(int32_t) * ((size_t)NT + 1), st));  // -1: tile without units
+  unit_scatter_kernel<<<grid, block, 0, st>>>(flag, uid, perm, item_of, R->irow, n, unit_begin, unit_item, unit_tile);
+  const int ugrid = (NUN + block - 1) / block;
+  unit_len_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_tile, NUN, n, unit_len, skey, ids, tile_count);
+  // ---- sort units by (tile, length desc); stable => canonical order among equal lengths
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, skey, skey_out, ids, sorted_id, NUN, 0, kUnitBits + tbits, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, skey, skey_out, ids, sorted_id, NUN, 0, kUnitBits + tbits, st);
+  std::vector<int32_t> h_count((size_t)NT + 1, 0), h_unit_ptr((size_t)NT + 1, 0);
+  MRS_CUDA(cudaMemcpyAsync(h_count.data(), tile_count, sizeof(int32_t) * (size_t)NT, cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  h_count[NT] = NUN;  // h_count holds the first unit of every tile; tiles without units take the next tile's first
+  for (int32_t t = NT - 1; t >= 0; --t)
+    if (h_count[t] < 0) h_count[t] = h_count[t + 1];
+  for (int32_t t = 0; t < NT; ++t) {
+    const int32_t cnt = h_count[t + 1] - h_count[t];
+    h_unit_ptr[t + 1] = h_unit_ptr[t] + cnt;
+    h_tile_slice[t + 1] = h_tile_slice[t] + (cnt + 31) / 32;
+  }
+  const int32_t NS = h_tile_slice[NT];
+  T.n_slices = NS;
+  MRS_CUDA(cudaMemcpyAsync(d_tile_unit_ptr, h_unit_ptr.data(), sizeof(int32_t) * ((size_t)NT + 1), cudaMemcpyHostToDevice, st));
+  MRS_CUDA(cudaMemcpyAsync(T.tile_slice_ptr, h_tile_slice.data(), sizeof(int32_t) * ((size_t)NT + 1), cudaMemcpyHostToDevice, st));
+  MRS_TRY(dev_alloc(&slice_width, (size_t)NS + 1));
+  MRS_TRY(dev_alloc(&T.slice_off, (size_t)NS + 1));
+  MRS_CUDA(cudaMemsetAsync(slice_width, 0, sizeof(int32_t) * ((size_t)NS + 1), st));
+  slot_assign_kernel<<<ugrid, block, 0, st>>>(sorted_id, unit_tile, unit_len, d_tile_unit_ptr, T.tile_slice_ptr, NUN, unit_slot, slice_width);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, slice_width, T.slice_off, NS + 1, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceScan::ExclusiveSum(e->scratch, tmp, slice_width, T.slice_off, NS + 1, st);
+  int32_t rows = 0;
+  MRS_CUDA(cudaMemcpyAsync(&rows, T.slice_off + NS, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MRS_CUDA(cudaStreamSynchronize(st));
+  T.n_slots = (int64_t)rows * 32;
+  MRS_TRY(dev_alloc(&T.entry, (size_t)T.n_slots));
+  MRS_CUDA(cudaMemsetAsync(T.entry, 0, sizeof(uint32_t) * (size_t)T.n_slots, st));
+  entry_fill_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, T.slice_off, T.entry);
+  // ---- item of every slot (empty slots: -1)
+  MRS_TRY(dev_alloc(&T.slot_item, (size_t)NS * 32));
+  MRS_CUDA(cudaMemsetAsync(T.slot_item, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
+  slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, T.slot_item);
+  // ---- static work partition of the item pass: CTAs dealt out to the tiles by cost, then slices to the warps of each CTA.
+  // Laid down here, behind the layout's final synchronisation: the item pass reads warp_part in its prologue, before
+  // griddepcontrol.wait, so the table must never be written by a kernel of the pass itself.
+  {
+    std::vector<int32_t> h_slice_off((size_t)NS + 1);
+    MRS_CUDA(cudaMemcpyAsync(h_slice_off.data(), T.slice_off, sizeof(int32_t) * ((size_t)NS + 1), cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    std::vector<int64_t> cost((size_t)NT, 0);
+    for (int32_t t = 0; t < NT; ++t) {
+      const int32_t s0 = h_tile_slice[t], s1 = h_tile_slice[t + 1];
+      cost[(size_t)t] = (int64_t)(h_slice_off[(size_t)s1] - h_slice_off[(size_t)s0]) + (int64_t)kSliceCost * (s1 - s0);
+    }
+    const std::vector<int3> desc = deal_ctas(cost, e->sm_count);
+    T.n_ctas = (int32_t)desc.size();
+    MRS_TRY(dev_alloc(&T.cta_desc, std::max<size_t>(1, desc.size())));
+    MRS_TRY(dev_alloc(&T.warp_part, std::max<size_t>(1, desc.size()) * (kTiledThreads / 32)));
+    if (T.n_ctas > 0) {
+      MRS_CUDA(cudaMemcpyAsync(T.cta_desc, desc.data(), sizeof(int3) * desc.size(), cudaMemcpyHostToDevice, st));
+      item_partition_kernel<<<T.n_ctas, kTiledThreads, 0, st>>>(T.slice_off, T.tile_slice_ptr, T.cta_desc, T.warp_part);
+      MRS_CUDA(cudaStreamSynchronize(st));  // `desc` (pageable host memory) must outlive the copy
+    }
+  }
+  count_launch(21);
+  MRS_CUDA(cudaGetLastError());
+  MRS_CUDA(cudaStreamSynchronize(st));
+  for (void* p : {(void*)tk_in, (void*)tk_out, (void*)pos_in, (void*)perm, (void*)item_of, (void*)head, (void*)seg_start, (void*)flag,
+                  (void*)uid, (void*)unit_begin, (void*)unit_item, (void*)unit_tile, (void*)unit_len, (void*)ids, (void*)sorted_id,
+                  (void*)skey, (void*)skey_out, (void*)tile_count, (void*)unit_slot, (void*)slice_width,
+                  (void*)d_tile_unit_ptr})
+    dev_free(p);
+  T.built = true;
+  return MRS_OK;
+}
+
+int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused) {
+  const auto& T = R->tl;
+  cudaStream_t st = e->stream;
+  if (!(e->smem_attr_done & 1u)) {
+    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
+    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
+    e->smem_attr_done |= 1u;
+  }
+  // one CTA of 1024 threads per SM: the grid (T.n_ctas <= SM count unless there are more busy tiles than SMs) is one wave
+  const dim3 grid2(T.n_ctas), block2(kTiledThreads);
+  if (T.n_ctas > 0) {
+    if (m->want_item_avg)
+      MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
+                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline));
+    else
+      MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
+                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline));
+  }
+  mark(e, "item_tiled");
+  MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
+                      m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg, e->d_timeline));
+  mark(e, "item_tiled_finalize");
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+}  // namespace mrs

@@ -22,8 +22,8 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
              -5: "MRS_ERR_IO", -6: "MRS_ERR_UNSUPPORTED"}
 
 EXPORTS = [
-    "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync",
-    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy", "mrs_debug_pass_stamps", "mrs_debug_timeline",
+    "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync", "mrs_debug_timeline",
+    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
     "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
@@ -71,6 +71,7 @@ def lib():
         "mrs_engine_create": (i32, [i32, vp, P(vp)]),
         "mrs_engine_destroy": (None, [vp]),
         "mrs_engine_sync": (i32, [vp]),
+        "mrs_debug_timeline": (i32, [vp, vp]),
         "mrs_graph_begin": (i32, [vp]),
         "mrs_graph_end": (i32, [vp, P(vp)]),
         "mrs_graph_launch": (i32, [vp]),
@@ -87,8 +88,6 @@ def lib():
         "mrs_ratings_bytes": (i32, [vp, P(i64)]),
         "mrs_ratings_layout_info": (i32, [vp, P(i64)]),
         "mrs_ratings_destroy": (None, [vp]),
-        "mrs_debug_pass_stamps": (i32, [vp, i32]),
-        "mrs_debug_timeline": (i32, [vp, vp]),
         "mrs_fit": (i32, [vp, vp, P(vp)]),
         "mrs_fit_local": (i32, [vp, vp, P(vp)]),
         "mrs_fit_async": (i32, [vp, vp, P(vp)]),

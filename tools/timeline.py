@@ -14,7 +14,7 @@ from mrs_b200 import engine as E, synth  # noqa: E402
 stream = torch.cuda.Stream()
 eng = E.Engine(0, stream=stream.cuda_stream)
 d = synth.cached("ml25m")
-names = ["user_sum", "user_tables", "item_pass", "item_finalize", "test_pass", "item_sum"]
+names = ["user_sum", "item_pass", "item_finalize", "test_pass"]
 with torch.cuda.stream(stream):
     R, T = eng.ratings(*d["train"]), eng.ratings(*d["test"])
     m = E.Model(eng, R)
@@ -36,8 +36,8 @@ with torch.cuda.stream(stream):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream); g.launch(); b.record(stream); torch.cuda.synchronize()
         E._check(E.lib().mrs_debug_timeline(eng._h, buf.ctypes.data))
-        t0 = min(int(buf[2 * k]) for k in range(5))
+        t0 = min(int(buf[2 * k]) for k in range(4))
         line = f"step {a.elapsed_time(b) * 1e3:6.1f} us |"
-        for k in range(5):
+        for k in range(4):
             line += f" {names[k]} {(int(buf[2 * k]) - t0) / 1e3:5.1f}-{(int(buf[2 * k + 1]) - t0) / 1e3:5.1f} |"
         print(line)
