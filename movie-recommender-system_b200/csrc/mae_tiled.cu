@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
       const uint32_t code = ev[k].y >> 16;
       const double d = s_dev[ev[k].y & 0xffffu];
       const double p = ua[k] < 0.0 ? gavg : combine_fn(ua[k], d);   // P:222-229
-      const double err = fabs(fma((double)code, 0.5, -p));          // |r - p|, P:71
+      const double err = fabs(fma((double)code, 0.5, -p));
       acc += (code != 0xffu) ? err : 0.0;                           // 0xFF = padding slot
     }
   }

@@ -134,13 +134,21 @@ int grid_for(int64_t n, int block, int sm_count) {
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// full-precision reciprocal without the IEEE division sequence: hardware seed + 2 Newton steps (4 DFMA)
+// full-precision reciprocal without the IEEE division sequence: hardware seed (good to ~2^-21) + r(1 + e + e^2), which
+// leaves e^3 ~ 2^-63 with 3 DFMA (two Newton steps take 4).  Measured on the same box (tools/ab.sh): replacing the two I2F
+// of the deviation by mantissa tricks (LOP + DADD) made the pass 3 us SLOWER -- the fp64 pipe, not the conversion unit,
+// is the scarce one here.
 __device__ __forceinline__ double fast_rcp(double s) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+#ifdef MRS_AB_NEWTON2
   r = fma(r, fma(-s, r, 1.0), r);
   r = fma(r, fma(-s, r, 1.0), r);
   return r;
+#else
+  const double e = fma(-s, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+#endif
 }
 
 // K2: one CTA = (tile, share of the tile's work), 32 warps, one CTA per SM.
@@ -151,8 +159,16 @@ __device__ __forceinline__ double fast_rcp(double s) {
 // lane's unit sum is handed over.  Unit sums are fp64 (fixed order inside the unit); they are combined across units
 // with integer atomics on a 2^-40 grid, which is exact, so the item sums do not depend on the order of arrival.
 constexpr int kTiledThreads = 1024;
+#ifdef MRS_AB_ROWS16
+constexpr int kRows = 16;
+constexpr int kStages = 2;
+#elif defined(MRS_AB_STAGES3)
+constexpr int kRows = 8;
+constexpr int kStages = 3;
+#else
 constexpr int kRows = 8;    // rows per ring stage (1 KB)
 constexpr int kStages = 4;  // ring depth per warp
+#endif
 constexpr int kSliceCost = 3;
 constexpr double kFixScale = 1099511627776.0;  // 2^40
 constexpr size_t kTiledSmem = (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128 + (size_t)(kTiledThreads / 32 * kStages) * 8;

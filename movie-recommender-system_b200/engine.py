@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrs_b200.so")
+LIB_PATH = os.environ.get("MRS_LIB") or os.path.join(_HERE, "libmrs_b200.so")   # MRS_LIB: another build of the same library (A/B timing)
 
 # mrs_vec_kind / mrs_pred_kind / mrs_sim_kind
 GLOBAL_AVG, USER_AVG, ITEM_AVG, ITEM_AVG_DEV = range(4)
