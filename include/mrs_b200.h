@@ -39,6 +39,7 @@ typedef struct mrs_model mrs_model;
 typedef struct mrs_sim mrs_sim;
 typedef struct mrs_graph mrs_graph;
 typedef struct mrs_exchange mrs_exchange;
+typedef struct mrs_multi mrs_multi;       /* several devices driven from one process */
 typedef struct mrs_upload mrs_upload;     /* host -> device copies of one rating set in flight */
 
 typedef enum {
@@ -123,6 +124,13 @@ MRS_API int32_t mrs_ratings_from_coo(mrs_engine* e, const int32_t* users, const 
 MRS_API int32_t mrs_upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
                                  mrs_upload** out);
 MRS_API int32_t mrs_ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
+/* Compact host form for half-star data: the rating as a 1-byte code = 2 x rating (0 .. 254), i.e. 9 bytes per Rating over
+ * PCIe instead of 16 -- the link is what bounds an end-to-end step (the device stores codes anyway).  A JNI caller packs
+ * Rating.rating into the byte while it fills its pinned buffers.  mrs_ratings_from_coo_codes == begin + from_upload. */
+MRS_API int32_t mrs_upload_begin_codes(mrs_engine* e, const int32_t* users, const int32_t* items, const uint8_t* codes, int64_t n,
+                                       mrs_upload** out);
+MRS_API int32_t mrs_ratings_from_coo_codes(mrs_engine* e, const int32_t* users, const int32_t* items, const uint8_t* codes, int64_t n,
+                                           int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out);
 MRS_API void mrs_upload_destroy(mrs_upload* up);
 /* Same parse rules as P:35-49: split on `sep`, trim, keep the row iff column 0 parses as an Int. */
 MRS_API int32_t mrs_ratings_from_file(mrs_engine* e, const char* path, const char* sep, mrs_ratings** out);
@@ -176,6 +184,8 @@ MRS_API void mrs_model_destroy(mrs_model* m);
  * mrs_exchange_status reads; once the host has seen it the handle refuses further exchanges (MRS_ERR_CUDA). */
 MRS_API int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t rank, int32_t world, void* ipc_handle_out64, mrs_exchange** out);
 MRS_API int32_t mrs_exchange_connect(mrs_exchange* x, const void* all_handles_world_x_64);
+/* all ranks are devices of the calling process (peer access enabled): connect xs[0..world) to each other without IPC */
+MRS_API int32_t mrs_exchange_connect_local(mrs_exchange** xs, int32_t world);
 MRS_API int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout, int64_t n_doubles);
 /* Same over the positions device_idx[0..n_idx) of `device_inout` only (int32, on the device, identical on every rank): the
  * other positions neither travel nor change.  The exchange buffer of a model is indexed by item id; with sparse ids most of
@@ -225,6 +235,24 @@ MRS_API int32_t mrs_mae(const mrs_model* m, const mrs_sim* sim_or_null, int32_t 
 /* asynchronous form: writes {sum |r - p|, count} as two fp64 to device memory (a sharded run adds them across ranks) */
 MRS_API int32_t mrs_mae_async(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind, const mrs_ratings* test,
                               void* device_out2);
+
+/* ---- several GPUs from ONE process (what a single JVM can drive; distributed/DistributedBaseline.scala:30-47 with
+ * --master local[N] is one process over N partitions).  mrs_multi_create takes the CUDA device ids, enables peer access
+ * between all pairs and creates one engine per device; mrs_multi_load shards both rating sets by user (contiguous id
+ * ranges balanced by train rating count) and builds one train set, test set, model and exchange object per device;
+ * mrs_multi_baseline_mae runs fit_local on every device, the per-item exchange (our NVLink peer-memory kernel; the peers
+ * are plain pointers inside one process), fit_finish, the fused MAE over each device's test pairs and the 16-byte
+ * exchange -- every launch asynchronous on its device's stream -- and returns
+ * MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test).  mrs_multi_model lends the model of a device slot for the
+ * query entry points (item vectors and the global average are global after a pass; a user's average lives on the slot
+ * mrs_multi_owner names). ---- */
+MRS_API int32_t mrs_multi_create(const int32_t* device_ids, int32_t n_devices, mrs_multi** out);
+MRS_API int32_t mrs_multi_load(mrs_multi* m, const int32_t* train_users, const int32_t* train_items, const double* train_ratings, int64_t n_train,
+                               const int32_t* test_users, const int32_t* test_items, const double* test_ratings, int64_t n_test);
+MRS_API int32_t mrs_multi_baseline_mae(mrs_multi* m, double* mae_out);
+MRS_API int32_t mrs_multi_model(mrs_multi* m, int32_t slot, mrs_model** out);
+MRS_API int32_t mrs_multi_owner(const mrs_multi* m, int32_t user, int32_t* slot_out);
+MRS_API void mrs_multi_destroy(mrs_multi* m);
 
 /* ---- recommendations (P:651-674; call site recommend/Recommender.scala:82-88) ---- */
 MRS_API int32_t mrs_recommend(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind, int32_t user, int32_t n,

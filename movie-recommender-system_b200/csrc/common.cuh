@@ -120,6 +120,7 @@ struct mrs_upload {
   int32_t* d_u = nullptr;
   int32_t* d_i = nullptr;
   double* d_r = nullptr;
+  uint8_t* d_c = nullptr;           // compact form: half-star codes (2 x rating) instead of fp64 ratings
   cudaEvent_t ev_ids = nullptr;     // users and items have arrived
   cudaEvent_t ev_values = nullptr;  // ratings have arrived
 };

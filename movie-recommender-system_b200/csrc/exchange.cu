@@ -31,6 +31,7 @@ struct mrs_exchange {
   int32_t* d_error = nullptr;
   unsigned long long* d_stamps = nullptr;  // [8] globaltimer stamps of block 0 in the last exchange (diagnostics)
   bool connected = false;
+  bool local = false;            // peers live in this process: plain pointers, nothing to unmap
   bool failed = false;           // a timed-out exchange was observed by the host: the handle refuses further exchanges
   long long timeout_cycles = 4000000000LL;  // bound of every flag wait (~2 s at 1.9 GHz); mrs_exchange_set_timeout_ms
 };
@@ -279,6 +280,22 @@ extern "C" int32_t mrs_exchange_connect(mrs_exchange* x, const void* all_handles
   return MRS_OK;
 }
 
+// the ranks are devices of THIS process (mrs_multi_*): with peer access enabled their buffers are plain pointers
+extern "C" int32_t mrs_exchange_connect_local(mrs_exchange** xs, int32_t world) {
+  MRS_REQUIRE(xs && world >= 1, MRS_ERR_INVALID, "mrs_exchange_connect_local: bad argument");
+  for (int r = 0; r < world; ++r) MRS_REQUIRE(xs[r] && xs[r]->world == world && xs[r]->rank == r, MRS_ERR_INVALID, "mrs_exchange_connect_local: handle %d does not match", r);
+  for (int r = 0; r < world; ++r) {
+    mrs_exchange* x = xs[r];
+    use_engine(x->eng);
+    x->peer_base.assign((size_t)world, nullptr);
+    for (int p = 0; p < world; ++p) x->peer_base[(size_t)p] = xs[p]->base;
+    MRS_CUDA(cudaMemcpy(x->d_peer, x->peer_base.data(), sizeof(void*) * (size_t)world, cudaMemcpyHostToDevice));
+    x->connected = true;
+    x->local = true;
+  }
+  return MRS_OK;
+}
+
 static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_doubles, const int32_t* device_idx);
 
 extern "C" int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout, int64_t n_doubles) {
@@ -340,7 +357,7 @@ extern "C" void mrs_exchange_destroy(mrs_exchange* x) {
   if (!x) return;
   if (x->eng) { cudaSetDevice(x->eng->device); cudaStreamSynchronize(x->eng->stream); }
   for (int p = 0; p < (int)x->peer_base.size(); ++p)
-    if (p != x->rank && x->peer_base[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
+    if (!x->local && p != x->rank && x->peer_base[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
   if (x->d_peer) cudaFree(x->d_peer);
   if (x->d_done) cudaFree(x->d_done);
   if (x->d_epoch) cudaFree(x->d_epoch);

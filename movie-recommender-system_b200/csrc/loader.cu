@@ -52,6 +52,14 @@ __global__ void scan_values_kernel(const double* __restrict__ r, int64_t n, int3
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&stats[3], bad);
 }
 
+// stats[3] = number of codes equal to 0xFF (the padding mark of the item-tiled test layout: not a legal code)
+__global__ void scan_codes_kernel(const uint8_t* __restrict__ c, int64_t n, int32_t* __restrict__ stats) {
+  int32_t bad = 0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) bad += (c[p] == 0xFF);
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&stats[3], bad);
+}
+
 __global__ void make_keys_kernel(const int32_t* __restrict__ hi, const int32_t* __restrict__ lo, int64_t n,
                                  uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
@@ -258,7 +266,7 @@ int32_t sort_ids(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_
 }
 
 template <typename VT>
-int32_t finish_values(mrs_engine* e, mrs_ratings* R, const double* d_r, sort_buffers* B) {
+int32_t finish_values(mrs_engine* e, mrs_ratings* R, const double* d_r, sort_buffers* B, const uint8_t* d_codes = nullptr) {
   cudaStream_t st = e->stream;
   const int64_t n = R->n;
   const int block = 256;
@@ -269,7 +277,8 @@ int32_t finish_values(mrs_engine* e, mrs_ratings* R, const double* d_r, sort_buf
   R->uval = uval;
   R->ival = ival;
   if (n) {
-    gather_sorted_kernel<VT, true><<<grid, block, 0, st>>>(B->perm_u, n, d_r, uval);
+    if (d_codes) gather_sorted_kernel<VT, false><<<grid, block, 0, st>>>(B->perm_u, n, d_codes, uval);   // compact form: codes as given
+    else gather_sorted_kernel<VT, true><<<grid, block, 0, st>>>(B->perm_u, n, d_r, uval);
     gather_sorted_kernel<VT, false><<<grid, block, 0, st>>>(R->csc_src, n, uval, ival);
     count_launch(2);
     MRS_CUDA(cudaGetLastError());
@@ -289,7 +298,7 @@ void free_upload(mrs_upload* up) {
   if (!up) return;
   use_engine(up->eng);
   if (up->ev_values) cudaEventSynchronize(up->ev_values);  // the copies read host memory and write these buffers
-  dev_free(up->d_u); dev_free(up->d_i); dev_free(up->d_r);
+  dev_free(up->d_u); dev_free(up->d_i); dev_free(up->d_r); dev_free(up->d_c);
   if (up->ev_ids) cudaEventDestroy(up->ev_ids);
   if (up->ev_values) cudaEventDestroy(up->ev_values);
   delete up;
@@ -297,17 +306,19 @@ void free_upload(mrs_upload* up) {
 
 // Enqueue the three host -> device copies on the engine's copy stream and return at once.  The ids go first: the first
 // sort of the build needs only them and runs while the (twice as large) rating array is still on its way.
-int32_t upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n, mrs_upload** out) {
+int32_t upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n, mrs_upload** out,
+                     const uint8_t* codes = nullptr) {
   MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_upload_begin: NULL engine or output");
   MRS_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, MRS_ERR_UNSUPPORTED, "mrs_ratings_from_coo: n=%lld outside [0, 2^31)", (long long)n);
-  MRS_REQUIRE(n == 0 || (users && items && ratings), MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL input array");
+  MRS_REQUIRE(n == 0 || (users && items && (ratings || codes)), MRS_ERR_INVALID, "mrs_ratings_from_coo: NULL input array");
   use_engine(e);
   mrs_upload* up = new mrs_upload();
   up->eng = e;
   up->n = n;
   int32_t rc = dev_alloc(&up->d_u, (size_t)n);
   if (rc == MRS_OK) rc = dev_alloc(&up->d_i, (size_t)n);
-  if (rc == MRS_OK) rc = dev_alloc(&up->d_r, (size_t)n);
+  if (rc == MRS_OK && !codes) rc = dev_alloc(&up->d_r, (size_t)n);
+  if (rc == MRS_OK && codes) rc = dev_alloc(&up->d_c, (size_t)n + 16);
   cudaError_t ce = cudaSuccess;
   if (rc == MRS_OK) ce = cudaEventCreateWithFlags(&up->ev_ids, cudaEventDisableTiming);
   if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventCreateWithFlags(&up->ev_values, cudaEventDisableTiming);
@@ -319,7 +330,8 @@ int32_t upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, 
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(up->d_i, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->copy_stream);
   }
   if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(up->ev_ids, e->copy_stream);
-  if (rc == MRS_OK && ce == cudaSuccess && n) ce = cudaMemcpyAsync(up->d_r, ratings, sizeof(double) * n, cudaMemcpyHostToDevice, e->copy_stream);
+  if (rc == MRS_OK && ce == cudaSuccess && n && !codes) ce = cudaMemcpyAsync(up->d_r, ratings, sizeof(double) * n, cudaMemcpyHostToDevice, e->copy_stream);
+  if (rc == MRS_OK && ce == cudaSuccess && n && codes) ce = cudaMemcpyAsync(up->d_c, codes, (size_t)n, cudaMemcpyHostToDevice, e->copy_stream);
   if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(up->ev_values, e->copy_stream);
   if (rc == MRS_OK && ce != cudaSuccess) { set_error("mrs_upload_begin: %s", cudaGetErrorString(ce)); rc = MRS_ERR_CUDA; }
   if (rc != MRS_OK) { free_upload(up); return rc; }
@@ -372,14 +384,19 @@ int32_t ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items
   if (s != MRS_OK) return fail(s);
   ce = cudaStreamWaitEvent(st, up->ev_values, 0);
   if (ce == cudaSuccess && n) {
-    scan_values_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_r, n, d_stats);
+    if (up->d_c) scan_codes_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_c, n, d_stats);
+    else scan_values_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_r, n, d_stats);
     count_launch();
   }
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_stats + 3, d_stats + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) { set_error("mrs_ratings_from_coo: %s", cudaGetErrorString(ce)); return fail(MRS_ERR_CUDA); }
+  if (up->d_c && h_stats[3] != 0) {
+    set_error("mrs_upload_begin_codes: %d rating code(s) are 255 (ratings of 127.5 are not representable in the compact form)", h_stats[3]);
+    return fail(MRS_ERR_INVALID);
+  }
   R->value_kind = (h_stats[3] == 0) ? kValueCode : kValueF64;
-  s = (R->value_kind == kValueCode) ? finish_values<uint8_t>(e, R, up->d_r, &B) : finish_values<double>(e, R, up->d_r, &B);
+  s = (R->value_kind == kValueCode) ? finish_values<uint8_t>(e, R, up->d_r, &B, up->d_c) : finish_values<double>(e, R, up->d_r, &B);
   int32_t dup = 0;
   if (s == MRS_OK) {
     ce = cudaMemcpy(&dup, d_dup, sizeof(int32_t), cudaMemcpyDeviceToHost);
@@ -414,6 +431,20 @@ using namespace mrs;
 extern "C" int32_t mrs_upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
                                     mrs_upload** out) {
   return upload_begin(e, users, items, ratings, n, out);
+}
+
+extern "C" int32_t mrs_upload_begin_codes(mrs_engine* e, const int32_t* users, const int32_t* items, const uint8_t* codes, int64_t n,
+                                          mrs_upload** out) {
+  MRS_REQUIRE(n == 0 || codes, MRS_ERR_INVALID, "mrs_upload_begin_codes: NULL code array");
+  return upload_begin(e, users, items, nullptr, n, out, codes ? codes : reinterpret_cast<const uint8_t*>(""));
+}
+
+extern "C" int32_t mrs_ratings_from_coo_codes(mrs_engine* e, const int32_t* users, const int32_t* items, const uint8_t* codes, int64_t n,
+                                              int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {
+  MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_ratings_from_coo_codes: NULL engine or output");
+  mrs_upload* up = nullptr;
+  MRS_TRY(mrs_upload_begin_codes(e, users, items, codes, n, &up));
+  return ratings_from_upload(up, n_users_dim, n_items_dim, out);
 }
 
 extern "C" int32_t mrs_ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items_dim, mrs_ratings** out) {

@@ -23,8 +23,8 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync", "mrs_debug_timeline",
-    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
-    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
+    "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_upload_begin_codes", "mrs_ratings_from_coo_codes", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
+    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_connect_local", "mrs_multi_create", "mrs_multi_load", "mrs_multi_baseline_mae", "mrs_multi_model", "mrs_multi_owner", "mrs_multi_destroy", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
@@ -80,6 +80,8 @@ def lib():
         "mrs_profile_end": (i32, [vp, C.c_char_p, i64, P(C.c_float), i32, P(i32)]),
         "mrs_ratings_from_coo": (i32, [vp, vp, vp, vp, i64, i32, i32, P(vp)]),
         "mrs_upload_begin": (i32, [vp, vp, vp, vp, i64, P(vp)]),
+        "mrs_upload_begin_codes": (i32, [vp, vp, vp, vp, i64, P(vp)]),
+        "mrs_ratings_from_coo_codes": (i32, [vp, vp, vp, vp, i64, i32, i32, P(vp)]),
         "mrs_ratings_from_upload": (i32, [vp, i32, i32, P(vp)]),
         "mrs_upload_destroy": (None, [vp]),
         "mrs_ratings_from_file": (i32, [vp, C.c_char_p, C.c_char_p, P(vp)]),
@@ -97,6 +99,13 @@ def lib():
         "mrs_model_destroy": (None, [vp]),
         "mrs_exchange_create": (i32, [vp, i64, i32, i32, vp, P(vp)]),
         "mrs_exchange_connect": (i32, [vp, vp]),
+        "mrs_exchange_connect_local": (i32, [vp, i32]),
+        "mrs_multi_create": (i32, [vp, i32, P(vp)]),
+        "mrs_multi_load": (i32, [vp, vp, vp, vp, i64, vp, vp, vp, i64]),
+        "mrs_multi_baseline_mae": (i32, [vp, P(dbl)]),
+        "mrs_multi_model": (i32, [vp, i32, P(vp)]),
+        "mrs_multi_owner": (i32, [vp, i32, P(i32)]),
+        "mrs_multi_destroy": (None, [vp]),
         "mrs_exchange_allreduce_async": (i32, [vp, vp, i64]),
         "mrs_exchange_allreduce_indexed_async": (i32, [vp, vp, vp, i64]),
         "mrs_exchange_status": (i32, [vp, P(i32)]),
@@ -182,6 +191,13 @@ class Engine:
     def ratings(self, users, items, ratings, n_users_dim=0, n_items_dim=0):
         return Ratings(self, users, items, ratings, n_users_dim, n_items_dim)
 
+    def upload_codes(self, users, items, codes):
+        """Staged upload of the compact form: ``codes`` = 2 x rating as uint8 (9 bytes per rating over PCIe instead of 16)."""
+        return Upload(self, users, items, codes, codes=True)
+
+    def ratings_from_codes(self, users, items, codes, n_users_dim=0, n_items_dim=0):
+        return self.upload_codes(users, items, codes).ratings(n_users_dim, n_items_dim)
+
     def upload(self, users, items, ratings):
         """Start the host -> device copies of a rating set on the engine's copy stream and return at once; build the set
         with ``Upload.ratings()``.  Lets the copies of a second set (test) run while the first (train) is being built."""
@@ -192,6 +208,44 @@ class Engine:
 
     def ratings_from_file(self, path, sep):
         return Ratings.from_file(self, path, sep)
+
+
+class MultiEngine:
+    """Several GPUs driven from this one process (``mrs_multi_*``): users sharded over the devices, one exchange."""
+
+    def __init__(self, device_ids):
+        ids = np.ascontiguousarray(device_ids, dtype=np.int32)
+        self._h = C.c_void_p()
+        _check(lib().mrs_multi_create(_ptr(ids), ids.size, C.byref(self._h)))
+        self.n = int(ids.size)
+
+    def load(self, train, test):
+        a = [np.ascontiguousarray(x, dtype=t) for x, t in zip((*train, *test), (np.int32, np.int32, np.float64) * 2)]
+        _check(lib().mrs_multi_load(self._h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), a[0].size, _ptr(a[3]), _ptr(a[4]), _ptr(a[5]), a[3].size))
+
+    def baseline_mae(self):
+        out = C.c_double()
+        _check(lib().mrs_multi_baseline_mae(self._h, C.byref(out)))
+        return out.value
+
+    def model(self, slot):
+        """The model of one device slot as a (borrowed) Model for the query methods."""
+        h = C.c_void_p()
+        _check(lib().mrs_multi_model(self._h, int(slot), C.byref(h)))
+        m = Model.__new__(Model)
+        m.engine, m.train, m._h = None, None, h
+        m.close = lambda: None          # owned by the multi handle
+        return m
+
+    def owner(self, user):
+        s = C.c_int32()
+        _check(lib().mrs_multi_owner(self._h, int(user), C.byref(s)))
+        return s.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mrs_multi_destroy(self._h)
+            self._h = None
 
 
 class PeerExchange:
@@ -261,16 +315,17 @@ class Graph:
 class Upload:
     """A rating set on its way to the device (``mrs_upload_begin``); the host arrays are kept alive until it is consumed."""
 
-    def __init__(self, engine, users, items, ratings):
+    def __init__(self, engine, users, items, ratings, codes=False):
         self.engine = engine
         u = np.ascontiguousarray(users, dtype=np.int32)
         i = np.ascontiguousarray(items, dtype=np.int32)
-        r = np.ascontiguousarray(ratings, dtype=np.float64)
+        r = np.ascontiguousarray(ratings, dtype=np.uint8 if codes else np.float64)
         if not (u.shape == i.shape == r.shape and u.ndim == 1):
             raise ValueError("users, items, ratings must be 1-D arrays of equal length")
         self._keep = (u, i, r)
         self._h = C.c_void_p()
-        _check(lib().mrs_upload_begin(engine._h, _ptr(u), _ptr(i), _ptr(r), u.size, C.byref(self._h)))
+        begin = lib().mrs_upload_begin_codes if codes else lib().mrs_upload_begin
+        _check(begin(engine._h, _ptr(u), _ptr(i), _ptr(r), u.size, C.byref(self._h)))
 
     def ratings(self, n_users_dim=0, n_items_dim=0):
         h, self._h = self._h, None

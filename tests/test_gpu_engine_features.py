@@ -153,3 +153,19 @@ def test_staged_upload_equals_direct_build(eng, ml100k):
     assert Rf.value_kind == 1
     for h in (m, m0, R, T, R0, T0, Rf):
         h.close()
+
+
+def test_compact_code_upload_matches_fp64_upload(eng, ml100k):
+    """mrs_ratings_from_coo_codes: (int32, int32, uint8 code = 2 x rating), 9 bytes per rating over PCIe instead of 16."""
+    tr, te = ml100k["train"], ml100k["test"]
+    R, T = eng.ratings(*tr), eng.ratings(*te)
+    Rc = eng.ratings_from_codes(tr[0], tr[1], (tr[2] * 2).astype(np.uint8))
+    Tc = eng.upload_codes(te[0], te[1], (te[2] * 2).astype(np.uint8)).ratings()
+    m, mc = E.Model(eng, R), E.Model(eng, Rc)
+    assert mc.mae(Tc, E.PRED_BASELINE) == m.mae(T, E.PRED_BASELINE)
+    for kind in (E.USER_AVG, E.ITEM_AVG, E.ITEM_AVG_DEV):
+        assert mc.vector(kind)[0].tolist() == m.vector(kind)[0].tolist()
+    with pytest.raises(E.MrsError):
+        eng.ratings_from_codes(tr[0][:10], tr[1][:10], np.full(10, 255, dtype=np.uint8))   # 255 is not a legal code
+    for h in (mc, m, Tc, Rc, T, R):
+        h.close()

@@ -147,3 +147,27 @@ def test_two_processes_two_gpus(flag):
         assert r["mae"] == r["mae_eager"]                      # graph replay == eager launches, bit for bit
         assert r["items_wrong_without_exchange"] > r["items"] // 2   # the exchange is doing the work
         assert not r["timed_out"]
+
+
+@pytest.mark.parametrize("n_dev", [1, 2])
+def test_one_process_drives_the_devices(n_dev):
+    """mrs_multi_*: ONE process (what a JVM is) owns the devices; peers are plain pointers after cudaDeviceEnablePeerAccess."""
+    if _n_gpus() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    d = synth.ml25m(seed=6, n_users=15000, n_items=3000, n_ratings=600_000, max_item_id=9000)
+    tr, te = d["train"], d["test"]
+    me = E.MultiEngine(list(range(n_dev)))
+    me.load(tr, te)
+    o = O.Oracle(*tr)
+    ref = o.mae(te, kind=O.BASELINE)
+    assert me.baseline_mae() == pytest.approx(ref, rel=REL)
+    assert me.baseline_mae() == pytest.approx(ref, rel=REL)            # a second pass on the same buffers
+    items = np.unique(tr[1])
+    oid = [o.item_avg_dev(int(i)) for i in items]
+    for slot in range(n_dev):
+        m = me.model(slot)
+        assert close(m.vector(E.ITEM_AVG_DEV)[0][items], oid)
+        assert m.global_avg == o.global_avg
+    u = int(tr[0][0])
+    assert me.model(me.owner(u)).lookup(E.USER_AVG, u)[0] == o.user_avg(u)
+    me.close()
