@@ -481,6 +481,7 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
 
 int32_t fit_finish(mrs_model* m) {
   MRS_REQUIRE(m, MRS_ERR_INVALID, "mrs_fit_finish: NULL model");
+  use_engine(m->eng);
   MRS_CUDA(launch_pdl(item_finalize_kernel, dim3((m->n_items + 255) / 256), dim3(256), 0, m->eng->stream, m->xbuf, m->n_items, m->idevavg,
                       m->iavg, m->gavg));
   mark(m->eng, "item_finalize");
@@ -492,6 +493,7 @@ int32_t fit_finish(mrs_model* m) {
 
 int32_t mae_baseline_async(const mrs_model* m, int32_t kind, const mrs_ratings* T, double* d_out2) {
   MRS_REQUIRE(m && T && d_out2, MRS_ERR_INVALID, "mrs_mae: NULL argument");
+  use_engine(m->eng);
   MRS_REQUIRE(m->finished, MRS_ERR_INVALID, "mrs_mae: model not finished (call mrs_fit_finish)");
   MRS_REQUIRE(kind != MRS_PRED_ITEM || m->want_item_avg, MRS_ERR_INVALID, "mrs_mae: item averages were switched off for this model");
   if (kind == MRS_PRED_BASELINE && T->value_kind == kValueCode && T->n > 0) return launch_mae_tiled_baseline(m, T, d_out2);
@@ -501,6 +503,7 @@ int32_t mae_baseline_async(const mrs_model* m, int32_t kind, const mrs_ratings* 
 int32_t predict_baseline_async(const mrs_model* m, int32_t kind, const int32_t* d_users, const int32_t* d_items, int64_t n,
                                double* d_out) {
   MRS_REQUIRE(m && m->finished, MRS_ERR_INVALID, "mrs_predict: model missing or not finished");
+  use_engine(m->eng);
   MRS_REQUIRE(kind != MRS_PRED_ITEM || m->want_item_avg, MRS_ERR_INVALID, "mrs_predict: item averages were switched off for this model");
   if (n == 0) return MRS_OK;
   int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)m->eng->sm_count * 16);

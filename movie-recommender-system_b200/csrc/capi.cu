@@ -214,6 +214,7 @@ extern "C" int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32) {
 
 extern "C" int32_t mrs_engine_sync(mrs_engine* e) {
   MRS_REQUIRE(e, MRS_ERR_INVALID, "mrs_engine_sync: NULL engine");
+  use_engine(e);
   MRS_CUDA(cudaStreamSynchronize(e->stream));
   return MRS_OK;
 }
@@ -252,6 +253,7 @@ extern "C" int32_t mrs_graph_end(mrs_engine* e, mrs_graph** out) {
 
 extern "C" int32_t mrs_graph_launch(mrs_graph* g) {
   MRS_REQUIRE(g, MRS_ERR_INVALID, "mrs_graph_launch: NULL graph");
+  use_engine(g->eng);
   MRS_CUDA(cudaGraphLaunch(g->exec, g->eng->stream));
   return MRS_OK;
 }
@@ -345,6 +347,7 @@ extern "C" void mrs_model_destroy(mrs_model* m) {
 
 // ------------------------------------------------------------------ model queries
 static int32_t model_gavg(const mrs_model* m, double* out) {
+  use_engine(m->eng);
   MRS_REQUIRE(m->finished, MRS_ERR_INVALID, "model not finished (call mrs_fit_finish)");
   if (!m->host_valid) {
     MRS_CUDA(cudaMemcpyAsync(&m->h_gavg, m->gavg, sizeof(double), cudaMemcpyDeviceToHost, m->eng->stream));
@@ -363,6 +366,7 @@ extern "C" int32_t mrs_model_scalar(const mrs_model* m, int32_t kind, double* ou
 
 // copies `count` elements starting at `first` of a per-id table, plus the matching counts
 static int32_t fetch_table(const mrs_model* m, int32_t kind, int64_t first, int64_t count, double* vals, int32_t* counts) {
+  use_engine(m->eng);
   const mrs_ratings* R = m->train;
   cudaStream_t st = m->eng->stream;
   const double* src = nullptr;

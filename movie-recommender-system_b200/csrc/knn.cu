@@ -740,6 +740,7 @@ extern "C" int32_t mrs_sim_set_k(mrs_sim* s, int32_t k) {
 extern "C" int32_t mrs_sim_entry_values(const mrs_sim* s, int32_t which, int32_t* users_out, int32_t* items_out, double* vals_out,
                                         int64_t cap, int64_t* n_out) {
   MRS_REQUIRE(s && n_out, MRS_ERR_INVALID, "mrs_sim_entry_values: NULL argument");
+  use_engine(s->model->eng);
   MRS_REQUIRE(which == 0 || which == 1, MRS_ERR_INVALID, "mrs_sim_entry_values: which must be 0 (deviation) or 1 (preprocessed)");
   const mrs_ratings* R = s->model->train;
   *n_out = R->n;
@@ -782,6 +783,7 @@ static int32_t host_cidx(const mrs_ratings* R, int32_t u, int32_t* c) {
 
 extern "C" int32_t mrs_similarity(const mrs_sim* s, int32_t u, int32_t v, double* out) {
   MRS_REQUIRE(s && out, MRS_ERR_INVALID, "mrs_similarity: NULL argument");
+  use_engine(s->model->eng);
   const mrs_ratings* R = s->model->train;
   cudaStream_t st = R->eng->stream;
   int32_t cu = -1, cv = -1;
@@ -825,6 +827,7 @@ extern "C" int32_t mrs_similarity(const mrs_sim* s, int32_t u, int32_t v, double
 
 extern "C" int32_t mrs_neighbors(const mrs_sim* s, int32_t u, int32_t k, int32_t* ids_out, double* sims_out, int32_t cap, int32_t* n_out) {
   MRS_REQUIRE(s && n_out, MRS_ERR_INVALID, "mrs_neighbors: NULL argument");
+  use_engine(s->model->eng);
   const mrs_ratings* R = s->model->train;
   cudaStream_t st = R->eng->stream;
   int32_t cu = -1;
