@@ -236,7 +236,7 @@ def run_ours(args):
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
     from mrs_b200 import sharded
-    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl) if world > 1 else None
+    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl, fused=not args.no_fused) if world > 1 else None
 
     def enqueue():
         if sb is not None:       # local pass -> all-reduce of the exchange buffer -> finish -> MAE -> 16-byte all-reduce
@@ -309,10 +309,10 @@ def run_ours(args):
                 model.mae_async(T, out2.data_ptr())
             else:            # same number of exchanges on every rank
                 sb.fit_local(); sb.exchange()
-                if sb.peer is not None and rank == 0 and _ == reps - 1:
+                if sb.peer is not None and not sb.fused and rank == 0 and _ == reps - 1:
                     log(f"[rank 0] big exchange stamps (ns after start: published, barrier1, reduced, barrier2, done): {sb.peer.stamps()}")
                 sb.fit_finish(); sb.mae_local(); sb.mae_exchange()
-                if sb.peer is not None and rank == 0 and _ == reps - 1:
+                if sb.peer is not None and not sb.fused and rank == 0 and _ == reps - 1:
                     log(f"[rank 0] small exchange stamps: {sb.peer.stamps()}")
             for name, ms in eng.profile_end():
                 per_kernel.setdefault(name, []).append(ms)
@@ -473,11 +473,13 @@ def run_ours(args):
                                  "note": "the same with fp64 ratings on the host (int32,int32,f64: 16 B per rating, mrs_upload_begin)"}},
             "gpu_launches": int(launches) if graph is None else int(args.steps * kernels_per_step),
             "launch_mode": ("cuda graph replay (1 cudaGraphLaunch per step)" if world == 1 else
-                            ("1 cuda graph per step incl. the 2 peer-memory exchange kernels" if not args.nccl else
+                            ("1 cuda graph per step (exchanges fused into the kernels)" if not args.nccl and not args.no_fused else
+                             "1 cuda graph per step incl. the 2 peer-memory exchange kernels" if not args.nccl else
                              "2 cuda graphs + 2 NCCL all-reduces per step")) if graph is not None else "stream launches", "clocks": clocks, "mae": mae, "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae),
             "wall_ms_per_step_incl_flush": 1000.0 * t_wall / args.steps,
             "exchange": None if sb is None else ("nccl" if sb.peer is None else
-                                                 {"kind": "own NVLink peer-memory kernel", "timed_out": sb.peer.timed_out()}),
+                                                 {"kind": "fused into the pass' own kernels: partial sums pushed into every rank's receive buffer over NVLink"
+                                                          if sb.fused else "own NVLink peer-memory all-reduce kernel", "timed_out": sb.peer.timed_out()}),
             "step_ms_min_max": [min(step_ms), max(step_ms)],
             "strong_scaling": strong,
             "knn": knn,
@@ -507,7 +509,7 @@ def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, pee
     mtr, mte = sharded.shard_of(tr[0], bounds, rank), sharded.shard_of(te[0], bounds, rank)
     R = eng.ratings(tr[0][mtr], tr[1][mtr], tr[2][mtr], nu_dim, ni_dim)
     T = eng.ratings(te[0][mte], te[1][mte], te[2][mte], nu_dim, ni_dim)
-    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=peer)
+    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=peer, fused=not args.no_fused)
     sb.step()
     torch.cuda.synchronize(dev)
     if not args.no_graph:
@@ -547,7 +549,7 @@ def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, pee
                "user_bounds": [int(b) for b in bounds], "train_ratings_rank0": int(mtr.sum()), "test_ratings_rank0": int(mte.sum()),
                "mae": mae, "oracle_mae": ref_mae, "mae_matches_cpu_port": bool(abs(mae - ref_mae) <= 1e-6 * abs(ref_mae)),
                "item_avg_dev_matches_single_gpu_fit": bool(np.all(np.abs(idev - idev1) <= tol)), "item_avg_dev_worst_rel": worst,
-               "exchange": "nccl" if sb.peer is None else "own NVLink peer-memory kernel"}
+               "exchange": "nccl" if sb.peer is None else ("fused into the pass' kernels (NVLink push)" if sb.fused else "own NVLink peer-memory kernel")}
         m1.close(); R1.close()
     torch.cuda.synchronize(dev)
     dist.barrier()                 # nobody may still be reading our symmetric buffers when they are unmapped
@@ -688,6 +690,7 @@ def main():
     ap.add_argument("--no-knn25m", action="store_true", help="skip the kNN k=300 leg at ml-25m shape (BASELINE config 5)")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
                     help="L2 flush between timed iterations: 256 MiB write, or write followed by a 256 MiB read (cold and clean L2)")
+    ap.add_argument("--no-fused", action="store_true", help="N>1: separate exchange kernels between the pass' kernels instead of the fused push exchange")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling leg (ONE ml-25m set user-sharded over the ranks)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -191,6 +191,20 @@ MRS_API int32_t mrs_exchange_allreduce_async(mrs_exchange* x, void* device_inout
  * other positions neither travel nor change.  The exchange buffer of a model is indexed by item id; with sparse ids most of
  * its slots are zero on every rank (72 % at ml-25m shape), and the slots in use are known once the rating sets are loaded. */
 MRS_API int32_t mrs_exchange_allreduce_indexed_async(mrs_exchange* x, void* device_inout, const int32_t* device_idx, int64_t n_idx);
+/* Fused compute + collective: the exchange happens INSIDE the pass' own kernels instead of between them.
+ * mrs_fit_local_push = mrs_fit_local whose last kernel delivers this rank's per-item partial sums straight into every
+ * rank's symmetric receive buffer with NVLink stores and raises a flag (no publish copy, no waiting);
+ * mrs_fit_finish_pull = mrs_fit_finish that first waits for every rank's delivery and adds them from its OWN memory in
+ * rank order (bit-identical totals everywhere, no remote loads); mrs_mae_push_async = the fused baseline MAE whose last
+ * block delivers {sum |err|, n} to every rank, waits for the others and writes the global pair to device_out2.
+ * `device_known_items`: the n_known item ids (ascending, int32, on the device, identical on every rank) that occur on
+ * SOME rank -- only their slots travel.  The model must have item averages switched off.  Each of the two exchanges of a
+ * pass needs its own handle (capacities >= 2*n_known+2 and >= 2 doubles); a missing peer poisons the results with NaN
+ * and is reported by mrs_exchange_status like in the unfused form. */
+MRS_API int32_t mrs_fit_local_push(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, mrs_exchange* x,
+                                   const int32_t* device_known_items, int32_t n_known);
+MRS_API int32_t mrs_fit_finish_pull(mrs_model* m, mrs_exchange* x);
+MRS_API int32_t mrs_mae_push_async(const mrs_model* m, const mrs_ratings* test, mrs_exchange* x, void* device_out2);
 MRS_API int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out);
 MRS_API int32_t mrs_exchange_set_timeout_ms(mrs_exchange* x, int64_t milliseconds);
 /* diagnostics: %globaltimer (ns) of block 0 in the last exchange: [0] start, [1] published, [2] first barrier passed,

@@ -352,12 +352,12 @@ inline int chunk_grid(int32_t n_chunks, int sm_count) {
 }
 
 // code path: K1 (user code sums) -> K2 tiled item pass (forms the user averages on the way) -> K2b finalize
-int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused) {
+int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push) {
   MRS_CUDA(cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream));
   user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, e->d_timeline);
   mark(e, "user_sum");
   MRS_CUDA(cudaGetLastError());
-  return launch_item_tiled(e, R, m, fused);
+  return launch_item_tiled(e, R, m, fused, push);
 }
 
 template <typename VT>
@@ -417,7 +417,7 @@ int32_t dispatch_mae(const mrs_model* m, int32_t kind, const mrs_ratings* T, dou
 
 }  // namespace
 
-int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool fused_finalize) {
+int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool fused_finalize, const PushDev* push) {
   MRS_REQUIRE(e && R && inout, MRS_ERR_INVALID, "mrs_fit: NULL argument");
   use_engine(e);
   const bool codes = (R->value_kind == kValueCode);
@@ -470,10 +470,12 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
   m->finished = false;
   m->host_valid = false;
   if (codes) {
-    MRS_TRY(launch_fit_codes(e, R, m, fused_finalize));
+    MRS_REQUIRE(!push || !m->want_item_avg, MRS_ERR_UNSUPPORTED, "mrs_fit_local_push: switch item averages off (mrs_model_set_item_averages): they do not travel in the fused exchange");
+    MRS_TRY(launch_fit_codes(e, R, m, fused_finalize, push));
     if (fused_finalize) m->finished = true;
     return MRS_OK;
   }
+  MRS_REQUIRE(!push, MRS_ERR_UNSUPPORTED, "mrs_fit_local_push: the fused exchange needs a half-star coded rating set");
   MRS_TRY(launch_fit_local<double>(e, R, m));
   if (fused_finalize) return fit_finish(m);
   return MRS_OK;

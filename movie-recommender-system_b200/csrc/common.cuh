@@ -70,6 +70,39 @@ __device__ __forceinline__ void tl_end(unsigned long long* tl, int k) {
   if (tl && threadIdx.x == 0) atomicMax(tl + 2 * k + 1, gtimer_ns());
 }
 
+// ---- fused compute + collective over NVLink peer memory ("push" exchange): what a kernel needs to deliver its partial
+// sums straight into every rank's symmetric receive buffer and to wait for the other ranks' deliveries (exchange.cu)
+struct PushDev {
+  double* const* peer;           // device array: base of every rank's symmetric allocation (own = local memory)
+  int32_t rank, world;
+  int64_t cap;                   // doubles per (parity, rank) receive slot
+  int64_t recv_off;              // offset, in doubles from a base, of recv[2][world][cap]
+  int64_t flag_off;              // offset, in 8-byte words from a base, of the delivery flags [world] (epoch numbers)
+  unsigned long long* epoch;     // device: completed push exchanges on this handle (graph replays read it on the device)
+  unsigned int* done;            // device: [2] block counters (deliveries, completions)
+  int32_t* error;                // device: set when a peer did not deliver in time
+  long long timeout_cycles;
+};
+__device__ __forceinline__ double* push_slot(const PushDev& x, int p, int parity, int from) {
+  return x.peer[p] + x.recv_off + ((size_t)parity * x.world + from) * x.cap;
+}
+__device__ __forceinline__ void push_flag_raise(const PushDev& x, int p, unsigned long long epoch) {
+  unsigned long long* f = reinterpret_cast<unsigned long long*>(x.peer[p]) + x.flag_off + x.rank;
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+}
+// thread p (< world) waits until rank p has delivered epoch `epoch`; returns false on time-out (error word set)
+__device__ __forceinline__ bool push_flag_wait(const PushDev& x, int p, unsigned long long epoch) {
+  const unsigned long long* f = reinterpret_cast<const unsigned long long*>(x.peer[x.rank]) + x.flag_off + p;
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= epoch) return true;
+  } while (clock64() - t0 <= x.timeout_cycles);
+  atomicExch(x.error, 1);
+  return false;
+}
+
 // P:57-61 -- strict comparisons, equality -> 1
 __host__ __device__ inline double scale_fn(double x, double y) {
   if (x > y) return 5.0 - y;
@@ -234,6 +267,9 @@ struct mrs_model {
   double* mae_part = nullptr;   // per-block partials of |err| sums
   unsigned int* counters = nullptr;  // small set of device counters (last-block-done patterns)
   int32_t mae_part_cap = 0;
+  // fused push exchange (mrs_fit_local_push): compact slot of every item in the exchange (-1: the item occurs on no rank)
+  int32_t* slot_of_item = nullptr;  // [n_items]
+  int32_t n_slots_known = 0;        // K: items that occur on some rank; a delivery is [K dev sums | K counts | sum, n]
   bool finished = false;
   // host mirrors, filled lazily by queries
   mutable bool host_valid = false;
@@ -323,18 +359,21 @@ constexpr int kUnitLen = 64;      // (tile,item) segments are cut into units of 
 constexpr int kUnitBits = 7;      // bits of (kUnitLen - len) in the unit sort key
 int32_t build_tiled_layout(const mrs_ratings* R);
 void free_tiled_layout(const mrs_ratings* R);
-int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize);
+int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize, const PushDev* push = nullptr);
+int32_t launch_finish_pull(mrs_model* m, const PushDev& push);
 // mae_tiled.cu
 constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item deviations in shared memory
 int32_t build_mae_layout(const mrs_ratings* T);
 void free_mae_layout(const mrs_ratings* T);
-int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2);
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push = nullptr);
 // baseline.cu
-int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize);
+int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize, const PushDev* push = nullptr);
 int32_t fit_finish(mrs_model* m);
 int32_t mae_baseline_async(const mrs_model* m, int32_t pred_kind, const mrs_ratings* test, double* d_out2);
 int32_t predict_baseline_async(const mrs_model* m, int32_t pred_kind, const int32_t* d_users, const int32_t* d_items,
                                int64_t n, double* d_out);
+// exchange.cu
+int32_t exchange_push_dev(mrs_exchange* x, int64_t n_doubles, PushDev* out);
 // knn.cu
 int32_t sim_fit_async(mrs_model* m, int32_t sim_kind, int32_t k, mrs_sim** inout);
 int32_t mae_personalized_async(const mrs_model* m, const mrs_sim* s, const mrs_ratings* test, double* d_out2);

@@ -23,7 +23,10 @@ struct mrs_exchange {
   mrs_engine* eng = nullptr;
   int32_t rank = 0, world = 1;
   int64_t n = 0;                 // capacity in doubles of one parity buffer
-  unsigned char* base = nullptr; // own symmetric allocation: publish [2][n] | result [2][n] doubles | flags [2][world] u64
+  unsigned char* base = nullptr; // own symmetric allocation: publish [2][n] | result [2][n] doubles | flags [2][world] u64 |
+                                 // push mode: recv [2][world][n] doubles | delivery flags [world] u64
+  unsigned long long* d_pepoch = nullptr;  // completed push exchanges
+  unsigned int* d_pdone = nullptr;         // [2]
   std::vector<void*> peer_base;  // mapped bases of all ranks (own = base)
   double** d_peer = nullptr;     // device array of the mapped bases
   unsigned long long* d_epoch = nullptr;  // number of completed exchanges (device side, so that launches can be graph-captured)
@@ -227,6 +230,26 @@ __global__ void __launch_bounds__(kExThreads) peer_allreduce_kernel(double* cons
 }
 
 }  // namespace
+
+// device-side view of an exchange handle for the kernels that deliver their own partial sums (tiled.cu, mae_tiled.cu)
+int32_t exchange_push_dev(mrs_exchange* x, int64_t n_doubles, PushDev* out) {
+  MRS_REQUIRE(x && out, MRS_ERR_INVALID, "push exchange: NULL argument");
+  MRS_REQUIRE(x->connected, MRS_ERR_INVALID, "push exchange: call mrs_exchange_connect first");
+  MRS_REQUIRE(!x->failed, MRS_ERR_CUDA, "push exchange: an earlier exchange on this handle timed out; the handle is dead");
+  MRS_REQUIRE(n_doubles > 0 && n_doubles <= x->n, MRS_ERR_INVALID, "push exchange: %lld doubles exceed the capacity %lld", (long long)n_doubles,
+              (long long)x->n);
+  out->peer = x->d_peer;
+  out->rank = x->rank; out->world = x->world;
+  out->cap = x->n;
+  out->recv_off = 4 * x->n + 2 * (int64_t)x->world;
+  out->flag_off = out->recv_off + 2 * (int64_t)x->world * x->n;
+  out->epoch = x->d_pepoch;
+  out->done = x->d_pdone;
+  out->error = x->d_error;
+  out->timeout_cycles = x->timeout_cycles;
+  return MRS_OK;
+}
+
 }  // namespace mrs
 
 using namespace mrs;
@@ -241,13 +264,18 @@ extern "C" int32_t mrs_exchange_create(mrs_engine* e, int64_t n_doubles, int32_t
   mrs_exchange* x = new mrs_exchange();
   x->eng = e; x->rank = rank; x->world = world;
   x->n = (n_doubles + 1) & ~(int64_t)1;
-  const size_t bytes = 4 * (size_t)x->n * sizeof(double) + 2 * (size_t)world * sizeof(unsigned long long) + 64;
+  const size_t bytes = 4 * (size_t)x->n * sizeof(double) + 2 * (size_t)world * sizeof(unsigned long long) +
+                       2 * (size_t)world * (size_t)x->n * sizeof(double) + (size_t)world * sizeof(unsigned long long) + 64;
   // IPC-shareable memory must come from cudaMalloc directly (not from the engine's block cache)
   cudaError_t ce = cudaMalloc((void**)&x->base, bytes);
   if (ce != cudaSuccess) { delete x; set_error("mrs_exchange_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(ce)); return MRS_ERR_NOMEM; }
   MRS_CUDA(cudaMemset(x->base, 0, bytes));
   MRS_CUDA(cudaMalloc((void**)&x->d_done, 4 * sizeof(unsigned int)));
   MRS_CUDA(cudaMemset(x->d_done, 0, 4 * sizeof(unsigned int)));
+  MRS_CUDA(cudaMalloc((void**)&x->d_pepoch, sizeof(unsigned long long)));
+  MRS_CUDA(cudaMemset(x->d_pepoch, 0, sizeof(unsigned long long)));
+  MRS_CUDA(cudaMalloc((void**)&x->d_pdone, 4 * sizeof(unsigned int)));
+  MRS_CUDA(cudaMemset(x->d_pdone, 0, 4 * sizeof(unsigned int)));
   MRS_CUDA(cudaMalloc((void**)&x->d_epoch, sizeof(unsigned long long)));
   MRS_CUDA(cudaMemset(x->d_epoch, 0, sizeof(unsigned long long)));
   MRS_CUDA(cudaMalloc((void**)&x->d_error, sizeof(int32_t)));
@@ -330,6 +358,59 @@ static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_dou
   return MRS_OK;
 }
 
+// ---- fused compute + collective entry points (the exchange happens inside the fit's and the test pass' own kernels)
+namespace mrs {
+namespace {
+__global__ void slot_fill_kernel(int32_t* __restrict__ slot_of_item, int32_t n_items, const int32_t* __restrict__ known, int32_t n_known) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_known) {
+    const int32_t i = known[t];
+    if (i >= 0 && i < n_items) slot_of_item[i] = t;
+  }
+}
+}  // namespace
+}  // namespace mrs
+
+extern "C" int32_t mrs_fit_local_push(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, mrs_exchange* x, const int32_t* device_known_items,
+                                      int32_t n_known) {
+  MRS_REQUIRE(e && train && inout && x && device_known_items && n_known >= 0, MRS_ERR_INVALID, "mrs_fit_local_push: NULL argument");
+  MRS_REQUIRE(*inout, MRS_ERR_INVALID, "mrs_fit_local_push: pass a model of this train set (mrs_fit_local once, with item averages switched off)");
+  mrs_model* m = *inout;
+  use_engine(e);
+  if (!m->slot_of_item || m->n_slots_known != n_known) {  // first use (never inside a graph capture): item id -> compact slot
+    dev_free(m->slot_of_item);
+    m->slot_of_item = nullptr;
+    MRS_TRY(dev_alloc(&m->slot_of_item, (size_t)m->n_items));
+    MRS_CUDA(cudaMemsetAsync(m->slot_of_item, 0xff, sizeof(int32_t) * (size_t)m->n_items, e->stream));
+    if (n_known) slot_fill_kernel<<<(n_known + 255) / 256, 256, 0, e->stream>>>(m->slot_of_item, m->n_items, device_known_items, n_known);
+    count_launch();
+    MRS_CUDA(cudaGetLastError());
+    m->n_slots_known = n_known;
+  }
+  PushDev pd;
+  MRS_TRY(exchange_push_dev(x, 2 * (int64_t)n_known + 2, &pd));
+  return fit_local(e, train, inout, false, &pd);
+}
+
+extern "C" int32_t mrs_fit_finish_pull(mrs_model* m, mrs_exchange* x) {
+  MRS_REQUIRE(m && x && m->slot_of_item, MRS_ERR_INVALID, "mrs_fit_finish_pull: call mrs_fit_local_push first");
+  use_engine(m->eng);
+  PushDev pd;
+  MRS_TRY(exchange_push_dev(x, 2 * (int64_t)m->n_slots_known + 2, &pd));
+  return launch_finish_pull(m, pd);
+}
+
+extern "C" int32_t mrs_mae_push_async(const mrs_model* m, const mrs_ratings* test, mrs_exchange* x, void* device_out2) {
+  MRS_REQUIRE(m && test && x && device_out2, MRS_ERR_INVALID, "mrs_mae_push_async: NULL argument");
+  MRS_REQUIRE(m->finished, MRS_ERR_INVALID, "mrs_mae_push_async: model not finished");
+  MRS_REQUIRE(m->eng == test->eng, MRS_ERR_INVALID, "mrs_mae_push_async: model and test set live on different engines");
+  MRS_REQUIRE(test->value_kind == kValueCode && test->n > 0, MRS_ERR_UNSUPPORTED, "mrs_mae_push_async: needs a non-empty half-star coded test set");
+  use_engine(m->eng);
+  PushDev pd;
+  MRS_TRY(exchange_push_dev(x, 2, &pd));
+  return launch_mae_tiled_baseline(m, test, (double*)device_out2, &pd);
+}
+
 extern "C" int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out) {
   MRS_REQUIRE(x && timed_out, MRS_ERR_INVALID, "mrs_exchange_status: NULL argument");
   use_engine(x->eng);
@@ -361,6 +442,8 @@ extern "C" void mrs_exchange_destroy(mrs_exchange* x) {
   if (x->d_peer) cudaFree(x->d_peer);
   if (x->d_done) cudaFree(x->d_done);
   if (x->d_epoch) cudaFree(x->d_epoch);
+  if (x->d_pepoch) cudaFree(x->d_pepoch);
+  if (x->d_pdone) cudaFree(x->d_pdone);
   if (x->d_error) cudaFree(x->d_error);
   if (x->d_stamps) cudaFree(x->d_stamps);
   if (x->base) cudaFree(x->base);

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
                                                                           const double* __restrict__ uavg, const double* __restrict__ idevavg,
                                                                           const double* __restrict__ gavg_p, double n_total,
                                                                           double* __restrict__ part, unsigned int* __restrict__ counter,
-                                                                          double* __restrict__ out2, unsigned long long* __restrict__ tl) {
+                                                                          double* __restrict__ out2, unsigned long long* __restrict__ tl,
+                                                                          int use_push, const PushDev x) {
   tl_begin(tl, 3);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_dev = reinterpret_cast<double*>(smem_raw);                                     // [kMaeTileItems]
@@ -168,12 +169,46 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     t = warp_sum(t);
     if (lane == 0) sh[wid] = t;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (int k = 0; k < wpb; ++k) s += sh[k];
-      out2[0] = s;
-      out2[1] = n_total;
-      *counter = 0;
+    if (!use_push) {
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < wpb; ++k) s += sh[k];
+        out2[0] = s;
+        out2[1] = n_total;
+        *counter = 0;
+      }
+    } else {
+      // sharded run, fused exchange of {sum |err|, n}: this last block delivers the rank's pair into every rank's receive
+      // slot (NVLink stores), raises the flags, waits for the other ranks' pairs and adds them in rank order
+      const unsigned long long epoch = *x.epoch + 1;
+      const int parity = (int)(epoch & 1);
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < wpb; ++k) s += sh[k];
+        for (int p = 0; p < x.world; ++p) {
+          double* slot = push_slot(x, p, parity, x.rank);
+          slot[0] = s;
+          slot[1] = n_total;
+        }
+        __threadfence_system();
+        for (int p = 0; p < x.world; ++p) push_flag_raise(x, p, epoch);
+      }
+      __syncthreads();
+      int good = 1;
+      if ((int)threadIdx.x < x.world) good = push_flag_wait(x, threadIdx.x, epoch) ? 1 : 0;
+      const bool ok = __syncthreads_and(good) != 0;
+      if (threadIdx.x == 0) {
+        double s = 0.0, c = 0.0;
+        for (int p = 0; p < x.world; ++p) {
+          const double* slot = push_slot(x, x.rank, parity, p);
+          s += slot[0];
+          c += slot[1];
+        }
+        out2[0] = ok ? s : nan("");  // a peer never delivered: the MAE becomes NaN
+        out2[1] = ok ? c : nan("");
+        *x.epoch = epoch;
+        *counter = 0;
+      }
     }
   }
   tl_end(tl, 3);
@@ -242,7 +277,7 @@ int32_t build_mae_layout(const mrs_ratings* T) {
   return MRS_OK;
 }
 
-int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2) {
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push) {
   MRS_TRY(build_mae_layout(T));
   const auto& L = T->ml;
   mrs_engine* e = m->eng;
@@ -254,7 +289,7 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
   MRS_REQUIRE(grid > 0 && grid <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set needs %d CTAs, more than the %d partial slots of the model", grid,
               m->mae_part_cap);
   MRS_CUDA(launch_pdl(predict_mae_tiled_kernel, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
-                      m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline));
+                      m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, push ? 1 : 0, push ? *push : PushDev{}));
   mark(e, "predict_mae_tiled");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

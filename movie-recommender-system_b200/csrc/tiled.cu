@@ -384,7 +384,124 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
   tl_end(tl, 2);
 }
 
+// ---- fused compute + collective (sharded runs): K2b delivers this rank's per-item partial sums straight into every
+// rank's symmetric receive buffer with NVLink stores (fire and forget) and raises a flag; the finishing kernel of every
+// rank then waits for the flags and adds the deliveries FROM ITS OWN MEMORY in rank order (bit-identical totals
+// everywhere).  Compared with K2b -> all-reduce kernel -> finalize kernel this saves one launch, the publish copy and
+// the round trip of the remote loads.  Only the K items that occur on some rank travel (slot_of_item).
+__global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restrict__ xdev_fix, unsigned long long* __restrict__ xcode_sum,
+                                                             const int32_t* __restrict__ icolp, int32_t n_items,
+                                                             unsigned long long* __restrict__ k1_part, double n_total,
+                                                             const int32_t* __restrict__ slot_of_item, int32_t K, const PushDev x,
+                                                             unsigned long long* __restrict__ tl) {
+  __shared__ int s_last;
+  tl_begin(tl, 2);
+  pdl_trigger();
+  pdl_wait();  // the accumulators are complete once the item pass has finished
+  const unsigned long long epoch = *x.epoch + 1;  // stable until the finishing kernel of this exchange has run
+  const int parity = (int)(epoch & 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
+    k1_part[0] = 0;                              // re-arm for the next pass
+    for (int p = 0; p < x.world; ++p) {
+      double* slot = push_slot(x, p, parity, x.rank);
+      slot[2 * (size_t)K] = gs;
+      slot[2 * (size_t)K + 1] = n_total;
+    }
+  }
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_items) {
+    const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
+    xdev_fix[i] = 0;
+    xcode_sum[i] = 0;
+    const int32_t j = __ldg(slot_of_item + i);
+    if (j >= 0) {
+      const double cnt = (double)(icolp[i + 1] - icolp[i]);
+      for (int p = 0; p < x.world; ++p) {
+        double* slot = push_slot(x, p, parity, x.rank);
+        slot[j] = ds;
+        slot[(size_t)K + j] = cnt;
+      }
+    }
+  }
+  // the last block of this rank makes all deliveries visible system-wide, then raises its flag in every rank's memory
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int last = (atomicAdd(x.done, 1u) + 1u == gridDim.x);
+    if (last) *x.done = 0;
+    __threadfence();
+    s_last = last;
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < x.world) {
+    __threadfence_system();
+    push_flag_raise(x, threadIdx.x, epoch);
+  }
+  tl_end(tl, 2);
+}
+
+__global__ void __launch_bounds__(256) item_finish_pull_kernel(int32_t n_items, const int32_t* __restrict__ slot_of_item, int32_t K, const PushDev x,
+                                                              double* __restrict__ xbuf, double* __restrict__ idevavg, double* __restrict__ iavg,
+                                                              double* __restrict__ gavg, unsigned long long* __restrict__ tl) {
+  tl_begin(tl, 4);
+  pdl_trigger();  // the test pass may set up its rings while this runs
+  pdl_wait();     // this rank's own delivery is complete (stream order)
+  const unsigned long long epoch = *x.epoch + 1;
+  const int parity = (int)(epoch & 1);
+  int good = 1;
+  if ((int)threadIdx.x < x.world) good = push_flag_wait(x, threadIdx.x, epoch) ? 1 : 0;  // every rank has delivered
+  const bool ok = __syncthreads_and(good) != 0;
+  const double bad = nan("");
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double gs = 0.0, gc = 0.0;
+    for (int p = 0; p < x.world; ++p) {  // rank order: identical totals on every rank
+      const double* slot = push_slot(x, x.rank, parity, p);
+      gs += slot[2 * (size_t)K];
+      gc += slot[2 * (size_t)K + 1];
+    }
+    if (!ok) gs = gc = bad;  // a peer never delivered: nothing downstream may pass for a result
+    xbuf[2 * (size_t)n_items] = gs;
+    xbuf[2 * (size_t)n_items + 1] = gc;
+    gavg[0] = ok ? (gc > 0.0 ? gs / gc : 0.0) : bad;  // P:18 mean of an empty Seq is 0.0
+  }
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_items) {
+    const int32_t j = __ldg(slot_of_item + i);
+    double ds = 0.0, cnt = 0.0;
+    if (j >= 0) {
+      for (int p = 0; p < x.world; ++p) {
+        const double* slot = push_slot(x, x.rank, parity, p);
+        ds += slot[j];
+        cnt += slot[(size_t)K + j];
+      }
+    }
+    if (!ok) ds = cnt = bad;
+    xbuf[i] = ds;
+    xbuf[(size_t)n_items + i] = cnt;
+    idevavg[i] = ok ? (cnt > 0.0 ? ds / cnt : 0.0) : bad;  // P:185 ; unknown item -> 0.0 (P:197)
+    iavg[i] = bad;                                           // (per-item rating averages do not travel in this mode)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(x.done + 1, 1u) + 1u == gridDim.x) {  // last block out: this exchange is complete
+    x.done[1] = 0;
+    *x.epoch = epoch;
+  }
+  tl_end(tl, 4);
+}
+
 }  // namespace
+
+int32_t launch_finish_pull(mrs_model* m, const PushDev& push) {
+  mrs_engine* e = m->eng;
+  MRS_CUDA(launch_pdl(item_finish_pull_kernel, dim3((m->n_items + 255) / 256), dim3(256), 0, e->stream, m->n_items, m->slot_of_item, m->n_slots_known,
+                      push, m->xbuf, m->idevavg, m->iavg, m->gavg, e->d_timeline));
+  mark(e, "item_finish_pull");
+  MRS_CUDA(cudaGetLastError());
+  m->finished = true;
+  m->host_valid = false;
+  return MRS_OK;
+}
 
 void free_tiled_layout(const mrs_ratings* R) {
   auto& T = R->tl;
@@ -529,7 +646,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   return MRS_OK;
 }
 
-int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused) {
+int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push) {
   const auto& T = R->tl;
   cudaStream_t st = e->stream;
   if (!(e->smem_attr_done & 1u)) {
@@ -548,6 +665,13 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
                           R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline));
   }
   mark(e, "item_tiled");
+  if (push) {  // sharded run with the fused exchange: K2b delivers the partial sums to every rank itself
+    MRS_CUDA(launch_pdl(item_tiled_push_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
+                        m->k1_part, (double)R->n, m->slot_of_item, m->n_slots_known, *push, e->d_timeline));
+    mark(e, "item_tiled_push");
+    MRS_CUDA(cudaGetLastError());
+    return MRS_OK;
+  }
   MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
                       m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg, e->d_timeline));
   mark(e, "item_tiled_finalize");

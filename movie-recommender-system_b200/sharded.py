@@ -89,11 +89,15 @@ class ShardedBaseline:
 
     `engine` must have been created on the CUDA stream the collectives run on (``torch.cuda.current_stream()``)."""
 
-    def __init__(self, engine, train, test, group=None, item_averages=False, peer_exchange=False, peer=None, indexed=True):
+    def __init__(self, engine, train, test, group=None, item_averages=False, peer_exchange=False, peer=None, indexed=True, fused=False):
         """``peer_exchange``: create the library's peer-memory exchange object for the two all-reduces (else NCCL through
         torch.distributed).  ``peer``: an existing PeerExchange to reuse instead (its buffers are long-lived IPC mappings;
         a pass that is rebuilt every step, like the end-to-end arm of bench.py, must not create one per step);
-        ``indexed=False`` then exchanges the whole buffer, so no set-up collective is needed for the new rating sets."""
+        ``indexed=False`` then exchanges the whole buffer, so no set-up collective is needed for the new rating sets.
+        ``fused`` (with ``peer_exchange``): the exchanges happen INSIDE the pass' own kernels -- the fit's last kernel
+        delivers its partial sums into every rank's receive buffer over NVLink, the finishing kernel adds the deliveries
+        from its own memory, the test pass' last block exchanges {sum |err|, n} itself (``mrs_fit_local_push`` /
+        ``mrs_fit_finish_pull`` / ``mrs_mae_push_async``): two launches and the remote-load round trip fewer per step."""
         import torch
         from . import engine as E
         self.E, self.torch, self.group = E, torch, group
@@ -108,6 +112,9 @@ class ShardedBaseline:
         self.out2 = torch.zeros(2, dtype=torch.float64, device=self.device)
         # peer_exchange: the two all-reduces run as the library's own NVLink peer-memory kernel instead of NCCL
         self.peer = peer
+        self.peer_small = None           # fused mode: the 16-byte exchange has its own handle (its own epoch counter)
+        self.fused = False
+        self.known = None
         self.xidx = None
         if peer is not None and indexed:
             import torch.distributed as dist
@@ -123,6 +130,9 @@ class ShardedBaseline:
                     return out
                 self.peer = E.PeerExchange(engine, max(int(self.xbuf.numel()), 2), rank, world, gather)
                 self.xidx = self._slots_in_use(dist, item_averages)
+                if fused and not item_averages:
+                    self.peer_small = E.PeerExchange(engine, 2, rank, world, gather)
+                    self.fused = True
 
     def _slots_in_use(self, dist, item_averages):
         """Positions of the exchange buffer that are non-zero on SOME rank: the slots of the items that occur in some rank's
@@ -134,6 +144,7 @@ class ShardedBaseline:
         used = (self.xbuf[n_items:2 * n_items] > 0).to(torch.int32)
         dist.all_reduce(used, op=dist.ReduceOp.MAX, group=self.group)      # set-up time only
         known = torch.nonzero(used, as_tuple=False).flatten().to(torch.int32)
+        self.known = known.contiguous()
         parts = [known, known + n_items, torch.tensor([2 * n_items, 2 * n_items + 1], dtype=torch.int32, device=self.device)]
         if item_averages:
             parts.append(known + (2 * n_items + 2))
@@ -144,9 +155,15 @@ class ShardedBaseline:
 
     # ---- the five pieces of a step (all asynchronous on the engine's stream)
     def fit_local(self):
+        if self.fused:                                 # the last kernel of the local pass delivers the partial sums itself
+            self.E._check(self.E.lib().mrs_fit_local_push(self.engine._h, self.train._h, self.E.C.byref(self.model._h), self.peer._h,
+                                                          self.E.C.c_void_p(self.known.data_ptr()), int(self.known.numel())))
+            return
         self.E._check(self.E.lib().mrs_fit_local(self.engine._h, self.train._h, self.E.C.byref(self.model._h)))
 
     def exchange(self):                                # THE collective of the fit (P:267-268, P:247)
+        if self.fused:
+            return                                     # (inside fit_local / fit_finish)
         if self.peer is not None and self.xidx is not None:
             self.peer.allreduce_indexed_async(self.xbuf.data_ptr(), self.xidx.data_ptr(), self.xidx.numel())
         elif self.peer is not None:
@@ -155,12 +172,21 @@ class ShardedBaseline:
             all_reduce_sum(self.xbuf, self.group)
 
     def fit_finish(self):
+        if self.fused:                                 # waits for every rank's delivery, adds them from local memory
+            self.E._check(self.E.lib().mrs_fit_finish_pull(self.model._h, self.peer._h))
+            return
         self.E._check(self.E.lib().mrs_fit_finish(self.model._h))
 
     def mae_local(self):
+        if self.fused:                                 # the last block of the test pass exchanges {sum |err|, n} itself
+            self.E._check(self.E.lib().mrs_mae_push_async(self.model._h, self.test._h, self.peer_small._h,
+                                                          self.E.C.c_void_p(self.out2.data_ptr())))
+            return
         self.model.mae_async(self.test, self.out2.data_ptr(), self.E.PRED_BASELINE)
 
     def mae_exchange(self):                            # 16 bytes: {sum |err|, n}
+        if self.fused:
+            return
         if self.peer is not None:
             self.peer.allreduce_async(self.out2.data_ptr(), 2)
         else:
@@ -201,11 +227,16 @@ class ShardedBaseline:
         if close_peer and self.peer is not None:
             self.peer.close()
             self.peer = None
+        if close_peer and self.peer_small is not None:
+            self.peer_small.close()
+            self.peer_small = None
 
     def check(self):
         """Raise if a peer-memory exchange of this pass timed out (host sync).  Call it wherever a result is read."""
         if self.peer is not None:
             self.peer.check()
+        if self.peer_small is not None:
+            self.peer_small.check()
 
     def result(self):
         """{sum |err|, n} of the last step as an MAE (host sync); raises if an exchange timed out."""

@@ -29,6 +29,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--nccl", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="exchanges fused into the pass' kernels (mrs_fit_local_push ...)")
     ap.add_argument("--users", type=int, default=30000)
     ap.add_argument("--items", type=int, default=6000)
     ap.add_argument("--ratings", type=int, default=1_500_000)
@@ -40,12 +41,13 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     eng = E.Engine(local, stream=stream.cuda_stream)
     d = synth.ml25m(seed=5, n_users=args.users, n_items=args.items, n_ratings=args.ratings, max_item_id=4 * args.items)
-    out = {"world": world, "exchange": "nccl" if args.nccl else "peer"}
+    out = {"world": world, "exchange": "nccl" if args.nccl else ("fused" if args.fused else "peer")}
 
     def run(tr, te, nu, ni, ref_tr, ref_te, tag):
         with torch.cuda.stream(stream):
             R, T = eng.ratings(*tr, nu, ni), eng.ratings(*te, nu, ni)
-            sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl)
+            sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl, fused=args.fused)
+            assert sb.fused == (args.fused and not args.nccl)
             sb.step()
             mae_eager = sb.result()
             sb.capture()
@@ -55,7 +57,9 @@ def main():
             idev = sb.model.vector(E.ITEM_AVG_DEV)[0]
             gavg = sb.model.global_avg
             # what this rank would get WITHOUT the exchange (local sums only): must differ, or the check is vacuous
+            was_fused, sb.fused = sb.fused, False
             sb.fit_local(); sb.fit_finish()
+            sb.fused = was_fused
             idev_local = sb.model.vector(E.ITEM_AVG_DEV)[0]
             torch.cuda.synchronize(dev)
         if rank == 0:
