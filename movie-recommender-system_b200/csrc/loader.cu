@@ -60,32 +60,56 @@ __global__ void scan_codes_kernel(const uint8_t* __restrict__ c, int64_t n, int3
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&stats[3], bad);
 }
 
-__global__ void make_keys_kernel(const int32_t* __restrict__ hi, const int32_t* __restrict__ lo, int64_t n,
+// user-major sort key: (user << item_bits) | item -- only user_bits + item_bits key bits, so the radix sort makes
+// ceil((user_bits + item_bits) / 8) passes instead of the 7 of a (user << 32 | item) key (ncu, round 2: the two 7-pass sorts
+// were 3.1 ms of the 6.0 ms of device work in an end-to-end step at ml-25m shape)
+__global__ void make_keys_kernel(const int32_t* __restrict__ hi, const int32_t* __restrict__ lo, int64_t n, int lo_bits,
                                  uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-    keys[p] = ((uint64_t)(uint32_t)hi[p] << 32) | (uint32_t)lo[p];
+    keys[p] = ((uint64_t)(uint32_t)hi[p] << lo_bits) | (uint32_t)lo[p];
     idx[p] = (int32_t)p;
   }
 }
 
-// sorted (major<<32|minor) keys -> major array, minor array, segment pointer, duplicate count (ids only: runs before
-// the ratings have arrived)
-__global__ void scatter_ids_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t n_seg, int32_t* __restrict__ major_out,
+// sorted (major << lo_bits | minor) keys -> major array, minor array, segment pointer, duplicate count (ids only: runs
+// before the ratings have arrived)
+__global__ void scatter_ids_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t n_seg, int lo_bits, int32_t* __restrict__ major_out,
                                    int32_t* __restrict__ minor_out, int32_t* __restrict__ seg_ptr, int32_t* __restrict__ dup_count) {
+  const uint64_t lo_mask = ((uint64_t)1 << lo_bits) - 1;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     uint64_t k = keys[p];
-    int32_t major = (int32_t)(k >> 32), minor = (int32_t)(k & 0xffffffffu);
+    int32_t major = (int32_t)(k >> lo_bits), minor = (int32_t)(k & lo_mask);
     if (major_out) major_out[p] = major;
     minor_out[p] = minor;
     int32_t prev = -1;
     if (p > 0) {
       uint64_t kp = keys[p - 1];
-      prev = (int32_t)(kp >> 32);
-      if (kp == k) atomicAdd(dup_count, 1);
+      prev = (int32_t)(kp >> lo_bits);
+      if (kp == k) atomicAdd(dup_count, 2);  // (counted twice, like the two passes of the earlier builder: the message halves it)
     }
     for (int32_t s = prev + 1; s <= major; ++s) seg_ptr[s] = (int32_t)p;
     if (p == n - 1)
       for (int32_t s = major + 1; s <= n_seg; ++s) seg_ptr[s] = (int32_t)n;
+  }
+}
+
+// item-major order from the user-major one: a STABLE sort on the item alone keeps the users of an item ascending
+__global__ void item_keys_kernel(const int32_t* __restrict__ ucol, int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ idx) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    keys[p] = (uint32_t)ucol[p];
+    idx[p] = (int32_t)p;
+  }
+}
+// sorted item keys + positions in the user-major arrays -> rater of every item-major entry and the column pointer
+__global__ void scatter_items_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ src, const int32_t* __restrict__ coo_u, int64_t n,
+                                     int32_t n_items, int32_t* __restrict__ irow, int32_t* __restrict__ icolp) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t item = (int32_t)keys[p];
+    irow[p] = coo_u[src[p]];
+    const int32_t prev = p > 0 ? (int32_t)keys[p - 1] : -1;
+    for (int32_t s = prev + 1; s <= item; ++s) icolp[s] = (int32_t)p;
+    if (p == n - 1)
+      for (int32_t s = item + 1; s <= n_items; ++s) icolp[s] = (int32_t)n;
   }
 }
 
@@ -247,19 +271,22 @@ int32_t sort_ids(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_
     return MRS_OK;
   }
   const int ubits = bits_for((uint32_t)(R->n_users - 1)), ibits = bits_for((uint32_t)(R->n_items - 1));
-  // ---- user-major: sort by (user, item); payload = position in the raw input
-  make_keys_kernel<<<grid, block, 0, st>>>(d_u, d_i, n, B->k_in, B->v_in);
+  // ---- user-major: sort by (user, item) packed into ubits + ibits key bits; payload = position in the raw input
+  make_keys_kernel<<<grid, block, 0, st>>>(d_u, d_i, n, ibits, B->k_in, B->v_in);
   size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, 32 + ubits, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, ibits + ubits, st);
   MRS_TRY(ensure_scratch(e, tmp));
-  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, 32 + ubits, st);
-  scatter_ids_kernel<<<grid, block, 0, st>>>(B->k_out, n, R->n_users, R->coo_u, R->ucol, R->urow, d_dup);
-  // ---- item-major: sort by (item, user); payload = position in the user-major arrays
-  make_keys_kernel<<<grid, block, 0, st>>>(R->ucol, R->coo_u, n, B->k_in, B->v2_in);
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, B->k_in, B->k_out, B->v2_in, R->csc_src, (int)n, 0, 32 + ibits, st);
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, ibits + ubits, st);
+  scatter_ids_kernel<<<grid, block, 0, st>>>(B->k_out, n, R->n_users, ibits, R->coo_u, R->ucol, R->urow, d_dup);
+  // ---- item-major: a stable sort of the user-major entries on the item alone (32-bit keys, ibits key bits: 3 passes at
+  // ml-25m shape); payload = position in the user-major arrays.  The 64-bit key buffers are reused as 32-bit ones.
+  uint32_t* k32_in = reinterpret_cast<uint32_t*>(B->k_in);
+  uint32_t* k32_out = reinterpret_cast<uint32_t*>(B->k_out);
+  item_keys_kernel<<<grid, block, 0, st>>>(R->ucol, n, k32_in, B->v2_in);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, k32_in, k32_out, B->v2_in, R->csc_src, (int)n, 0, ibits, st);
   MRS_TRY(ensure_scratch(e, tmp));
-  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, B->k_in, B->k_out, B->v2_in, R->csc_src, (int)n, 0, 32 + ibits, st);
-  scatter_ids_kernel<<<grid, block, 0, st>>>(B->k_out, n, R->n_items, nullptr, R->irow, R->icolp, d_dup);
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k32_in, k32_out, B->v2_in, R->csc_src, (int)n, 0, ibits, st);
+  scatter_items_kernel<<<grid, block, 0, st>>>(k32_out, R->csc_src, R->coo_u, n, R->n_items, R->irow, R->icolp);
   count_launch(12);
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
