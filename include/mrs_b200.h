@@ -229,6 +229,12 @@ MRS_API int32_t mrs_fit_similarity_async(mrs_model* m, int32_t sim_kind, int32_t
  * kept (k > 0): mrs_sim_set_k accepts 0 < k' <= k, queries for users outside the range fail (mrs_predict / mrs_mae write
  * NaN for them).  mrs_fit_similarity itself takes this path over all users above 16,384 users. */
 MRS_API int32_t mrs_fit_similarity_rows_async(mrs_model* m, int32_t sim_kind, int32_t k, int32_t user_lo, int32_t user_hi, mrs_sim** inout);
+/* Order of neighbours whose similarities are EXACTLY equal (typically the block of zero similarities that a large k reaches).
+ * The reference's stable sort (P:610) keeps the candidate order of `(allUsers - u).toSeq` (P:608), i.e. the iteration order of
+ * a Scala 2.11 immutable.HashSet[Int]; BASELINE's north_star asks for index order.  mode 0 (default): ascending user id;
+ * mode 1: that HashSet order (hash-trie walk of improve(id), SURVEY A.6 -- recalled from the 2.11 library source, not
+ * verifiable without a JVM).  Applies to similarity handles fitted AFTER the call.  Only exact ties move. */
+MRS_API int32_t mrs_model_set_tie_order(mrs_model* m, int32_t mode);
 /* change k without recomputing similarities (the sorted lists have the prefix property) */
 MRS_API int32_t mrs_sim_set_k(mrs_sim* s, int32_t k);
 MRS_API int32_t mrs_similarity(const mrs_sim* s, int32_t u, int32_t v, double* out);

@@ -270,6 +270,12 @@ struct mrs_model {
   // fused push exchange (mrs_fit_local_push): compact slot of every item in the exchange (-1: the item occurs on no rank)
   int32_t* slot_of_item = nullptr;  // [n_items]
   int32_t n_slots_known = 0;        // K: items that occur on some rank; a delivery is [K dev sums | K counts | sum, n]
+  // order of neighbours with EXACTLY equal similarity: 0 = ascending user id, 1 = iteration order of a Scala 2.11
+  // immutable.HashSet[Int] (what the reference's stable sort keeps, P:608-610).  tie_rank[c] = place of compact user index c in
+  // that order, tie_inv = its inverse; NULL for mode 0
+  int32_t tie_mode = 0;
+  int32_t* tie_rank = nullptr;
+  int32_t* tie_inv = nullptr;
   bool finished = false;
   // host mirrors, filled lazily by queries
   mutable bool host_valid = false;

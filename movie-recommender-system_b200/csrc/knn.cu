@@ -317,7 +317,8 @@ __device__ void bitonic_sort_shared(double* key, int32_t* id, int32_t P) {
 
 __global__ void __launch_bounds__(512) sort_rank_kernel(const double* __restrict__ S, const int32_t* __restrict__ known_user,
                                                        int32_t n_known, int32_t P, int32_t* __restrict__ rank,
-                                                       int32_t* __restrict__ nbr_id, double* __restrict__ nbr_sim) {
+                                                       int32_t* __restrict__ nbr_id, double* __restrict__ nbr_sim,
+                                                       const int32_t* __restrict__ tie_rank, const int32_t* __restrict__ tie_inv) {
   extern __shared__ double sh_key[];
   int32_t* sh_id = (int32_t*)(sh_key + P);
   pdl_trigger();
@@ -326,12 +327,12 @@ __global__ void __launch_bounds__(512) sort_rank_kernel(const double* __restrict
   for (int32_t x = threadIdx.x; x < P; x += blockDim.x) {
     const bool cand = (x < n_known && x != cu);  // P:608 allUsers - u
     sh_key[x] = cand ? sort_key(S[(int64_t)cu * n_known + x]) : -INFINITY;
-    sh_id[x] = cand ? x : INT_MAX;
+    sh_id[x] = cand ? (tie_rank ? tie_rank[x] : x) : INT_MAX;  // the tie key: the user's place in the tie order
   }
   bitonic_sort_shared(sh_key, sh_id, P);
   const int32_t nn = n_known - 1;
   for (int32_t j = threadIdx.x; j < nn; j += blockDim.x) {
-    const int32_t cv = sh_id[j];
+    const int32_t cv = tie_inv ? tie_inv[sh_id[j]] : sh_id[j];
     nbr_id[(int64_t)cu * nn + j] = known_user[cv];
     nbr_sim[(int64_t)cu * nn + j] = sh_key[j];
     rank[(int64_t)cu * n_known + cv] = j;
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(512) sort_rank_kernel(const double* __restrict
 template <int P>
 __global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __restrict__ S, const int32_t* __restrict__ known_user,
                                                              int32_t n_known, int32_t* __restrict__ rank, int32_t* __restrict__ nbr_id,
-                                                             double* __restrict__ nbr_sim) {
+                                                             double* __restrict__ nbr_sim, const int32_t* __restrict__ tie_rank,
+                                                             const int32_t* __restrict__ tie_inv) {
   __shared__ double sk[P];
   __shared__ int32_t si[P];
   pdl_trigger();
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __re
   const int32_t e0 = 2 * threadIdx.x, e1 = e0 + 1;
   const bool c0 = (e0 < n_known && e0 != cu), c1 = (e1 < n_known && e1 != cu);  // P:608 allUsers - u
   double k0 = c0 ? sort_key(S[(int64_t)cu * n_known + e0]) : -INFINITY, k1 = c1 ? sort_key(S[(int64_t)cu * n_known + e1]) : -INFINITY;
-  int32_t i0 = c0 ? e0 : INT_MAX, i1 = c1 ? e1 : INT_MAX;
+  int32_t i0 = c0 ? (tie_rank ? tie_rank[e0] : e0) : INT_MAX, i1 = c1 ? (tie_rank ? tie_rank[e1] : e1) : INT_MAX;  // tie keys
 #pragma unroll 1
   for (int32_t size = 2; size <= P; size <<= 1) {
     const bool up = ((e0 & size) == 0);
@@ -390,14 +392,16 @@ __global__ void __launch_bounds__(P / 2) sort_rank_reg_kernel(const double* __re
   }
   const int32_t nn = n_known - 1;
   if (e0 < nn) {
-    nbr_id[(int64_t)cu * nn + e0] = known_user[i0];
+    const int32_t cv = tie_inv ? tie_inv[i0] : i0;
+    nbr_id[(int64_t)cu * nn + e0] = known_user[cv];
     nbr_sim[(int64_t)cu * nn + e0] = k0;
-    rank[(int64_t)cu * n_known + i0] = e0;
+    rank[(int64_t)cu * n_known + cv] = e0;
   }
   if (e1 < nn) {
-    nbr_id[(int64_t)cu * nn + e1] = known_user[i1];
+    const int32_t cv = tie_inv ? tie_inv[i1] : i1;
+    nbr_id[(int64_t)cu * nn + e1] = known_user[cv];
     nbr_sim[(int64_t)cu * nn + e1] = k1;
-    rank[(int64_t)cu * n_known + i1] = e1;
+    rank[(int64_t)cu * n_known + cv] = e1;
   }
   if (threadIdx.x == 0) rank[(int64_t)cu * n_known + cu] = INT_MAX;  // s_k(u,u) = 0 (A.5)
 }
@@ -632,15 +636,15 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
   int32_t P = 2;
   while (P < L.n_known) P <<= 1;
   if (P <= 512) {
-    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<512>, dim3(L.n_known), dim3(256), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim));
+    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<512>, dim3(L.n_known), dim3(256), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim, m->tie_rank, m->tie_inv));
   } else if (P == 1024) {
-    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<1024>, dim3(L.n_known), dim3(512), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim));
+    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<1024>, dim3(L.n_known), dim3(512), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim, m->tie_rank, m->tie_inv));
   } else if (P == 2048) {
-    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<2048>, dim3(L.n_known), dim3(1024), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim));
+    MRS_CUDA(launch_pdl(sort_rank_reg_kernel<2048>, dim3(L.n_known), dim3(1024), 0, st, s->S, L.known_user, L.n_known, s->rank, s->nbr_id, s->nbr_sim, m->tie_rank, m->tie_inv));
   } else {
     const size_t smem = (size_t)P * (sizeof(double) + sizeof(int32_t));
     MRS_CUDA(cudaFuncSetAttribute(sort_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MRS_CUDA(launch_pdl(sort_rank_kernel, dim3(L.n_known), dim3(512), smem, st, s->S, L.known_user, L.n_known, P, s->rank, s->nbr_id, s->nbr_sim));
+    MRS_CUDA(launch_pdl(sort_rank_kernel, dim3(L.n_known), dim3(512), smem, st, s->S, L.known_user, L.n_known, P, s->rank, s->nbr_id, s->nbr_sim, m->tie_rank, m->tie_inv));
   }
   mark(e, "sort_rank");
   MRS_CUDA(cudaGetLastError());
@@ -726,6 +730,40 @@ extern "C" int32_t mrs_fit_similarity(mrs_model* m, int32_t sim_kind, int32_t k,
     *out = nullptr;
     return MRS_ERR_CUDA;
   }
+  return MRS_OK;
+}
+
+// place of an Int in the iteration order of a Scala 2.11 immutable.HashSet[Int]: the hash trie is walked in
+// ascending order of successive 5-bit groups, least significant first, of improve(hashCode) -- recalled from the 2.11
+// standard library (scala.collection.immutable.HashSet.improve), not verifiable here without a JVM
+static uint64_t hashset_order_key(int32_t id) {
+  uint32_t h = (uint32_t)id + ~((uint32_t)id << 9);
+  h ^= h >> 14;
+  h += h << 4;
+  h ^= h >> 10;
+  uint64_t key = 0;
+  for (int k = 0; k < 7; ++k) key = (key << 5) | ((h >> (5 * k)) & 31u);
+  return key;
+}
+
+extern "C" int32_t mrs_model_set_tie_order(mrs_model* m, int32_t mode) {
+  MRS_REQUIRE(m && (mode == 0 || mode == 1), MRS_ERR_INVALID, "mrs_model_set_tie_order: mode must be 0 (user id) or 1 (Scala 2.11 HashSet order)");
+  use_engine(m->eng);
+  dev_free(m->tie_rank); dev_free(m->tie_inv);
+  m->tie_rank = m->tie_inv = nullptr;
+  m->tie_mode = mode;
+  if (mode == 0) return MRS_OK;
+  MRS_TRY(build_sim_layout(m->train, false));
+  const auto& L = m->train->sl;
+  const int32_t nk = L.n_known;
+  std::vector<int32_t> order((size_t)nk), rank((size_t)nk);
+  for (int32_t c = 0; c < nk; ++c) order[(size_t)c] = c;
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hashset_order_key(L.h_known[(size_t)a]) < hashset_order_key(L.h_known[(size_t)b]); });
+  for (int32_t r = 0; r < nk; ++r) rank[(size_t)order[(size_t)r]] = r;
+  MRS_TRY(dev_alloc(&m->tie_rank, (size_t)std::max(nk, 1)));
+  MRS_TRY(dev_alloc(&m->tie_inv, (size_t)std::max(nk, 1)));
+  MRS_CUDA(cudaMemcpy(m->tie_rank, rank.data(), sizeof(int32_t) * (size_t)nk, cudaMemcpyHostToDevice));
+  MRS_CUDA(cudaMemcpy(m->tie_inv, order.data(), sizeof(int32_t) * (size_t)nk, cudaMemcpyHostToDevice));
   return MRS_OK;
 }
 

@@ -29,8 +29,15 @@
 namespace mrs {
 namespace {
 
-constexpr int kRowsSub = 512;     // compact user indices per warp (4 KB of fp64 accumulators)
-constexpr int kRowsWarps = 32;    // warps per CTA -> 16,384 indices, 128 KB of shared memory, one CTA per SM
+#ifndef MRS_ROWS_SUB
+#define MRS_ROWS_SUB 512
+#endif
+#ifndef MRS_ROWS_WARPS
+#define MRS_ROWS_WARPS 32
+#endif
+constexpr int kRowsSub = MRS_ROWS_SUB;      // compact user indices per warp (4 KB of fp64 accumulators at 512)
+constexpr int kRowsWarps = MRS_ROWS_WARPS;  // warps per CTA -> 16,384 indices, 128 KB of shared memory, one CTA per SM
+static_assert(kRowsSub * kRowsWarps == 16384, "a range is 16,384 compact indices (128 KB of accumulators)");
 constexpr int kRowsDepth = 4;     // column slices requested ahead of the one being accumulated
 constexpr int kSelTile = 2048;    // row elements examined between two checks of the candidate buffer
 constexpr int kSelCap = 4096;     // candidate buffer (a tile can add at most kSelTile to at most kSelCap - kSelTile)
@@ -123,7 +130,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1)
                     const int32_t* __restrict__ known_user, const int32_t* __restrict__ clen, const int32_t* __restrict__ rows,
                     const int32_t* __restrict__ seg, int32_t seg_stride, const int32_t* __restrict__ ccv,
                     const double* __restrict__ cpre, int32_t n_known, int32_t n_ranges, int32_t kk, int32_t row_lo,
-                    int32_t* __restrict__ nbr_id, double* __restrict__ nbr_sim) {
+                    int32_t* __restrict__ nbr_id, double* __restrict__ nbr_sim, const int32_t* __restrict__ tie_rank,
+                    const int32_t* __restrict__ tie_inv) {
   extern __shared__ __align__(16) double acc_all[];             // [kRowsWarps * kRowsSub] accumulators
   double* c_key = acc_all + kRowsWarps * kRowsSub;              // [kSelCap] candidate similarities
   int32_t* c_id = (int32_t*)(c_key + kSelCap);                  // [kSelCap] candidate compact indices
@@ -211,23 +219,25 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1)
       const double tk = tau_key;
       const int32_t ti = tau_id;
 #pragma unroll
-      for (int r = 0; r < kSelTile / 1024; ++r) {
-        const int32_t xl = tile0 + r * 1024 + threadIdx.x;
+      for (int r = 0; r < kSelTile / (kRowsWarps * 32); ++r) {
+        const int32_t xl = tile0 + r * (kRowsWarps * 32) + threadIdx.x;
         const int32_t x = range_base + xl;
         double s = 0.0;
         bool ok = false;
+        int32_t x_key = x;
         if (x < n_known && x != cu) {  // P:608 allUsers - u
           s = acc_all[xl];
           if (MODE == 2) s = s / (double)(nu + clen[x] - (int32_t)s);  // P:458
           if (s != s) s = -INFINITY;  // NaN has no place in the (sim desc, id asc) order: it ranks last (see knn.cu sort_key)
-          ok = before(s, x, tk, ti);
+          if (tie_rank) x_key = tie_rank[x];  // ties are ordered by the user's place in the tie order
+          ok = before(s, x_key, tk, ti);
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (m) {
           int32_t pos = 0;
           if (lane == 0) pos = atomicAdd(&count, __popc(m));
           pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-          if (ok) { c_key[pos] = s; c_id[pos] = x; }
+          if (ok) { c_key[pos] = s; c_id[pos] = x_key; }
         }
       }
       __syncthreads();
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1)
   bitonic_sort_shared(c_key, c_id, P);
   const int64_t off = (int64_t)(cu - row_lo) * kk;
   for (int32_t j = threadIdx.x; j < kk; j += blockDim.x) {
-    nbr_id[off + j] = known_user[c_id[j]];
+    nbr_id[off + j] = known_user[tie_inv ? tie_inv[c_id[j]] : c_id[j]];
     nbr_sim[off + j] = c_key[j];
   }
 }
@@ -415,10 +425,10 @@ int32_t rows_fit_async(mrs_model* m, mrs_sim* s, bool /*first*/) {
   // rows are listed longest first: the hardware hands the next CTA to the first SM that frees up (longest-processing-time order)
   if (s->kind == MRS_SIM_COSINE)
     knn_rows_kernel<1><<<n_rows, kRowsWarps * 32, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.clen, s->row_order, L.seg, L.n_sub + 1,
-                                                            L.ccv, s->cpre, L.n_known, n_ranges, s->k_fit, s->row_lo, s->nbr_id, s->nbr_sim);
+                                                            L.ccv, s->cpre, L.n_known, n_ranges, s->k_fit, s->row_lo, s->nbr_id, s->nbr_sim, m->tie_rank, m->tie_inv);
   else
     knn_rows_kernel<2><<<n_rows, kRowsWarps * 32, smem, st>>>(R->urow, R->ucol, s->upre, L.known_user, L.clen, s->row_order, L.seg, L.n_sub + 1,
-                                                            L.ccv, s->cpre, L.n_known, n_ranges, s->k_fit, s->row_lo, s->nbr_id, s->nbr_sim);
+                                                            L.ccv, s->cpre, L.n_known, n_ranges, s->k_fit, s->row_lo, s->nbr_id, s->nbr_sim, m->tie_rank, m->tie_inv);
   mark(e, "knn_rows");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

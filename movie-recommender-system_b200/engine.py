@@ -26,7 +26,7 @@ EXPORTS = [
     "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_upload_begin_codes", "mrs_ratings_from_coo_codes", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
     "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_connect_local", "mrs_multi_create", "mrs_multi_load", "mrs_multi_baseline_mae", "mrs_multi_model", "mrs_multi_owner", "mrs_multi_destroy", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_fit_local_push", "mrs_fit_finish_pull", "mrs_mae_push_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
-    "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_sim_set_k",
+    "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_model_set_tie_order", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
     "mrs_mae_async", "mrs_recommend",
 ]
@@ -121,6 +121,7 @@ def lib():
         "mrs_fit_similarity": (i32, [vp, i32, i32, P(vp)]),
         "mrs_fit_similarity_async": (i32, [vp, i32, i32, P(vp)]),
         "mrs_fit_similarity_rows_async": (i32, [vp, i32, i32, i32, i32, P(vp)]),
+        "mrs_model_set_tie_order": (i32, [vp, i32]),
         "mrs_sim_set_k": (i32, [vp, i32]),
         "mrs_similarity": (i32, [vp, i32, i32, P(dbl)]),
         "mrs_neighbors": (i32, [vp, i32, i32, vp, vp, i32, P(i32)]),
@@ -424,6 +425,11 @@ class Model:
     def set_item_averages(self, enabled):
         """Per-item rating averages are not needed by the baseline predictor; switching them off saves work in the fit."""
         _check(lib().mrs_model_set_item_averages(self._h, 1 if enabled else 0))
+
+    def set_tie_order(self, mode):
+        """0: neighbours with exactly equal similarity in ascending user id; 1: in the Scala 2.11 HashSet order the reference's
+        stable sort keeps.  Applies to similarities fitted afterwards."""
+        _check(lib().mrs_model_set_tie_order(self._h, int(mode)))
 
     def exchange_buffer(self):
         p, n = C.c_void_p(), C.c_int64()

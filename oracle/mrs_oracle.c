@@ -289,10 +289,29 @@ static double base_sim(const orc_model *m, int simkind, int32_t u, int32_t v) {
 }
 
 typedef struct { double s; int32_t id; } nbr;
+/* Candidate order of `(allUsers - u).toSeq` (P:608), which the stable sort of P:610 keeps among equal similarities:
+ * mode 0 = ascending id (north_star: "index-ordered tie-breaking"); mode 1 = iteration order of a Scala 2.11
+ * immutable.HashSet[Int]: hash-trie walk in ascending successive 5-bit groups (least significant first) of
+ * improve(id) = { h = id + ~(id << 9); h ^= h >>> 14; h += h << 4; h ^ (h >>> 10) } -- recalled from the 2.11 library
+ * source, not verifiable without a JVM. */
+static int g_tie_mode = 0;
+static uint64_t hashset_order_key(int32_t id) {
+  uint32_t h = (uint32_t)id + ~((uint32_t)id << 9);
+  h ^= h >> 14;
+  h += h << 4;
+  h ^= h >> 10;
+  uint64_t key = 0;
+  for (int k = 0; k < 7; ++k) key = (key << 5) | ((h >> (5 * k)) & 31u);
+  return key;
+}
 static int cmp_nbr(const void *a, const void *b) {
   const nbr *x = a, *y = b;
   if (x->s > y->s) return -1; /* P:610 sortWith(_._2 > _._2), stable */
   if (y->s > x->s) return 1;
+  if (g_tie_mode == 1) {
+    uint64_t kx = hashset_order_key(x->id), ky = hashset_order_key(y->id);
+    return (kx > ky) - (kx < ky);
+  }
   return (x->id > y->id) - (x->id < y->id); /* stable w.r.t. ascending-id candidate order */
 }
 
@@ -336,6 +355,18 @@ static void neighbours_full(orc_model *m, int simkind, int32_t u, const int32_t 
   free(tmp);
   *ids = oi; *sims = os;
   m->nb_ids[simkind][slot] = oi; m->nb_sims[simkind][slot] = os;
+}
+
+/* tie order of the neighbour lists built from now on (see cmp_nbr); drops the cached lists of this model */
+ORC_API void orc_set_tie_order(orc_model *m, int32_t mode) {
+  g_tie_mode = mode == 1 ? 1 : 0;
+  for (int s = 0; s < 3; ++s) {
+    if (m->nb_ids[s]) {
+      for (int32_t u = 0; u <= m->umax + 1; ++u) { free(m->nb_ids[s][u]); free(m->nb_sims[s][u]); }
+      free(m->nb_ids[s]); free(m->nb_sims[s]);
+      m->nb_ids[s] = NULL; m->nb_sims[s] = NULL;
+    }
+  }
 }
 
 /* P:603-616: first k of the sorted list.  Returns the number written (min(k, candidates)). */

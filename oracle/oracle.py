@@ -64,6 +64,7 @@ def _lib():
         "orc_baseline_mae_spark": (C.c_double, [_i32p, _i32p, _f64p, C.c_int64, _i32p, _i32p, _f64p, C.c_int64,
                                                 C.c_int32, C.POINTER(C.c_double)]),
         "orc_max_threads": (C.c_int32, []),
+        "orc_set_tie_order": (None, [C.c_void_p, C.c_int32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -190,6 +191,10 @@ class Oracle:
 
     def jaccard(self, u, v):
         return self._L.orc_jaccard(self._h, int(u), int(v))
+
+    def set_tie_order(self, mode):
+        """0: equal similarities in ascending user id; 1: in the Scala 2.11 HashSet iteration order."""
+        self._L.orc_set_tie_order(self._h, int(mode))
 
     def neighbors(self, u, k, simkind=SIM_COSINE):
         cap = max(int(k), 1)

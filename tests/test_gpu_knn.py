@@ -213,3 +213,34 @@ def test_sort_kernels_at_other_sizes(eng, n_users):
         assert ids.tolist() == oi.tolist() and sims.tolist() == os_.tolist()
     for h in (s, m, R):
         h.close()
+
+
+def test_tie_order_matches_the_oracle_in_both_modes(small):
+    """mrs_model_set_tie_order: neighbours with exactly equal similarity in user-id order (default) or in the Scala 2.11
+    HashSet iteration order that the reference's stable sort keeps; dense path and row-block path."""
+    tr = small["train"]
+    eng = E.Engine(0)
+    R = eng.ratings(*tr)
+    m = E.Model(eng, R)
+    o = O.Oracle(*tr)
+    n = int(np.unique(tr[0]).size) - 1
+    users = [int(u) for u in np.unique(tr[0])[:10]]
+    differ = 0
+    for mode in (1, 0):
+        m.set_tie_order(mode)
+        o.set_tie_order(mode)
+        s = m.similarity(E.SIM_COSINE, n)
+        sr = m.similarity(E.SIM_COSINE, n, rows=(0, 2**31 - 1))
+        for u in users:
+            oi, os_ = o.neighbors(u, n)
+            for h in (s, sr):
+                ids, sims = h.neighbors(u, n)
+                assert ids.tolist() == oi.tolist() and sims.tolist() == os_.tolist()
+            if mode == 1:
+                o.set_tie_order(0)
+                differ += o.neighbors(u, n)[0].tolist() != oi.tolist()
+                o.set_tie_order(1)
+        sr.close(); s.close()
+    assert differ > 0
+    o.set_tie_order(0)
+    m.close(); R.close(); eng.close()

@@ -141,3 +141,40 @@ def test_mean_std_and_empty():
     o = O.Oracle(np.array([1], np.int32), np.array([1], np.int32), np.array([3.0]))
     e = (np.array([], np.int32), np.array([], np.int32), np.array([], np.float64))
     assert math.isnan(o.mae(e))  # 0.0/0 in applyAndMean (P:85)
+
+
+def _tie_key(i):
+    h = (i + (~(i << 9))) & 0xFFFFFFFF
+    h ^= h >> 14
+    h = (h + (h << 4)) & 0xFFFFFFFF
+    h ^= h >> 10
+    key = 0
+    for k in range(7):
+        key = (key << 5) | ((h >> (5 * k)) & 31)
+    return key
+
+
+def test_tie_order_only_moves_exact_ties(small):
+    """(sim desc, tie_rank asc); tie_rank = user id (default) or the Scala 2.11 HashSet iteration order."""
+    tr = small["train"]
+    o = O.Oracle(*tr)
+    n = int(np.unique(tr[0]).size) - 1
+    moved = 0
+    for u in np.unique(tr[0])[:12]:
+        ids0, s0 = o.neighbors(int(u), n)
+        o.set_tie_order(1)
+        ids1, s1 = o.neighbors(int(u), n)
+        o.set_tie_order(0)
+        assert s0.tolist() == s1.tolist()                       # the similarities are the same sorted sequence
+        assert sorted(ids0.tolist()) == sorted(ids1.tolist())
+        j = 0
+        while j < n:                                            # group by exactly equal similarity
+            k = j
+            while k < n and s0[k] == s0[j]:
+                k += 1
+            g0, g1 = ids0[j:k].tolist(), ids1[j:k].tolist()
+            assert sorted(g0) == sorted(g1)                     # only members of one tie group change places
+            assert g0 == sorted(g0) and g1 == sorted(g1, key=_tie_key)
+            moved += g0 != g1
+            j = k
+    assert moved > 0                                            # the data do have ties (zero-similarity blocks)
