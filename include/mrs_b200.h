@@ -274,6 +274,12 @@ MRS_API int32_t mrs_multi_model(mrs_multi* m, int32_t slot, mrs_model** out);
 MRS_API int32_t mrs_multi_owner(const mrs_multi* m, int32_t user, int32_t* slot_out);
 MRS_API void mrs_multi_destroy(mrs_multi* m);
 
+/* The whole timed closure of distributed/DistributedBaseline.scala:45-47 / predict/Baseline.scala:66-69,
+ * MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test), as one asynchronous call on an existing model of `train` with
+ * item averages switched off: user sums, item pass and a test pass that finishes the fit in its own prologue (one kernel
+ * and one dependency less than mrs_fit_async + mrs_mae_async; same results, same model arrays afterwards). */
+MRS_API int32_t mrs_fit_mae_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, const mrs_ratings* test, void* device_out2);
+
 /* ---- recommendations (P:651-674; call site recommend/Recommender.scala:82-88) ---- */
 MRS_API int32_t mrs_recommend(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind, int32_t user, int32_t n,
                               int32_t* items_out, double* scores_out, int32_t* n_out);

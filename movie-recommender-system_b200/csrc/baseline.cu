@@ -57,10 +57,12 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
 // atomicAdd per (warp, user).  Integer sums are exact: the result does not depend on the order of the atomics.
 __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
                                                       uint32_t* __restrict__ usum, unsigned long long* __restrict__ gsum_codes,
-                                                      unsigned long long* __restrict__ tl) {
+                                                      long long* __restrict__ xdev_fix, unsigned long long* __restrict__ xcode_sum,
+                                                      int32_t n_items, unsigned long long* __restrict__ tl) {
   __shared__ uint32_t sh[8];
   tl_begin(tl, 0);
   pdl_trigger();  // the item pass may start its prologue (ring prefetch) while this kernel runs
+
   const int lane = threadIdx.x & 31;
   constexpr int V = 2;  // vectors per thread (both loads are issued before the first use)
   const int32_t t0 = blockIdx.x * (blockDim.x * V) + threadIdx.x;
@@ -72,6 +74,12 @@ __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict
     const bool in = t < n_vec;
     x[k] = in ? __ldg(reinterpret_cast<const uint4*>(uval16) + t) : make_uint4(0u, 0u, 0u, 0u);
     row[k] = in ? __ldg(vec_row + t) : -1;
+  }
+  // re-arm the per-item accumulators of the item pass while the loads above are in flight (whoever read them last -- K2b,
+  // the push kernel or the fused test pass -- has finished: this kernel is a plain stream-ordered launch)
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    xdev_fix[i] = 0;
+    xcode_sum[i] = 0;
   }
   uint32_t total = 0;
 #pragma unroll
@@ -352,12 +360,14 @@ inline int chunk_grid(int32_t n_chunks, int sm_count) {
 }
 
 // code path: K1 (user code sums) -> K2 tiled item pass (forms the user averages on the way) -> K2b finalize
-int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push) {
-  MRS_CUDA(cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream));
-  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, e->d_timeline);
+int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push, bool no_finalize) {
+  // (the user sums are zero on entry: cleared when the model is created and re-armed by the kernel that consumes them last --
+  // K2b, the push kernel or the fused test pass -- so no memset node opens the pass)
+  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, m->xdev_fix, m->xcode_sum, R->n_items,
+                                                       e->d_timeline);
   mark(e, "user_sum");
   MRS_CUDA(cudaGetLastError());
-  return launch_item_tiled(e, R, m, fused, push);
+  return launch_item_tiled(e, R, m, fused, push, no_finalize);
 }
 
 template <typename VT>
@@ -417,7 +427,7 @@ int32_t dispatch_mae(const mrs_model* m, int32_t kind, const mrs_ratings* T, dou
 
 }  // namespace
 
-int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool fused_finalize, const PushDev* push) {
+int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool fused_finalize, const PushDev* push, bool no_finalize) {
   MRS_REQUIRE(e && R && inout, MRS_ERR_INVALID, "mrs_fit: NULL argument");
   use_engine(e);
   const bool codes = (R->value_kind == kValueCode);
@@ -438,6 +448,7 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
     int32_t s = MRS_OK;
     if (codes) {
       if (s == MRS_OK) s = dev_alloc(&m->usum, (size_t)R->n_users);
+      if (s == MRS_OK && cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
       if (s == MRS_OK) s = dev_alloc(&m->k1_part, 1);
       if (s == MRS_OK && cudaMemsetAsync(m->k1_part, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
       if (s == MRS_OK) s = dev_alloc(&m->xdev_fix, (size_t)R->n_items);
@@ -471,7 +482,8 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
   m->host_valid = false;
   if (codes) {
     MRS_REQUIRE(!push || !m->want_item_avg, MRS_ERR_UNSUPPORTED, "mrs_fit_local_push: switch item averages off (mrs_model_set_item_averages): they do not travel in the fused exchange");
-    MRS_TRY(launch_fit_codes(e, R, m, fused_finalize, push));
+    MRS_REQUIRE(!no_finalize || !m->want_item_avg, MRS_ERR_UNSUPPORTED, "mrs_fit_mae_async: switch item averages off first (mrs_model_set_item_averages)");
+    MRS_TRY(launch_fit_codes(e, R, m, fused_finalize, push, no_finalize));
     if (fused_finalize) m->finished = true;
     return MRS_OK;
   }

@@ -267,8 +267,8 @@ struct mrs_model {
   double* mae_part = nullptr;   // per-block partials of |err| sums
   unsigned int* counters = nullptr;  // small set of device counters (last-block-done patterns)
   int32_t mae_part_cap = 0;
-  // fused push exchange (mrs_fit_local_push): compact slot of every item in the exchange (-1: the item occurs on no rank)
-  int32_t* slot_of_item = nullptr;  // [n_items]
+  // fused push exchange (mrs_fit_local_push): the items that occur on some rank, ascending (compact slot j <-> item slot_of_item[j])
+  int32_t* slot_of_item = nullptr;  // [n_slots_known]
   int32_t n_slots_known = 0;        // K: items that occur on some rank; a delivery is [K dev sums | K counts | sum, n]
   // order of neighbours with EXACTLY equal similarity: 0 = ascending user id, 1 = iteration order of a Scala 2.11
   // immutable.HashSet[Int] (what the reference's stable sort keeps, P:608-610).  tie_rank[c] = place of compact user index c in
@@ -365,15 +365,15 @@ constexpr int kUnitLen = 64;      // (tile,item) segments are cut into units of 
 constexpr int kUnitBits = 7;      // bits of (kUnitLen - len) in the unit sort key
 int32_t build_tiled_layout(const mrs_ratings* R);
 void free_tiled_layout(const mrs_ratings* R);
-int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize, const PushDev* push = nullptr);
+int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused_finalize, const PushDev* push = nullptr, bool no_finalize = false);
 int32_t launch_finish_pull(mrs_model* m, const PushDev& push);
 // mae_tiled.cu
 constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item deviations in shared memory
 int32_t build_mae_layout(const mrs_ratings* T);
 void free_mae_layout(const mrs_ratings* T);
-int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push = nullptr);
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push = nullptr, bool fold = false);
 // baseline.cu
-int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize, const PushDev* push = nullptr);
+int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize, const PushDev* push = nullptr, bool no_finalize = false);
 int32_t fit_finish(mrs_model* m);
 int32_t mae_baseline_async(const mrs_model* m, int32_t pred_kind, const mrs_ratings* test, double* d_out2);
 int32_t predict_baseline_async(const mrs_model* m, int32_t pred_kind, const int32_t* d_users, const int32_t* d_items,

@@ -359,32 +359,20 @@ static int32_t allreduce_impl(mrs_exchange* x, void* device_inout, int64_t n_dou
 }
 
 // ---- fused compute + collective entry points (the exchange happens inside the fit's and the test pass' own kernels)
-namespace mrs {
-namespace {
-__global__ void slot_fill_kernel(int32_t* __restrict__ slot_of_item, int32_t n_items, const int32_t* __restrict__ known, int32_t n_known) {
-  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n_known) {
-    const int32_t i = known[t];
-    if (i >= 0 && i < n_items) slot_of_item[i] = t;
-  }
-}
-}  // namespace
-}  // namespace mrs
-
 extern "C" int32_t mrs_fit_local_push(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, mrs_exchange* x, const int32_t* device_known_items,
                                       int32_t n_known) {
   MRS_REQUIRE(e && train && inout && x && device_known_items && n_known >= 0, MRS_ERR_INVALID, "mrs_fit_local_push: NULL argument");
   MRS_REQUIRE(*inout, MRS_ERR_INVALID, "mrs_fit_local_push: pass a model of this train set (mrs_fit_local once, with item averages switched off)");
   mrs_model* m = *inout;
   use_engine(e);
-  if (!m->slot_of_item || m->n_slots_known != n_known) {  // first use (never inside a graph capture): item id -> compact slot
+  if (!m->slot_of_item || m->n_slots_known != n_known) {  // first use (never inside a graph capture): keep our own copy of the list
     dev_free(m->slot_of_item);
     m->slot_of_item = nullptr;
-    MRS_TRY(dev_alloc(&m->slot_of_item, (size_t)m->n_items));
-    MRS_CUDA(cudaMemsetAsync(m->slot_of_item, 0xff, sizeof(int32_t) * (size_t)m->n_items, e->stream));
-    if (n_known) slot_fill_kernel<<<(n_known + 255) / 256, 256, 0, e->stream>>>(m->slot_of_item, m->n_items, device_known_items, n_known);
-    count_launch();
-    MRS_CUDA(cudaGetLastError());
+    MRS_TRY(dev_alloc(&m->slot_of_item, (size_t)std::max(n_known, 1)));
+    MRS_CUDA(cudaMemcpyAsync(m->slot_of_item, device_known_items, sizeof(int32_t) * (size_t)n_known, cudaMemcpyDeviceToDevice, e->stream));
+    // items known on no rank are never written by the finishing kernel: their deviation is 0.0 (P:197), their count 0
+    MRS_CUDA(cudaMemsetAsync(m->idevavg, 0, sizeof(double) * (size_t)m->n_items, e->stream));
+    MRS_CUDA(cudaMemsetAsync(m->xbuf, 0, sizeof(double) * (2 * (size_t)m->n_items + 2), e->stream));
     m->n_slots_known = n_known;
   }
   PushDev pd;

@@ -62,14 +62,30 @@ constexpr int kMaeRows = 8;    // rows (32 entries of 8 bytes = 256 B) per ring 
 constexpr int kMaeStages = 2;
 constexpr size_t kMaeSmem = (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 32) * kMaeStages * kMaeRows * 256 + (size_t)(kMaeThreads / 32) * kMaeStages * 8;
 
+// FOLD: the test pass finishes the fit itself (single-GPU closure MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test),
+// mrs_fit_mae_async): the item pass' integer accumulators go straight into the tile's deviation table in shared memory, so
+// the finishing kernel K2b (5.7 us on the critical path between the item pass and this kernel, tools/timeline.py) is gone;
+// the model's arrays are written by all CTAs together (an equal share of the item ids each, independent of the tiling).
+struct FoldArgs {
+  const long long* xdev_fix;        // [n_items] per-item deviation sums on the 2^-40 grid (complete once K2 has finished)
+  const int32_t* icolp;             // [n_items+1] train column pointer (rating counts)
+  unsigned long long* k1_part;      // [1] sum of all train codes (K1)
+  double n_fit;                     // number of train ratings
+  double* idevavg;                  // model outputs
+  double* xbuf;
+  double* gavg;
+  uint32_t* usum;                   // consumed by K2: re-armed here for the next pass' K1
+};
+
 // one CTA = (item tile, share of the tile's rows); 32 warps, one CTA per SM
+template <bool FOLD>
 __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const uint2* __restrict__ entry, const int32_t* __restrict__ tile_row_ptr,
                                                                           const int3* __restrict__ cta_desc, int32_t n_users, int32_t n_items,
                                                                           const double* __restrict__ uavg, const double* __restrict__ idevavg,
                                                                           const double* __restrict__ gavg_p, double n_total,
                                                                           double* __restrict__ part, unsigned int* __restrict__ counter,
                                                                           double* __restrict__ out2, unsigned long long* __restrict__ tl,
-                                                                          int use_push, const PushDev x) {
+                                                                          int use_push, const PushDev x, const FoldArgs f) {
   tl_begin(tl, 3);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_dev = reinterpret_cast<double*>(smem_raw);                                     // [kMaeTileItems]
@@ -109,12 +125,51 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
   // ---- the tile's item deviations (unknown item -> 0.0, P:226-227)
   pdl_wait();  // barriers, partition and the first ring stages overlapped the end of the fit; its outputs are complete from here on
   const int32_t i0 = tile * kMaeTileItems;
+  double gavg;
+  if (FOLD) {
+    constexpr double kInvFix = 1.0 / 1099511627776.0;  // 2^-40
+    constexpr int kPer = kMaeTileItems / kMaeThreads;
+    long long fx[kPer];
+    int32_t c0[kPer], c1[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {  // all loads of the tile's 8 items per thread go out together
+      const int32_t i = i0 + k * kMaeThreads + threadIdx.x;
+      const bool in = i < n_items;
+      fx[k] = in ? __ldcg(f.xdev_fix + i) : 0;
+      c0[k] = in ? __ldg(f.icolp + i) : 0;
+      c1[k] = in ? __ldg(f.icolp + i + 1) : 0;
+    }
+    const double gs = 0.5 * (double)__ldcg(f.k1_part);  // integer sum of codes: exact
+    gavg = f.n_fit > 0.0 ? gs / f.n_fit : 0.0;           // P:18 mean of an empty Seq is 0.0
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const double cnt = (double)(c1[k] - c0[k]);
+      s_dev[k * kMaeThreads + threadIdx.x] = cnt > 0.0 ? ((double)fx[k] * kInvFix) / cnt : 0.0;  // P:185; unknown item -> 0.0 (P:197)
+    }
+    // the model's arrays: every CTA an equal share of the item ids
+    const int32_t per = (n_items + gridDim.x - 1) / gridDim.x;
+    const int32_t lo = blockIdx.x * per, hi = min(n_items, lo + per);
+    for (int32_t i = lo + threadIdx.x; i < hi; i += kMaeThreads) {
+      const double ds = (double)__ldcg(f.xdev_fix + i) * kInvFix;
+      const double cnt = (double)(__ldg(f.icolp + i + 1) - __ldg(f.icolp + i));
+      f.xbuf[i] = ds;
+      f.xbuf[(size_t)n_items + i] = cnt;
+      f.idevavg[i] = cnt > 0.0 ? ds / cnt : 0.0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      f.xbuf[2 * (size_t)n_items] = gs;
+      f.xbuf[2 * (size_t)n_items + 1] = f.n_fit;
+      f.gavg[0] = gavg;
+    }
+    for (int32_t u = blockIdx.x * kMaeThreads + threadIdx.x; u < n_users; u += gridDim.x * kMaeThreads) f.usum[u] = 0;
+  } else {
 #pragma unroll 4
-  for (int32_t x = threadIdx.x; x < kMaeTileItems; x += kMaeThreads) {
-    const int32_t i = i0 + x;
-    s_dev[x] = (i < n_items) ? __ldg(idevavg + i) : 0.0;
+    for (int32_t x = threadIdx.x; x < kMaeTileItems; x += kMaeThreads) {
+      const int32_t i = i0 + x;
+      s_dev[x] = (i < n_items) ? __ldg(idevavg + i) : 0.0;
+    }
+    gavg = gavg_p[0];
   }
-  const double gavg = gavg_p[0];
   __syncthreads();
 
   double acc = 0.0;
@@ -125,8 +180,13 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     tma::mbar_wait(bar + st, (uint32_t)(c / kMaeStages) & 1u);
     const uint2* rp = ring + st * kMaeRows * 32 + lane;
     uint2 ev[kMaeRows];
+    if (nrows == kMaeRows) {  // whole stage (all but a warp's last chunk): no per-row predicates
 #pragma unroll
-    for (int k = 0; k < kMaeRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : make_uint2(0u, 0xffu << 16);
+      for (int k = 0; k < kMaeRows; ++k) ev[k] = rp[k * 32];
+    } else {
+#pragma unroll
+      for (int k = 0; k < kMaeRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : make_uint2(0u, 0xffu << 16);
+    }
     __syncwarp();
     if (lane == 0 && c + kMaeStages < n_chunks) {
       const int32_t rr = r + kMaeStages * kMaeRows;
@@ -136,17 +196,19 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     }
     double ua[kMaeRows];
 #pragma unroll
-    for (int k = 0; k < kMaeRows; ++k) {  // the user averages: all gathers of the stage go out together
-      const int32_t u = (int32_t)ev[k].x;
-      ua[k] = (u >= 0 && u < n_users) ? __ldg(uavg + u) : -1.0;
-    }
+    for (int k = 0; k < kMaeRows; ++k)  // the user averages: all gathers of the stage go out together (unknown user: -1.0)
+      ua[k] = (ev[k].x < (uint32_t)n_users) ? __ldg(uavg + ev[k].x) : -1.0;
 #pragma unroll
-    for (int k = 0; k < kMaeRows; ++k) {
+    for (int k = 0; k < kMaeRows; ++k) {  // branch free: selects only, the eight rows overlap in the pipeline
       const uint32_t code = ev[k].y >> 16;
       const double d = s_dev[ev[k].y & 0xffffu];
-      const double p = ua[k] < 0.0 ? gavg : combine_fn(ua[k], d);   // P:222-229
-      const double err = fabs(fma((double)code, 0.5, -p));
-      acc += (code != 0xffu) ? err : 0.0;                           // 0xFF = padding slot
+      const double a = ua[k];
+      const double x = __dadd_rn(a, d);                                      // P:229: the branch is taken on the rounded sum
+      const double sc = x > a ? 5.0 - a : (x < a ? a - 1.0 : 1.0);           // scale(x, a), P:57-61
+      const double pb = __dadd_rn(a, __dmul_rn(d, sc));                      // no FMA: the JVM multiplies, then adds
+      const double p = a < 0.0 ? gavg : pb;                                  // unknown user -> global average (P:222-224)
+      const double err = fabs(fma((double)code, 0.5, -p));                   // |r - p|, P:71
+      acc += (code != 0xffu) ? err : 0.0;                                    // 0xFF = padding slot
     }
   }
   acc = warp_sum(acc);
@@ -176,6 +238,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
         out2[0] = s;
         out2[1] = n_total;
         *counter = 0;
+        if (FOLD) f.k1_part[0] = 0;  // every CTA has read the code sum: re-arm it for the next pass' K1
       }
     } else {
       // sharded run, fused exchange of {sum |err|, n}: this last block delivers the rank's pair into every rank's receive
@@ -277,19 +340,30 @@ int32_t build_mae_layout(const mrs_ratings* T) {
   return MRS_OK;
 }
 
-int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push) {
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push, bool fold) {
   MRS_TRY(build_mae_layout(T));
   const auto& L = T->ml;
   mrs_engine* e = m->eng;
   if (!(e->smem_attr_done & 2u)) {
-    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
+    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
+    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
     e->smem_attr_done |= 2u;
   }
   const int32_t grid = L.n_ctas;
   MRS_REQUIRE(grid > 0 && grid <= m->mae_part_cap, MRS_ERR_UNSUPPORTED, "test set needs %d CTAs, more than the %d partial slots of the model", grid,
               m->mae_part_cap);
-  MRS_CUDA(launch_pdl(predict_mae_tiled_kernel, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
-                      m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, push ? 1 : 0, push ? *push : PushDev{}));
+  FoldArgs f = {};
+  if (fold) {
+    const mrs_ratings* R = m->train;
+    f.xdev_fix = m->xdev_fix; f.icolp = R->icolp; f.k1_part = m->k1_part; f.n_fit = (double)R->n;
+    f.idevavg = m->idevavg; f.xbuf = m->xbuf; f.gavg = m->gavg; f.usum = m->usum;
+    MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<true>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
+                        m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, 0, PushDev{}, f));
+  } else {
+    MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<false>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
+                        m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, push ? 1 : 0,
+                        push ? *push : PushDev{}, f));
+  }
   mark(e, "predict_mae_tiled");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

@@ -75,6 +75,27 @@ extern "C" int32_t mrs_mae_async(const mrs_model* m, const mrs_sim* sim, int32_t
   return mae_baseline_async(m, kind, test, (double*)device_out2);
 }
 
+// MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test) / MAE(computePrediction(train), test) as ONE closure
+// (distributed/DistributedBaseline.scala:45-47, predict/Baseline.scala:66-69): three kernels -- user sums, item pass, and a
+// test pass that finishes the fit in its prologue -- instead of four.  Falls back to mrs_fit_async + mrs_mae_async for
+// rating sets the tiled kernels do not take (fp64-valued ratings, an empty test set, item averages switched on).
+extern "C" int32_t mrs_fit_mae_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, const mrs_ratings* test, void* device_out2) {
+  MRS_REQUIRE(e && train && inout && test && device_out2, MRS_ERR_INVALID, "mrs_fit_mae_async: NULL argument");
+  MRS_REQUIRE(train->eng == e && test->eng == e, MRS_ERR_INVALID, "mrs_fit_mae_async: the rating sets live on another engine");
+  use_engine(e);
+  const bool tiled = train->value_kind == kValueCode && test->value_kind == kValueCode && test->n > 0 && train->n > 0 && *inout &&
+                     !(*inout)->want_item_avg;
+  if (!tiled) {
+    MRS_TRY(fit_local(e, train, inout, true));
+    return mae_baseline_async(*inout, MRS_PRED_BASELINE, test, (double*)device_out2);
+  }
+  MRS_TRY(fit_local(e, train, inout, false, nullptr, true));
+  MRS_TRY(launch_mae_tiled_baseline(*inout, test, (double*)device_out2, nullptr, true));
+  (*inout)->finished = true;   // the test pass has written the model's arrays
+  (*inout)->host_valid = false;
+  return MRS_OK;
+}
+
 extern "C" int32_t mrs_mae(const mrs_model* m, const mrs_sim* sim, int32_t kind, const mrs_ratings* test, double* mae_out) {
   MRS_REQUIRE(m && test && mae_out, MRS_ERR_INVALID, "mrs_mae: NULL argument");
   mrs_engine* e = m->eng;

@@ -357,10 +357,12 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
                                                                  unsigned long long* __restrict__ k1_part, int32_t n_k1, double n_total,
                                                                  double* __restrict__ xbuf, int fused, double* __restrict__ idevavg,
                                                                  double* __restrict__ iavg, double* __restrict__ gavg,
+                                                                 uint32_t* __restrict__ usum, int32_t n_users,
                                                                  unsigned long long* __restrict__ tl) {
   tl_begin(tl, 2);
   pdl_trigger();
   pdl_wait();  // the accumulators are complete once the item pass has finished
+  for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += gridDim.x * blockDim.x) usum[u] = 0;  // consumed by K2: re-arm for K1
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
     k1_part[0] = 0;                              // re-arm for the next pass
@@ -371,9 +373,7 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) { tl_end(tl, 2); return; }
   const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
-  const double rs = 0.5 * (double)xcode_sum[i];
-  xdev_fix[i] = 0;
-  xcode_sum[i] = 0;
+  const double rs = 0.5 * (double)xcode_sum[i];  // (K1 of the next pass re-arms both accumulators)
   const double cnt = (double)(icolp[i + 1] - icolp[i]);
   xbuf[i] = ds;
   xbuf[(size_t)n_items + i] = cnt;
@@ -390,15 +390,18 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
 // rank then waits for the flags and adds the deliveries FROM ITS OWN MEMORY in rank order (bit-identical totals
 // everywhere).  Compared with K2b -> all-reduce kernel -> finalize kernel this saves one launch, the publish copy and
 // the round trip of the remote loads.  Only the K items that occur on some rank travel (slot_of_item).
-__global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restrict__ xdev_fix, unsigned long long* __restrict__ xcode_sum,
-                                                             const int32_t* __restrict__ icolp, int32_t n_items,
+// One thread per KNOWN item (compact slot j, item known[j]): the 32 lanes of a warp store 256 contiguous bytes into every
+// rank's buffer (a thread per item id would leave 9 of 32 lanes active at ml-25m shape, whose ids are sparse, and send
+// 72-byte fragments over NVLink: 36 us for the kernel at 8 ranks against 10 us unfused).
+__global__ void __launch_bounds__(256) item_tiled_push_kernel(const long long* __restrict__ xdev_fix, const int32_t* __restrict__ icolp,
                                                              unsigned long long* __restrict__ k1_part, double n_total,
-                                                             const int32_t* __restrict__ slot_of_item, int32_t K, const PushDev x,
-                                                             unsigned long long* __restrict__ tl) {
+                                                             const int32_t* __restrict__ known, int32_t K, const PushDev x,
+                                                             uint32_t* __restrict__ usum, int32_t n_users, unsigned long long* __restrict__ tl) {
   __shared__ int s_last;
   tl_begin(tl, 2);
   pdl_trigger();
   pdl_wait();  // the accumulators are complete once the item pass has finished
+  for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += gridDim.x * blockDim.x) usum[u] = 0;  // consumed by K2: re-arm for K1
   const unsigned long long epoch = *x.epoch + 1;  // stable until the finishing kernel of this exchange has run
   const int parity = (int)(epoch & 1);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -410,19 +413,15 @@ __global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restr
       slot[2 * (size_t)K + 1] = n_total;
     }
   }
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_items) {
-    const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
-    xdev_fix[i] = 0;
-    xcode_sum[i] = 0;
-    const int32_t j = __ldg(slot_of_item + i);
-    if (j >= 0) {
-      const double cnt = (double)(icolp[i + 1] - icolp[i]);
-      for (int p = 0; p < x.world; ++p) {
-        double* slot = push_slot(x, p, parity, x.rank);
-        slot[j] = ds;
-        slot[(size_t)K + j] = cnt;
-      }
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < K) {
+    const int32_t i = __ldg(known + j);
+    const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);  // (K1 of the next pass re-arms the accumulators)
+    const double cnt = (double)(__ldg(icolp + i + 1) - __ldg(icolp + i));
+    for (int p = 0; p < x.world; ++p) {
+      double* slot = push_slot(x, p, parity, x.rank);
+      slot[j] = ds;
+      slot[(size_t)K + j] = cnt;
     }
   }
   // the last block of this rank makes all deliveries visible system-wide, then raises its flag in every rank's memory
@@ -442,9 +441,9 @@ __global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restr
   tl_end(tl, 2);
 }
 
-__global__ void __launch_bounds__(256) item_finish_pull_kernel(int32_t n_items, const int32_t* __restrict__ slot_of_item, int32_t K, const PushDev x,
-                                                              double* __restrict__ xbuf, double* __restrict__ idevavg, double* __restrict__ iavg,
-                                                              double* __restrict__ gavg, unsigned long long* __restrict__ tl) {
+__global__ void __launch_bounds__(256) item_finish_pull_kernel(int32_t n_items, const int32_t* __restrict__ known, int32_t K, const PushDev x,
+                                                              double* __restrict__ xbuf, double* __restrict__ idevavg, double* __restrict__ gavg,
+                                                              unsigned long long* __restrict__ tl) {
   tl_begin(tl, 4);
   pdl_trigger();  // the test pass may set up its rings while this runs
   pdl_wait();     // this rank's own delivery is complete (stream order)
@@ -466,22 +465,19 @@ __global__ void __launch_bounds__(256) item_finish_pull_kernel(int32_t n_items, 
     xbuf[2 * (size_t)n_items + 1] = gc;
     gavg[0] = ok ? (gc > 0.0 ? gs / gc : 0.0) : bad;  // P:18 mean of an empty Seq is 0.0
   }
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_items) {
-    const int32_t j = __ldg(slot_of_item + i);
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < K) {
     double ds = 0.0, cnt = 0.0;
-    if (j >= 0) {
-      for (int p = 0; p < x.world; ++p) {
-        const double* slot = push_slot(x, x.rank, parity, p);
-        ds += slot[j];
-        cnt += slot[(size_t)K + j];
-      }
+    for (int p = 0; p < x.world; ++p) {
+      const double* slot = push_slot(x, x.rank, parity, p);
+      ds += slot[j];
+      cnt += slot[(size_t)K + j];
     }
     if (!ok) ds = cnt = bad;
+    const int32_t i = __ldg(known + j);
     xbuf[i] = ds;
     xbuf[(size_t)n_items + i] = cnt;
-    idevavg[i] = ok ? (cnt > 0.0 ? ds / cnt : 0.0) : bad;  // P:185 ; unknown item -> 0.0 (P:197)
-    iavg[i] = bad;                                           // (per-item rating averages do not travel in this mode)
+    idevavg[i] = ok ? (cnt > 0.0 ? ds / cnt : 0.0) : bad;  // P:185; items known on no rank keep 0.0 (P:197) from the model's creation
   }
   __syncthreads();
   if (threadIdx.x == 0 && atomicAdd(x.done + 1, 1u) + 1u == gridDim.x) {  // last block out: this exchange is complete
@@ -495,8 +491,8 @@ __global__ void __launch_bounds__(256) item_finish_pull_kernel(int32_t n_items, 
 
 int32_t launch_finish_pull(mrs_model* m, const PushDev& push) {
   mrs_engine* e = m->eng;
-  MRS_CUDA(launch_pdl(item_finish_pull_kernel, dim3((m->n_items + 255) / 256), dim3(256), 0, e->stream, m->n_items, m->slot_of_item, m->n_slots_known,
-                      push, m->xbuf, m->idevavg, m->iavg, m->gavg, e->d_timeline));
+  MRS_CUDA(launch_pdl(item_finish_pull_kernel, dim3((m->n_slots_known + 255) / 256 + 1), dim3(256), 0, e->stream, m->n_items, m->slot_of_item,
+                      m->n_slots_known, push, m->xbuf, m->idevavg, m->gavg, e->d_timeline));
   mark(e, "item_finish_pull");
   MRS_CUDA(cudaGetLastError());
   m->finished = true;
@@ -648,7 +644,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   return MRS_OK;
 }
 
-int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push) {
+int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push, bool no_finalize) {
   const auto& T = R->tl;
   cudaStream_t st = e->stream;
   if (!(e->smem_attr_done & 1u)) {
@@ -667,15 +663,16 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
                           R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline));
   }
   mark(e, "item_tiled");
+  if (no_finalize) return MRS_OK;  // mrs_fit_mae_async: the test pass finishes the fit itself
   if (push) {  // sharded run with the fused exchange: K2b delivers the partial sums to every rank itself
-    MRS_CUDA(launch_pdl(item_tiled_push_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
-                        m->k1_part, (double)R->n, m->slot_of_item, m->n_slots_known, *push, e->d_timeline));
+    MRS_CUDA(launch_pdl(item_tiled_push_kernel, dim3((m->n_slots_known + 255) / 256 + 1), dim3(256), 0, st, m->xdev_fix, R->icolp, m->k1_part,
+                        (double)R->n, m->slot_of_item, m->n_slots_known, *push, m->usum, R->n_users, e->d_timeline));
     mark(e, "item_tiled_push");
     MRS_CUDA(cudaGetLastError());
     return MRS_OK;
   }
   MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
-                      m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg, e->d_timeline));
+                      m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg, m->usum, R->n_users, e->d_timeline));
   mark(e, "item_tiled_finalize");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;

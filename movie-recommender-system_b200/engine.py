@@ -28,7 +28,7 @@ EXPORTS = [
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_model_set_tie_order", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
-    "mrs_mae_async", "mrs_recommend",
+    "mrs_mae_async", "mrs_fit_mae_async", "mrs_recommend",
 ]
 
 
@@ -130,6 +130,7 @@ def lib():
         "mrs_predict": (i32, [vp, vp, i32, vp, vp, i64, vp]),
         "mrs_mae": (i32, [vp, vp, i32, vp, P(dbl)]),
         "mrs_mae_async": (i32, [vp, vp, i32, vp, vp]),
+        "mrs_fit_mae_async": (i32, [vp, vp, P(vp), vp, vp]),
         "mrs_recommend": (i32, [vp, vp, i32, i32, i32, vp, vp, P(i32)]),
     }
     for name, (res, args) in sig.items():
@@ -470,6 +471,11 @@ class Model:
     def mae_async(self, test, device_out_ptr, kind=PRED_BASELINE, sim=None):
         """Enqueue predict+|err| reduction; {sum, count} (2 fp64) land at ``device_out_ptr``; no host sync."""
         _check(lib().mrs_mae_async(self._h, sim._h if sim is not None else None, int(kind), test._h, C.c_void_p(device_out_ptr)))
+
+    def fit_mae_async(self, test, device_out_ptr):
+        """The closure MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test) in one call: refit + fused MAE, the test pass
+        finishing the fit itself (three kernels); {sum |err|, count} land at ``device_out_ptr``; no host sync."""
+        _check(lib().mrs_fit_mae_async(self.engine._h, self.train._h, C.byref(self._h), test._h, C.c_void_p(device_out_ptr)))
 
     def similarity(self, kind=SIM_COSINE, k=0, sync=True, rows=None):
         return Sim(self, kind, k, sync=sync, rows=rows)

@@ -169,3 +169,31 @@ def test_compact_code_upload_matches_fp64_upload(eng, ml100k):
         eng.ratings_from_codes(tr[0][:10], tr[1][:10], np.full(10, 255, dtype=np.uint8))   # 255 is not a legal code
     for h in (mc, m, Tc, Rc, T, R):
         h.close()
+
+
+def test_fit_mae_closure_equals_fit_then_mae(eng):
+    """mrs_fit_mae_async: the test pass finishes the fit in its own prologue (no K2b); same MAE bits, same model arrays."""
+    import torch
+    from mrs_b200 import synth
+    d = synth.ml25m(seed=8, n_users=30000, n_items=9000, n_ratings=1_200_000, max_item_id=30000)   # several item tiles and user tiles
+    R, T = eng.ratings(*d["train"]), eng.ratings(*d["test"])
+    m = E.Model(eng, R)
+    m.set_item_averages(False)
+    with torch.cuda.stream(eng._keep):
+        out = torch.zeros(2, dtype=torch.float64, device="cuda")
+        m.refit()
+        m.mae_async(T, out.data_ptr())
+        eng.sync()
+        ref = out.cpu().numpy().copy()
+        idev, ua, g = m.vector(E.ITEM_AVG_DEV)[0], m.vector(E.USER_AVG)[0], m.global_avg
+        for _ in range(3):                              # repeated: the accumulators and the user sums are re-armed correctly
+            out.zero_()
+            m.fit_mae_async(T, out.data_ptr())
+            eng.sync()
+            assert out.cpu().numpy().tolist() == ref.tolist()
+        assert m.vector(E.ITEM_AVG_DEV)[0].tolist() == idev.tolist() and m.vector(E.USER_AVG)[0].tolist() == ua.tolist() and m.global_avg == g
+        m.refit(); m.mae_async(T, out.data_ptr()); eng.sync()    # and the four-kernel form still works afterwards
+        assert out.cpu().numpy().tolist() == ref.tolist()
+    assert ref[0] / ref[1] == pytest.approx(O.Oracle(*d["train"]).mae(d["test"], kind=O.BASELINE), rel=1e-6)
+    for h in (m, T, R):
+        h.close()
