@@ -619,7 +619,21 @@ def bench_knn(eng, stream, torch):
     mae = float(r[0] / r[1])
     for h in (s, m, T, R):
         h.close()
-    return {"metric": "knn_k300_ml100k_fit_predict_mae_ms", "value": statistics.median(ms), "unit": "ms", "min_ms": min(ms),
+    # roofline of the dominant kernel: the similarity SpGEMM is fp64 multiply-add work on an L2-resident working set
+    # (about 1 MB of inputs, S = 943^2 x 8 B = 7.1 MB), so the denominator is the measured fp64 FMA rate of the device
+    import numpy as np
+    cnt_i = np.bincount(tr[1]).astype(np.float64)
+    n_known = int(np.unique(tr[0]).size)
+    executed = float(n_known) * float(tr[0].size)            # dense-staged kernel: every user row against every rating
+    useful = float((cnt_i * cnt_i).sum())                    # products over item intersections (both triangles)
+    fp64 = eng.fp64_fma_per_s()
+    sim_s = per_kernel.get("similarity", 0.0) * 1e-3
+    knn_roof = {"bound": "fp64 FMA rate (latency bound in practice: 118 CTAs of 16 warps on 148 SMs)", "kernel": "similarity",
+                "achieved": executed / sim_s if sim_s else None, "peak": fp64, "unit": "fp64 multiply-adds/s",
+                "frac": (executed / sim_s / fp64) if sim_s else None, "executed_macs": executed, "useful_products": useful,
+                "kernel_ms": per_kernel.get("similarity"), "peak_source": "measured in this run (mrs_debug_fp64_fma_per_s: 8 DFMA chains per thread, all SMs)",
+                "traffic": None}
+    return {"roofline": knn_roof, "metric": "knn_k300_ml100k_fit_predict_mae_ms", "value": statistics.median(ms), "unit": "ms", "min_ms": min(ms),
             "mean_ms": sum(ms) / len(ms), "reps": reps, "launch_mode": mode, "mae": mae, "per_kernel_ms": per_kernel,
             "l2": "not flushed: the whole working set (about 25 MB) is L2-resident by design",
             "cpu_port_ms": cpu_ms, "cpu_port_mae": cpu_mae, "published_reference_ms": 26198.54,
@@ -668,7 +682,16 @@ def bench_knn25m(eng, stream, torch, dist, d, rank, world, dev, peer, k=300, rep
             oi, os_ = o.neighbors(int(u), k)
             same &= ids.tolist() == oi.tolist() and sims.tolist() == os_.tolist()
         ms = statistics.median(times)
-        out = {"metric": "knn_k300_ml25m_fit_predict_mae_s", "value": ms / 1000.0, "unit": "s", "n_gpus": world, "reps": reps,
+        cnt_i = np.bincount(tr[1]).astype(np.float64)
+        products = float((cnt_i * cnt_i).sum())                  # sum_i cnt_i^2 pair products, all ranks together
+        fp64 = eng.fp64_fma_per_s()
+        rows_s = prof.get("knn_rows", 0.0) * 1e-3
+        roof = {"bound": "fp64 FMA rate as the reference; the kernel is latency bound (L2 gathers of column slices + a shared-memory "
+                         "read-modify-write per product)", "kernel": "knn_rows", "achieved": products / world / rows_s if rows_s else None,
+                "peak": fp64, "unit": "fp64 multiply-adds/s per GPU", "frac": (products / world / rows_s / fp64) if rows_s else None,
+                "pair_products": products, "kernel_ms_rank0": prof.get("knn_rows"),
+                "peak_source": "measured in this run (mrs_debug_fp64_fma_per_s)", "traffic": None}
+        out = {"roofline": roof, "metric": "knn_k300_ml25m_fit_predict_mae_s", "value": ms / 1000.0, "unit": "s", "n_gpus": world, "reps": reps,
                "scaling": "strong", "mae": mae, "times_ms": times, "rows_rank0": [sk.user_lo, sk.user_hi],
                "test_pairs_rank0": sk.n_test_local, "pairs_per_s": float(te[0].size) / (ms / 1000.0),
                "rank0_kernel_ms": {a: round(b, 3) for a, b in prof.items()},

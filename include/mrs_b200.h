@@ -92,6 +92,8 @@ MRS_API int32_t mrs_engine_sync(mrs_engine* e);
  * sums, 1 item pass, 2 item finalize, 3 test pass), the earliest block start out32[2k] and the latest block end out32[2k+1]
  * in %globaltimer nanoseconds; the call synchronises, copies them out and re-arms the slots (tools/timeline.py) */
 MRS_API int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32);
+/* diagnostics: measured fp64 FMA rate of the engine's device, FMA per second (denominator of the kNN similarity rooflines) */
+MRS_API int32_t mrs_debug_fp64_fma_per_s(mrs_engine* e, double* out);
 
 /* CUDA-graph capture of any sequence of the asynchronous entry points (mrs_fit_async, mrs_fit_local, mrs_fit_finish,
  * mrs_fit_similarity_async, mrs_mae_async) on this engine's stream: the kernels of a pass take tens of microseconds, so

@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
   __syncthreads();
 
   double acc = 0.0;
+  const double* ua_base = uavg;
+  asm volatile("" : "+l"(ua_base));  // keep the table base in registers (ptxas otherwise reloads it from the constant bank per gather)
   for (int32_t c = 0; c < n_chunks; ++c) {
     const int st = c % kMaeStages;
     const int32_t r = r0 + c * kMaeRows;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     double ua[kMaeRows];
 #pragma unroll
     for (int k = 0; k < kMaeRows; ++k)  // the user averages: all gathers of the stage go out together (unknown user: -1.0)
-      ua[k] = (ev[k].x < (uint32_t)n_users) ? __ldg(uavg + ev[k].x) : -1.0;
+      ua[k] = (ev[k].x < (uint32_t)n_users) ? __ldg(ua_base + ev[k].x) : -1.0;
 #pragma unroll
     for (int k = 0; k < kMaeRows; ++k) {  // branch free: selects only, the eight rows overlap in the pipeline
       const uint32_t code = ev[k].y >> 16;

@@ -59,10 +59,54 @@ int32_t predict_async(const mrs_model* m, const mrs_sim* sim, int32_t kind, cons
   return predict_baseline_async(m, kind, d_u, d_i, n, d_out);
 }
 
+// fp64 FMA throughput of the device (the denominator of the kNN similarity rooflines: there is no fp64 figure in
+// MEASURED_PEAKS.json): 8 independent DFMA chains per thread, all SMs full
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ out, int iters) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+  const double b = 1.0000001, c = 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+
 }  // namespace
 }  // namespace mrs
 
 using namespace mrs;
+
+// measured fp64 FMA rate of the engine's device in FMA/s (diagnostics; bench.py uses it as the kNN roofline denominator)
+extern "C" int32_t mrs_debug_fp64_fma_per_s(mrs_engine* e, double* out) {
+  MRS_REQUIRE(e && out, MRS_ERR_INVALID, "mrs_debug_fp64_fma_per_s: NULL argument");
+  use_engine(e);
+  double* d = nullptr;
+  MRS_CUDA(cudaMalloc((void**)&d, sizeof(double)));
+  cudaEvent_t a, b;
+  MRS_CUDA(cudaEventCreate(&a));
+  MRS_CUDA(cudaEventCreate(&b));
+  const int iters = 20000, grid = e->sm_count * 8;
+  fp64_peak_kernel<<<grid, 256, 0, e->stream>>>(d, 1000);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    MRS_CUDA(cudaEventRecord(a, e->stream));
+    fp64_peak_kernel<<<grid, 256, 0, e->stream>>>(d, iters);
+    MRS_CUDA(cudaEventRecord(b, e->stream));
+    MRS_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    MRS_CUDA(cudaEventElapsedTime(&ms, a, b));
+    best = ms < best ? ms : best;
+  }
+  count_launch(4);
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  *out = (double)grid * 256.0 * 8.0 * (double)iters / ((double)best * 1e-3);
+  return MRS_OK;
+}
 
 extern "C" int32_t mrs_mae_async(const mrs_model* m, const mrs_sim* sim, int32_t kind, const mrs_ratings* test, void* device_out2) {
   MRS_REQUIRE(m && test && device_out2, MRS_ERR_INVALID, "mrs_mae_async: NULL argument");
