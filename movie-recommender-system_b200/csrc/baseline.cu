@@ -57,8 +57,7 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
 // atomicAdd per (warp, user).  Integer sums are exact: the result does not depend on the order of the atomics.
 __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
                                                       uint32_t* __restrict__ usum, unsigned long long* __restrict__ gsum_codes,
-                                                      long long* __restrict__ xdev_fix, unsigned long long* __restrict__ xcode_sum,
-                                                      int32_t n_items, unsigned long long* __restrict__ tl) {
+                                                      unsigned long long* __restrict__ tl) {
   __shared__ uint32_t sh[8];
   tl_begin(tl, 0);
   pdl_trigger();  // the item pass may start its prologue (ring prefetch) while this kernel runs
@@ -74,12 +73,6 @@ __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict
     const bool in = t < n_vec;
     x[k] = in ? __ldg(reinterpret_cast<const uint4*>(uval16) + t) : make_uint4(0u, 0u, 0u, 0u);
     row[k] = in ? __ldg(vec_row + t) : -1;
-  }
-  // re-arm the per-item accumulators of the item pass while the loads above are in flight (whoever read them last -- K2b,
-  // the push kernel or the fused test pass -- has finished: this kernel is a plain stream-ordered launch)
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-    xdev_fix[i] = 0;
-    xcode_sum[i] = 0;
   }
   uint32_t total = 0;
 #pragma unroll
@@ -363,8 +356,7 @@ inline int chunk_grid(int32_t n_chunks, int sm_count) {
 int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push, bool no_finalize) {
   // (the user sums are zero on entry: cleared when the model is created and re-armed by the kernel that consumes them last --
   // K2b, the push kernel or the fused test pass -- so no memset node opens the pass)
-  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, m->xdev_fix, m->xcode_sum, R->n_items,
-                                                       e->d_timeline);
+  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, e->d_timeline);
   mark(e, "user_sum");
   MRS_CUDA(cudaGetLastError());
   return launch_item_tiled(e, R, m, fused, push, no_finalize);
@@ -451,9 +443,9 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
       if (s == MRS_OK && cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
       if (s == MRS_OK) s = dev_alloc(&m->k1_part, 1);
       if (s == MRS_OK && cudaMemsetAsync(m->k1_part, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
-      if (s == MRS_OK) s = dev_alloc(&m->xdev_fix, (size_t)R->n_items);
+      if (s == MRS_OK) s = dev_alloc(&m->xdev_fix, 2 * (size_t)R->n_items);  // two buffers, used alternately by the folded closure (tiled.cu)
       if (s == MRS_OK) s = dev_alloc(&m->xcode_sum, (size_t)R->n_items);
-      if (s == MRS_OK && cudaMemsetAsync(m->xdev_fix, 0, sizeof(long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+      if (s == MRS_OK && cudaMemsetAsync(m->xdev_fix, 0, 2 * sizeof(long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
       if (s == MRS_OK && cudaMemsetAsync(m->xcode_sum, 0, sizeof(unsigned long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
     }
     if (s == MRS_OK) s = dev_alloc(&m->upart, (size_t)R->uch.n_chunks);

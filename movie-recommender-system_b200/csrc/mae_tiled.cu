@@ -67,7 +67,8 @@ constexpr size_t kMaeSmem = (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 3
 // the finishing kernel K2b (5.7 us on the critical path between the item pass and this kernel, tools/timeline.py) is gone;
 // the model's arrays are written by all CTAs together (an equal share of the item ids each, independent of the tiling).
 struct FoldArgs {
-  const long long* xdev_fix;        // [n_items] per-item deviation sums on the 2^-40 grid (complete once K2 has finished)
+  long long* xdev_fix;              // [2][n_items] per-item deviation sums on the 2^-40 grid: buffer *parity is complete once K2 has finished
+  unsigned int* parity;             // which buffer this pass uses; the other one is re-armed here, the last block flips the parity
   const int32_t* icolp;             // [n_items+1] train column pointer (rating counts)
   unsigned long long* k1_part;      // [1] sum of all train codes (K1)
   double n_fit;                     // number of train ratings
@@ -129,13 +130,16 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
   if (FOLD) {
     constexpr double kInvFix = 1.0 / 1099511627776.0;  // 2^-40
     constexpr int kPer = kMaeTileItems / kMaeThreads;
+    const unsigned int par = *f.parity & 1u;
+    const long long* __restrict__ fix = f.xdev_fix + (size_t)par * n_items;
+    long long* __restrict__ fix_other = f.xdev_fix + (size_t)(par ^ 1u) * n_items;
     long long fx[kPer];
     int32_t c0[kPer], c1[kPer];
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {  // all loads of the tile's 8 items per thread go out together
       const int32_t i = i0 + k * kMaeThreads + threadIdx.x;
       const bool in = i < n_items;
-      fx[k] = in ? __ldcg(f.xdev_fix + i) : 0;
+      fx[k] = in ? __ldcg(fix + i) : 0;
       c0[k] = in ? __ldg(f.icolp + i) : 0;
       c1[k] = in ? __ldg(f.icolp + i + 1) : 0;
     }
@@ -150,7 +154,8 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     const int32_t per = (n_items + gridDim.x - 1) / gridDim.x;
     const int32_t lo = blockIdx.x * per, hi = min(n_items, lo + per);
     for (int32_t i = lo + threadIdx.x; i < hi; i += kMaeThreads) {
-      const double ds = (double)__ldcg(f.xdev_fix + i) * kInvFix;
+      const double ds = (double)__ldcg(fix + i) * kInvFix;
+      fix_other[i] = 0;  // re-arm the buffer of the NEXT pass (its last reader, the previous pass, is long done)
       const double cnt = (double)(__ldg(f.icolp + i + 1) - __ldg(f.icolp + i));
       f.xbuf[i] = ds;
       f.xbuf[(size_t)n_items + i] = cnt;
@@ -240,7 +245,10 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
         out2[0] = s;
         out2[1] = n_total;
         *counter = 0;
-        if (FOLD) f.k1_part[0] = 0;  // every CTA has read the code sum: re-arm it for the next pass' K1
+        if (FOLD) {
+          f.k1_part[0] = 0;  // every CTA has read the code sum: re-arm it for the next pass' K1
+          *f.parity ^= 1u;   // ... and the accumulators: the next pass uses the buffer re-armed above
+        }
       }
     } else {
       // sharded run, fused exchange of {sum |err|, n}: this last block delivers the rank's pair into every rank's receive
@@ -358,7 +366,7 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
   if (fold) {
     const mrs_ratings* R = m->train;
     f.xdev_fix = m->xdev_fix; f.icolp = R->icolp; f.k1_part = m->k1_part; f.n_fit = (double)R->n;
-    f.idevavg = m->idevavg; f.xbuf = m->xbuf; f.gavg = m->gavg; f.usum = m->usum;
+    f.idevavg = m->idevavg; f.xbuf = m->xbuf; f.gavg = m->gavg; f.usum = m->usum; f.parity = m->counters + 4;
     MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<true>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
                         m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, 0, PushDev{}, f));
   } else {

@@ -18,6 +18,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -125,9 +126,100 @@ __global__ void entry_fill_kernel(const int32_t* __restrict__ unit_begin, const 
 }
 
 __global__ void slot_item_kernel(const int32_t* __restrict__ unit_slot, const int32_t* __restrict__ unit_item, int32_t n_units,
-                                 int32_t* __restrict__ slot_item) {
+                                 int32_t* __restrict__ slot_item, int32_t* __restrict__ slot_unit) {
   const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id < n_units) slot_item[unit_slot[id]] = unit_item[id];
+  if (id < n_units) {
+    slot_item[unit_slot[id]] = unit_item[id];
+    if (slot_unit) slot_unit[unit_slot[id]] = id;
+  }
+}
+
+// Entry placement that avoids shared-memory bank conflicts in the pass (MRS_REORDER=1; A/B in profiles/r02_summary.md).  The
+// pass gathers the 8-byte (code sum, count) pair of every entry's user; a 64-bit shared-memory load is served 16 lanes at a
+// time and is conflict free only if those lanes hit 16 different bank pairs = (user & 15).  With entries in (item, user)
+// order the keys of a row are random: ~3.2 wavefronts per half warp instead of 1.  The order of the entries INSIDE a unit is
+// free (it only fixes the summation order), so one warp per slice deals them out position by position: every lane offers
+// an entry whose key is still free in its half warp (lowest lane wins a contested key, the others offer another key in the
+// next round); a lane without such an entry leaves the position to padding if it has slack, else takes a conflict.
+__global__ void __launch_bounds__(128) entry_fill_ordered_kernel(const int32_t* __restrict__ slot_unit, const int32_t* __restrict__ unit_begin,
+                                                                const int32_t* __restrict__ unit_len, const int32_t* __restrict__ unit_tile,
+                                                                int32_t n_slices, const int32_t* __restrict__ perm,
+                                                                const int32_t* __restrict__ irow, const uint8_t* __restrict__ ival,
+                                                                const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry) {
+  __shared__ uint32_t s_ent[4][32 * kUnitLen];   // entries of the lane's unit, grouped by key
+  __shared__ uint8_t s_next[4][32][16];          // next unplaced entry of every key group
+  __shared__ uint8_t s_end[4][32][16];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int32_t slice = blockIdx.x * 4 + w;
+  if (slice >= n_slices) return;
+  const int32_t id = slot_unit[slice * 32 + lane];
+  const int32_t len = id >= 0 ? unit_len[id] : 0;
+  const int32_t b = id >= 0 ? unit_begin[id] : 0;
+  const int32_t ubase = id >= 0 ? unit_tile[id] * kTileUsers : 0;
+  uint32_t* ent = s_ent[w] + lane * kUnitLen;
+  uint8_t* nxt = s_next[w][lane];
+  uint8_t* end = s_end[w][lane];
+  int32_t cnt[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cnt[k] = 0;
+  for (int32_t j = 0; j < len; ++j) {
+    const int32_t key = (irow[perm[b + j]] - ubase) & 15;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cnt[k] += (key == k);
+  }
+  uint32_t avail = 0;
+  {
+    int32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      nxt[k] = (uint8_t)run;
+      run += cnt[k];
+      end[k] = (uint8_t)run;
+      if (cnt[k]) avail |= 1u << k;
+    }
+  }
+  for (int32_t j = 0; j < len; ++j) {
+    const int32_t p = perm[b + j];
+    const int32_t x = irow[p] - ubase;
+    ent[nxt[x & 15]++] = 0x80000000u | ((uint32_t)ival[p] << 16) | (uint32_t)x;
+  }
+  {
+    int32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { nxt[k] = (uint8_t)run; run += cnt[k]; }
+  }
+  __syncwarp();
+  const int64_t row0 = slice_off[slice];
+  const int32_t n_pos = slice_off[slice + 1] - slice_off[slice];
+  const int half = lane >> 4;
+  int32_t remaining = len;
+  for (int32_t pos = 0; pos < n_pos; ++pos) {
+    uint32_t taken = 0;
+    int32_t mine = -1;
+    const bool need = remaining > 0;
+    const int rot = (lane + pos) & 15;
+    while (true) {
+      const uint32_t cand = (need && mine < 0) ? (avail & ~taken) : 0u;
+      int32_t prop = -1;
+      if (cand) {
+        const uint32_t r = ((cand >> rot) | (cand << (16 - rot))) & 0xffffu;
+        prop = (__ffs(r) - 1 + rot) & 15;
+      }
+      if (!__any_sync(0xffffffffu, prop >= 0)) break;
+      const uint32_t same = __match_any_sync(0xffffffffu, prop >= 0 ? (prop | (half << 4)) : (64 + lane));
+      const bool win = prop >= 0 && (__ffs(same) - 1 == lane);
+      if (win) mine = prop;
+      const uint32_t won = __reduce_or_sync(0xffffffffu, win ? (1u << (prop + 16 * half)) : 0u);
+      taken |= (won >> (16 * half)) & 0xffffu;
+    }
+    if (need && mine < 0 && remaining >= n_pos - pos) mine = __ffs(avail) - 1;  // no slack left: take a conflict
+    if (mine >= 0) {
+      const uint32_t e = ent[nxt[mine]++];
+      if (nxt[mine] == end[mine]) avail &= ~(1u << mine);
+      --remaining;
+      entry[((row0 + pos) << 5) + lane] = e;
+    }
+  }
 }
 
 int grid_for(int64_t n, int block, int sm_count) {
@@ -231,10 +323,14 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
                                                                      const int2* __restrict__ warp_part, const int3* __restrict__ cta_desc,
                                                                      const uint32_t* __restrict__ usum, const int32_t* __restrict__ urow,
                                                                      int32_t n_users, const int32_t* __restrict__ slot_item,
-                                                                     double* __restrict__ uavg, long long* __restrict__ xdev_fix,
-                                                                     unsigned long long* __restrict__ xcode_sum, unsigned long long* __restrict__ tl) {
+                                                                     double* __restrict__ uavg, long long* __restrict__ xdev_fix_both,
+                                                                     unsigned long long* __restrict__ xcode_sum, unsigned long long* __restrict__ tl,
+                                                                     const unsigned int* __restrict__ parity, int32_t n_items_acc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   tl_begin(tl, 1);
+  // the accumulator buffer of this pass (two buffers alternate when the test pass finishes the fit itself: it cannot re-arm
+  // the buffer it reads, so it re-arms the other one; the parity only changes between passes)
+  long long* __restrict__ xdev_fix = xdev_fix_both + (size_t)(*parity & 1u) * n_items_acc;
   uint2* s_sc = reinterpret_cast<uint2*>(smem_raw);                                       // [kTileUsers] (code sum, count)
   uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTileUsers * 8);      // [warps][kStages][kRows*32]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128);
@@ -358,8 +454,9 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
                                                                  double* __restrict__ xbuf, int fused, double* __restrict__ idevavg,
                                                                  double* __restrict__ iavg, double* __restrict__ gavg,
                                                                  uint32_t* __restrict__ usum, int32_t n_users,
-                                                                 unsigned long long* __restrict__ tl) {
+                                                                 unsigned long long* __restrict__ tl, const unsigned int* __restrict__ parity) {
   tl_begin(tl, 2);
+  xdev_fix += (size_t)(*parity & 1u) * n_items;
   pdl_trigger();
   pdl_wait();  // the accumulators are complete once the item pass has finished
   for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += gridDim.x * blockDim.x) usum[u] = 0;  // consumed by K2: re-arm for K1
@@ -373,7 +470,9 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) { tl_end(tl, 2); return; }
   const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
-  const double rs = 0.5 * (double)xcode_sum[i];  // (K1 of the next pass re-arms both accumulators)
+  const double rs = 0.5 * (double)xcode_sum[i];
+  xdev_fix[i] = 0;  // re-arm for the next pass
+  xcode_sum[i] = 0;
   const double cnt = (double)(icolp[i + 1] - icolp[i]);
   xbuf[i] = ds;
   xbuf[(size_t)n_items + i] = cnt;
@@ -393,12 +492,14 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
 // One thread per KNOWN item (compact slot j, item known[j]): the 32 lanes of a warp store 256 contiguous bytes into every
 // rank's buffer (a thread per item id would leave 9 of 32 lanes active at ml-25m shape, whose ids are sparse, and send
 // 72-byte fragments over NVLink: 36 us for the kernel at 8 ranks against 10 us unfused).
-__global__ void __launch_bounds__(256) item_tiled_push_kernel(const long long* __restrict__ xdev_fix, const int32_t* __restrict__ icolp,
+__global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restrict__ xdev_fix, const int32_t* __restrict__ icolp,
                                                              unsigned long long* __restrict__ k1_part, double n_total,
                                                              const int32_t* __restrict__ known, int32_t K, const PushDev x,
-                                                             uint32_t* __restrict__ usum, int32_t n_users, unsigned long long* __restrict__ tl) {
+                                                             uint32_t* __restrict__ usum, int32_t n_users, unsigned long long* __restrict__ tl,
+                                                             const unsigned int* __restrict__ acc_parity, int32_t n_items) {
   __shared__ int s_last;
   tl_begin(tl, 2);
+  xdev_fix += (size_t)(*acc_parity & 1u) * n_items;
   pdl_trigger();
   pdl_wait();  // the accumulators are complete once the item pass has finished
   for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += gridDim.x * blockDim.x) usum[u] = 0;  // consumed by K2: re-arm for K1
@@ -416,7 +517,8 @@ __global__ void __launch_bounds__(256) item_tiled_push_kernel(const long long* _
   const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < K) {
     const int32_t i = __ldg(known + j);
-    const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);  // (K1 of the next pass re-arms the accumulators)
+    const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
+    xdev_fix[i] = 0;  // re-arm (items known on no rank never leave zero)
     const double cnt = (double)(__ldg(icolp + i + 1) - __ldg(icolp + i));
     for (int p = 0; p < x.world; ++p) {
       double* slot = push_slot(x, p, parity, x.rank);
@@ -605,11 +707,24 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   T.n_slots = (int64_t)rows * 32;
   MRS_TRY(dev_alloc(&T.entry, (size_t)T.n_slots));
   MRS_CUDA(cudaMemsetAsync(T.entry, 0, sizeof(uint32_t) * (size_t)T.n_slots, st));
-  entry_fill_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, T.slice_off, T.entry);
+  const bool reorder = getenv("MRS_REORDER") && atoi(getenv("MRS_REORDER"));
+  if (!reorder)
+    entry_fill_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, T.slice_off, T.entry);
   // ---- item of every slot (empty slots: -1)
   MRS_TRY(dev_alloc(&T.slot_item, (size_t)NS * 32));
   MRS_CUDA(cudaMemsetAsync(T.slot_item, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
-  slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, T.slot_item);
+  int32_t* slot_unit = nullptr;
+  if (reorder) {
+    MRS_TRY(dev_alloc(&slot_unit, (size_t)NS * 32));
+    MRS_CUDA(cudaMemsetAsync(slot_unit, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
+  }
+  slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, T.slot_item, slot_unit);
+  if (reorder) {
+    entry_fill_ordered_kernel<<<(NS + 3) / 4, 128, 0, st>>>(slot_unit, unit_begin, unit_len, unit_tile, NS, perm, R->irow, (const uint8_t*)R->ival, T.slice_off,
+                                                         T.entry);
+    MRS_CUDA(cudaStreamSynchronize(st));
+    dev_free(slot_unit);
+  }
   // ---- static work partition of the item pass: CTAs dealt out to the tiles by cost, then slices to the warps of each CTA.
   // Laid down here, behind the layout's final synchronisation: the item pass reads warp_part in its prologue, before
   // griddepcontrol.wait, so the table must never be written by a kernel of the pass itself.
@@ -657,22 +772,22 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
   if (T.n_ctas > 0) {
     if (m->want_item_avg)
       MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
-                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline));
+                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline, m->counters + 4, R->n_items));
     else
       MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
-                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline));
+                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline, m->counters + 4, R->n_items));
   }
   mark(e, "item_tiled");
   if (no_finalize) return MRS_OK;  // mrs_fit_mae_async: the test pass finishes the fit itself
   if (push) {  // sharded run with the fused exchange: K2b delivers the partial sums to every rank itself
     MRS_CUDA(launch_pdl(item_tiled_push_kernel, dim3((m->n_slots_known + 255) / 256 + 1), dim3(256), 0, st, m->xdev_fix, R->icolp, m->k1_part,
-                        (double)R->n, m->slot_of_item, m->n_slots_known, *push, m->usum, R->n_users, e->d_timeline));
+                        (double)R->n, m->slot_of_item, m->n_slots_known, *push, m->usum, R->n_users, e->d_timeline, m->counters + 4, R->n_items));
     mark(e, "item_tiled_push");
     MRS_CUDA(cudaGetLastError());
     return MRS_OK;
   }
   MRS_CUDA(launch_pdl(item_tiled_finalize_kernel, dim3((R->n_items + 255) / 256), dim3(256), 0, st, m->xdev_fix, m->xcode_sum, R->icolp, R->n_items,
-                      m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg, m->usum, R->n_users, e->d_timeline));
+                      m->k1_part, m->k1_blocks, (double)R->n, m->xbuf, fused ? 1 : 0, m->idevavg, m->iavg, m->gavg, m->usum, R->n_users, e->d_timeline, m->counters + 4));
   mark(e, "item_tiled_finalize");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
