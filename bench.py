@@ -236,10 +236,12 @@ def run_ours(args):
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
     from mrs_b200 import sharded
-    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl, fused=not args.no_fused) if world > 1 else None
+    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl, fused=not args.no_fused, closure=args.closure) if world > 1 else None
 
     def enqueue():
-        if sb is not None:       # local pass -> all-reduce of the exchange buffer -> finish -> MAE -> 16-byte all-reduce
+        if sb is not None and sb.closure:  # three kernels: both exchanges happen inside the test pass (mrs_fit_mae_push_async)
+            sb.closure_step()
+        elif sb is not None:     # local pass -> all-reduce of the exchange buffer -> finish -> MAE -> 16-byte all-reduce
             sb.fit()
             sb.mae_async()
         elif args.no_fold:
@@ -309,6 +311,8 @@ def run_ours(args):
             if sb is None:
                 model.refit()
                 model.mae_async(T, out2.data_ptr())
+            elif sb.closure:
+                sb.closure_step()
             else:            # same number of exchanges on every rank
                 sb.fit_local(); sb.exchange()
                 if sb.peer is not None and not sb.fused and rank == 0 and _ == reps - 1:
@@ -480,7 +484,8 @@ def run_ours(args):
                              "2 cuda graphs + 2 NCCL all-reduces per step")) if graph is not None else "stream launches", "clocks": clocks, "mae": mae, "mae_matches_cpu_port": abs(mae - cpu_mae) <= 1e-6 * abs(cpu_mae),
             "wall_ms_per_step_incl_flush": 1000.0 * t_wall / args.steps,
             "exchange": None if sb is None else ("nccl" if sb.peer is None else
-                                                 {"kind": "fused into the pass' own kernels: partial sums pushed into every rank's receive buffer over NVLink"
+                                                 {"kind": ("both exchanges inside the test pass kernel (mrs_fit_mae_push_async): its CTAs push the per-item partial sums into every rank's receive buffer over NVLink, wait for all flags and sum locally; 3 kernels per step"
+                                                           if sb.closure else "fused into the pass' own kernels: partial sums pushed into every rank's receive buffer over NVLink")
                                                           if sb.fused else "own NVLink peer-memory all-reduce kernel", "timed_out": sb.peer.timed_out()}),
             "step_ms_min_max": [min(step_ms), max(step_ms)],
             "strong_scaling": strong,
@@ -511,7 +516,7 @@ def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, pee
     mtr, mte = sharded.shard_of(tr[0], bounds, rank), sharded.shard_of(te[0], bounds, rank)
     R = eng.ratings(tr[0][mtr], tr[1][mtr], tr[2][mtr], nu_dim, ni_dim)
     T = eng.ratings(te[0][mte], te[1][mte], te[2][mte], nu_dim, ni_dim)
-    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=peer, fused=not args.no_fused)
+    sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=peer, fused=not args.no_fused, closure=args.closure)
     sb.step()
     torch.cuda.synchronize(dev)
     if not args.no_graph:
@@ -551,7 +556,7 @@ def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, pee
                "user_bounds": [int(b) for b in bounds], "train_ratings_rank0": int(mtr.sum()), "test_ratings_rank0": int(mte.sum()),
                "mae": mae, "oracle_mae": ref_mae, "mae_matches_cpu_port": bool(abs(mae - ref_mae) <= 1e-6 * abs(ref_mae)),
                "item_avg_dev_matches_single_gpu_fit": bool(np.all(np.abs(idev - idev1) <= tol)), "item_avg_dev_worst_rel": worst,
-               "exchange": "nccl" if sb.peer is None else ("fused into the pass' kernels (NVLink push)" if sb.fused else "own NVLink peer-memory kernel")}
+               "exchange": "nccl" if sb.peer is None else (("both exchanges inside the test pass kernel (mrs_fit_mae_push_async, 3 kernels per step, NVLink push)" if sb.closure else "fused into the pass' kernels (NVLink push)") if sb.fused else "own NVLink peer-memory kernel")}
         m1.close(); R1.close()
     torch.cuda.synchronize(dev)
     dist.barrier()                 # nobody may still be reading our symmetric buffers when they are unmapped
@@ -716,6 +721,8 @@ def main():
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
                     help="L2 flush between timed iterations: 256 MiB write, or write followed by a 256 MiB read (cold and clean L2)")
     ap.add_argument("--no-fold", action="store_true", help="N=1: mrs_fit_async + mrs_mae_async (4 kernels) instead of mrs_fit_mae_async (3 kernels)")
+    ap.add_argument("--closure", action="store_true", help="N>1: the whole step as mrs_fit_mae_push_async (3 kernels, both exchanges inside the test pass) instead of the "
+                    "fused exchange with its own delivering / finishing kernels (5 kernels); measured slower at 2 ranks (96.1 vs 93.2 us), kept as an option")
     ap.add_argument("--no-fused", action="store_true", help="N>1: separate exchange kernels between the pass' kernels instead of the fused push exchange")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling leg (ONE ml-25m set user-sharded over the ranks)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")

@@ -282,6 +282,17 @@ MRS_API void mrs_multi_destroy(mrs_multi* m);
  * and one dependency less than mrs_fit_async + mrs_mae_async; same results, same model arrays afterwards). */
 MRS_API int32_t mrs_fit_mae_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, const mrs_ratings* test, void* device_out2);
 
+/* The same closure for ONE RANK of a user-sharded run (distributed/DistributedBaseline.scala:30-47 over N partitions): both
+ * exchanges of the pass happen inside the test pass kernel.  Its CTAs first deliver this rank's per-item partial sums
+ * (P:267-268 reduceByKey/collect, P:247 sum/count) into every rank's receive buffer with NVLink stores -- an equal share per
+ * CTA -- then wait for all ranks' flags, build their tile's item deviations from the deliveries in their OWN memory in rank
+ * order (bit-identical on every rank) and write the model's arrays; the last block exchanges {sum |err|, n} (P:256-258).
+ * Three kernels per step and no separate exchange or finishing kernel.  x_items (capacity >= 2*n_known+2 doubles) and
+ * x_pair (>= 2) are two connected exchange handles; device_known_items lists, ascending, the items that occur on SOME rank. */
+MRS_API int32_t mrs_fit_mae_push_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, const mrs_ratings* test,
+                                       mrs_exchange* x_items, mrs_exchange* x_pair, const int32_t* device_known_items, int32_t n_known,
+                                       void* device_out2);
+
 /* ---- recommendations (P:651-674; call site recommend/Recommender.scala:82-88) ---- */
 MRS_API int32_t mrs_recommend(const mrs_model* m, const mrs_sim* sim_or_null, int32_t pred_kind, int32_t user, int32_t n,
                               int32_t* items_out, double* scores_out, int32_t* n_out);

@@ -341,7 +341,7 @@ extern "C" void mrs_model_destroy(mrs_model* m) {
   dev_free(m->uinv_hi); dev_free(m->uinv_lo);
   dev_free(m->usum); dev_free(m->k1_part); dev_free(m->xdev_fix); dev_free(m->xcode_sum);
   dev_free(m->upart); dev_free(m->uavg); dev_free(m->ipart); dev_free(m->xbuf); dev_free(m->idevavg); dev_free(m->iavg);
-  dev_free(m->gavg); dev_free(m->mae_part); dev_free(m->counters); dev_free(m->slot_of_item); dev_free(m->tie_rank); dev_free(m->tie_inv);
+  dev_free(m->gavg); dev_free(m->mae_part); dev_free(m->counters); dev_free(m->slot_of_item); dev_free(m->item_slot); dev_free(m->tie_rank); dev_free(m->tie_inv);
   delete m;
 }
 

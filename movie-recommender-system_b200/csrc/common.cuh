@@ -269,6 +269,7 @@ struct mrs_model {
   int32_t mae_part_cap = 0;
   // fused push exchange (mrs_fit_local_push): the items that occur on some rank, ascending (compact slot j <-> item slot_of_item[j])
   int32_t* slot_of_item = nullptr;  // [n_slots_known]
+  int32_t* item_slot = nullptr;     // [n_items] inverse map (-1: the item occurs on no rank); mrs_fit_mae_push_async
   int32_t n_slots_known = 0;        // K: items that occur on some rank; a delivery is [K dev sums | K counts | sum, n]
   // order of neighbours with EXACTLY equal similarity: 0 = ascending user id, 1 = iteration order of a Scala 2.11
   // immutable.HashSet[Int] (what the reference's stable sort keeps, P:608-610).  tie_rank[c] = place of compact user index c in
@@ -371,7 +372,8 @@ int32_t launch_finish_pull(mrs_model* m, const PushDev& push);
 constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item deviations in shared memory
 int32_t build_mae_layout(const mrs_ratings* T);
 void free_mae_layout(const mrs_ratings* T);
-int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push = nullptr, bool fold = false);
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push = nullptr, bool fold = false,
+                                  const PushDev* big = nullptr);
 // baseline.cu
 int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize, const PushDev* push = nullptr, bool no_finalize = false);
 int32_t fit_finish(mrs_model* m);

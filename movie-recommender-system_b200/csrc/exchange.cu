@@ -399,6 +399,57 @@ extern "C" int32_t mrs_mae_push_async(const mrs_model* m, const mrs_ratings* tes
   return launch_mae_tiled_baseline(m, test, (double*)device_out2, &pd);
 }
 
+namespace mrs {
+namespace {
+__global__ void item_slot_kernel(const int32_t* __restrict__ known, int32_t K, int32_t* __restrict__ item_slot) {
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < K) item_slot[known[j]] = j;
+}
+}  // namespace
+}  // namespace mrs
+
+// The sharded closure MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test) (distributed/DistributedBaseline.scala:45-47)
+// of one rank as THREE kernels: user sums, item pass, and a test pass whose prologue is the exchange of the fit -- every CTA
+// delivers an equal share of the per-item partial sums to every rank, waits for all ranks' flags, builds its tile's
+// deviations from the deliveries in its own memory -- and whose last block exchanges {sum |err|, n}.
+extern "C" int32_t mrs_fit_mae_push_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, const mrs_ratings* test, mrs_exchange* x_items,
+                                          mrs_exchange* x_pair, const int32_t* device_known_items, int32_t n_known, void* device_out2) {
+  MRS_REQUIRE(e && train && inout && *inout && test && x_items && x_pair && device_known_items && device_out2 && n_known >= 0, MRS_ERR_INVALID,
+              "mrs_fit_mae_push_async: NULL argument (pass a model of this train set)");
+  MRS_REQUIRE(x_items != x_pair, MRS_ERR_INVALID, "mrs_fit_mae_push_async: the two exchanges need their own handles (own epoch counters)");
+  MRS_REQUIRE(train->eng == e && test->eng == e, MRS_ERR_INVALID, "mrs_fit_mae_push_async: the rating sets live on another engine");
+  MRS_REQUIRE(train->value_kind == kValueCode && test->value_kind == kValueCode && test->n > 0 && train->n > 0, MRS_ERR_UNSUPPORTED,
+              "mrs_fit_mae_push_async: needs non-empty half-star coded train and test shards");
+  mrs_model* m = *inout;
+  MRS_REQUIRE(!m->want_item_avg, MRS_ERR_UNSUPPORTED, "mrs_fit_mae_push_async: switch item averages off first (mrs_model_set_item_averages)");
+  use_engine(e);
+  if (!m->slot_of_item || !m->item_slot || m->n_slots_known != n_known) {  // first use (never inside a graph capture)
+    dev_free(m->slot_of_item); m->slot_of_item = nullptr;
+    dev_free(m->item_slot); m->item_slot = nullptr;
+    MRS_TRY(dev_alloc(&m->slot_of_item, (size_t)std::max(n_known, 1)));
+    MRS_TRY(dev_alloc(&m->item_slot, (size_t)std::max(m->n_items, 1)));
+    MRS_CUDA(cudaMemcpyAsync(m->slot_of_item, device_known_items, sizeof(int32_t) * (size_t)n_known, cudaMemcpyDeviceToDevice, e->stream));
+    MRS_CUDA(cudaMemsetAsync(m->item_slot, 0xff, sizeof(int32_t) * (size_t)m->n_items, e->stream));  // -1: occurs on no rank
+    if (n_known > 0) {
+      item_slot_kernel<<<(n_known + 255) / 256, 256, 0, e->stream>>>(m->slot_of_item, n_known, m->item_slot);
+      count_launch();
+      MRS_CUDA(cudaGetLastError());
+    }
+    // items known on no rank are never written by the test pass: their deviation is 0.0 (P:197), their count 0
+    MRS_CUDA(cudaMemsetAsync(m->idevavg, 0, sizeof(double) * (size_t)m->n_items, e->stream));
+    MRS_CUDA(cudaMemsetAsync(m->xbuf, 0, sizeof(double) * (2 * (size_t)m->n_items + 2), e->stream));
+    m->n_slots_known = n_known;
+  }
+  PushDev big, pair;
+  MRS_TRY(exchange_push_dev(x_items, 2 * (int64_t)n_known + 2, &big));
+  MRS_TRY(exchange_push_dev(x_pair, 2, &pair));
+  MRS_TRY(fit_local(e, train, inout, false, nullptr, true));
+  MRS_TRY(launch_mae_tiled_baseline(m, test, (double*)device_out2, &pair, true, &big));
+  m->finished = true;  // the test pass has written the model's arrays
+  m->host_valid = false;
+  return MRS_OK;
+}
+
 extern "C" int32_t mrs_exchange_status(mrs_exchange* x, int32_t* timed_out) {
   MRS_REQUIRE(x && timed_out, MRS_ERR_INVALID, "mrs_exchange_status: NULL argument");
   use_engine(x->eng);

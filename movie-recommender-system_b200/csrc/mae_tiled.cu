@@ -76,10 +76,15 @@ struct FoldArgs {
   double* xbuf;
   double* gavg;
   uint32_t* usum;                   // consumed by K2: re-armed here for the next pass' K1
+  // FOLD == 2 (sharded run, mrs_fit_mae_push_async): the per-item exchange of the fit happens in this kernel's prologue
+  const int32_t* known;             // [K] items that occur on some rank, ascending (compact slot j <-> item known[j])
+  const int32_t* item_slot;         // [n_items] inverse: compact slot of an item, -1 if it occurs on no rank
+  int32_t K;
+  PushDev big;                      // exchange handle of the per-item partial sums (2K + 2 doubles per rank)
 };
 
 // one CTA = (item tile, share of the tile's rows); 32 warps, one CTA per SM
-template <bool FOLD>
+template <int FOLD>  // 0: the model is finished; 1: finish it here (single GPU); 2: exchange across ranks + finish it here
 __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const uint2* __restrict__ entry, const int32_t* __restrict__ tile_row_ptr,
                                                                           const int3* __restrict__ cta_desc, int32_t n_users, int32_t n_items,
                                                                           const double* __restrict__ uavg, const double* __restrict__ idevavg,
@@ -127,7 +132,103 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
   pdl_wait();  // barriers, partition and the first ring stages overlapped the end of the fit; its outputs are complete from here on
   const int32_t i0 = tile * kMaeTileItems;
   double gavg;
-  if (FOLD) {
+  bool shard_ok = true;
+  unsigned long long big_epoch = 0;
+  if (FOLD == 2) {
+    // ---- sharded closure: every CTA delivers an equal share of this rank's per-item partial sums into every rank's
+    // receive buffer (NVLink stores), the last CTA to finish raises this rank's flag everywhere, then every CTA waits for
+    // all ranks' flags, builds its tile's deviations from the deliveries in its OWN memory (rank order: bit-identical
+    // totals on every rank) and writes its share of the model's arrays.  No separate exchange or finishing kernel.
+    constexpr double kInvFix = 1.0 / 1099511627776.0;  // 2^-40
+    __shared__ int s_last_cta;
+    const PushDev& x2 = f.big;
+    big_epoch = *x2.epoch + 1;
+    const int xpar = (int)(big_epoch & 1);
+    const unsigned int par = *f.parity & 1u;
+    const long long* __restrict__ fix = f.xdev_fix + (size_t)par * n_items;
+    long long* __restrict__ fix_other = f.xdev_fix + (size_t)(par ^ 1u) * n_items;
+    const int32_t K = f.K;
+    const int32_t perK = (K + gridDim.x - 1) / gridDim.x;
+    const int32_t jlo = blockIdx.x * perK, jhi = min(K, jlo + perK);
+    for (int32_t j = jlo + threadIdx.x; j < jhi; j += kMaeThreads) {
+      const int32_t i = __ldg(f.known + j);
+      const double ds = (double)__ldcg(fix + i) * kInvFix;
+      fix_other[i] = 0;  // re-arm the buffer of the NEXT pass
+      const double cnt = (double)(__ldg(f.icolp + i + 1) - __ldg(f.icolp + i));
+      for (int p = 0; p < x2.world; ++p) {
+        double* slot = push_slot(x2, p, xpar, x2.rank);
+        slot[j] = ds;
+        slot[(size_t)K + j] = cnt;
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const double gs = 0.5 * (double)__ldcg(f.k1_part);
+      for (int p = 0; p < x2.world; ++p) {
+        double* slot = push_slot(x2, p, xpar, x2.rank);
+        slot[2 * (size_t)K] = gs;
+        slot[2 * (size_t)K + 1] = f.n_fit;
+      }
+    }
+    for (int32_t u = blockIdx.x * kMaeThreads + threadIdx.x; u < n_users; u += gridDim.x * kMaeThreads) f.usum[u] = 0;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int last = (atomicAdd(x2.done, 1u) + 1u == gridDim.x);
+      if (last) *x2.done = 0;
+      __threadfence();
+      s_last_cta = last;
+    }
+    __syncthreads();
+    if (s_last_cta && (int)threadIdx.x < x2.world) {
+      __threadfence_system();
+      push_flag_raise(x2, threadIdx.x, big_epoch);
+    }
+    int good = 1;
+    if ((int)threadIdx.x < x2.world) good = push_flag_wait(x2, threadIdx.x, big_epoch) ? 1 : 0;  // every rank has delivered
+    shard_ok = __syncthreads_and(good) != 0;
+    const double bad = nan("");
+    {
+      double gs = 0.0, gc = 0.0;
+      for (int p = 0; p < x2.world; ++p) {  // rank order
+        const double* slot = push_slot(x2, x2.rank, xpar, p);
+        gs += slot[2 * (size_t)K];
+        gc += slot[2 * (size_t)K + 1];
+      }
+      gavg = shard_ok ? (gc > 0.0 ? gs / gc : 0.0) : bad;
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        f.xbuf[2 * (size_t)n_items] = shard_ok ? gs : bad;
+        f.xbuf[2 * (size_t)n_items + 1] = shard_ok ? gc : bad;
+        f.gavg[0] = gavg;
+      }
+    }
+    constexpr int kPer = kMaeTileItems / kMaeThreads;
+#pragma unroll 2
+    for (int k = 0; k < kPer; ++k) {
+      const int32_t i = i0 + k * kMaeThreads + threadIdx.x;
+      const int32_t j = (i < n_items) ? __ldg(f.item_slot + i) : -1;
+      double ds = 0.0, cnt = 0.0;
+      if (j >= 0) {
+        for (int p = 0; p < x2.world; ++p) {
+          const double* slot = push_slot(x2, x2.rank, xpar, p);
+          ds += slot[j];
+          cnt += slot[(size_t)K + j];
+        }
+      }
+      s_dev[k * kMaeThreads + threadIdx.x] = shard_ok ? (cnt > 0.0 ? ds / cnt : 0.0) : bad;
+    }
+    for (int32_t j = jlo + threadIdx.x; j < jhi; j += kMaeThreads) {  // this CTA's share of the model's arrays
+      double ds = 0.0, cnt = 0.0;
+      for (int p = 0; p < x2.world; ++p) {
+        const double* slot = push_slot(x2, x2.rank, xpar, p);
+        ds += slot[j];
+        cnt += slot[(size_t)K + j];
+      }
+      const int32_t i = __ldg(f.known + j);
+      f.xbuf[i] = shard_ok ? ds : bad;
+      f.xbuf[(size_t)n_items + i] = shard_ok ? cnt : bad;
+      f.idevavg[i] = shard_ok ? (cnt > 0.0 ? ds / cnt : 0.0) : bad;
+    }
+  } else if (FOLD == 1) {
     constexpr double kInvFix = 1.0 / 1099511627776.0;  // 2^-40
     constexpr int kPer = kMaeTileItems / kMaeThreads;
     const unsigned int par = *f.parity & 1u;
@@ -248,6 +349,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
         if (FOLD) {
           f.k1_part[0] = 0;  // every CTA has read the code sum: re-arm it for the next pass' K1
           *f.parity ^= 1u;   // ... and the accumulators: the next pass uses the buffer re-armed above
+          if (FOLD == 2) *f.big.epoch = big_epoch;  // every CTA is done with the deliveries of this exchange
         }
       }
     } else {
@@ -277,10 +379,15 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
           s += slot[0];
           c += slot[1];
         }
-        out2[0] = ok ? s : nan("");  // a peer never delivered: the MAE becomes NaN
-        out2[1] = ok ? c : nan("");
+        out2[0] = (ok && shard_ok) ? s : nan("");  // a peer never delivered: the MAE becomes NaN
+        out2[1] = (ok && shard_ok) ? c : nan("");
         *x.epoch = epoch;
         *counter = 0;
+        if (FOLD) {
+          f.k1_part[0] = 0;
+          *f.parity ^= 1u;
+          if (FOLD == 2) *f.big.epoch = big_epoch;
+        }
       }
     }
   }
@@ -350,13 +457,14 @@ int32_t build_mae_layout(const mrs_ratings* T) {
   return MRS_OK;
 }
 
-int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push, bool fold) {
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push, bool fold, const PushDev* big) {
   MRS_TRY(build_mae_layout(T));
   const auto& L = T->ml;
   mrs_engine* e = m->eng;
   if (!(e->smem_attr_done & 2u)) {
-    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
-    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
+    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
+    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
+    MRS_CUDA(cudaFuncSetAttribute(predict_mae_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaeSmem));
     e->smem_attr_done |= 2u;
   }
   const int32_t grid = L.n_ctas;
@@ -367,10 +475,17 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
     const mrs_ratings* R = m->train;
     f.xdev_fix = m->xdev_fix; f.icolp = R->icolp; f.k1_part = m->k1_part; f.n_fit = (double)R->n;
     f.idevavg = m->idevavg; f.xbuf = m->xbuf; f.gavg = m->gavg; f.usum = m->usum; f.parity = m->counters + 4;
-    MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<true>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
-                        m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, 0, PushDev{}, f));
+    if (big) {  // sharded closure: both exchanges inside this kernel
+      MRS_REQUIRE(push && grid <= e->sm_count, MRS_ERR_UNSUPPORTED, "sharded closure: the test pass must be one wave (%d CTAs)", grid);
+      f.known = m->slot_of_item; f.item_slot = m->item_slot; f.K = m->n_slots_known; f.big = *big;
+      MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<2>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
+                          m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, 1, *push, f));
+    } else {
+      MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<1>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
+                          m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, 0, PushDev{}, f));
+    }
   } else {
-    MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<false>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
+    MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<0>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
                         m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, push ? 1 : 0,
                         push ? *push : PushDev{}, f));
   }

@@ -28,7 +28,7 @@ EXPORTS = [
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_model_set_tie_order", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
-    "mrs_mae_async", "mrs_fit_mae_async", "mrs_recommend",
+    "mrs_mae_async", "mrs_fit_mae_async", "mrs_fit_mae_push_async", "mrs_recommend",
 ]
 
 
@@ -132,6 +132,7 @@ def lib():
         "mrs_mae": (i32, [vp, vp, i32, vp, P(dbl)]),
         "mrs_mae_async": (i32, [vp, vp, i32, vp, vp]),
         "mrs_fit_mae_async": (i32, [vp, vp, P(vp), vp, vp]),
+        "mrs_fit_mae_push_async": (i32, [vp, vp, P(vp), vp, vp, vp, vp, i32, vp]),
         "mrs_recommend": (i32, [vp, vp, i32, i32, i32, vp, vp, P(i32)]),
     }
     for name, (res, args) in sig.items():

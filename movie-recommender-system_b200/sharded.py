@@ -89,7 +89,8 @@ class ShardedBaseline:
 
     `engine` must have been created on the CUDA stream the collectives run on (``torch.cuda.current_stream()``)."""
 
-    def __init__(self, engine, train, test, group=None, item_averages=False, peer_exchange=False, peer=None, indexed=True, fused=False):
+    def __init__(self, engine, train, test, group=None, item_averages=False, peer_exchange=False, peer=None, indexed=True, fused=False,
+                 closure=False):
         """``peer_exchange``: create the library's peer-memory exchange object for the two all-reduces (else NCCL through
         torch.distributed).  ``peer``: an existing PeerExchange to reuse instead (its buffers are long-lived IPC mappings;
         a pass that is rebuilt every step, like the end-to-end arm of bench.py, must not create one per step);
@@ -97,7 +98,10 @@ class ShardedBaseline:
         ``fused`` (with ``peer_exchange``): the exchanges happen INSIDE the pass' own kernels -- the fit's last kernel
         delivers its partial sums into every rank's receive buffer over NVLink, the finishing kernel adds the deliveries
         from its own memory, the test pass' last block exchanges {sum |err|, n} itself (``mrs_fit_local_push`` /
-        ``mrs_fit_finish_pull`` / ``mrs_mae_push_async``): two launches and the remote-load round trip fewer per step."""
+        ``mrs_fit_finish_pull`` / ``mrs_mae_push_async``): two launches and the remote-load round trip fewer per step.
+        ``closure`` (with ``fused``): the whole step is ``mrs_fit_mae_push_async`` -- three kernels; the test pass' CTAs deliver
+        the per-item partial sums themselves (an equal share each), wait for all ranks and build their tile's deviations
+        from the deliveries: no separate delivering or finishing kernel."""
         import torch
         from . import engine as E
         self.E, self.torch, self.group = E, torch, group
@@ -114,6 +118,7 @@ class ShardedBaseline:
         self.peer = peer
         self.peer_small = None           # fused mode: the 16-byte exchange has its own handle (its own epoch counter)
         self.fused = False
+        self.closure = False
         self.known = None
         self.xidx = None
         if peer is not None and indexed:
@@ -133,6 +138,7 @@ class ShardedBaseline:
                 if fused and not item_averages:
                     self.peer_small = E.PeerExchange(engine, 2, rank, world, gather)
                     self.fused = True
+                    self.closure = bool(closure)
 
     def _slots_in_use(self, dist, item_averages):
         """Positions of the exchange buffer that are non-zero on SOME rank: the slots of the items that occur in some rank's
@@ -198,15 +204,27 @@ class ShardedBaseline:
         self.step()                                    # first use allocates layouts
         self.torch.cuda.synchronize(self.device)
         if self.peer is not None:                      # our exchange kernels are plain launches: the whole step is ONE graph
+            if self.closure:
+                self._g_all = self.engine.capture(self.closure_step)
+                return
             self._g_all = self.engine.capture(lambda: (self.fit_local(), self.exchange(), self.fit_finish(), self.mae_local(),
                                                        self.mae_exchange()))
             return
         self._g1 = self.engine.capture(self.fit_local)
         self._g2 = self.engine.capture(lambda: (self.fit_finish(), self.mae_local()))
 
+    def closure_step(self):
+        """fit + both exchanges + MAE of this rank's shard as ONE call (three kernels)."""
+        E = self.E
+        E._check(E.lib().mrs_fit_mae_push_async(self.engine._h, self.train._h, E.C.byref(self.model._h), self.test._h, self.peer._h,
+                                                self.peer_small._h, E.C.c_void_p(self.known.data_ptr()), int(self.known.numel()),
+                                                E.C.c_void_p(self.out2.data_ptr())))
+
     def step(self):
         if getattr(self, "_g_all", None) is not None:
             self._g_all.launch()
+        elif self.closure:
+            self.closure_step()
         elif getattr(self, "_g1", None) is not None:
             self._g1.launch(); self.exchange(); self._g2.launch(); self.mae_exchange()
         else:

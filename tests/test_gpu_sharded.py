@@ -132,12 +132,12 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("flag", [[], ["--nccl"], ["--fused"]])
+@pytest.mark.parametrize("flag", [[], ["--nccl"], ["--fused"], ["--fused", "--closure"]])
 def test_two_processes_two_gpus(flag):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", {"": "29615", "--nccl": "29617", "--fused": "29619"}["".join(flag)], os.path.join(ROOT, "tools", "sharded_check.py")] + flag
+           "--master-port", {"": "29615", "--nccl": "29617", "--fused": "29619", "--fused--closure": "29621"}["".join(flag)], os.path.join(ROOT, "tools", "sharded_check.py")] + flag
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-3000:]
     out = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])

@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nccl", action="store_true")
     ap.add_argument("--fused", action="store_true", help="exchanges fused into the pass' kernels (mrs_fit_local_push ...)")
+    ap.add_argument("--closure", action="store_true", help="with --fused: the whole step is mrs_fit_mae_push_async (three kernels)")
     ap.add_argument("--users", type=int, default=30000)
     ap.add_argument("--items", type=int, default=6000)
     ap.add_argument("--ratings", type=int, default=1_500_000)
@@ -41,13 +42,13 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     eng = E.Engine(local, stream=stream.cuda_stream)
     d = synth.ml25m(seed=5, n_users=args.users, n_items=args.items, n_ratings=args.ratings, max_item_id=4 * args.items)
-    out = {"world": world, "exchange": "nccl" if args.nccl else ("fused" if args.fused else "peer")}
+    out = {"world": world, "exchange": "nccl" if args.nccl else (("closure" if args.closure else "fused") if args.fused else "peer")}
 
     def run(tr, te, nu, ni, ref_tr, ref_te, tag):
         with torch.cuda.stream(stream):
             R, T = eng.ratings(*tr, nu, ni), eng.ratings(*te, nu, ni)
-            sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl, fused=args.fused)
-            assert sb.fused == (args.fused and not args.nccl)
+            sb = sharded.ShardedBaseline(eng, R, T, peer_exchange=not args.nccl, fused=args.fused, closure=args.closure)
+            assert sb.fused == (args.fused and not args.nccl) and sb.closure == (sb.fused and args.closure)
             sb.step()
             mae_eager = sb.result()
             sb.capture()
@@ -61,6 +62,9 @@ def main():
             sb.fit_local(); sb.fit_finish()
             sb.fused = was_fused
             idev_local = sb.model.vector(E.ITEM_AVG_DEV)[0]
+            if sb.closure:                                 # ... and the closure still works on the model after that detour
+                sb.step()
+                assert sb.result() == mae, (sb.result(), mae)
             torch.cuda.synchronize(dev)
         if rank == 0:
             from oracle import oracle as O
