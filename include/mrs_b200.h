@@ -92,6 +92,10 @@ MRS_API int32_t mrs_engine_sync(mrs_engine* e);
  * sums, 1 item pass, 2 item finalize, 3 test pass), the earliest block start out32[2k] and the latest block end out32[2k+1]
  * in %globaltimer nanoseconds; the call synchronises, copies them out and re-arms the slots (tools/timeline.py) */
 MRS_API int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32);
+/* per-CTA stamps of the last baseline pass, 4 x 256 values: item pass "table built" and "done", test pass "table built" and "done" */
+MRS_API int32_t mrs_debug_cta_stamps(mrs_engine* e, uint64_t* out1024);
+/* per-warp end stamps and (rows << 32 | slices) of the item pass; filled only by a library built with -DMRS_WARP_STAMPS */
+MRS_API int32_t mrs_debug_warp_stamps(mrs_engine* e, uint64_t* out16384);
 /* diagnostics: measured fp64 FMA rate of the engine's device, FMA per second (denominator of the kNN similarity rooflines) */
 MRS_API int32_t mrs_debug_fp64_fma_per_s(mrs_engine* e, double* out);
 

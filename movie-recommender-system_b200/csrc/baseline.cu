@@ -9,6 +9,7 @@
 // run-to-run bit-reproducible.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -52,9 +53,15 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
   }
 }
 
-// ---- K1 (half-star codes): flat streaming of the padded user-major code array, one 128-bit load (16 codes of ONE
-// user) per thread; lanes of the same user are contiguous, so a segmented shuffle reduction leaves one integer
+// ---- K1 (half-star codes): streaming of the padded user-major code array, one 128-bit load (16 codes of ONE user) per
+// thread and vector; lanes of the same user are contiguous, so a segmented shuffle reduction leaves one integer
 // atomicAdd per (warp, user).  Integer sums are exact: the result does not depend on the order of the atomics.
+// Persistent grid (8 blocks of 256 threads per SM, V = 2 vectors per thread in flight = 80 KB per SM): 5.8 us for 26.5 MB at
+// ml-25m shape; the one-shot grid of 2,590 blocks this replaced took 11-13 us, 4 blocks per SM with V = 4 take 7.5 us
+// (tools/timeline.py, same box).
+#ifndef MRS_K1_V
+#define MRS_K1_V 2
+#endif
 __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
                                                       uint32_t* __restrict__ usum, unsigned long long* __restrict__ gsum_codes,
                                                       unsigned long long* __restrict__ tl) {
@@ -63,31 +70,33 @@ __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict
   pdl_trigger();  // the item pass may start its prologue (ring prefetch) while this kernel runs
 
   const int lane = threadIdx.x & 31;
-  constexpr int V = 2;  // vectors per thread (both loads are issued before the first use)
-  const int32_t t0 = blockIdx.x * (blockDim.x * V) + threadIdx.x;
-  uint4 x[V];
-  int32_t row[V];
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    const int32_t t = t0 + k * blockDim.x;
-    const bool in = t < n_vec;
-    x[k] = in ? __ldg(reinterpret_cast<const uint4*>(uval16) + t) : make_uint4(0u, 0u, 0u, 0u);
-    row[k] = in ? __ldg(vec_row + t) : -1;
-  }
+  constexpr int V = MRS_K1_V;  // vectors per thread and iteration (all loads are issued before the first use)
+  const int32_t T = gridDim.x * blockDim.x;
   uint32_t total = 0;
+  for (int32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 - lane < n_vec; t0 += V * T) {  // warp-uniform trip count
+    uint4 x[V];
+    int32_t row[V];
 #pragma unroll
-  for (int k = 0; k < V; ++k) {
-    uint32_t s = __dp4a(x[k].x, 0x01010101u, __dp4a(x[k].y, 0x01010101u, __dp4a(x[k].z, 0x01010101u, __dp4a(x[k].w, 0x01010101u, 0u))));
-    total += s;
-    // segmented suffix sums over runs of equal row ids (lanes of one user are contiguous)
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_down_sync(0xffffffffu, s, o);
-      const int32_t r = __shfl_down_sync(0xffffffffu, row[k], o);
-      if (lane + o < 32 && r == row[k]) s += v;
+    for (int k = 0; k < V; ++k) {
+      const int64_t t = (int64_t)t0 + (int64_t)k * T;
+      const bool in = t < n_vec;
+      x[k] = in ? __ldg(reinterpret_cast<const uint4*>(uval16) + t) : make_uint4(0u, 0u, 0u, 0u);
+      row[k] = in ? __ldg(vec_row + t) : -1;
     }
-    const int32_t prev = __shfl_up_sync(0xffffffffu, row[k], 1);
-    if (row[k] >= 0 && (lane == 0 || prev != row[k])) atomicAdd(usum + row[k], s);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      uint32_t s = __dp4a(x[k].x, 0x01010101u, __dp4a(x[k].y, 0x01010101u, __dp4a(x[k].z, 0x01010101u, __dp4a(x[k].w, 0x01010101u, 0u))));
+      total += s;
+      // segmented suffix sums over runs of equal row ids (lanes of one user are contiguous)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, s, o);
+        const int32_t r = __shfl_down_sync(0xffffffffu, row[k], o);
+        if (lane + o < 32 && r == row[k]) s += v;
+      }
+      const int32_t prev = __shfl_up_sync(0xffffffffu, row[k], 1);
+      if (row[k] >= 0 && (lane == 0 || prev != row[k])) atomicAdd(usum + row[k], s);
+    }
   }
   total = __reduce_add_sync(0xffffffffu, total);
   if (lane == 0) sh[threadIdx.x >> 5] = total;
@@ -436,7 +445,10 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
     m->n_users = R->n_users;
     m->n_items = R->n_items;
     m->mae_part_cap = e->sm_count * 16;
-    m->k1_blocks = std::max(1, (R->n_vec + 511) / 512);
+    {  // persistent K1: MRS_K1_BPS blocks per SM (default 8), never more blocks than vectors need
+      const int bps = getenv("MRS_K1_BPS") ? std::max(1, atoi(getenv("MRS_K1_BPS"))) : 8;
+      m->k1_blocks = std::max(1, std::min(e->sm_count * bps, (R->n_vec + 255) / 256));
+    }
     int32_t s = MRS_OK;
     if (codes) {
       if (s == MRS_OK) s = dev_alloc(&m->usum, (size_t)R->n_users);

@@ -176,8 +176,8 @@ extern "C" int32_t mrs_engine_create(int32_t device, void* cuda_stream, mrs_engi
     return MRS_ERR_CUDA;
   }
   if (getenv("MRS_TIMELINE") && atoi(getenv("MRS_TIMELINE"))) {  // diagnostics: per-kernel start/end stamps of a pass
-    if (cudaMalloc((void**)&e->d_timeline, 32 * sizeof(unsigned long long)) != cudaSuccess) e->d_timeline = nullptr;
-    if (e->d_timeline) cudaMemset(e->d_timeline, 0, 32 * sizeof(unsigned long long));
+    if (cudaMalloc((void**)&e->d_timeline, (32 + 1024 + 16384) * sizeof(unsigned long long)) != cudaSuccess) e->d_timeline = nullptr;
+    if (e->d_timeline) cudaMemset(e->d_timeline, 0, (32 + 1024 + 16384) * sizeof(unsigned long long));
   }
   cudaError_t he = cudaMallocHost((void**)&e->h_pinned, 64 * sizeof(double));
   if (he != cudaSuccess) { set_error("cudaMallocHost failed: %s", cudaGetErrorString(he)); mrs_engine_destroy(e); return MRS_ERR_NOMEM; }
@@ -209,6 +209,25 @@ extern "C" int32_t mrs_debug_timeline(mrs_engine* e, uint64_t* out32) {
   uint64_t init[32];
   for (int k = 0; k < 32; ++k) init[k] = (k & 1) ? 0ull : ~0ull;
   MRS_CUDA(cudaMemcpy(e->d_timeline, init, sizeof(init), cudaMemcpyHostToDevice));
+  return MRS_OK;
+}
+
+// per-CTA stamps of the last pass (MRS_TIMELINE=1): [0,256) item pass: table built, streaming starts; [256,512) item pass: CTA done;
+// [512,768) test pass: table built; [768,1024) test pass: CTA done (ns of %globaltimer; 0 = CTA index not used)
+extern "C" int32_t mrs_debug_cta_stamps(mrs_engine* e, uint64_t* out1024) {
+  MRS_REQUIRE(e && out1024, MRS_ERR_INVALID, "mrs_debug_cta_stamps: NULL argument");
+  MRS_REQUIRE(e->d_timeline, MRS_ERR_INVALID, "mrs_debug_cta_stamps: the engine was created without MRS_TIMELINE=1");
+  MRS_CUDA(cudaStreamSynchronize(e->stream));
+  MRS_CUDA(cudaMemcpy(out1024, e->d_timeline + 32, 1024 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  MRS_CUDA(cudaMemset(e->d_timeline + 32, 0, 1024 * sizeof(uint64_t)));
+  return MRS_OK;
+}
+// per-warp stamps of the item pass (library built with -DMRS_WARP_STAMPS): [0,8192) end time of warp (cta*32 + w), [8192,16384) rows << 32 | slices
+extern "C" int32_t mrs_debug_warp_stamps(mrs_engine* e, uint64_t* out16384) {
+  MRS_REQUIRE(e && out16384, MRS_ERR_INVALID, "mrs_debug_warp_stamps: NULL argument");
+  MRS_REQUIRE(e->d_timeline, MRS_ERR_INVALID, "mrs_debug_warp_stamps: the engine was created without MRS_TIMELINE=1");
+  MRS_CUDA(cudaStreamSynchronize(e->stream));
+  MRS_CUDA(cudaMemcpy(out16384, e->d_timeline + 32 + 1024, 16384 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return MRS_OK;
 }
 

@@ -66,6 +66,10 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 __device__ __forceinline__ void tl_begin(unsigned long long* tl, int k) {
   if (tl && threadIdx.x == 0) atomicMin(tl + 2 * k, gtimer_ns());
 }
+// per-CTA stamp (slot 0..3, see mrs_debug_cta_stamps)
+__device__ __forceinline__ void tl_cta(unsigned long long* tl, int slot) {
+  if (tl && threadIdx.x == 0 && blockIdx.x < 256) tl[32 + slot * 256 + blockIdx.x] = gtimer_ns();
+}
 __device__ __forceinline__ void tl_end(unsigned long long* tl, int k) {
   if (tl && threadIdx.x == 0) atomicMax(tl + 2 * k + 1, gtimer_ns());
 }
@@ -139,7 +143,7 @@ struct mrs_engine {
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remembered per engine, not per process
   // (bit 0: item pass kernels, bit 1: test pass kernel)
   uint32_t smem_attr_done = 0;
-  unsigned long long* d_timeline = nullptr;  // [32] diagnostics, allocated when MRS_TIMELINE=1 (mrs_debug_timeline)
+  unsigned long long* d_timeline = nullptr;  // [32 + 1024] diagnostics, allocated when MRS_TIMELINE=1 (mrs_debug_timeline, mrs_debug_cta_stamps)
   // diagnostics: event after every launch while profiling (mrs_profile_begin/end)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -220,7 +224,9 @@ struct mrs_ratings {
     int32_t n_units = 0;
     int32_t n_slices = 0;
     int64_t n_slots = 0;               // 32 * (rows of all slices)
-    uint32_t* entry = nullptr;         // [n_slots] bit31 valid | code << 16 | user id local to the tile
+    uint32_t* entry = nullptr;         // [n_slots] form 0: bit31 valid | code << 16 | user id local to the tile
+                                       //           form 1: top 15 bits of the fp64 (code-2)/8 | bit16 padding | local user << 3
+    int32_t form = 0;                  // 1 when every code is <= kAlphaMaxCode and every user has < 2^17 ratings (tiled.cu)
     int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
     int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
     int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
@@ -229,7 +235,7 @@ struct mrs_ratings {
     // cost, tiles without ratings (a rank of a sharded run owns a user range) get none
     int32_t n_ctas = 0;
     int3* cta_desc = nullptr;          // [n_ctas]
-    int2* warp_part = nullptr;         // [n_ctas * 32] slices [x, y) of every warp
+    int4* warp_part = nullptr;         // [n_ctas * 32] rows [x, y) of every warp, first slice, one past the last slice
   };
   mutable tiled_layout tl;
   // ---- lazily built item-tiled layout for the fused predict + |error| kernel (mae_tiled.cu); half-star codes only

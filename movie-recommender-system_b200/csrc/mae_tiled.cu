@@ -58,8 +58,14 @@ __global__ void mae_scatter_kernel(const uint16_t* __restrict__ key, const int32
 }
 
 constexpr int kMaeThreads = 1024;
-constexpr int kMaeRows = 8;    // rows (32 entries of 8 bytes = 256 B) per ring stage: 2 KB
-constexpr int kMaeStages = 2;
+#ifndef MRS_K3_ROWS
+#define MRS_K3_ROWS 8
+#endif
+#ifndef MRS_K3_STAGES
+#define MRS_K3_STAGES 2
+#endif
+constexpr int kMaeRows = MRS_K3_ROWS;      // rows (32 entries of 8 bytes = 256 B) per ring stage
+constexpr int kMaeStages = MRS_K3_STAGES;
 constexpr size_t kMaeSmem = (size_t)kMaeTileItems * 8 + (size_t)(kMaeThreads / 32) * kMaeStages * kMaeRows * 256 + (size_t)(kMaeThreads / 32) * kMaeStages * 8;
 
 // FOLD: the test pass finishes the fit itself (single-GPU closure MeanAbsoluteErrorSpark(baselinePredictorSpark(train), test),
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     gavg = gavg_p[0];
   }
   __syncthreads();
+  tl_cta(tl, 2);
 
   double acc = 0.0;
   const double* ua_base = uavg;
@@ -322,6 +329,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
   acc = warp_sum(acc);
   if (lane == 0) sh[wid] = acc;
   __syncthreads();
+  tl_cta(tl, 3);
   if (threadIdx.x < 32) {
     double t = (threadIdx.x < wpb) ? sh[threadIdx.x] : 0.0;
     t = warp_sum(t);

@@ -109,10 +109,38 @@ __global__ void slot_assign_kernel(const int32_t* __restrict__ sorted_id, const 
   if (lane == 0) slice_width[slice] = unit_len[id];
 }
 
+// Entry word of one rating.  Form 0 (any half-star code): valid bit | code << 16 | local user.  Form 1 (codes <= kAlphaMaxCode,
+// i.e. every MovieLens-style scale): the pass works in fp64 on exact small integers, so the word carries what the inner loop
+// would otherwise have to compute or convert per rating: bits 31..17 = the top 15 bits (sign, exponent, 3 mantissa bits) of
+// the fp64 number alpha = (code - 2)/8 -- all of it, the rest of the mantissa is zero -- and bits 15..3 = the local user,
+// already scaled to the byte offset of its 8-byte table record.  Bit 16 marks padding: it selects the all-zero record
+// behind the tile's users, which makes the deviation of a padding slot exactly 0 without a test.
+constexpr int kAlphaMaxCode = 17;
+constexpr uint32_t kAlphaPadding = 0x00010000u;
+__device__ __forceinline__ uint32_t make_entry(int form, uint32_t code, uint32_t local_user) {
+  if (form == 0) return 0x80000000u | (code << 16) | local_user;
+  const double alpha = (double)((int32_t)code - 2) * 0.125;
+  return ((uint32_t)__double2hiint(alpha) & 0xfffe0000u) | (local_user << 3);
+}
+
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t v) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) p[q] = v;
+}
+
+// largest code of the set and largest rating count of a user: decide the entry form
+__global__ void form_scan_kernel(const uint8_t* __restrict__ ival, int64_t n, const int32_t* __restrict__ urow, int32_t n_users, int32_t* __restrict__ out2) {
+  int32_t mc = 0, mu = 0;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) mc = max(mc, (int32_t)ival[q]);
+  for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += gridDim.x * blockDim.x) mu = max(mu, urow[u + 1] - urow[u]);
+  mc = __reduce_max_sync(0xffffffffu, mc);
+  mu = __reduce_max_sync(0xffffffffu, mu);
+  if ((threadIdx.x & 31) == 0) { atomicMax(out2, mc); atomicMax(out2 + 1, mu); }
+}
+
 __global__ void entry_fill_kernel(const int32_t* __restrict__ unit_begin, const int32_t* __restrict__ unit_len,
                                   const int32_t* __restrict__ unit_slot, const int32_t* __restrict__ unit_tile, int32_t n_units,
                                   const int32_t* __restrict__ perm, const int32_t* __restrict__ irow, const uint8_t* __restrict__ ival,
-                                  const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry) {
+                                  const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry, int form) {
   const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_units) return;
   const int32_t b = unit_begin[id], len = unit_len[id], slot = unit_slot[id];
@@ -121,7 +149,7 @@ __global__ void entry_fill_kernel(const int32_t* __restrict__ unit_begin, const 
   const int32_t ubase = unit_tile[id] * kTileUsers;
   for (int32_t j = 0; j < len; ++j) {
     const int32_t p = perm[b + j];
-    entry[((row0 + j) << 5) + lane] = 0x80000000u | ((uint32_t)ival[p] << 16) | (uint32_t)(irow[p] - ubase);
+    entry[((row0 + j) << 5) + lane] = make_entry(form, (uint32_t)ival[p], (uint32_t)(irow[p] - ubase));
   }
 }
 
@@ -145,7 +173,7 @@ __global__ void __launch_bounds__(128) entry_fill_ordered_kernel(const int32_t* 
                                                                 const int32_t* __restrict__ unit_len, const int32_t* __restrict__ unit_tile,
                                                                 int32_t n_slices, const int32_t* __restrict__ perm,
                                                                 const int32_t* __restrict__ irow, const uint8_t* __restrict__ ival,
-                                                                const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry) {
+                                                                const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry, int form) {
   __shared__ uint32_t s_ent[4][32 * kUnitLen];   // entries of the lane's unit, grouped by key
   __shared__ uint8_t s_next[4][32][16];          // next unplaced entry of every key group
   __shared__ uint8_t s_end[4][32][16];
@@ -181,7 +209,7 @@ __global__ void __launch_bounds__(128) entry_fill_ordered_kernel(const int32_t* 
   for (int32_t j = 0; j < len; ++j) {
     const int32_t p = perm[b + j];
     const int32_t x = irow[p] - ubase;
-    ent[nxt[x & 15]++] = 0x80000000u | ((uint32_t)ival[p] << 16) | (uint32_t)x;
+    ent[nxt[x & 15]++] = make_entry(form, (uint32_t)ival[p], (uint32_t)x);
   }
   {
     int32_t run = 0;
@@ -252,19 +280,18 @@ __device__ __forceinline__ double fast_rcp(double s) {
 // lane's unit sum is handed over.  Unit sums are fp64 (fixed order inside the unit); they are combined across units
 // with integer atomics on a 2^-40 grid, which is exact, so the item sums do not depend on the order of arrival.
 constexpr int kTiledThreads = 1024;
-#ifdef MRS_AB_ROWS16
-constexpr int kRows = 16;
-constexpr int kStages = 2;
-#elif defined(MRS_AB_STAGES3)
-constexpr int kRows = 8;
-constexpr int kStages = 3;
-#else
-constexpr int kRows = 8;    // rows per ring stage (1 KB)
-constexpr int kStages = 4;  // ring depth per warp
+#ifndef MRS_K2_ROWS
+#define MRS_K2_ROWS 8
 #endif
-constexpr int kSliceCost = 3;
+#ifndef MRS_K2_STAGES
+#define MRS_K2_STAGES 4
+#endif
+constexpr int kRows = MRS_K2_ROWS;      // rows per ring stage (128 B each)
+constexpr int kStages = MRS_K2_STAGES;  // ring depth per warp
+constexpr int kSliceCost = 4;  // rows a slice boundary is worth (per-warp stamps, least squares: 0.092 us per row, 0.33 us per slice)
 constexpr double kFixScale = 1099511627776.0;  // 2^40
-constexpr size_t kTiledSmem = (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128 + (size_t)(kTiledThreads / 32 * kStages) * 8;
+constexpr size_t kTabBytes = (size_t)kTileUsers * 8 + 128;  // the tile's user records + the all-zero record of the padding slots (form 1)
+constexpr size_t kTiledSmem = kTabBytes + (size_t)(kTiledThreads / 32) * kStages * kRows * 128 + (size_t)(kTiledThreads / 32 * kStages) * 8;
 
 // first slice s in [lo, hi) whose cost prefix (rows before it + kSliceCost * slices before it) is >= v
 __device__ __forceinline__ int32_t lower_bound_cost(const int32_t* __restrict__ slice_off, int32_t lo, int32_t hi, int32_t row_base, int32_t v) {
@@ -291,6 +318,36 @@ __device__ __forceinline__ double tiled_dev(uint32_t e, const uint2* __restrict_
   return (N != 0 && (int32_t)e < 0) ? dev : 0.0;        // r == avg -> 0/1 = 0; padding (valid bit clear) contributes nothing
 }
 
+// Form 1: the same quotient N/D with every per-rating integer operation and conversion moved out of the loop.  The record
+// of a user holds the HIGH WORDS of the two fp64 numbers Dup = 10c - S and Ddn = S - 2c (integers below 2^21: their low
+// words are zero), the entry holds the high word of alpha = (code - 2)/8.  With t = Dup + Ddn = 8c,
+//     N = c*code - S = alpha*t - Ddn          (one DADD, one DFMA, both exact: small integers)
+// the sign of N is read off its high word, D is picked by a 32-bit select, and N == 0 (r == avg, P:60 scale 1, and every
+// padding slot, whose record is all zero) takes D = 1.0 so that the product is an exact 0.  Per rating: 2 shared-memory
+// loads, 1 MUFU, 7 fp64 operations and a handful of integer ones, against 2 I2F + MUFU + 5 fp64 + ~20 integer before.
+__device__ __forceinline__ double tiled_dev_alpha(uint32_t e, const unsigned char* __restrict__ s_tab) {
+#ifdef MRS_AB_NOGATHER  // timing experiment only: every entry reads the record of its lane (conflict free)
+  const uint2 rec = *reinterpret_cast<const uint2*>(s_tab + ((threadIdx.x & 31u) << 3) + (e & 0x100u));
+#else
+  const uint2 rec = *reinterpret_cast<const uint2*>(s_tab + (e & 0x1fff8u));
+#endif
+#ifdef MRS_AB_NOMATH    // timing experiment only: no reciprocal
+  return __hiloint2double((int)rec.x, (int)(e & 0xfffe0000u));
+#endif
+  const double dup = __hiloint2double((int)rec.x, 0), ddn = __hiloint2double((int)rec.y, 0);
+  const double alpha = __hiloint2double((int)(e & 0xfffe0000u), 0);
+  const double N = fma(alpha, dup + ddn, -ddn);
+  const int nh = __double2hiint(N);
+  int dh = nh > 0 ? (int)rec.x : (int)rec.y;
+  dh = nh == 0 ? 0x3ff00000 : dh;  // N is an exact integer and never -0.0: alpha*t is +0 or non-zero, and +0 - (+0) = +0
+  return N * fast_rcp(__hiloint2double(dh, 0));
+}
+// code of a form-1 entry (only the pass that also sums the ratings per item needs it): 8*alpha + 2, 0 for padding
+__device__ __forceinline__ uint32_t alpha_code(uint32_t e) {
+  const double alpha = __hiloint2double((int)(e & 0xfffe0000u), 0);
+  return (e & kAlphaPadding) ? 0u : (uint32_t)(__double2int_rn(alpha * 8.0) + 2);
+}
+
 template <bool WITH_SUM>
 __device__ __forceinline__ void hand_over(int32_t item, double acc, uint32_t csum, long long* __restrict__ xdev_fix,
                                           unsigned long long* __restrict__ xcode_sum) {
@@ -300,9 +357,23 @@ __device__ __forceinline__ void hand_over(int32_t item, double acc, uint32_t csu
   }
 }
 
-// slices [x, y) of every warp of the item pass: an equal share of its tile's cost, rounded to whole slices
+// Rows [x, y) of every warp of the item pass, .z = the slice that holds row x, .w = one past the slice that holds row y-1: an
+// equal share of its tile's cost (rows + kSliceCost per slice), cut at ROW granularity.  A range may begin or end inside a
+// slice: the two warps then hand over one partial sum each for the units of that slice (exact integer atomics, so the item
+// sums stay deterministic).  Cutting at whole slices left the warps with 2 or 3 of the 64-row slices of the popular items --
+// 128 against 192 rows, and every CTA as slow as its 192-row warps (per-warp stamps: 33 us against 42 us).
+__device__ __forceinline__ int2 cost_position(const int32_t* __restrict__ slice_off, int32_t ts0, int32_t ts1, int32_t ra, int32_t v) {
+  const int32_t f = lower_bound_cost(slice_off, ts0, ts1, ra, v);  // first slice whose cost prefix is >= v
+  if (f < ts1 && __ldg(slice_off + f) - ra + kSliceCost * (f - ts0) == v) return make_int2(f, __ldg(slice_off + f));
+  const int32_t sl = f - 1;                                        // the slice that holds cost value v
+  const int32_t b = __ldg(slice_off + sl), e = __ldg(slice_off + sl + 1);
+  const int32_t off = v - (b - ra + kSliceCost * (sl - ts0)) - kSliceCost;  // the slice's fixed cost is paid at its start
+  const int32_t row = b + max(0, min(off, e - b));
+  return row == e ? make_int2(sl + 1, row) : make_int2(sl, row);
+}
+
 __global__ void __launch_bounds__(kTiledThreads) item_partition_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ tile_slice_ptr,
-                                                                      const int3* __restrict__ cta_desc, int2* __restrict__ warp_part) {
+                                                                      const int3* __restrict__ cta_desc, int4* __restrict__ warp_part) {
   if ((threadIdx.x & 31) != 0) return;
   const int3 cd = cta_desc[blockIdx.x];
   const int32_t tile = cd.x, share = cd.y, ctas_per_tile = cd.z;
@@ -313,14 +384,15 @@ __global__ void __launch_bounds__(kTiledThreads) item_partition_kernel(const int
   const int32_t nw = ctas_per_tile * wpb, w = share * wpb + wid;
   const int64_t total_cost = (int64_t)(rb - ra) + (int64_t)kSliceCost * (ts1 - ts0);
   const int32_t c_lo = (int32_t)((total_cost * w) / nw), c_hi = (int32_t)((total_cost * (w + 1)) / nw);
-  const int32_t cur = lower_bound_cost(slice_off, ts0, ts1, ra, c_lo);   // slices whose cost prefix lies in [c_lo, c_hi)
-  const int32_t s_hi = lower_bound_cost(slice_off, ts0, ts1, ra, c_hi);
-  warp_part[(size_t)blockIdx.x * wpb + wid] = make_int2(cur, s_hi);
+  const int2 lo = (w == 0) ? make_int2(ts0, ra) : cost_position(slice_off, ts0, ts1, ra, c_lo);
+  const int2 hi = (w == nw - 1) ? make_int2(ts1, rb) : cost_position(slice_off, ts0, ts1, ra, c_hi);
+  const int32_t s_hi = (hi.x < ts1 && hi.y > __ldg(slice_off + hi.x)) ? hi.x + 1 : hi.x;
+  warp_part[(size_t)blockIdx.x * wpb + wid] = (lo.y < hi.y) ? make_int4(lo.y, hi.y, lo.x, s_hi) : make_int4(0, 0, 0, 0);
 }
 
-template <bool WITH_SUM>
+template <bool WITH_SUM, int FORM>
 __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint32_t* __restrict__ entry, const int32_t* __restrict__ slice_off,
-                                                                     const int2* __restrict__ warp_part, const int3* __restrict__ cta_desc,
+                                                                     const int4* __restrict__ warp_part, const int3* __restrict__ cta_desc,
                                                                      const uint32_t* __restrict__ usum, const int32_t* __restrict__ urow,
                                                                      int32_t n_users, const int32_t* __restrict__ slot_item,
                                                                      double* __restrict__ uavg, long long* __restrict__ xdev_fix_both,
@@ -331,9 +403,9 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
   // the accumulator buffer of this pass (two buffers alternate when the test pass finishes the fit itself: it cannot re-arm
   // the buffer it reads, so it re-arms the other one; the parity only changes between passes)
   long long* __restrict__ xdev_fix = xdev_fix_both + (size_t)(*parity & 1u) * n_items_acc;
-  uint2* s_sc = reinterpret_cast<uint2*>(smem_raw);                                       // [kTileUsers] (code sum, count)
-  uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTileUsers * 8);      // [warps][kStages][kRows*32]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTileUsers * 8 + (size_t)(kTiledThreads / 32) * kStages * kRows * 128);
+  uint2* s_sc = reinterpret_cast<uint2*>(smem_raw);                           // [kTileUsers (+ the padding record)] (code sum, count) or (Dup, Ddn)
+  uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw + kTabBytes);       // [warps][kStages][kRows*32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + kTabBytes + (size_t)(kTiledThreads / 32) * kStages * kRows * 128);
   const int3 cd = cta_desc[blockIdx.x];
   const int32_t tile = cd.x, share = cd.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -348,15 +420,13 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
   }
   __syncwarp();
 
-  // ---- this warp's slices: an equal share of the tile's cost, rounded to whole slices
-  // (cost of a slice = its rows + kSliceCost for handing over 32 unit sums; the tail of a tile is made of 1-2 row slices)
-  // (the partition is static: item_partition_kernel ran the two binary searches per warp once, when the layout was built --
-  // 28 dependent loads that used to open every pass)
-  const int2 part = __ldg(warp_part + (size_t)blockIdx.x * wpb + wid);
-  int32_t cur = part.x;
-  const int32_t s_hi = part.y;
-  const int32_t r0 = (cur < s_hi) ? __ldg(slice_off + cur) : 0;
-  const int32_t r_end = (cur < s_hi) ? __ldg(slice_off + s_hi) : 0;
+  // ---- this warp's rows: an equal share of the tile's cost (a row costs 1, a slice boundary kSliceCost: handing over 32 unit
+  // sums and fetching the next slice's items), cut at row granularity.  The partition is static: item_partition_kernel ran
+  // the binary searches once, when the layout was built -- 28 dependent loads that used to open every pass.
+  const int4 part = __ldg(warp_part + (size_t)blockIdx.x * wpb + wid);
+  const int32_t r0 = part.x, r_end = part.y;   // rows of this warp; the first and the last slice may be shared with a neighbour
+  int32_t cur = part.z;
+  const int32_t s_hi = part.w;
   const int32_t n_chunks = (r_end - r0 + kRows - 1) / kRows;
   if (lane == 0) {  // the first kStages chunks go out before the averages are formed
 #pragma unroll
@@ -387,12 +457,19 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
       const bool in = u < n_users;
       const uint32_t S = in ? __ldg(usum + u) : 0u;
       const uint32_t cnt = in ? (uint32_t)(__ldg(urow + u + 1) - __ldg(urow + u)) : 0u;
-      s_sc[x] = make_uint2(S, cnt);
+      if (FORM == 0) {
+        s_sc[x] = make_uint2(S, cnt);
+      } else {  // high words of the fp64 numbers 10c - S and S - 2c (below 2^21 in magnitude: the low words are zero)
+        s_sc[x] = make_uint2((uint32_t)__double2hiint((double)((int32_t)(10u * cnt) - (int32_t)S)),
+                             (uint32_t)__double2hiint((double)((int32_t)S - (int32_t)(2u * cnt))));
+      }
       if (share == 0 && in)  // exact sum, one correctly rounded division (P:18); -1.0: no ratings (the reference's sentinel, P:222)
         uavg[u] = cnt ? (0.5 * (double)S) / (double)cnt : -1.0;
     }
+    if (FORM == 1 && threadIdx.x == 0) s_sc[kTileUsers] = make_uint2(0u, 0u);  // the record of the padding slots
   }
   __syncthreads();
+  tl_cta(tl, 0);
 
   double acc = 0.0;
   uint32_t csum = 0;
@@ -402,14 +479,18 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
     const int32_t nrows = min(kRows, r_end - r);
     tma::mbar_wait(bar + st, (uint32_t)(c / kStages) & 1u);
     const uint32_t* rp = ring + st * kRows * 32 + lane;  // conflict free: lane l reads word l of a row
+#ifdef MRS_AB_NOBOUND  // timing experiment only (wrong sums): no slice boundaries, one hand-over per warp
+    const bool plain = (nrows == kRows);
+#else
     const bool plain = (nrows == kRows) && (end1 > r) && (end1 >= r + kRows);  // whole chunk inside the current slice
+#endif
     uint32_t ev[kRows];
     if (plain) {
 #pragma unroll
       for (int k = 0; k < kRows; ++k) ev[k] = rp[k * 32];
     } else {
 #pragma unroll
-      for (int k = 0; k < kRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : 0u;
+      for (int k = 0; k < kRows; ++k) ev[k] = (k < nrows) ? rp[k * 32] : (FORM == 1 ? kAlphaPadding : 0u);
     }
     __syncwarp();
     if (lane == 0 && c + kStages < n_chunks) {  // the stage is free again: request the chunk kStages ahead
@@ -420,12 +501,13 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
     }
     double dv[kRows];
 #pragma unroll
-    for (int k = 0; k < kRows; ++k) dv[k] = tiled_dev(ev[k], s_sc);  // heavy part: no branches, 8 independent chains
+    for (int k = 0; k < kRows; ++k)  // heavy part: no branches, 8 independent chains
+      dv[k] = FORM == 1 ? tiled_dev_alpha(ev[k], smem_raw) : tiled_dev(ev[k], s_sc);
     if (plain) {
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         acc += dv[k];
-        if (WITH_SUM) csum += (ev[k] >> 16) & 0xffu;
+        if (WITH_SUM) csum += FORM == 1 ? alpha_code(ev[k]) : ((ev[k] >> 16) & 0xffu);
       }
     } else {
 #pragma unroll
@@ -439,12 +521,18 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
           item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
         }
         acc += dv[k];
-        if (WITH_SUM) csum += (ev[k] >> 16) & 0xffu;
+        if (WITH_SUM) csum += FORM == 1 ? alpha_code(ev[k]) : ((ev[k] >> 16) & 0xffu);
       }
     }
   }
   if (cur < s_hi) hand_over<WITH_SUM>(item1, acc, csum, xdev_fix, xcode_sum);  // last slice of the range
-  if (tl) { __syncthreads(); tl_end(tl, 1); }
+#ifdef MRS_WARP_STAMPS
+  if (tl && lane == 0 && blockIdx.x < 256) {
+    tl[32 + 1024 + blockIdx.x * 32 + wid] = gtimer_ns();
+    tl[32 + 1024 + 8192 + blockIdx.x * 32 + wid] = ((unsigned long long)(r_end - r0) << 32) | (unsigned int)(s_hi - part.z);
+  }
+#endif
+  if (tl) { __syncthreads(); tl_cta(tl, 1); tl_end(tl, 1); }
 }
 
 // K2b: per item, integer accumulators -> exchange buffer (and re-arm them for the next pass); optionally finish the fit
@@ -706,10 +794,26 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   MRS_CUDA(cudaStreamSynchronize(st));
   T.n_slots = (int64_t)rows * 32;
   MRS_TRY(dev_alloc(&T.entry, (size_t)T.n_slots));
-  MRS_CUDA(cudaMemsetAsync(T.entry, 0, sizeof(uint32_t) * (size_t)T.n_slots, st));
+  {  // entry form: the fp64 form needs codes <= kAlphaMaxCode and |10c - S|, |S - 2c| < 2^21 (MRS_FORM=0 forces the integer form)
+    int32_t* d_mx = nullptr;
+    int32_t h_mx[2] = {0, 0};
+    MRS_TRY(dev_alloc(&d_mx, 2));
+    MRS_CUDA(cudaMemsetAsync(d_mx, 0, 2 * sizeof(int32_t), st));
+    form_scan_kernel<<<grid, block, 0, st>>>((const uint8_t*)R->ival, n, R->urow, R->n_users, d_mx);
+    MRS_CUDA(cudaMemcpyAsync(h_mx, d_mx, sizeof(h_mx), cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_mx);
+    const bool forced0 = getenv("MRS_FORM") && atoi(getenv("MRS_FORM")) == 0;
+    T.form = (!forced0 && h_mx[0] <= kAlphaMaxCode && h_mx[1] < (1 << 17)) ? 1 : 0;
+  }
+  if (T.form == 1)
+    fill_u32_kernel<<<grid_for(T.n_slots, block, e->sm_count), block, 0, st>>>(T.entry, T.n_slots, kAlphaPadding);
+  else
+    MRS_CUDA(cudaMemsetAsync(T.entry, 0, sizeof(uint32_t) * (size_t)T.n_slots, st));
   const bool reorder = getenv("MRS_REORDER") && atoi(getenv("MRS_REORDER"));
   if (!reorder)
-    entry_fill_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, T.slice_off, T.entry);
+    entry_fill_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, T.slice_off, T.entry,
+                                               T.form);
   // ---- item of every slot (empty slots: -1)
   MRS_TRY(dev_alloc(&T.slot_item, (size_t)NS * 32));
   MRS_CUDA(cudaMemsetAsync(T.slot_item, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
@@ -721,7 +825,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, T.slot_item, slot_unit);
   if (reorder) {
     entry_fill_ordered_kernel<<<(NS + 3) / 4, 128, 0, st>>>(slot_unit, unit_begin, unit_len, unit_tile, NS, perm, R->irow, (const uint8_t*)R->ival, T.slice_off,
-                                                         T.entry);
+                                                         T.entry, T.form);
     MRS_CUDA(cudaStreamSynchronize(st));
     dev_free(slot_unit);
   }
@@ -747,7 +851,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
       MRS_CUDA(cudaStreamSynchronize(st));  // `desc` (pageable host memory) must outlive the copy
     }
   }
-  count_launch(21);
+  count_launch(23);
   MRS_CUDA(cudaGetLastError());
   MRS_CUDA(cudaStreamSynchronize(st));
   for (void* p : {(void*)tk_in, (void*)tk_out, (void*)pos_in, (void*)perm, (void*)item_of, (void*)head, (void*)seg_start, (void*)flag,
@@ -763,19 +867,24 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
   const auto& T = R->tl;
   cudaStream_t st = e->stream;
   if (!(e->smem_attr_done & 1u)) {
-    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
-    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
+    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
+    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
+    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
+    MRS_CUDA(cudaFuncSetAttribute(item_tiled_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmem));
     e->smem_attr_done |= 1u;
   }
   // one CTA of 1024 threads per SM: the grid (T.n_ctas <= SM count unless there are more busy tiles than SMs) is one wave
   const dim3 grid2(T.n_ctas), block2(kTiledThreads);
   if (T.n_ctas > 0) {
-    if (m->want_item_avg)
-      MRS_CUDA(launch_pdl(item_tiled_kernel<true>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
-                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline, m->counters + 4, R->n_items));
-    else
-      MRS_CUDA(launch_pdl(item_tiled_kernel<false>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow,
-                          R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline, m->counters + 4, R->n_items));
+#define MRS_LAUNCH_K2(SUM, FORM)                                                                                                               \
+  MRS_CUDA(launch_pdl(item_tiled_kernel<SUM, FORM>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow, \
+                      R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline, m->counters + 4, R->n_items))
+    if (m->want_item_avg) {
+      if (T.form == 1) MRS_LAUNCH_K2(true, 1); else MRS_LAUNCH_K2(true, 0);
+    } else {
+      if (T.form == 1) MRS_LAUNCH_K2(false, 1); else MRS_LAUNCH_K2(false, 0);
+    }
+#undef MRS_LAUNCH_K2
   }
   mark(e, "item_tiled");
   if (no_finalize) return MRS_OK;  // mrs_fit_mae_async: the test pass finishes the fit itself

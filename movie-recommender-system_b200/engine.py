@@ -22,7 +22,7 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
              -5: "MRS_ERR_IO", -6: "MRS_ERR_UNSUPPORTED"}
 
 EXPORTS = [
-    "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync", "mrs_debug_timeline", "mrs_debug_fp64_fma_per_s",
+    "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync", "mrs_debug_timeline", "mrs_debug_cta_stamps", "mrs_debug_warp_stamps", "mrs_debug_fp64_fma_per_s",
     "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_upload_begin_codes", "mrs_ratings_from_coo_codes", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
     "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_connect_local", "mrs_multi_create", "mrs_multi_load", "mrs_multi_baseline_mae", "mrs_multi_model", "mrs_multi_owner", "mrs_multi_destroy", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_fit_local_push", "mrs_fit_finish_pull", "mrs_mae_push_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
@@ -72,6 +72,8 @@ def lib():
         "mrs_engine_destroy": (None, [vp]),
         "mrs_engine_sync": (i32, [vp]),
         "mrs_debug_timeline": (i32, [vp, vp]),
+        "mrs_debug_cta_stamps": (i32, [vp, vp]),
+        "mrs_debug_warp_stamps": (i32, [vp, vp]),
         "mrs_debug_fp64_fma_per_s": (i32, [vp, P(dbl)]),
         "mrs_graph_begin": (i32, [vp]),
         "mrs_graph_end": (i32, [vp, P(vp)]),

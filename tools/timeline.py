@@ -45,3 +45,28 @@ with torch.cuda.stream(stream):
         for k in ks:
             line += f" {names[k]} {(int(buf[2 * k]) - t0) / 1e3:5.1f}-{(int(buf[2 * k + 1]) - t0) / 1e3:5.1f} |"
         print(line)
+        if os.environ.get("MRS_WARP_STAMPS") and it == 5:
+            ws = np.zeros(16384, dtype=np.uint64)
+            E._check(E.lib().mrs_debug_warp_stamps(eng._h, ws.ctypes.data))
+            end = (ws[:8192].astype(np.int64) - t0) / 1e3
+            rows = (ws[8192:] >> np.uint64(32)).astype(np.int64); slices = (ws[8192:] & np.uint64(0xffffffff)).astype(np.int64)
+            for cta in (0, 3, 7, 8, 14, 15, 22, 60, 100):
+                sl = slice(cta * 32, cta * 32 + 32)
+                print(f"cta {cta}: rows/warp {rows[sl].min()}-{rows[sl].max()} slices/warp {slices[sl].min()}-{slices[sl].max()} warp end min/mean/max "
+                      f"{end[sl].min():.1f}/{end[sl].mean():.1f}/{end[sl].max():.1f}")
+                print("   ", " ".join(f"{x:.0f}" for x in end[sl]))
+            used = rows > 0
+            x = np.stack([rows[used], slices[used], np.ones(used.sum())], axis=1).astype(np.float64)
+            coef, *_ = np.linalg.lstsq(x, end[used] - 17.0, rcond=None)
+            print("least squares: busy us =", coef, "(per row, per slice, const)")
+        if os.environ.get("MRS_CTA_STAMPS") and it == 5:
+            st = np.zeros(1024, dtype=np.uint64)
+            E._check(E.lib().mrs_debug_cta_stamps(eng._h, st.ctypes.data))
+            st = st.astype(np.int64).reshape(4, 256)
+            for nm, a, b in (("item", 0, 1), ("test", 2, 3)):
+                used = st[b] > 0
+                s0, s1 = (st[a][used] - t0) / 1e3, (st[b][used] - t0) / 1e3
+                print(f"{nm} pass per-CTA: stream start min/mean/max {s0.min():.1f}/{s0.mean():.1f}/{s0.max():.1f} | end min/mean/max "
+                      f"{s1.min():.1f}/{s1.mean():.1f}/{s1.max():.1f} | busy mean {(s1 - s0).mean():.1f} max {(s1 - s0).max():.1f}")
+                print("  start:", " ".join(f"{x:.0f}" for x in s0))
+                print("  end:  ", " ".join(f"{x:.0f}" for x in s1))
