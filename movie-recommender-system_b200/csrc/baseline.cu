@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) user_chunk_sum_kernel(const VT* __restric
 #endif
 __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict__ uval16, const int32_t* __restrict__ vec_row, int32_t n_vec,
                                                       uint32_t* __restrict__ usum, unsigned long long* __restrict__ gsum_codes,
-                                                      unsigned long long* __restrict__ tl) {
+                                                      unsigned long long* __restrict__ tl, int count_off) {
   __shared__ uint32_t sh[8];
   tl_begin(tl, 0);
   pdl_trigger();  // the item pass may start its prologue (ring prefetch) while this kernel runs
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += sh[k];
     atomicAdd(gsum_codes, a);  // integer: exact, order independent
   }
+  if (count_off) flag_count_off(gsum_codes + 1);  // opt-in flag protocol: the item pass waits for the count, not for the grid
   tl_end(tl, 0);
 }
 
@@ -365,7 +366,7 @@ inline int chunk_grid(int32_t n_chunks, int sm_count) {
 int32_t launch_fit_codes(mrs_engine* e, const mrs_ratings* R, mrs_model* m, bool fused, const PushDev* push, bool no_finalize) {
   // (the user sums are zero on entry: cleared when the model is created and re-armed by the kernel that consumes them last --
   // K2b, the push kernel or the fused test pass -- so no memset node opens the pass)
-  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, e->d_timeline);
+  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, e->d_timeline, m->flag_sync ? 1 : 0);
   mark(e, "user_sum");
   MRS_CUDA(cudaGetLastError());
   return launch_item_tiled(e, R, m, fused, push, no_finalize);
@@ -453,8 +454,9 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
     if (codes) {
       if (s == MRS_OK) s = dev_alloc(&m->usum, (size_t)R->n_users);
       if (s == MRS_OK && cudaMemsetAsync(m->usum, 0, sizeof(uint32_t) * (size_t)R->n_users, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
-      if (s == MRS_OK) s = dev_alloc(&m->k1_part, 1);
-      if (s == MRS_OK && cudaMemsetAsync(m->k1_part, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+      if (s == MRS_OK) s = dev_alloc(&m->k1_part, 4);
+      if (s == MRS_OK && cudaMemsetAsync(m->k1_part, 0, 4 * sizeof(unsigned long long), e->stream) != cudaSuccess) s = MRS_ERR_CUDA;
+      m->flag_sync = getenv("MRS_FLAGSYNC") && atoi(getenv("MRS_FLAGSYNC")) != 0;  // opt-in: measured slower (profiles/r02_summary.md)
       if (s == MRS_OK) s = dev_alloc(&m->xdev_fix, 2 * (size_t)R->n_items);  // two buffers, used alternately by the folded closure (tiled.cu)
       if (s == MRS_OK) s = dev_alloc(&m->xcode_sum, (size_t)R->n_items);
       if (s == MRS_OK && cudaMemsetAsync(m->xdev_fix, 0, 2 * sizeof(long long) * (size_t)R->n_items, e->stream) != cudaSuccess) s = MRS_ERR_CUDA;

@@ -66,6 +66,28 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 __device__ __forceinline__ void tl_begin(unsigned long long* tl, int k) {
   if (tl && threadIdx.x == 0) atomicMin(tl + 2 * k, gtimer_ns());
 }
+// ---- kernel-to-kernel hand-over inside the baseline pass without waiting for grid completion: the producer's CTAs count
+// themselves off in flags[k] behind a fence once their results are out (release), the consumer -- launched early by
+// programmatic dependent launch -- has one thread spin on the count (acquire) and then releases its CTA.  Measured against
+// OPT-IN (MRS_FLAGSYNC=1): measured SLOWER than griddepcontrol.wait at ml-25m shape -- the fence behind a CTA's ~10^4
+// outstanding reductions costs more than the hand-over saves (70.5 us against 62.8 us per step, tools/timeline.py).
+// flags = mrs_model::k1_part: [0] sum of all codes, [1] user-sum blocks done, [2] item-pass CTAs done; all re-armed together.
+__device__ __forceinline__ void flag_count_off(unsigned long long* flag) {  // all threads of the CTA
+  __syncthreads();  // the CTA's writes and atomics happen before thread 0's fence (cumulative): one fence, not one per thread
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(flag, 1ull);
+  }
+}
+__device__ __forceinline__ void flag_wait(const unsigned long long* flag, unsigned long long target) {  // all threads of the CTA
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
 // per-CTA stamp (slot 0..3, see mrs_debug_cta_stamps)
 __device__ __forceinline__ void tl_cta(unsigned long long* tl, int slot) {
   if (tl && threadIdx.x == 0 && blockIdx.x < 256) tl[32 + slot * 256 + blockIdx.x] = gtimer_ns();
@@ -229,6 +251,7 @@ struct mrs_ratings {
     int32_t form = 0;                  // 1 when every code is <= kAlphaMaxCode and every user has < 2^17 ratings (tiled.cu)
     int32_t* slice_off = nullptr;      // [n_slices+1] first 32-wide row of each slice
     int32_t* tile_slice_ptr = nullptr; // [n_tiles+1]
+    int32_t* tile_ubegin = nullptr;    // [n_tiles+1] first user of every tile (tiles are user ranges of <= kTileUsers users, cut by cost)
     int32_t* slot_item = nullptr;      // [n_slices*32] item of the unit held by each slot, -1 = empty slot
     // static work partition of the item pass (depends on the layout and the SM count only; laid down with the layout):
     // CTA b works on tile cta_desc[b].x as share .y of .z -- CTAs are dealt out to the tiles in proportion to their
@@ -256,7 +279,9 @@ struct mrs_model {
   const mrs_ratings* train = nullptr;
   int32_t n_users = 0, n_items = 0;
   uint32_t* usum = nullptr;     // [n_users] sum of half-star codes per user (code path)
-  unsigned long long* k1_part = nullptr;  // [1] sum of all half-star codes (integer atomics in K1, re-armed by K2b)
+  unsigned long long* k1_part = nullptr;  // [4] sum of all half-star codes (integer atomics in K1), user-sum blocks done, item-pass CTAs
+                                          // done (flag_count_off / flag_wait); re-armed together by the last consumer of a pass
+  bool flag_sync = true;                  // MRS_FLAGSYNC=0: hand-overs by griddepcontrol.wait only
   int32_t k1_blocks = 0;
   long long* xdev_fix = nullptr;            // [n_items] per-item deviation sums in units of 2^-40 (exact integer accumulation)
   unsigned long long* xcode_sum = nullptr;  // [n_items] per-item sums of half-star codes
@@ -367,7 +392,14 @@ int32_t build_ratings(mrs_engine* e, const int32_t* users, const int32_t* items,
 // one as long as there are enough CTAs): desc[b] = (tile, share, shares of that tile), tiles ascending.
 std::vector<int3> deal_ctas(const std::vector<int64_t>& tile_cost, int32_t n_ctas);
 // tiled.cu
-constexpr int kTileUsers = 8192;  // users per tile: 64 KB of fp64 averages in shared memory
+#ifndef MRS_TILE_USERS
+#define MRS_TILE_USERS 16384
+#endif
+// user records per tile of the item pass: 8 bytes each in shared memory (128 KB).  The last record is the all-zero one the
+// padding slots point at, so a tile holds at most kTileCap users.  Larger tiles mean fewer (tile, item) segments -- fewer
+// units, slice boundaries and hand-over atomics: 1.10 M segments with 8,192 users per tile at ml-25m shape.
+constexpr int kTileUsers = MRS_TILE_USERS;
+constexpr int kTileCap = kTileUsers - 1;
 constexpr int kUnitLen = 64;      // (tile,item) segments are cut into units of at most this many entries
 constexpr int kUnitBits = 7;      // bits of (kUnitLen - len) in the unit sort key
 int32_t build_tiled_layout(const mrs_ratings* R);

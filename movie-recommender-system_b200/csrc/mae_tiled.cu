@@ -76,7 +76,8 @@ struct FoldArgs {
   long long* xdev_fix;              // [2][n_items] per-item deviation sums on the 2^-40 grid: buffer *parity is complete once K2 has finished
   unsigned int* parity;             // which buffer this pass uses; the other one is re-armed here, the last block flips the parity
   const int32_t* icolp;             // [n_items+1] train column pointer (rating counts)
-  unsigned long long* k1_part;      // [1] sum of all train codes (K1)
+  unsigned long long* k1_part;      // [4] sum of all train codes (K1) + the hand-over counts of the pass (common.cuh flag_wait)
+  int32_t n_k2_ctas;                // > 0: wait for that many item-pass CTAs to count themselves off instead of for the grid
   double n_fit;                     // number of train ratings
   double* idevavg;                  // model outputs
   double* xbuf;
@@ -135,8 +136,18 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     }
   }
   // ---- the tile's item deviations (unknown item -> 0.0, P:226-227)
-  pdl_wait();  // barriers, partition and the first ring stages overlapped the end of the fit; its outputs are complete from here on
   const int32_t i0 = tile * kMaeTileItems;
+  constexpr int kPerTile = kMaeTileItems / kMaeThreads;
+  int32_t cnt_of[FOLD == 1 ? kPerTile : 1];
+  if (FOLD == 1) {  // rating counts of the tile's items: layout data, fetched before the wait
+#pragma unroll
+    for (int k = 0; k < kPerTile; ++k) {
+      const int32_t i = i0 + k * kMaeThreads + threadIdx.x;
+      cnt_of[k] = (i < n_items) ? __ldg(f.icolp + i + 1) - __ldg(f.icolp + i) : 0;
+    }
+  }
+  // barriers, partition, the first ring stages and the counts overlapped the end of the fit; its outputs are complete from here on
+  if (FOLD && f.n_k2_ctas > 0) flag_wait(f.k1_part + 2, (unsigned long long)f.n_k2_ctas); else pdl_wait();
   double gavg;
   bool shard_ok = true;
   unsigned long long big_epoch = 0;
@@ -241,20 +252,16 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     const long long* __restrict__ fix = f.xdev_fix + (size_t)par * n_items;
     long long* __restrict__ fix_other = f.xdev_fix + (size_t)(par ^ 1u) * n_items;
     long long fx[kPer];
-    int32_t c0[kPer], c1[kPer];
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {  // all loads of the tile's 8 items per thread go out together
       const int32_t i = i0 + k * kMaeThreads + threadIdx.x;
-      const bool in = i < n_items;
-      fx[k] = in ? __ldcg(fix + i) : 0;
-      c0[k] = in ? __ldg(f.icolp + i) : 0;
-      c1[k] = in ? __ldg(f.icolp + i + 1) : 0;
+      fx[k] = (i < n_items) ? __ldcg(fix + i) : 0;
     }
     const double gs = 0.5 * (double)__ldcg(f.k1_part);  // integer sum of codes: exact
     gavg = f.n_fit > 0.0 ? gs / f.n_fit : 0.0;           // P:18 mean of an empty Seq is 0.0
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
-      const double cnt = (double)(c1[k] - c0[k]);
+      const double cnt = (double)cnt_of[k];
       s_dev[k * kMaeThreads + threadIdx.x] = cnt > 0.0 ? ((double)fx[k] * kInvFix) / cnt : 0.0;  // P:185; unknown item -> 0.0 (P:197)
     }
     // the model's arrays: every CTA an equal share of the item ids
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
         out2[1] = n_total;
         *counter = 0;
         if (FOLD) {
-          f.k1_part[0] = 0;  // every CTA has read the code sum: re-arm it for the next pass' K1
+          f.k1_part[0] = 0; f.k1_part[1] = 0; f.k1_part[2] = 0;  // every CTA has read the code sum and passed its wait: re-arm for the next pass
           *f.parity ^= 1u;   // ... and the accumulators: the next pass uses the buffer re-armed above
           if (FOLD == 2) *f.big.epoch = big_epoch;  // every CTA is done with the deliveries of this exchange
         }
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
         *x.epoch = epoch;
         *counter = 0;
         if (FOLD) {
-          f.k1_part[0] = 0;
+          f.k1_part[0] = 0; f.k1_part[1] = 0; f.k1_part[2] = 0;
           *f.parity ^= 1u;
           if (FOLD == 2) *f.big.epoch = big_epoch;
         }
@@ -482,6 +489,7 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
   if (fold) {
     const mrs_ratings* R = m->train;
     f.xdev_fix = m->xdev_fix; f.icolp = R->icolp; f.k1_part = m->k1_part; f.n_fit = (double)R->n;
+    f.n_k2_ctas = m->flag_sync ? R->tl.n_ctas : 0;
     f.idevavg = m->idevavg; f.xbuf = m->xbuf; f.gavg = m->gavg; f.usum = m->usum; f.parity = m->counters + 4;
     if (big) {  // sharded closure: both exchanges inside this kernel
       MRS_REQUIRE(push && grid <= e->sm_count, MRS_ERR_UNSUPPORTED, "sharded closure: the test pass must be one wave (%d CTAs)", grid);

@@ -40,22 +40,28 @@ __global__ void item_expand_kernel(const int32_t* __restrict__ icolp, int32_t n_
     for (int32_t p = b + lane; p < e; p += 32) item_of[p] = i;
   }
 }
+// tile of every user: tiles are contiguous user ranges [ubegin[t], ubegin[t+1]) (users between two tiles have no ratings)
+__global__ void user_tile_kernel(const int32_t* __restrict__ ubegin, int32_t n_tiles, uint16_t* __restrict__ utile) {
+  const int32_t t = blockIdx.x;
+  for (int32_t u = ubegin[t] + threadIdx.x; u < ubegin[t + 1]; u += blockDim.x) utile[u] = (uint16_t)t;
+}
 // the sort key is the user tile only; the radix sort is stable so (item, user) order survives inside a tile
-__global__ void tile_keys_kernel(const int32_t* __restrict__ irow, int64_t n, uint16_t* __restrict__ tile_key, int32_t* __restrict__ pos) {
+__global__ void tile_keys_kernel(const int32_t* __restrict__ irow, const uint16_t* __restrict__ utile, int64_t n, uint16_t* __restrict__ tile_key,
+                                 int32_t* __restrict__ pos) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-    tile_key[p] = (uint16_t)(irow[p] / kTileUsers);
+    tile_key[p] = utile[irow[p]];
     pos[p] = (int32_t)p;
   }
 }
 
 // q = position in (tile, item, user) order.  head_pos[q] = q at the first entry of a (tile,item) segment, else 0
 __global__ void seg_head_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ item_of, const int32_t* __restrict__ irow,
-                                int64_t n, int32_t* __restrict__ head_pos) {
+                                const uint16_t* __restrict__ utile, int64_t n, int32_t* __restrict__ head_pos) {
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     bool head = (q == 0);
     if (!head) {
       const int32_t p = perm[q], pp = perm[q - 1];
-      head = (item_of[p] != item_of[pp]) || (irow[p] / kTileUsers != irow[pp] / kTileUsers);
+      head = (item_of[p] != item_of[pp]) || (utile[irow[p]] != utile[irow[pp]]);
     }
     head_pos[q] = head ? (int32_t)q : 0;
   }
@@ -67,14 +73,14 @@ __global__ void unit_flag_kernel(const int32_t* __restrict__ seg_start, int64_t 
 }
 
 __global__ void unit_scatter_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ uid, const int32_t* __restrict__ perm,
-                                    const int32_t* __restrict__ item_of, const int32_t* __restrict__ irow, int64_t n,
-                                    int32_t* __restrict__ unit_begin, int32_t* __restrict__ unit_item, int32_t* __restrict__ unit_tile) {
+                                    const int32_t* __restrict__ item_of, const int32_t* __restrict__ irow, const uint16_t* __restrict__ utile,
+                                    int64_t n, int32_t* __restrict__ unit_begin, int32_t* __restrict__ unit_item, int32_t* __restrict__ unit_tile) {
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     if (flag[q]) {
       const int32_t id = uid[q], p = perm[q];
       unit_begin[id] = (int32_t)q;
       unit_item[id] = item_of[p];
-      unit_tile[id] = irow[p] / kTileUsers;
+      unit_tile[id] = utile[irow[p]];
     }
   }
 }
@@ -113,10 +119,12 @@ __global__ void slot_assign_kernel(const int32_t* __restrict__ sorted_id, const 
 // i.e. every MovieLens-style scale): the pass works in fp64 on exact small integers, so the word carries what the inner loop
 // would otherwise have to compute or convert per rating: bits 31..17 = the top 15 bits (sign, exponent, 3 mantissa bits) of
 // the fp64 number alpha = (code - 2)/8 -- all of it, the rest of the mantissa is zero -- and bits 15..3 = the local user,
-// already scaled to the byte offset of its 8-byte table record.  Bit 16 marks padding: it selects the all-zero record
-// behind the tile's users, which makes the deviation of a padding slot exactly 0 without a test.
+// already scaled to the byte offset of its 8-byte table record.  A padding slot names the last record of the table, which
+// is all zero: that makes its deviation exactly 0 without a test.
 constexpr int kAlphaMaxCode = 17;
-constexpr uint32_t kAlphaPadding = 0x00010000u;
+constexpr uint32_t kUserMask = (uint32_t)(kTileUsers - 1) << 3;  // byte offset of a user record inside the tile's table
+constexpr uint32_t kAlphaPadding = kUserMask;                    // alpha = 0, the all-zero record behind the tile's users
+static_assert(kTileUsers <= 16384 && (kTileUsers & (kTileUsers - 1)) == 0, "the user field of an entry is bits 16..3");
 __device__ __forceinline__ uint32_t make_entry(int form, uint32_t code, uint32_t local_user) {
   if (form == 0) return 0x80000000u | (code << 16) | local_user;
   const double alpha = (double)((int32_t)code - 2) * 0.125;
@@ -140,13 +148,13 @@ __global__ void form_scan_kernel(const uint8_t* __restrict__ ival, int64_t n, co
 __global__ void entry_fill_kernel(const int32_t* __restrict__ unit_begin, const int32_t* __restrict__ unit_len,
                                   const int32_t* __restrict__ unit_slot, const int32_t* __restrict__ unit_tile, int32_t n_units,
                                   const int32_t* __restrict__ perm, const int32_t* __restrict__ irow, const uint8_t* __restrict__ ival,
-                                  const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry, int form) {
+                                  const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry, int form, const int32_t* __restrict__ tile_ubegin) {
   const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_units) return;
   const int32_t b = unit_begin[id], len = unit_len[id], slot = unit_slot[id];
   const int32_t slice = slot >> 5, lane = slot & 31;
   const int64_t row0 = slice_off[slice];
-  const int32_t ubase = unit_tile[id] * kTileUsers;
+  const int32_t ubase = tile_ubegin[unit_tile[id]];
   for (int32_t j = 0; j < len; ++j) {
     const int32_t p = perm[b + j];
     entry[((row0 + j) << 5) + lane] = make_entry(form, (uint32_t)ival[p], (uint32_t)(irow[p] - ubase));
@@ -173,7 +181,8 @@ __global__ void __launch_bounds__(128) entry_fill_ordered_kernel(const int32_t* 
                                                                 const int32_t* __restrict__ unit_len, const int32_t* __restrict__ unit_tile,
                                                                 int32_t n_slices, const int32_t* __restrict__ perm,
                                                                 const int32_t* __restrict__ irow, const uint8_t* __restrict__ ival,
-                                                                const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry, int form) {
+                                                                const int32_t* __restrict__ slice_off, uint32_t* __restrict__ entry, int form,
+                                                                const int32_t* __restrict__ tile_ubegin) {
   __shared__ uint32_t s_ent[4][32 * kUnitLen];   // entries of the lane's unit, grouped by key
   __shared__ uint8_t s_next[4][32][16];          // next unplaced entry of every key group
   __shared__ uint8_t s_end[4][32][16];
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(128) entry_fill_ordered_kernel(const int32_t* 
   const int32_t id = slot_unit[slice * 32 + lane];
   const int32_t len = id >= 0 ? unit_len[id] : 0;
   const int32_t b = id >= 0 ? unit_begin[id] : 0;
-  const int32_t ubase = id >= 0 ? unit_tile[id] * kTileUsers : 0;
+  const int32_t ubase = id >= 0 ? tile_ubegin[unit_tile[id]] : 0;
   uint32_t* ent = s_ent[w] + lane * kUnitLen;
   uint8_t* nxt = s_next[w][lane];
   uint8_t* end = s_end[w][lane];
@@ -284,13 +293,13 @@ constexpr int kTiledThreads = 1024;
 #define MRS_K2_ROWS 8
 #endif
 #ifndef MRS_K2_STAGES
-#define MRS_K2_STAGES 4
+#define MRS_K2_STAGES 2
 #endif
 constexpr int kRows = MRS_K2_ROWS;      // rows per ring stage (128 B each)
 constexpr int kStages = MRS_K2_STAGES;  // ring depth per warp
 constexpr int kSliceCost = 4;  // rows a slice boundary is worth (per-warp stamps, least squares: 0.092 us per row, 0.33 us per slice)
 constexpr double kFixScale = 1099511627776.0;  // 2^40
-constexpr size_t kTabBytes = (size_t)kTileUsers * 8 + 128;  // the tile's user records + the all-zero record of the padding slots (form 1)
+constexpr size_t kTabBytes = (size_t)kTileUsers * 8;  // the tile's user records; the last one is the all-zero record of the padding slots
 constexpr size_t kTiledSmem = kTabBytes + (size_t)(kTiledThreads / 32) * kStages * kRows * 128 + (size_t)(kTiledThreads / 32 * kStages) * 8;
 
 // first slice s in [lo, hi) whose cost prefix (rows before it + kSliceCost * slices before it) is >= v
@@ -329,7 +338,7 @@ __device__ __forceinline__ double tiled_dev_alpha(uint32_t e, const unsigned cha
 #ifdef MRS_AB_NOGATHER  // timing experiment only: every entry reads the record of its lane (conflict free)
   const uint2 rec = *reinterpret_cast<const uint2*>(s_tab + ((threadIdx.x & 31u) << 3) + (e & 0x100u));
 #else
-  const uint2 rec = *reinterpret_cast<const uint2*>(s_tab + (e & 0x1fff8u));
+  const uint2 rec = *reinterpret_cast<const uint2*>(s_tab + (e & kUserMask));
 #endif
 #ifdef MRS_AB_NOMATH    // timing experiment only: no reciprocal
   return __hiloint2double((int)rec.x, (int)(e & 0xfffe0000u));
@@ -345,7 +354,7 @@ __device__ __forceinline__ double tiled_dev_alpha(uint32_t e, const unsigned cha
 // code of a form-1 entry (only the pass that also sums the ratings per item needs it): 8*alpha + 2, 0 for padding
 __device__ __forceinline__ uint32_t alpha_code(uint32_t e) {
   const double alpha = __hiloint2double((int)(e & 0xfffe0000u), 0);
-  return (e & kAlphaPadding) ? 0u : (uint32_t)(__double2int_rn(alpha * 8.0) + 2);
+  return ((e & kUserMask) == kAlphaPadding) ? 0u : (uint32_t)(__double2int_rn(alpha * 8.0) + 2);
 }
 
 template <bool WITH_SUM>
@@ -397,7 +406,9 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
                                                                      int32_t n_users, const int32_t* __restrict__ slot_item,
                                                                      double* __restrict__ uavg, long long* __restrict__ xdev_fix_both,
                                                                      unsigned long long* __restrict__ xcode_sum, unsigned long long* __restrict__ tl,
-                                                                     const unsigned int* __restrict__ parity, int32_t n_items_acc) {
+                                                                     const unsigned int* __restrict__ parity, int32_t n_items_acc,
+                                                                     const int32_t* __restrict__ tile_ubegin, unsigned long long* __restrict__ flags,
+                                                                     int32_t k1_blocks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   tl_begin(tl, 1);
   // the accumulator buffer of this pass (two buffers alternate when the test pass finishes the fit itself: it cannot re-arm
@@ -444,19 +455,33 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
   int32_t item1 = (cur < s_hi) ? __ldg(slot_item + cur * 32 + lane) : -1;       // item of this lane's unit in the current slice
   int32_t item2 = (cur + 1 < s_hi) ? __ldg(slot_item + (cur + 1) * 32 + lane) : -1;
 
-  // ---- the tile's users: (code sum from K1, rating count); the first CTA of the tile also publishes the averages
-  pdl_trigger();  // K2b may be scheduled as SMs free up
-  pdl_wait();     // everything above (barriers, partition, first ring stages) overlapped K1; usum is complete from here on
+  pdl_trigger();  // the next kernel may be scheduled as SMs free up
+  // ---- the tile's users: (code sum from K1, rating count); the first CTA of the tile also publishes the averages.
+  // The rating counts are layout data: they are fetched before the wait, only the code sums behind it.
+  const int32_t u0 = __ldg(tile_ubegin + tile), u1 = __ldg(tile_ubegin + tile + 1);
+  constexpr int kPer = kTileUsers / kTiledThreads;
+  uint32_t cnt_of[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int32_t u = u0 + k * kTiledThreads + (int32_t)threadIdx.x;
+    cnt_of[k] = (u < u1) ? (uint32_t)(__ldg(urow + u + 1) - __ldg(urow + u)) : 0u;
+  }
+  // everything above (barriers, partition, first ring stages, counts) overlapped K1; the user sums are complete once all its
+  // blocks have counted themselves off (k1_blocks > 0) or, without the flag protocol, once its grid has completed
+  if (k1_blocks > 0) flag_wait(flags + 1, (unsigned long long)k1_blocks); else pdl_wait();
   {
-    const int32_t u0 = tile * kTileUsers;
-    constexpr int kPer = kTileUsers / kTiledThreads;
+    uint32_t S_of[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int32_t u = u0 + k * kTiledThreads + (int32_t)threadIdx.x;
+      S_of[k] = (u < u1) ? __ldcg(usum + u) : 0u;  // written by K1's atomics while this kernel was already resident: L2, not L1
+    }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const int32_t x = k * kTiledThreads + threadIdx.x;
       const int32_t u = u0 + x;
-      const bool in = u < n_users;
-      const uint32_t S = in ? __ldg(usum + u) : 0u;
-      const uint32_t cnt = in ? (uint32_t)(__ldg(urow + u + 1) - __ldg(urow + u)) : 0u;
+      const bool in = u < u1;
+      const uint32_t S = S_of[k], cnt = cnt_of[k];
       if (FORM == 0) {
         s_sc[x] = make_uint2(S, cnt);
       } else {  // high words of the fp64 numbers 10c - S and S - 2c (below 2^21 in magnitude: the low words are zero)
@@ -466,7 +491,7 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
       if (share == 0 && in)  // exact sum, one correctly rounded division (P:18); -1.0: no ratings (the reference's sentinel, P:222)
         uavg[u] = cnt ? (0.5 * (double)S) / (double)cnt : -1.0;
     }
-    if (FORM == 1 && threadIdx.x == 0) s_sc[kTileUsers] = make_uint2(0u, 0u);  // the record of the padding slots
+    // (the last record, kTileCap, belongs to no user -- a tile holds at most kTileCap of them -- and stays all zero: padding)
   }
   __syncthreads();
   tl_cta(tl, 0);
@@ -532,7 +557,8 @@ __global__ void __launch_bounds__(kTiledThreads, 1) item_tiled_kernel(const uint
     tl[32 + 1024 + 8192 + blockIdx.x * 32 + wid] = ((unsigned long long)(r_end - r0) << 32) | (unsigned int)(s_hi - part.z);
   }
 #endif
-  if (tl) { __syncthreads(); tl_cta(tl, 1); tl_end(tl, 1); }
+  if (k1_blocks > 0) flag_count_off(flags + 2);  // opt-in flag protocol: the fused test pass waits for the count
+  if (tl) { tl_cta(tl, 1); tl_end(tl, 1); }
 }
 
 // K2b: per item, integer accumulators -> exchange buffer (and re-arm them for the next pass); optionally finish the fit
@@ -550,7 +576,7 @@ __global__ void __launch_bounds__(256) item_tiled_finalize_kernel(long long* __r
   for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += gridDim.x * blockDim.x) usum[u] = 0;  // consumed by K2: re-arm for K1
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
-    k1_part[0] = 0;                              // re-arm for the next pass
+    k1_part[0] = 0; k1_part[1] = 0; k1_part[2] = 0;  // re-arm the sum and the hand-over counts for the next pass
     xbuf[2 * (size_t)n_items] = gs;
     xbuf[2 * (size_t)n_items + 1] = n_total;
     if (fused) gavg[0] = n_total > 0.0 ? gs / n_total : 0.0;
@@ -595,7 +621,7 @@ __global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restr
   const int parity = (int)(epoch & 1);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
-    k1_part[0] = 0;                              // re-arm for the next pass
+    k1_part[0] = 0; k1_part[1] = 0; k1_part[2] = 0;  // re-arm the sum and the hand-over counts for the next pass
     for (int p = 0; p < x.world; ++p) {
       double* slot = push_slot(x, p, parity, x.rank);
       slot[2 * (size_t)K] = gs;
@@ -692,7 +718,7 @@ int32_t launch_finish_pull(mrs_model* m, const PushDev& push) {
 
 void free_tiled_layout(const mrs_ratings* R) {
   auto& T = R->tl;
-  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.slot_item); dev_free(T.warp_part); dev_free(T.cta_desc);
+  dev_free(T.entry); dev_free(T.slice_off); dev_free(T.tile_slice_ptr); dev_free(T.tile_ubegin); dev_free(T.slot_item); dev_free(T.warp_part); dev_free(T.cta_desc);
   T = mrs_ratings::tiled_layout();
 }
 
@@ -704,13 +730,80 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   cudaStream_t st = e->stream;
   const int64_t n = R->n;
   const int32_t NI = R->n_items;
-  const int32_t NT = (R->n_users + kTileUsers - 1) / kTileUsers;
+  // ---- user tiles: contiguous user ranges of at most kTileUsers users, CUT BY COST so that every CTA of the pass gets the
+  // same number of ratings: a tile takes the users that hold k quotas of n / #SMs ratings (k = as many as fit into
+  // kTileUsers users) and is worked on by k CTAs.  Equal-sized tiles of 8,192 users got 7 or 8 CTAs each at ml-25m shape:
+  // 161 against 144 rows per warp, and the pass as slow as its 7-CTA tiles (per-CTA stamps: 38 us against 35 us).
+  // MRS_TILES=0 keeps equal-sized tiles with CTAs dealt out by cost.
+  std::vector<int32_t> h_ubegin, h_kctas;
+  bool cost_tiles = !(getenv("MRS_TILES") && atoi(getenv("MRS_TILES")) == 0) && n > 0;
+  if (cost_tiles) {
+    const int32_t NU = R->n_users, C = e->sm_count;
+    std::vector<int32_t> h_urow((size_t)NU + 1);
+    MRS_CUDA(cudaMemcpyAsync(h_urow.data(), R->urow, sizeof(int32_t) * ((size_t)NU + 1), cudaMemcpyDeviceToHost, st));
+    MRS_CUDA(cudaStreamSynchronize(st));
+    auto skip_empty = [&](int32_t u) { while (u < NU && h_urow[(size_t)u + 1] == h_urow[(size_t)u]) ++u; return u; };
+    // first user index whose rating prefix reaches m quotas of n / C (m = C: behind the last user)
+    int32_t end_all = NU;  // one past the last user with ratings
+    while (end_all > 0 && h_urow[(size_t)end_all] == h_urow[(size_t)end_all - 1]) --end_all;
+    auto cut = [&](int64_t m) -> int32_t {
+      if (m >= C) return end_all;
+      const int64_t target = (n * m + C - 1) / C;
+      return (int32_t)(std::lower_bound(h_urow.begin(), h_urow.end(), (int32_t)target) - h_urow.begin());
+    };
+    // fewest tiles any cut needs: greedily as many quotas per tile as fit into kTileUsers users
+    int32_t nt_min = 0;
+    {
+      int32_t u = skip_empty(0);
+      int64_t done = 0;
+      while (u < NU && done < C) {
+        int64_t k = 1;
+        while (done + k < C && cut(done + k + 1) - u <= kTileCap) ++k;
+        done += k;
+        u = skip_empty(std::max(cut(done), u + 1));
+        ++nt_min;
+      }
+    }
+    // then the same number of CTAs per tile (+-1): tiles of very different sizes would not cost the same per rating
+    bool ok = false;
+    for (int32_t nt = std::max(1, nt_min); nt <= nt_min + 8 && !ok; ++nt) {
+      const int32_t base = C / nt;
+      int32_t extra = C % nt;
+      if (base == 0) break;
+      h_ubegin.clear(); h_kctas.clear();
+      int32_t u = skip_empty(0);
+      int64_t done = 0;
+      bool fail = false;
+      for (int32_t t = 0; t < nt && !fail; ++t) {
+        if (u >= NU) { fail = true; break; }
+        int32_t k = base + (extra > 0 ? 1 : 0);
+        int32_t end = std::max(cut(done + k), u + 1);
+        if (end - u > kTileCap && k > base && extra < nt - t) { k = base; end = std::max(cut(done + k), u + 1); }
+        if (end - u > kTileCap) { fail = true; break; }
+        if (k > base) --extra;
+        h_ubegin.push_back(u);
+        h_kctas.push_back(k);
+        done += k;
+        u = skip_empty(end);
+      }
+      ok = !fail && done == C && u >= NU;
+    }
+    if (ok) h_ubegin.push_back(NU); else cost_tiles = false;
+  }
+  if (!cost_tiles) {
+    h_ubegin.clear(); h_kctas.clear();
+    const int32_t nt = (R->n_users + kTileCap - 1) / kTileCap;
+    for (int32_t t = 0; t <= nt; ++t) h_ubegin.push_back((int32_t)std::min<int64_t>((int64_t)t * kTileCap, R->n_users));
+  }
+  const int32_t NT = (int32_t)h_ubegin.size() - 1;
   MRS_REQUIRE(NT < 65536, MRS_ERR_UNSUPPORTED, "too many user tiles (%d)", NT);
   T.n_tiles = NT;
   const int block = 256;
   const int grid = grid_for(n, block, e->sm_count);
   std::vector<int32_t> h_tile_slice((size_t)NT + 1, 0);
   MRS_TRY(dev_alloc(&T.tile_slice_ptr, (size_t)NT + 1));
+  MRS_TRY(dev_alloc(&T.tile_ubegin, (size_t)NT + 1));
+  MRS_CUDA(cudaMemcpyAsync(T.tile_ubegin, h_ubegin.data(), sizeof(int32_t) * ((size_t)NT + 1), cudaMemcpyHostToDevice, st));
   if (n == 0) {
     MRS_CUDA(cudaMemsetAsync(T.tile_slice_ptr, 0, sizeof(int32_t) * ((size_t)NT + 1), st));
     MRS_TRY(dev_alloc(&T.slice_off, 1));
@@ -728,8 +821,11 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   MRS_TRY(dev_alloc(&pos_in, (size_t)n)); MRS_TRY(dev_alloc(&perm, (size_t)n));
   MRS_TRY(dev_alloc(&item_of, (size_t)n)); MRS_TRY(dev_alloc(&head, (size_t)n));
   MRS_TRY(dev_alloc(&seg_start, (size_t)n)); MRS_TRY(dev_alloc(&flag, (size_t)n)); MRS_TRY(dev_alloc(&uid, (size_t)n + 1));
+  uint16_t* utile = nullptr;
+  MRS_TRY(dev_alloc(&utile, (size_t)R->n_users + 1));
+  user_tile_kernel<<<NT, 256, 0, st>>>(T.tile_ubegin, NT, utile);
   item_expand_kernel<<<std::max(1, std::min((NI + 7) / 8, e->sm_count * 32)), 256, 0, st>>>(R->icolp, NI, item_of);
-  tile_keys_kernel<<<grid, block, 0, st>>>(R->irow, n, tk_in, pos_in);
+  tile_keys_kernel<<<grid, block, 0, st>>>(R->irow, utile, n, tk_in, pos_in);
   int tbits = 1;
   while ((1 << tbits) < NT) ++tbits;
   size_t tmp = 0;
@@ -737,7 +833,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   MRS_TRY(ensure_scratch(e, tmp));
   cub::DeviceRadixSort::SortPairs(e->scratch, tmp, tk_in, tk_out, pos_in, perm, (int)n, 0, tbits, st);
   // ---- units
-  seg_head_kernel<<<grid, block, 0, st>>>(perm, item_of, R->irow, n, head);
+  seg_head_kernel<<<grid, block, 0, st>>>(perm, item_of, R->irow, utile, n, head);
   cub::DeviceScan::InclusiveScan(nullptr, tmp, head, seg_start, MaxOp(), (int)n, st);
   MRS_TRY(ensure_scratch(e, tmp));
   cub::DeviceScan::InclusiveScan(e->scratch, tmp, head, seg_start, MaxOp(), (int)n, st);
@@ -760,7 +856,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   MRS_TRY(dev_alloc(&tile_count, (size_t)NT + 1)); MRS_TRY(dev_alloc(&unit_slot, (size_t)NUN));
   MRS_TRY(dev_alloc(&d_tile_unit_ptr, (size_t)NT + 1));
   MRS_CUDA(cudaMemsetAsync(tile_count, 0xff, sizeof(int32_t) * ((size_t)NT + 1), st));  // -1: tile without units
-  unit_scatter_kernel<<<grid, block, 0, st>>>(flag, uid, perm, item_of, R->irow, n, unit_begin, unit_item, unit_tile);
+  unit_scatter_kernel<<<grid, block, 0, st>>>(flag, uid, perm, item_of, R->irow, utile, n, unit_begin, unit_item, unit_tile);
   const int ugrid = (NUN + block - 1) / block;
   unit_len_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_tile, NUN, n, unit_len, skey, ids, tile_count);
   // ---- sort units by (tile, length desc); stable => canonical order among equal lengths
@@ -813,7 +909,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   const bool reorder = getenv("MRS_REORDER") && atoi(getenv("MRS_REORDER"));
   if (!reorder)
     entry_fill_kernel<<<ugrid, block, 0, st>>>(unit_begin, unit_len, unit_slot, unit_tile, NUN, perm, R->irow, (const uint8_t*)R->ival, T.slice_off, T.entry,
-                                               T.form);
+                                               T.form, T.tile_ubegin);
   // ---- item of every slot (empty slots: -1)
   MRS_TRY(dev_alloc(&T.slot_item, (size_t)NS * 32));
   MRS_CUDA(cudaMemsetAsync(T.slot_item, 0xff, sizeof(int32_t) * (size_t)NS * 32, st));
@@ -825,7 +921,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   slot_item_kernel<<<ugrid, block, 0, st>>>(unit_slot, unit_item, NUN, T.slot_item, slot_unit);
   if (reorder) {
     entry_fill_ordered_kernel<<<(NS + 3) / 4, 128, 0, st>>>(slot_unit, unit_begin, unit_len, unit_tile, NS, perm, R->irow, (const uint8_t*)R->ival, T.slice_off,
-                                                         T.entry, T.form);
+                                                         T.entry, T.form, T.tile_ubegin);
     MRS_CUDA(cudaStreamSynchronize(st));
     dev_free(slot_unit);
   }
@@ -841,7 +937,14 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
       const int32_t s0 = h_tile_slice[t], s1 = h_tile_slice[t + 1];
       cost[(size_t)t] = (int64_t)(h_slice_off[(size_t)s1] - h_slice_off[(size_t)s0]) + (int64_t)kSliceCost * (s1 - s0);
     }
-    const std::vector<int3> desc = deal_ctas(cost, e->sm_count);
+    std::vector<int3> desc;
+    if (cost_tiles) {  // every tile was cut to hold k quotas: k CTAs
+      for (int32_t t = 0; t < NT; ++t)
+        for (int32_t k = 0; k < h_kctas[(size_t)t]; ++k)
+          if (cost[(size_t)t] > 0) desc.push_back(make_int3(t, k, h_kctas[(size_t)t]));
+    } else {
+      desc = deal_ctas(cost, e->sm_count);
+    }
     T.n_ctas = (int32_t)desc.size();
     MRS_TRY(dev_alloc(&T.cta_desc, std::max<size_t>(1, desc.size())));
     MRS_TRY(dev_alloc(&T.warp_part, std::max<size_t>(1, desc.size()) * (kTiledThreads / 32)));
@@ -857,7 +960,7 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   for (void* p : {(void*)tk_in, (void*)tk_out, (void*)pos_in, (void*)perm, (void*)item_of, (void*)head, (void*)seg_start, (void*)flag,
                   (void*)uid, (void*)unit_begin, (void*)unit_item, (void*)unit_tile, (void*)unit_len, (void*)ids, (void*)sorted_id,
                   (void*)skey, (void*)skey_out, (void*)tile_count, (void*)unit_slot, (void*)slice_width,
-                  (void*)d_tile_unit_ptr})
+                  (void*)d_tile_unit_ptr, (void*)utile})
     dev_free(p);
   T.built = true;
   return MRS_OK;
@@ -878,7 +981,8 @@ int32_t launch_item_tiled(mrs_engine* e, const mrs_ratings* R, mrs_model* m, boo
   if (T.n_ctas > 0) {
 #define MRS_LAUNCH_K2(SUM, FORM)                                                                                                               \
   MRS_CUDA(launch_pdl(item_tiled_kernel<SUM, FORM>, grid2, block2, kTiledSmem, st, T.entry, T.slice_off, T.warp_part, T.cta_desc, m->usum, R->urow, \
-                      R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline, m->counters + 4, R->n_items))
+                      R->n_users, T.slot_item, m->uavg, m->xdev_fix, m->xcode_sum, e->d_timeline, m->counters + 4, R->n_items, T.tile_ubegin, m->k1_part, \
+                      m->flag_sync ? m->k1_blocks : 0))
     if (m->want_item_avg) {
       if (T.form == 1) MRS_LAUNCH_K2(true, 1); else MRS_LAUNCH_K2(true, 0);
     } else {
