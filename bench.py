@@ -370,13 +370,21 @@ def run_ours(args):
     keep = []
 
     def e2e_step(compact=True):
-        # both sets start travelling at once on the engine's copy stream ...
+        # both sets start travelling at once on the engine's copy stream, the (small) test set first: its layouts are built
+        # while the train ids are still in flight, the train set is sorted while its ratings arrive
+        test_first = not os.environ.get("MRS_E2E_TRAIN_FIRST")
+        if test_first:
+            up_t = eng.upload_codes(tu, ti, tc) if compact else eng.upload(tu, ti, tv)
         up_r = eng.upload_codes(hu, hi, hc) if compact else eng.upload(hu, hi, hr)
-        up_t = eng.upload_codes(tu, ti, tc) if compact else eng.upload(tu, ti, tv)
-        R2 = up_r.ratings(nu_dim, ni_dim)  # ... the train set is sorted while its ratings and the test set are still in flight
+        if not test_first:
+            up_t = eng.upload_codes(tu, ti, tc) if compact else eng.upload(tu, ti, tv)
+        if test_first and world == 1:
+            T2 = up_t.ratings(nu_dim, ni_dim)
+        R2 = up_r.ratings(nu_dim, ni_dim)
         if world == 1:
             m2 = E.Model(eng, R2, sync=False)
-            T2 = up_t.ratings(nu_dim, ni_dim)
+            if not test_first:
+                T2 = up_t.ratings(nu_dim, ni_dim)
             m2.mae_async(T2, out2.data_ptr())
             r = out2.cpu().numpy()       # D2H read of the result
             handles = (m2, T2, R2)

@@ -219,15 +219,16 @@ struct mrs_ratings {
   struct sim_layout {
     bool built = false;
     int32_t n_known = 0;           // users with at least one rating
-    int32_t n_slices = 0;          // ceil(n_known / 32)
     int32_t* known_user = nullptr; // [n_known] original id, ascending            (compact index c -> user)
     int32_t* cidx = nullptr;       // [n_users] compact index or -1
-    int32_t* perm = nullptr;       // [n_slices*32] compact index handled by (slice, lane), rows sorted by length desc; -1 = padding
-    int32_t* slice_off = nullptr;  // [n_slices+1] offset (in units of 32 entries) of each slice in the ELL arrays
-    int32_t* ell_col = nullptr;    // [slice_off[n_slices]*32] item id (0 for padding)
-    int32_t* ell_src = nullptr;    // [same] position of the entry in the CSR arrays, -1 for padding
-    int64_t ell_entries = 0;
-    bool ell_built = false;        // the ELL arrays are only built for the dense-matrix path
+    // ---- dense-matrix path (knn.cu similarity_wide_kernel): work partition, cached with the sparsity pattern
+    int4* vmeta = nullptr;         // [wide_p][wide_npos] user at each position of the length-sorted order (longest row first, -1 =
+                                   // padding) and the CSR range of its entries that fall into phase p
+    int32_t wide_npos = 0;         // positions: n_known rounded up to a multiple of 32
+    int4* wide_desc = nullptr;     // [n_wide] CTA b: row block .x (32 positions), column users = positions [.y, .z)
+    int32_t n_wide = 0;
+    int32_t wide_ic = 0, wide_p = 0;  // items per phase (the tile holds wide_ic x 32 fp64 values), number of phases
+    bool wide_built = false;       // built only for the dense-matrix path
     std::vector<int32_t> h_known;  // host copies used when a row range is laid out (knn_rows.cu)
     std::vector<int32_t> h_order;  // compact indices sorted by row length, longest first
     std::vector<int32_t> h_len;    // [n_known] row length
@@ -323,7 +324,7 @@ struct mrs_sim {
   double* upre = nullptr;   // [n] preprocessed rating r~ (P:470-481)
   double* unorm = nullptr;  // [n_known]
   double* cdev = nullptr;   // [n] deviation of each CSC entry
-  double* ell_val = nullptr;  // r~ (cosine) or 1.0 (jaccard) in sliced-ELL order
+  int4* pk = nullptr;       // [n] (item, r~ (cosine) or 1.0 (jaccard)) of each CSR entry as one 16-byte record {item, 0, lo, hi}
   double* S = nullptr;      // [n_known^2] similarity matrix in compact indices (cosine / jaccard)
   int32_t* rank = nullptr;  // [n_known^2] position of v in u's sorted neighbour list (INT_MAX for v == u)
   int32_t* nbr_id = nullptr;  // [n_known * (n_known-1)] neighbours of each user, original ids, (sim desc, id asc)
@@ -426,7 +427,7 @@ int32_t mae_personalized_async(const mrs_model* m, const mrs_sim* s, const mrs_r
 int32_t predict_personalized_async(const mrs_model* m, const mrs_sim* s, const int32_t* d_users, const int32_t* d_items,
                                    int64_t n, double* d_out, bool wsd_only);
 void free_sim_layout(const mrs_ratings* r);
-int32_t build_sim_layout(const mrs_ratings* R, bool with_ell);
+int32_t build_sim_layout(const mrs_ratings* R, bool with_wide);
 // knn_rows.cu
 int32_t rows_fit_async(mrs_model* m, mrs_sim* s, bool first);
 int32_t rows_alloc(mrs_model* m, mrs_sim* s, int32_t user_lo, int32_t user_hi);

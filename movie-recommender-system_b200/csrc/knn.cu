@@ -9,10 +9,11 @@
 // Bit-exact neighbour sets need the similarity bits to equal the oracle's, so everything that feeds the ranking
 // uses correctly-rounded, non-fused fp64 ops in ONE canonical order: deviations (sub, div), squared
 // norm (sequential, ascending item id), r~ (div), dot product (sequential, ascending item id).  The similarity
-// kernel is a shared-memory-staged SpGEMM: the dense r~ rows of a block of UB users sit in shared memory and
-// every other user's sparse row is streamed once per block from a sliced-ELL layout (coalesced); items the block
+// kernel is a shared-memory-staged SpGEMM: the dense r~ rows of a block of 32 users sit in shared memory (one lane per
+// row user) and the sparse rows of the other users are streamed past them, one entry per warp step; items the row
 // user did not rate contribute an exact +/-0 product, which leaves the running sum unchanged, so the result is
-// bit-identical to a sum over the item intersection.
+// bit-identical to a sum over the item intersection.  s(u,v) and s(v,u) are the same sequence of products: only one
+// of the two is computed, the other one is its copy.
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -25,7 +26,6 @@ namespace mrs {
 namespace {
 
 constexpr int32_t kMaxDenseUsers = 16384;
-constexpr int kSimMaxSmem = 220 * 1024;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -33,41 +33,57 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// ---------------- sliced-ELL structure (sparsity pattern only; cached on the rating set) ----------------
-__global__ void ell_fill_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol,
-                                const int32_t* __restrict__ known_user, const int32_t* __restrict__ perm,
-                                const int32_t* __restrict__ slice_off, int32_t n_slices, int32_t* __restrict__ ell_col,
-                                int32_t* __restrict__ ell_src) {
+// ---------------- work partition of the similarity kernel (sparsity pattern only; cached on the rating set) --------
+#ifndef MRS_WIDE_THREADS
+#define MRS_WIDE_THREADS 512
+#endif
+constexpr int kWideThreads = MRS_WIDE_THREADS;
+constexpr int kWideRows = 16;       // row users per CTA: one per lane of a half warp
+constexpr int kWideUserCost = 8;   // what picking up a column user costs per phase, in entries (work partition)
+// items per phase: the tile of items x 16 fp64 values and a 512-byte staging buffer per warp share the SM's 227 KB with one
+// CTA (1,747 with 16 warps: ml-100k's 1,682 items are one phase)
+constexpr int kWideMaxItems = (227 * 1024 - 512 - (kWideThreads / 32) * 512) / (kWideRows * 8) - 1;  // (- the all-zero row)
+#ifndef MRS_WIDE_BATCH
+#define MRS_WIDE_BATCH 8
+#endif
+
+// vmeta[p*npos + pos] = {compact index of the user at position pos of the length-sorted order (-1: padding), first and
+// one-past-last CSR position of that user's entries with p*ic <= item < (p+1)*ic, 0}: everything a warp needs to know
+// about a column user in phase p, in ONE 16-byte load
+__global__ void vmeta_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol, const int32_t* __restrict__ known_user,
+                             const int32_t* __restrict__ order, int32_t npos, int32_t ic, int32_t P, int4* __restrict__ vmeta) {
   const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t slice = t >> 5, lane = t & 31;
-  if (slice >= n_slices) return;
-  const int32_t c = perm[t];
-  const int32_t base = slice_off[slice], width = slice_off[slice + 1] - base;
-  int32_t b = 0, len = 0;
+  if (t >= npos * P) return;
+  const int32_t p = t / npos, pos = t % npos;
+  const int32_t c = order[pos];
+  int4 out = make_int4(-1, 0, 0, 0);
   if (c >= 0) {
     const int32_t u = known_user[c];
-    b = urow[u];
-    len = urow[u + 1] - b;
+    const int32_t b = urow[u], e = urow[u + 1];
+    int32_t bound[2];
+    for (int k = 0; k < 2; ++k) {
+      const int64_t want = (int64_t)(p + k) * ic;
+      int32_t lo = b, hi = e;
+      while (lo < hi) {  // items ascending inside a row
+        const int32_t mid = (lo + hi) >> 1;
+        if (ucol[mid] < want) lo = mid + 1; else hi = mid;
+      }
+      bound[k] = lo;
+    }
+    out = make_int4(c, bound[0], (p == P - 1) ? e : bound[1], 0);
   }
-  for (int32_t j = 0; j < width; ++j) {
-    const int64_t q = ((int64_t)(base + j) << 5) + lane;
-    ell_col[q] = j < len ? ucol[b + j] : 0;
-    ell_src[q] = j < len ? b + j : -1;
-  }
+  vmeta[t] = out;
 }
 
 }  // namespace
 
-int32_t build_sim_layout(const mrs_ratings* R, bool with_ell) {
+int32_t build_sim_layout(const mrs_ratings* R, bool with_wide) {
   mrs_ratings::sim_layout& L = R->sl;
   cudaStream_t st = R->eng->stream;
-  std::vector<int32_t> urow;
-  if (!L.built || (with_ell && !L.ell_built)) {
-    urow.resize((size_t)R->n_users + 1);
+  if (!L.built) {
+    std::vector<int32_t> urow((size_t)R->n_users + 1);
     MRS_CUDA(cudaMemcpyAsync(urow.data(), R->urow, sizeof(int32_t) * urow.size(), cudaMemcpyDeviceToHost, st));
     MRS_CUDA(cudaStreamSynchronize(st));
-  }
-  if (!L.built) {
     std::vector<int32_t>& known = L.h_known;
     std::vector<int32_t> cidx((size_t)R->n_users, -1);
     known.clear();
@@ -80,7 +96,6 @@ int32_t build_sim_layout(const mrs_ratings* R, bool with_ell) {
     std::iota(L.h_order.begin(), L.h_order.end(), 0);
     std::stable_sort(L.h_order.begin(), L.h_order.end(), [&](int32_t a, int32_t b) { return L.h_len[a] > L.h_len[b]; });
     L.n_known = nk;
-    L.n_slices = (nk + 31) / 32;
     MRS_TRY(dev_alloc(&L.known_user, (size_t)nk));
     MRS_TRY(dev_alloc(&L.cidx, (size_t)R->n_users));
     MRS_CUDA(cudaMemcpyAsync(L.known_user, known.data(), sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
@@ -88,30 +103,64 @@ int32_t build_sim_layout(const mrs_ratings* R, bool with_ell) {
     MRS_CUDA(cudaStreamSynchronize(st));  // cidx goes out of scope
     L.built = true;
   }
-  if (with_ell && !L.ell_built) {
-    const int32_t nk = L.n_known, ns = L.n_slices;
-    const std::vector<int32_t>& known = L.h_known;
-    std::vector<int32_t> perm((size_t)ns * 32, -1), soff((size_t)ns + 1, 0);
-    for (int32_t t = 0; t < nk; ++t) perm[t] = L.h_order[t];
-    for (int32_t s = 0; s < ns; ++s) {
-      const int32_t c = perm[(size_t)s * 32];
-      const int32_t w = urow[known[c] + 1] - urow[known[c]];  // longest row of the slice (rows sorted by length)
-      soff[s + 1] = soff[s] + w;
+  if (with_wide && !L.wide_built) {
+    // Row users in blocks of kWideRows positions of the length-sorted order; block b is compared with the users at
+    // positions >= kWideRows * b (s is symmetric: the rest is copied), so a block's work is the number of entries of those users.  Every
+    // block gets CTAs in proportion to its work, each CTA a contiguous range of positions with an equal share of the
+    // entries; inside a range the rows get shorter, so the warps that pick them up one by one finish together.
+    const int32_t nk = L.n_known, nb = (nk + kWideRows - 1) / kWideRows, npos = (nk + 31) / 32 * 32;
+    const int32_t P = std::max(1, (R->n_items + kWideMaxItems - 1) / kWideMaxItems);
+    const int32_t ic = std::max(1, (R->n_items + P - 1) / P);
+    std::vector<int32_t> order((size_t)npos, -1);
+    for (int32_t t = 0; t < nk; ++t) order[t] = L.h_order[t];
+    // (a user costs its entries plus a fixed amount per phase: descriptor, partial sum in and out)
+    const int user_cost = getenv("MRS_WIDE_USERCOST") ? atoi(getenv("MRS_WIDE_USERCOST")) : kWideUserCost;
+    std::vector<int64_t> suffix((size_t)nk + 1, 0);
+    for (int32_t t = nk - 1; t >= 0; --t) suffix[t] = suffix[(size_t)t + 1] + L.h_len[order[t]] + (int64_t)user_cost * P;
+    int64_t W = 0;
+    for (int32_t b = 0; b < nb; ++b) W += suffix[(size_t)b * kWideRows];
+    const int64_t G = R->eng->sm_count;
+    auto ctas_of = [&](int32_t b, int64_t target) { return std::max<int64_t>(1, (suffix[(size_t)b * kWideRows] + target - 1) / target); };
+    int64_t target = std::max<int64_t>(1, (W + G - 1) / G);
+    if (nb <= G) {  // one wave: raise the share until the CTAs fit the SMs
+      for (int it = 0; it < 200; ++it) {
+        int64_t count = 0;
+        for (int32_t b = 0; b < nb; ++b) count += ctas_of(b, target);
+        if (count <= G) break;
+        target += std::max<int64_t>(1, target / 50);
+      }
     }
-    L.ell_entries = (int64_t)soff[ns] * 32;
-    MRS_TRY(dev_alloc(&L.perm, perm.size()));
-    MRS_TRY(dev_alloc(&L.slice_off, soff.size()));
-    MRS_TRY(dev_alloc(&L.ell_col, (size_t)L.ell_entries));
-    MRS_TRY(dev_alloc(&L.ell_src, (size_t)L.ell_entries));
-    MRS_CUDA(cudaMemcpyAsync(L.perm, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice, st));
-    MRS_CUDA(cudaMemcpyAsync(L.slice_off, soff.data(), sizeof(int32_t) * soff.size(), cudaMemcpyHostToDevice, st));
-    if (ns > 0) {
-      ell_fill_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(R->urow, R->ucol, L.known_user, L.perm, L.slice_off, ns, L.ell_col, L.ell_src);
+    std::vector<int4> desc;
+    for (int32_t b = 0; b < nb; ++b) {
+      const int64_t k = ctas_of(b, target), work = suffix[(size_t)b * kWideRows];
+      int32_t pos = b * kWideRows;
+      for (int64_t j = 0; j < k && pos < nk; ++j) {
+        const int64_t stop = work - (work * (j + 1)) / k;  // entries left behind this CTA's range
+        int32_t end = pos + 1;
+        while (end < nk && suffix[end] > stop) ++end;
+        if (j == k - 1) end = nk;
+        desc.push_back(make_int4(b, pos, end, 0));
+        pos = end;
+      }
+    }
+    L.n_wide = (int32_t)desc.size();
+    L.wide_ic = ic;
+    L.wide_p = P;
+    int32_t* d_order = nullptr;
+    MRS_TRY(dev_alloc(&d_order, order.size()));
+    MRS_TRY(dev_alloc(&L.wide_desc, std::max<size_t>(1, desc.size())));
+    MRS_TRY(dev_alloc(&L.vmeta, std::max<size_t>(1, order.size() * (size_t)P)));
+    MRS_CUDA(cudaMemcpyAsync(d_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
+    if (!desc.empty()) MRS_CUDA(cudaMemcpyAsync(L.wide_desc, desc.data(), sizeof(int4) * desc.size(), cudaMemcpyHostToDevice, st));
+    if (nk > 0) {
+      vmeta_kernel<<<(npos * P + 255) / 256, 256, 0, st>>>(R->urow, R->ucol, L.known_user, d_order, npos, ic, P, L.vmeta);
       count_launch();
     }
+    L.wide_npos = npos;
     MRS_CUDA(cudaGetLastError());
     MRS_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
-    L.ell_built = true;
+    dev_free(d_order);
+    L.wide_built = true;
   }
   return MRS_OK;
 }
@@ -157,133 +206,146 @@ __global__ void __launch_bounds__(256) dev_pre_kernel(const VT* __restrict__ uva
   for (int32_t p = b + lane; p < e; p += 32) upre[p] = (w != 0.0) ? __ddiv_rn(udev[p], w) : 0.0;  // P:478-479
 }
 
-// ---------------- P2: values in the layouts the next kernels stream (ELL for similarity, CSC for prediction) --------
+// ---------------- P2: values in the layouts the next kernels stream (packed CSR for similarity, CSC for prediction) ----
 template <int MODE>  // 0: deviations only (uniform); 1: cosine; 2: jaccard
 __global__ void gather_values_kernel(const double* __restrict__ udev, const double* __restrict__ upre,
-                                     const int32_t* __restrict__ csc_src, int64_t n, const int32_t* __restrict__ ell_src,
-                                     int64_t ell_entries, double* __restrict__ cdev, double* __restrict__ ell_val) {
+                                     const int32_t* __restrict__ csc_src, int64_t n, const int32_t* __restrict__ ucol,
+                                     double* __restrict__ cdev, int4* __restrict__ pk) {
   pdl_trigger();
   pdl_wait();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += stride) cdev[p] = udev[csc_src[p]];
-  if (MODE != 0) {
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < ell_entries; q += stride) {
-      const int32_t s = ell_src[q];
-      ell_val[q] = s >= 0 ? (MODE == 1 ? upre[s] : 1.0) : 0.0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += stride) {
+    cdev[p] = udev[csc_src[p]];
+    if (MODE != 0) {  // one 16-byte record per rating: a warp fetches it with a single uniform load
+      const double x = (MODE == 1) ? upre[p] : 1.0;
+      pk[p] = make_int4(ucol[p], ucol[p] * (kWideRows * 8), __double2loint(x), __double2hiint(x));  // .y: byte offset of the item's tile row
     }
   }
 }
 
 // ---------------- P3: user-user similarity, shared-memory-staged SpGEMM --------------------------------------------
-constexpr int kSimThreads = 512;  // 16 warps with up to 128 registers each (see the slice loop)
-template <int UB, int MODE>  // MODE 1: cosine (P:424-426), 2: jaccard (P:454-458)
-__global__ void __launch_bounds__(kSimThreads) similarity_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ ucol,
-                                                        const double* __restrict__ upre, const int32_t* __restrict__ known_user,
-                                                        int32_t n_known, int32_t n_items, const int32_t* __restrict__ perm,
-                                                        const int32_t* __restrict__ slice_off, int32_t n_slices,
-                                                        const int32_t* __restrict__ ell_col, const double* __restrict__ ell_val,
-                                                        double* __restrict__ S) {
-  // [n_items][kStride]: r~ of the block's users, 0.0 where unrated.  A lane reads the UB values of its item with 128-bit
-  // loads; the row stride is padded from 8 to 10 doubles (80 B) so that the items of a quarter warp fall on 8 different
-  // bank groups (with a 64-byte stride every item sits on the same two: capture r01_knn counted 18.3 M bank conflicts
-  // in 23.7 M shared wavefronts, the kernel was bound by that)
-  constexpr int kStride = (UB >= 4) ? UB + 2 : UB;
-  extern __shared__ __align__(16) double su[];
-  const int32_t cu0 = blockIdx.x * UB;
+// One lane per ROW user, one column user per half warp: the tile holds r~ of the block's 16 row users as [item][16] (0.0
+// where unrated); a half warp takes a column user v and walks v's entries in ascending item order -- the entry (item,
+// r~_v) comes from a 16-byte broadcast read of the warp's staging buffer (filled 16 records at a time by one coalesced
+// load), the 16 row values of that item from one conflict-free 128-byte shared-memory row -- so 32 products cost three
+// memory wavefronts and no lane ever waits for another's item.  (The kernel this replaces held 8 row users per CTA and
+// gave a lane one column user: every lane gathered the 64 bytes of its own item, 0.16 wavefronts per product at the
+// measured conflict rate against 0.09 here, and it was bound by exactly that; profiles/r01_ncu_full_raw_knn_final.csv.)
+// If 16 rows x all items do not fit shared memory the items are cut into wide_p phases of wide_ic items; the partial sums
+// of a phase wait in S (the pair (row block, v) belongs to one CTA, the order of the additions is unchanged).  ml-100k's
+// 1,682 items are one phase.
+// Only v at or behind the block's own positions are visited: s(v,u) is the same sequence of products as s(u,v) and is
+// written as its copy.  Positions are places in the length-sorted order, so long rows meet long rows once, not twice.
+template <int MODE>  // 1: cosine (P:424-426), 2: jaccard (P:454-458)
+__global__ void __launch_bounds__(kWideThreads, 1) similarity_wide_kernel(const int32_t* __restrict__ urow, const int4* __restrict__ pk,
+                                                                        const int32_t* __restrict__ known_user, int32_t n_known,
+                                                                        const int4* __restrict__ vmeta, int32_t npos,
+                                                                        const int4* __restrict__ desc, int32_t ic, int32_t P,
+                                                                        double* __restrict__ S, unsigned long long* __restrict__ tl) {
+  extern __shared__ __align__(16) double tile[];  // [ic + 1][16] (the last row stays all zero), then one staging buffer of 2 x 16 records per warp
+  tl_cta(tl, 0);  // (MRS_TIMELINE=1: per-CTA stamps, tools/knn_once.py)
+  constexpr int nwarps = kWideThreads / 32;
+  constexpr int kR = kWideRows;
+  constexpr int kB = MRS_WIDE_BATCH;
+  const int4 d = desc[blockIdx.x];
+  const int32_t pos0 = d.x * kR, v0 = d.y, v1 = d.z;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t = lane & (kR - 1), h = lane >> 4;  // row user of this lane, half warp
+  int4* __restrict__ buf = reinterpret_cast<int4*>(tile + (size_t)(ic + 1) * kR) + wid * 32;
+  const int32_t my_cu = vmeta[pos0 + t].x;  // this lane's row user (-1: padding behind the last user)
+  const bool have = my_cu >= 0;
+  int32_t nu = 0;
+  if (MODE == 2 && have) { const int32_t u = known_user[my_cu]; nu = urow[u + 1] - urow[u]; }
+  double* __restrict__ Srow = S + (int64_t)(have ? my_cu : 0) * n_known;
+  const int4 none = make_int4(-1, 0, 0, 0);
   pdl_trigger();
-  for (int32_t x = threadIdx.x; x < n_items * kStride; x += blockDim.x) su[x] = 0.0;  // overlaps the previous kernel
-  pdl_wait();
-  __syncthreads();
-#pragma unroll
-  for (int t = 0; t < UB; ++t) {
-    const int32_t cu = cu0 + t;
-    if (cu < n_known) {
-      const int32_t u = known_user[cu];
-      for (int32_t p = urow[u] + threadIdx.x; p < urow[u + 1]; p += blockDim.x) su[ucol[p] * kStride + t] = (MODE == 1) ? upre[p] : 1.0;
-    }
+  {
+    double2* t2 = reinterpret_cast<double2*>(tile);
+    for (int32_t x = threadIdx.x; x < (ic + 1) * (kR / 2); x += kWideThreads) t2[x] = make_double2(0.0, 0.0);
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  // Slices are sorted by width (the 32 longest rows first: ~750 items against ~20 for the last slice) and the sum of one
-  // (u, v) pair is a serial chain over the slice's rows, so the kernel lasts as long as the warp that owns the widest slice
-  // (capture r01_ncu_full_raw_knn_final.csv: 18 % of the warp slots active, the critical warps waiting on the column loads
-  // of every batch and on each row's shared-memory loads in turn).  Hence: 16 warps with up to 128 registers each; slices
-  // dealt out in a snake so every warp gets wide and narrow ones; the next batch of (column, value) pairs is requested while
-  // the current one is accumulated; the shared-memory loads of four rows go out together before their products are added.
-  const int32_t nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5;
-  for (int32_t round = 0; round * nwarps < n_slices; ++round) {
-    const int32_t slice = round * nwarps + ((round & 1) ? nwarps - 1 - wid : wid);
-    if (slice >= n_slices) continue;
-    const int32_t cv = perm[slice * 32 + lane];
-    const int32_t base = slice_off[slice], width = slice_off[slice + 1] - base;
-    double acc[UB];
-#pragma unroll
-    for (int t = 0; t < UB; ++t) acc[t] = 0.0;
-    const int32_t* colp = ell_col + ((int64_t)base << 5) + lane;
-    const double* valp = ell_val + ((int64_t)base << 5) + lane;
-    constexpr int kB = 8;   // rows per batch of global loads
-    constexpr int kH = 4;   // rows whose shared-memory loads are issued together
-    int32_t ncol[kB];
-    double nval[kB];
-#pragma unroll
-    for (int q = 0; q < kB; ++q) {
-      const bool in = q < width;
-      ncol[q] = in ? __ldg(colp + ((int64_t)q << 5)) : 0;
-      nval[q] = in ? __ldg(valp + ((int64_t)q << 5)) : 0.0;  // padding: +/-0 products leave the sums unchanged
-    }
-    for (int32_t j0 = 0; j0 < width; j0 += kB) {
-      int32_t col[kB];
-      double val[kB];
-#pragma unroll
-      for (int q = 0; q < kB; ++q) { col[q] = ncol[q]; val[q] = nval[q]; }
-#pragma unroll
-      for (int q = 0; q < kB; ++q) {
-        const bool in = j0 + kB + q < width;
-        ncol[q] = in ? __ldg(colp + ((int64_t)(j0 + kB + q) << 5)) : 0;
-        nval[q] = in ? __ldg(valp + ((int64_t)(j0 + kB + q) << 5)) : 0.0;
-      }
-#pragma unroll
-      for (int h = 0; h < kB; h += kH) {
-        if (UB >= 2) {
-          double2 v[kH][UB >= 2 ? UB / 2 : 1];
-#pragma unroll
-          for (int q = 0; q < kH; ++q) {
-            const double* row = su + col[h + q] * kStride;
-#pragma unroll
-            for (int t = 0; t < UB; t += 2) v[q][t / 2] = *reinterpret_cast<const double2*>(row + t);
-          }
-#pragma unroll
-          for (int q = 0; q < kH; ++q) {
-#pragma unroll
-            for (int t = 0; t < UB; t += 2) {
-              acc[t] = __dadd_rn(acc[t], __dmul_rn(v[q][t / 2].x, val[h + q]));  // ascending item id, no FMA
-              acc[t + (UB >= 2 ? 1 : 0)] = __dadd_rn(acc[t + (UB >= 2 ? 1 : 0)], __dmul_rn(v[q][t / 2].y, val[h + q]));
-            }
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < kH; ++q) acc[0] = __dadd_rn(acc[0], __dmul_rn(su[col[h + q] * kStride], val[h + q]));
+  pdl_wait();  // the records are complete from here on; zeroing the tile overlapped the previous kernel
+  for (int32_t p = 0; p < P; ++p) {
+    const int32_t i0 = p * ic;
+    const bool last = (p == P - 1);
+    const int4* __restrict__ vm = vmeta + (size_t)p * npos;
+    __syncthreads();
+    for (int r = wid; r < kR; r += nwarps) {  // the row users' entries of this phase
+      const int4 m = vm[pos0 + r];
+      if (m.x >= 0) {
+        for (int32_t q = m.y + lane; q < m.z; q += 32) {
+          const int4 e = pk[q];
+          tile[(e.x - i0) * kR + r] = __hiloint2double(e.w, e.z);
         }
       }
     }
-    if (cv >= 0) {
-      int32_t nv = 0;
-      if (MODE == 2) { const int32_t v = known_user[cv]; nv = urow[v + 1] - urow[v]; }
+    __syncthreads();
+    if (p == 0) tl_cta(tl, 1);
+    const unsigned char* __restrict__ col = reinterpret_cast<const unsigned char*>(tile + t) - (int64_t)i0 * (kR * 8);
+    // what a half warp reads behind the end of its user: the all-zero row times 0.0 -- an exact +0 that leaves the sum as it is
+    const int4 safe = make_int4(i0 + ic, (i0 + ic) * (kR * 8), 0, 0);
+    // Column users are dealt out to the half warps round robin (the CTA's positions hold ever shorter rows, so every warp
+    // gets the same mix and its two halves rows of nearly the same length).  The addresses of everything a warp will need
+    // are known in advance: the descriptor of the user after next and the first records of the next one are in flight
+    // during the sums of the current one, so no load latency is paid between two users.
+    auto meta_of = [&](int32_t pos) { return (pos < v1) ? __ldg(vm + pos) : none; };
+    auto chunk_of = [&](const int4& m, int32_t q0) { return (q0 < m.z) ? __ldg(pk + min(q0 + t, m.z - 1)) : safe; };
+    int32_t pos_a = v0 + 2 * wid + h;
+    int4 ma = meta_of(pos_a), mb = meta_of(pos_a + 2 * nwarps), mc = meta_of(pos_a + 4 * nwarps);
+    int4 ent_a = chunk_of(ma, ma.y);
+    while (__any_sync(0xffffffffu, pos_a < v1)) {
+      const int4 ent_b = chunk_of(mb, mb.y);
+      const int4 md = meta_of(pos_a + 6 * nwarps);
+      const int32_t cv = ma.x, qa = ma.y, qb = ma.z;  // (a half without a user: -1, 0, 0)
+      const bool skip = (qa == qb && p > 0 && !last);  // nothing to add in this phase: the partial sum stays where it is
+      double acc = 0.0;
+      if (p > 0 && have && cv >= 0 && !skip) acc = __ldcg(Srow + cv);
+      int4 ent = ent_a;
+      const int32_t len = qb - qa;
+      const int32_t len_w = max(len, __shfl_xor_sync(0xffffffffu, len, 16));  // the longer of the warp's two rows
+      for (int32_t c0 = 0; c0 < len_w; c0 += kR) {
+        const int n = min(kR, len - c0);  // this half's records in the chunk (<= 0: none left)
+        __syncwarp();
+        buf[t * 2 + h] = (t < n) ? ent : safe;
+        __syncwarp();
+        ent = chunk_of(ma, qa + c0 + kR);  // the next chunk, requested ahead
 #pragma unroll
-      for (int t = 0; t < UB; ++t) {
-        const int32_t cu = cu0 + t;
-        if (cu < n_known) {
-          double s = acc[t];
-          if (MODE == 2) {
-            const int32_t u = known_user[cu];
-            const int32_t nu = urow[u + 1] - urow[u];
-            s = acc[t] / (double)(nu + nv - (int32_t)acc[t]);  // P:458
+        for (int k0 = 0; k0 < kR; k0 += kB) {
+          if (k0 < len_w - c0) {  // warp-uniform
+            int4 e[kB];
+            double x[kB];
+#pragma unroll
+            for (int j = 0; j < kB; ++j) e[j] = buf[(k0 + j) * 2 + h];  // one address per half warp: one wavefront
+#pragma unroll
+            for (int j = 0; j < kB; ++j) x[j] = *reinterpret_cast<const double*>(col + e[j].y);  // the item's 16 row values: 128 contiguous bytes
+#pragma unroll
+            for (int j = 0; j < kB; ++j) acc = __dadd_rn(acc, __dmul_rn(x[j], __hiloint2double(e[j].w, e[j].z)));  // ascending item id, no FMA
           }
-          S[(int64_t)cu * n_known + cv] = s;
         }
+      }
+      if (have && cv >= 0 && !skip) {
+        double s = acc;
+        if (MODE == 2 && last) {
+          const int32_t v = known_user[cv];
+          const int32_t nv = urow[v + 1] - urow[v];
+          s = acc / (double)(nu + nv - (int32_t)acc);  // P:458
+        }
+        __stcg(Srow + cv, s);
+        if (last && pos_a >= pos0 + kR) __stcg(S + (int64_t)cv * n_known + my_cu, s);  // s(v,u): the same products in the same order
+      }
+      pos_a += 2 * nwarps; ma = mb; ent_a = ent_b;
+      mb = mc; mc = md;
+    }
+    __syncthreads();  // every warp is done with the tile
+    if (p == 0) tl_cta(tl, 2);
+    if (!last) {  // take the row users' entries out again: the tile is all zero for the next phase
+      for (int r = wid; r < kR; r += nwarps) {
+        const int4 m = vm[pos0 + r];
+        if (m.x >= 0)
+          for (int32_t q = m.y + lane; q < m.z; q += 32) tile[(pk[q].x - i0) * kR + r] = 0.0;
       }
     }
   }
+  tl_cta(tl, 3);
 }
 
 // ---------------- P4: full sort of every row by (similarity desc, user id asc); P:610 + SURVEY A.6 ----------------
@@ -511,34 +573,24 @@ int sim_mode(const mrs_sim* s) {
   return s->k > 0 ? 2 : 1;
 }
 
-template <int UB, int MODE>
-int32_t launch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
+template <int MODE>
+int32_t dispatch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
   const auto& L = R->sl;
-  const size_t smem = (size_t)R->n_items * ((UB >= 4) ? UB + 2 : UB) * sizeof(double);
-  MRS_CUDA(cudaFuncSetAttribute(similarity_kernel<UB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (L.n_known + UB - 1) / UB;
-  MRS_CUDA(launch_pdl(similarity_kernel<UB, MODE>, dim3(grid), dim3(kSimThreads), smem, st, R->urow, R->ucol, s->upre, L.known_user, L.n_known,
-                      R->n_items, L.perm, L.slice_off, L.n_slices, L.ell_col, s->ell_val, s->S));
+  if (L.n_wide == 0) return MRS_OK;
+  const size_t smem = (size_t)(L.wide_ic + 1) * kWideRows * sizeof(double) + (size_t)(kWideThreads / 32) * 32 * sizeof(int4);
+  MRS_CUDA(cudaFuncSetAttribute(similarity_wide_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MRS_CUDA(launch_pdl(similarity_wide_kernel<MODE>, dim3(L.n_wide), dim3(kWideThreads), smem, st, R->urow, s->pk, L.known_user, L.n_known, L.vmeta,
+                      L.wide_npos, L.wide_desc, L.wide_ic, L.wide_p, s->S, R->eng->d_timeline));
   mark(R->eng, "similarity");
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
-}
-
-template <int MODE>
-int32_t dispatch_similarity(const mrs_ratings* R, mrs_sim* s, cudaStream_t st) {
-  const size_t row = (size_t)R->n_items * sizeof(double);
-  // 8 users per CTA: measured 127 us against 144 us with 4 users per CTA at ml-100k shape (profiles/r01_summary.md)
-  if (row * 10 <= (size_t)kSimMaxSmem) return launch_similarity<8, MODE>(R, s, st);
-  if (row * 6 <= (size_t)kSimMaxSmem) return launch_similarity<4, MODE>(R, s, st);
-  if (row * 2 <= (size_t)kSimMaxSmem) return launch_similarity<2, MODE>(R, s, st);
-  return launch_similarity<1, MODE>(R, s, st);
 }
 
 }  // namespace
 
 void free_sim_layout(const mrs_ratings* r) {
   auto& L = r->sl;
-  dev_free(L.known_user); dev_free(L.cidx); dev_free(L.perm); dev_free(L.slice_off); dev_free(L.ell_col); dev_free(L.ell_src);
+  dev_free(L.known_user); dev_free(L.cidx); dev_free(L.vmeta); dev_free(L.wide_desc);
   free_rows_layout(r);
   L = mrs_ratings::sim_layout();
 }
@@ -564,9 +616,6 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
     MRS_REQUIRE(k > 0, MRS_ERR_UNSUPPORTED,
                 "mrs_fit_similarity: with %d users only the first k neighbours of a user are kept (row-block path); k must be > 0",
                 L.n_known);
-  } else if (matrix) {
-    MRS_REQUIRE((size_t)R->n_items * sizeof(double) <= (size_t)kSimMaxSmem, MRS_ERR_UNSUPPORTED,
-                "mrs_fit_similarity: item dimension %d does not fit the shared-memory staged similarity kernel", R->n_items);
   }
   mrs_sim* s = *inout;
   if (s && (s->model != m || s->kind != kind || s->lists != rows)) {
@@ -592,7 +641,7 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
     if (rc == MRS_OK) rc = dev_alloc(&s->counter, 4);
     if (rc == MRS_OK && cudaMemsetAsync(s->counter, 0, 4 * sizeof(unsigned int), st) != cudaSuccess) rc = MRS_ERR_CUDA;
     if (matrix && !rows) {
-      if (rc == MRS_OK) rc = dev_alloc(&s->ell_val, (size_t)L.ell_entries);
+      if (rc == MRS_OK) rc = dev_alloc(&s->pk, (size_t)R->n);
       if (rc == MRS_OK) rc = dev_alloc(&s->S, nk * nk);
       if (rc == MRS_OK) rc = dev_alloc(&s->rank, nk * nk);
       if (rc == MRS_OK) rc = dev_alloc(&s->nbr_id, nk * (nk ? nk - 1 : 0));
@@ -621,11 +670,11 @@ static int32_t sim_fit_impl(mrs_model* m, int32_t kind, int32_t k, mrs_sim** ino
     return rows_fit_async(m, s, first);
   }
   // P2
-  const int64_t work = std::max<int64_t>(R->n, matrix ? L.ell_entries : 0);
+  const int64_t work = R->n;
   const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)e->sm_count * 8));
-  if (kind == MRS_SIM_UNIFORM) MRS_CUDA(launch_pdl(gather_values_kernel<0>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val));
-  else if (kind == MRS_SIM_COSINE) MRS_CUDA(launch_pdl(gather_values_kernel<1>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val));
-  else MRS_CUDA(launch_pdl(gather_values_kernel<2>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, L.ell_src, L.ell_entries, s->cdev, s->ell_val));
+  if (kind == MRS_SIM_UNIFORM) MRS_CUDA(launch_pdl(gather_values_kernel<0>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, R->ucol, s->cdev, s->pk));
+  else if (kind == MRS_SIM_COSINE) MRS_CUDA(launch_pdl(gather_values_kernel<1>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, R->ucol, s->cdev, s->pk));
+  else MRS_CUDA(launch_pdl(gather_values_kernel<2>, dim3(g2), dim3(256), 0, st, s->udev, s->upre, R->csc_src, R->n, R->ucol, s->cdev, s->pk));
   mark(e, "gather_values");
   MRS_CUDA(cudaGetLastError());
   if (!matrix) return MRS_OK;
@@ -795,7 +844,7 @@ extern "C" int32_t mrs_sim_entry_values(const mrs_sim* s, int32_t which, int32_t
 extern "C" void mrs_sim_destroy(mrs_sim* s) {
   if (!s) return;
   if (s->model && s->model->eng) use_engine(s->model->eng);
-  dev_free(s->udev); dev_free(s->upre); dev_free(s->unorm); dev_free(s->cdev); dev_free(s->ell_val); dev_free(s->S);
+  dev_free(s->udev); dev_free(s->upre); dev_free(s->unorm); dev_free(s->cdev); dev_free(s->pk); dev_free(s->S);
   dev_free(s->rank); dev_free(s->nbr_id); dev_free(s->nbr_sim); dev_free(s->mae_part); dev_free(s->counter);
   rows_free(s);
   delete s;

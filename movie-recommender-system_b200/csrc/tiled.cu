@@ -734,9 +734,11 @@ int32_t build_tiled_layout(const mrs_ratings* R) {
   // same number of ratings: a tile takes the users that hold k quotas of n / #SMs ratings (k = as many as fit into
   // kTileUsers users) and is worked on by k CTAs.  Equal-sized tiles of 8,192 users got 7 or 8 CTAs each at ml-25m shape:
   // 161 against 144 rows per warp, and the pass as slow as its 7-CTA tiles (per-CTA stamps: 38 us against 35 us).
-  // MRS_TILES=0 keeps equal-sized tiles with CTAs dealt out by cost.
+  // OPT-IN (MRS_TILES=1): on most boxes the pass is no faster than with equal-sized tiles and CTAs dealt out by cost
+  // (68.2 against 68.0-68.8 us, tools/timeline.py), while the host-side cut below (one D2H copy of the row pointer, a
+  // synchronisation and 162 k binary searches) costs 0.2 ms in every end-to-end step (tools/e2e_ab.py: 7.80 against 7.58 ms).
   std::vector<int32_t> h_ubegin, h_kctas;
-  bool cost_tiles = !(getenv("MRS_TILES") && atoi(getenv("MRS_TILES")) == 0) && n > 0;
+  bool cost_tiles = getenv("MRS_TILES") && atoi(getenv("MRS_TILES")) == 1 && n > 0;
   if (cost_tiles) {
     const int32_t NU = R->n_users, C = e->sm_count;
     std::vector<int32_t> h_urow((size_t)NU + 1);
