@@ -233,6 +233,31 @@ def run_ours(args):
             if self.b is not None:
                 self.sink += self.b.view(torch.int64).sum()
     flush = _Flush()
+
+    class _Align:
+        """N>1: a 16-byte all-reduce through the library's own peer-memory kernel right before a timed step, OUTSIDE the event
+        pair: the ranks leave it within a flag round trip of each other (about 2 us), so a step's time is the step and not the
+        skew with which the ranks finished flushing their L2 (the exchange inside the step waits for the slowest rank).
+        MRS_BENCH_ALIGN=0 switches it off."""
+        def __init__(self):
+            self.peer = None
+            self.buf = torch.zeros(2, dtype=torch.float64, device=dev)
+            if world > 1 and not args.nccl and os.environ.get("MRS_BENCH_ALIGN", "1") != "0":
+                def gather(b):
+                    out = [None] * world
+                    dist.all_gather_object(out, b)
+                    return out
+                self.peer = E.PeerExchange(eng, 2, rank, world, gather)
+
+        def __call__(self):
+            if self.peer is not None:
+                self.peer.allreduce_async(self.buf.data_ptr(), 2)
+
+        def close(self):
+            if self.peer is not None:
+                self.peer.close()
+                self.peer = None
+    align = _Align()
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
     from mrs_b200 import sharded
@@ -287,6 +312,7 @@ def run_ours(args):
         t_wall0 = time.perf_counter()
         for a, b in evs:
             flush.zero_()          # L2 flush, outside the timed pair
+            align()                # N>1: the ranks start the step together (outside the timed pair as well)
             a.record(stream)
             step()
             b.record(stream)
@@ -434,7 +460,7 @@ def run_ours(args):
     strong = None
     if world > 1 and not args.no_strong:
         with torch.cuda.stream(stream):
-            strong = bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, peer=not args.nccl)
+            strong = bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, peer=not args.nccl, align=align)
 
     line = None
     if rank == 0:
@@ -496,6 +522,8 @@ def run_ours(args):
                                                            if sb.closure else "fused into the pass' own kernels: partial sums pushed into every rank's receive buffer over NVLink")
                                                           if sb.fused else "own NVLink peer-memory all-reduce kernel", "timed_out": sb.peer.timed_out()}),
             "step_ms_min_max": [min(step_ms), max(step_ms)],
+            "rank_alignment": ("16-byte peer-memory all-reduce before every timed step, outside the event pair (the ranks start a step "
+                               "within a flag round trip of each other)") if align.peer is not None else None,
             "strong_scaling": strong,
             "knn": knn,
             "knn25m": knn25m,
@@ -504,12 +532,13 @@ def run_ours(args):
     if world > 1:
         torch.cuda.synchronize(dev)
         dist.barrier()
+        align.close()
         dist.destroy_process_group()
     sys.stdout.flush()
     return 0
 
 
-def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, peer):
+def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, peer, align=lambda: None):
     """BASELINE config 4 as worded: ONE ml-25m-shaped set, its users partitioned over the ranks
     (distributed/DistributedBaseline.scala:30-47 with --master local[N]; reduceByKey/collect of P:267-268 = the exchange).
     A rank holds the train rows and the test pairs of its user range (sharded.partition_users / shard_of), the tables are
@@ -537,6 +566,7 @@ def bench_strong(eng, stream, torch, dist, d, rank, world, dev, flush, args, pee
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in evs:
         flush.zero_()
+        align()
         a.record(stream)
         sb.step()
         b.record(stream)
@@ -632,19 +662,31 @@ def bench_knn(eng, stream, torch):
     mae = float(r[0] / r[1])
     for h in (s, m, T, R):
         h.close()
-    # roofline of the dominant kernel: the similarity SpGEMM is fp64 multiply-add work on an L2-resident working set
-    # (about 1 MB of inputs, S = 943^2 x 8 B = 7.1 MB), so the denominator is the measured fp64 FMA rate of the device
+    # roofline of the similarity SpGEMM: an L2-resident working set (about 1 MB of inputs, S = 943^2 x 8 B = 7.1 MB); what it
+    # is short of is shared-memory bandwidth, not fp64 rate (both are reported)
     import numpy as np
     cnt_i = np.bincount(tr[1]).astype(np.float64)
-    n_known = int(np.unique(tr[0]).size)
-    executed = float(n_known) * float(tr[0].size)            # dense-staged kernel: every user row against every rating
+    cnt_u = np.bincount(tr[0])
+    # Products the kernel executes: row users in blocks of 16 positions of the length-sorted order, block b meets the users at
+    # positions >= 16 b (one triangle, the other one is copied); a step = one entry of a column user against the 16 row users.
+    lens = np.sort(cnt_u[cnt_u > 0])[::-1].astype(np.int64)
+    steps = float((lens * (np.arange(lens.size) // 16 + 1)).sum())
+    executed = 16.0 * steps
     useful = float((cnt_i * cnt_i).sum())                    # products over item intersections (both triangles)
     fp64 = eng.fp64_fma_per_s()
     sim_s = per_kernel.get("similarity", 0.0) * 1e-3
-    knn_roof = {"bound": "fp64 FMA rate (latency bound in practice: 118 CTAs of 16 warps on 148 SMs)", "kernel": "similarity",
-                "achieved": executed / sim_s if sim_s else None, "peak": fp64, "unit": "fp64 multiply-adds/s",
-                "frac": (executed / sim_s / fp64) if sim_s else None, "executed_macs": executed, "useful_products": useful,
-                "kernel_ms": per_kernel.get("similarity"), "peak_source": "measured in this run (mrs_debug_fp64_fma_per_s: 8 DFMA chains per thread, all SMs)",
+    # Bound: shared-memory wavefronts.  A warp step (two column users x 16 rows = 32 products) reads two 16-byte records
+    # (2 wavefronts: one address per half warp) and two 128-byte tile rows (2 wavefronts); an SM serves one wavefront per clock.
+    wavefronts = 4.0 * steps / 2.0
+    sm_clock = 1.965e9
+    lsu_peak = 148 * sm_clock
+    knn_roof = {"bound": "shared-memory wavefronts (LSU): 4 per warp step of 32 products, 1 per clock per SM", "kernel": "similarity",
+                "achieved": wavefronts / sim_s if sim_s else None, "peak": lsu_peak, "unit": "shared-memory wavefronts/s",
+                "frac": (wavefronts / sim_s / lsu_peak) if sim_s else None, "executed_products": executed, "useful_products": useful,
+                "kernel_ms": per_kernel.get("similarity"),
+                "fp64": {"achieved_macs_per_s": executed / sim_s if sim_s else None, "peak": fp64,
+                         "peak_source": "measured in this run (mrs_debug_fp64_fma_per_s: 8 DFMA chains per thread, all SMs)"},
+                "peak_source": "148 SMs x 1.965 GHz x 1 wavefront per clock (ncu: l1tex__data_pipe_lsu_wavefronts, profiles/r02_ncu_knn_similarity.txt)",
                 "traffic": None}
     return {"roofline": knn_roof, "metric": "knn_k300_ml100k_fit_predict_mae_ms", "value": statistics.median(ms), "unit": "ms", "min_ms": min(ms),
             "mean_ms": sum(ms) / len(ms), "reps": reps, "launch_mode": mode, "mae": mae, "per_kernel_ms": per_kernel,

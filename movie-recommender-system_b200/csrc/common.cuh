@@ -412,7 +412,7 @@ constexpr int kMaeTileItems = 8192;  // items per tile: 64 KB of fp64 item devia
 int32_t build_mae_layout(const mrs_ratings* T);
 void free_mae_layout(const mrs_ratings* T);
 int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push = nullptr, bool fold = false,
-                                  const PushDev* big = nullptr);
+                                  const PushDev* big = nullptr, bool deliver = true);
 // baseline.cu
 int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize, const PushDev* push = nullptr, bool no_finalize = false);
 int32_t fit_finish(mrs_model* m);

@@ -443,8 +443,14 @@ extern "C" int32_t mrs_fit_mae_push_async(mrs_engine* e, const mrs_ratings* trai
   PushDev big, pair;
   MRS_TRY(exchange_push_dev(x_items, 2 * (int64_t)n_known + 2, &big));
   MRS_TRY(exchange_push_dev(x_pair, 2, &pair));
-  MRS_TRY(fit_local(e, train, inout, false, nullptr, true));
-  MRS_TRY(launch_mae_tiled_baseline(m, test, (double*)device_out2, &pair, true, &big));
+  // Who delivers the per-item partial sums: the test pass' CTAs in their prologue (default: three kernels per step) or the
+  // fit's own push kernel, with the test pass still waiting for the flags and summing the deliveries itself
+  // (MRS_CLOSURE_DELIVER=kernel: four kernels, no finishing kernel).  Measured at 2 ranks, weak step: 93.0 us (default),
+  // 99.0 us (kernel delivery), 92.5 us for the five-kernel fused form (mrs_fit_local_push / mrs_fit_finish_pull / mrs_mae_push_async).
+  const char* dv = getenv("MRS_CLOSURE_DELIVER");
+  const bool by_test_pass = !(dv && strcmp(dv, "kernel") == 0);
+  MRS_TRY(fit_local(e, train, inout, false, by_test_pass ? nullptr : &big, by_test_pass));
+  MRS_TRY(launch_mae_tiled_baseline(m, test, (double*)device_out2, &pair, true, &big, by_test_pass));
   m->finished = true;  // the test pass has written the model's arrays
   m->host_valid = false;
   return MRS_OK;

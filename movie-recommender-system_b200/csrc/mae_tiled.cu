@@ -78,6 +78,7 @@ struct FoldArgs {
   const int32_t* icolp;             // [n_items+1] train column pointer (rating counts)
   unsigned long long* k1_part;      // [4] sum of all train codes (K1) + the hand-over counts of the pass (common.cuh flag_wait)
   int32_t n_k2_ctas;                // > 0: wait for that many item-pass CTAs to count themselves off instead of for the grid
+  int32_t deliver;                  // FOLD == 2: 1 = this kernel's CTAs deliver the partial sums themselves, 0 = the fit's push kernel did
   double n_fit;                     // number of train ratings
   double* idevavg;                  // model outputs
   double* xbuf;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
     const int32_t K = f.K;
     const int32_t perK = (K + gridDim.x - 1) / gridDim.x;
     const int32_t jlo = blockIdx.x * perK, jhi = min(K, jlo + perK);
+    if (f.deliver) {
     for (int32_t j = jlo + threadIdx.x; j < jhi; j += kMaeThreads) {
       const int32_t i = __ldg(f.known + j);
       const double ds = (double)__ldcg(fix + i) * kInvFix;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
       __threadfence_system();
       push_flag_raise(x2, threadIdx.x, big_epoch);
     }
+    }  // (f.deliver)
     int good = 1;
     if ((int)threadIdx.x < x2.world) good = push_flag_wait(x2, threadIdx.x, big_epoch) ? 1 : 0;  // every rank has delivered
     shard_ok = __syncthreads_and(good) != 0;
@@ -472,7 +475,8 @@ int32_t build_mae_layout(const mrs_ratings* T) {
   return MRS_OK;
 }
 
-int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push, bool fold, const PushDev* big) {
+int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, double* d_out2, const PushDev* push, bool fold, const PushDev* big,
+                                  bool deliver) {
   MRS_TRY(build_mae_layout(T));
   const auto& L = T->ml;
   mrs_engine* e = m->eng;
@@ -493,7 +497,7 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
     f.idevavg = m->idevavg; f.xbuf = m->xbuf; f.gavg = m->gavg; f.usum = m->usum; f.parity = m->counters + 4;
     if (big) {  // sharded closure: both exchanges inside this kernel
       MRS_REQUIRE(push && grid <= e->sm_count, MRS_ERR_UNSUPPORTED, "sharded closure: the test pass must be one wave (%d CTAs)", grid);
-      f.known = m->slot_of_item; f.item_slot = m->item_slot; f.K = m->n_slots_known; f.big = *big;
+      f.known = m->slot_of_item; f.item_slot = m->item_slot; f.K = m->n_slots_known; f.big = *big; f.deliver = deliver ? 1 : 0;
       MRS_CUDA(launch_pdl(predict_mae_tiled_kernel<2>, dim3(grid), dim3(kMaeThreads), kMaeSmem, e->stream, L.entry, L.tile_row_ptr, L.cta_desc, m->n_users,
                           m->n_items, m->uavg, m->idevavg, m->gavg, (double)T->n, m->mae_part, m->counters, d_out2, e->d_timeline, 1, *push, f));
     } else {
