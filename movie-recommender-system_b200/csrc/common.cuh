@@ -227,6 +227,7 @@ struct mrs_ratings {
     int32_t wide_npos = 0;         // positions: n_known rounded up to a multiple of 32
     int4* wide_desc = nullptr;     // [n_wide] CTA b: row block .x (32 positions), column users = positions [.y, .z)
     int32_t n_wide = 0;
+    int32_t* ccd = nullptr;        // [n] compact user index of each CSC entry (prediction kernels)
     int32_t wide_ic = 0, wide_p = 0;  // items per phase (the tile holds wide_ic x 32 fp64 values), number of phases
     bool wide_built = false;       // built only for the dense-matrix path
     std::vector<int32_t> h_known;  // host copies used when a row range is laid out (knn_rows.cu)

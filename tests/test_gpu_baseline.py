@@ -225,3 +225,20 @@ def test_device_text_parser_follows_the_reference_rules(eng):
         assert ei.value.status == -5
     with pytest.raises(E.MrsError):
         eng.ratings_from_text(b"-1,2,3\n", ",")                        # negative id: rejected by the build, as from arrays
+
+
+def test_cost_cut_user_tiles(eng, small, monkeypatch):
+    """MRS_TILES=1 (opt-in): the item pass' user tiles are cut so that every CTA gets the same number of ratings instead of the
+    same number of users; the fit must not change by a bit."""
+    R, T, m, o = fit_both(eng, small)
+    want = m.vector(E.ITEM_AVG_DEV)[0].copy()
+    want_mae = m.mae(T, E.PRED_BASELINE)
+    monkeypatch.setenv("MRS_TILES", "1")
+    tr = small["train"]
+    R2 = eng.ratings(*tr)          # a new rating set: the tiled layout is built on its first fit, with the cut tiles
+    m2 = E.Model(eng, R2)
+    assert np.array_equal(m2.vector(E.ITEM_AVG_DEV)[0], want)
+    assert m2.mae(T, E.PRED_BASELINE) == want_mae
+    check_model(m2, o, small["test"])
+    for h in (m2, R2):
+        h.close()

@@ -244,3 +244,31 @@ def test_tie_order_matches_the_oracle_in_both_modes(small):
     assert differ > 0
     o.set_tie_order(0)
     m.close(); R.close(); eng.close()
+
+
+@pytest.mark.parametrize("kind", ["cosine", "jaccard"])
+def test_similarity_kernel_with_several_item_phases(eng, kind):
+    """The similarity kernel keeps 16 row users x all items in shared memory; above 1,746 items the items are cut into
+    phases and the partial sums wait in the matrix between two phases.  5,000 items = three phases: same bits as the oracle,
+    both triangles (only one is computed, the other one is its copy)."""
+    from mrs_b200 import synth
+    d = synth.small(seed=77, n_users=150, n_items=5000, n_ratings=9000)
+    tr = d["train"]
+    R = eng.ratings(*tr)
+    m = E.Model(eng, R)
+    o = O.Oracle(*tr)
+    simkind = E.SIM_COSINE if kind == "cosine" else E.SIM_JACCARD
+    s = m.similarity(simkind, 0)
+    users = [int(u) for u in np.unique(tr[0])]
+    rng = np.random.default_rng(5)
+    for _ in range(400):
+        u, v = (int(x) for x in rng.choice(users, 2))
+        want = o.cosine(u, v) if kind == "cosine" else o.jaccard(u, v)
+        assert s(u, v) == want and s(v, u) == s(u, v)
+    if kind == "cosine":
+        for u in users[::15]:
+            ids, sims = s.neighbors(u, len(users))
+            oi, os_ = o.neighbors(u, len(users))
+            assert ids.tolist() == oi.tolist() and sims.tolist() == os_.tolist()
+    for h in (s, m, R):
+        h.close()
