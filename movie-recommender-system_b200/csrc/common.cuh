@@ -180,6 +180,7 @@ struct mrs_upload {
   int32_t* d_i = nullptr;
   double* d_r = nullptr;
   uint8_t* d_c = nullptr;           // compact form: half-star codes (2 x rating) instead of fp64 ratings
+  cudaEvent_t ev_items = nullptr;   // the items have arrived (they travel first: their sort runs while the users are on the link); may be null
   cudaEvent_t ev_ids = nullptr;     // users and items have arrived
   cudaEvent_t ev_values = nullptr;  // ratings have arrived
 };

@@ -17,26 +17,48 @@ namespace mrs {
 
 namespace {
 
-// passes over the raw input: id ranges (needed before the first sort) and whether every rating is a half-star code
-// (needed when the values are gathered); separate kernels because the ids arrive before the ratings (mrs_upload_begin)
-__global__ void scan_ids_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ it, int64_t n, int32_t* __restrict__ stats) {
-  // stats: [0]=max user, [1]=max item, [2]=min id
-  int32_t mu = -1, mi = -1, mn = 0x7fffffff;
+// passes over the raw input: id ranges (needed before the sorts) and whether every rating is a half-star code (needed when
+// the values are gathered); separate kernels because the items arrive before the users and the ids before the ratings
+// stats of one id array: maximum and minimum (the items travel first and are scanned while the users are still on the link)
+__global__ void scan_id_kernel(const int32_t* __restrict__ a, int64_t n, int32_t* __restrict__ max_out, int32_t* __restrict__ min_out) {
+  int32_t mx = -1, mn = 0x7fffffff;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-    int32_t a = u[p], b = it[p];
-    mu = max(mu, a);
-    mi = max(mi, b);
-    mn = min(mn, min(a, b));
+    const int32_t v = a[p];
+    mx = max(mx, v);
+    mn = min(mn, v);
   }
   for (int o = 16; o > 0; o >>= 1) {
-    mu = max(mu, __shfl_xor_sync(0xffffffffu, mu, o));
-    mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicMax(&stats[0], mu);
-    atomicMax(&stats[1], mi);
-    atomicMin(&stats[2], mn);
+    atomicMax(max_out, mx);
+    atomicMin(min_out, mn);
+  }
+}
+
+// user of every entry of the item-sorted order: the key of the second (stable) sort
+__global__ void user_keys_kernel(const int32_t* __restrict__ d_u, const int32_t* __restrict__ perm_i, int64_t n, uint32_t* __restrict__ keys) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) keys[q] = (uint32_t)d_u[perm_i[q]];
+}
+
+// sorted users + raw position of every user-major entry -> user array, item array, row pointer, duplicate count (ids only: runs
+// before the ratings have arrived)
+__global__ void scatter_users_kernel(const uint32_t* __restrict__ users, const int32_t* __restrict__ perm_u, const int32_t* __restrict__ d_i, int64_t n,
+                                     int32_t n_users, int32_t* __restrict__ coo_u, int32_t* __restrict__ ucol, int32_t* __restrict__ urow,
+                                     int32_t* __restrict__ dup_count) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t user = (int32_t)users[p], item = d_i[perm_u[p]];
+    coo_u[p] = user;
+    ucol[p] = item;
+    int32_t prev = -1;
+    if (p > 0) {
+      prev = (int32_t)users[p - 1];
+      if (prev == user && d_i[perm_u[p - 1]] == item) atomicAdd(dup_count, 2);  // (counted twice: the message halves it)
+    }
+    for (int32_t s = prev + 1; s <= user; ++s) urow[s] = (int32_t)p;
+    if (p == n - 1)
+      for (int32_t s = user + 1; s <= n_users; ++s) urow[s] = (int32_t)n;
   }
 }
 
@@ -58,39 +80,6 @@ __global__ void scan_codes_kernel(const uint8_t* __restrict__ c, int64_t n, int3
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) bad += (c[p] == 0xFF);
   for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&stats[3], bad);
-}
-
-// user-major sort key: (user << item_bits) | item -- only user_bits + item_bits key bits, so the radix sort makes
-// ceil((user_bits + item_bits) / 8) passes instead of the 7 of a (user << 32 | item) key (ncu, round 2: the two 7-pass sorts
-// were 3.1 ms of the 6.0 ms of device work in an end-to-end step at ml-25m shape)
-__global__ void make_keys_kernel(const int32_t* __restrict__ hi, const int32_t* __restrict__ lo, int64_t n, int lo_bits,
-                                 uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-    keys[p] = ((uint64_t)(uint32_t)hi[p] << lo_bits) | (uint32_t)lo[p];
-    idx[p] = (int32_t)p;
-  }
-}
-
-// sorted (major << lo_bits | minor) keys -> major array, minor array, segment pointer, duplicate count (ids only: runs
-// before the ratings have arrived)
-__global__ void scatter_ids_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t n_seg, int lo_bits, int32_t* __restrict__ major_out,
-                                   int32_t* __restrict__ minor_out, int32_t* __restrict__ seg_ptr, int32_t* __restrict__ dup_count) {
-  const uint64_t lo_mask = ((uint64_t)1 << lo_bits) - 1;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t k = keys[p];
-    int32_t major = (int32_t)(k >> lo_bits), minor = (int32_t)(k & lo_mask);
-    if (major_out) major_out[p] = major;
-    minor_out[p] = minor;
-    int32_t prev = -1;
-    if (p > 0) {
-      uint64_t kp = keys[p - 1];
-      prev = (int32_t)(kp >> lo_bits);
-      if (kp == k) atomicAdd(dup_count, 2);  // (counted twice, like the two passes of the earlier builder: the message halves it)
-    }
-    for (int32_t s = prev + 1; s <= major; ++s) seg_ptr[s] = (int32_t)p;
-    if (p == n - 1)
-      for (int32_t s = major + 1; s <= n_seg; ++s) seg_ptr[s] = (int32_t)n;
-  }
 }
 
 // item-major order from the user-major one: a STABLE sort on the item alone keeps the users of an item ascending
@@ -247,18 +236,40 @@ struct sort_buffers {
   int32_t* v2_in = nullptr;
 };
 
-// Everything that needs the ids only -- both sorts, both index structures, the duplicate check -- so that it runs while the
-// ratings are still being copied.
-int32_t sort_ids(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_t* d_i, int32_t* d_dup, sort_buffers* B) {
+// Everything that needs the ids only -- the sorts, both index structures, the duplicate check -- so that it runs while the
+// ratings are still being copied.  The user-major order (items ascending inside a user) comes from two STABLE radix sorts with
+// 32-bit keys, least significant key first: by item (sort_items: needs the items only, so it runs while the users are still
+// on the PCIe link) and then by user (sort_ids: 3 passes at ml-25m shape).  One sort on a packed (user, item) key took 5 passes
+// on 64-bit keys, all of them behind the arrival of both id arrays: 1.24 ms against 0.67 ms on the critical path of an
+// end-to-end step (ncu launch lists, profiles/r02_summary.md).
+int32_t sort_items(mrs_engine* e, mrs_ratings* R, const int32_t* d_i, sort_buffers* B) {
   cudaStream_t st = e->stream;
   const int64_t n = R->n;
-  const int block = 256;
-  const int grid = grid_for(n, block, e->sm_count);
   MRS_TRY(dev_alloc(&B->k_in, (size_t)n));
   MRS_TRY(dev_alloc(&B->k_out, (size_t)n));
   MRS_TRY(dev_alloc(&B->v_in, (size_t)n));
   MRS_TRY(dev_alloc(&B->perm_u, (size_t)n));
   MRS_TRY(dev_alloc(&B->v2_in, (size_t)n));
+  if (n == 0) return MRS_OK;
+  const int grid = grid_for(n, 256, e->sm_count);
+  const int ibits = bits_for((uint32_t)(R->n_items - 1));
+  uint32_t* k32_in = reinterpret_cast<uint32_t*>(B->k_in);   // the 64-bit buffers hold two 32-bit key arrays each
+  uint32_t* k32_out = reinterpret_cast<uint32_t*>(B->k_out);
+  item_keys_kernel<<<grid, 256, 0, st>>>(d_i, n, k32_in, B->v_in);  // key = item, payload = position in the raw input
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, k32_in, k32_out, B->v_in, B->v2_in, (int)n, 0, ibits, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k32_in, k32_out, B->v_in, B->v2_in, (int)n, 0, ibits, st);  // v2_in: raw positions, item order
+  count_launch(4);
+  MRS_CUDA(cudaGetLastError());
+  return MRS_OK;
+}
+
+int32_t sort_ids(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_t* d_i, int32_t* d_dup, sort_buffers* B) {
+  cudaStream_t st = e->stream;
+  const int64_t n = R->n;
+  const int block = 256;
+  const int grid = grid_for(n, block, e->sm_count);
   MRS_TRY(dev_alloc(&R->ucol, (size_t)n));
   MRS_TRY(dev_alloc(&R->coo_u, (size_t)n));
   MRS_TRY(dev_alloc(&R->irow, (size_t)n));
@@ -271,23 +282,25 @@ int32_t sort_ids(mrs_engine* e, mrs_ratings* R, const int32_t* d_u, const int32_
     return MRS_OK;
   }
   const int ubits = bits_for((uint32_t)(R->n_users - 1)), ibits = bits_for((uint32_t)(R->n_items - 1));
-  // ---- user-major: sort by (user, item) packed into ubits + ibits key bits; payload = position in the raw input
-  make_keys_kernel<<<grid, block, 0, st>>>(d_u, d_i, n, ibits, B->k_in, B->v_in);
-  size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, ibits + ubits, st);
-  MRS_TRY(ensure_scratch(e, tmp));
-  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, B->k_in, B->k_out, B->v_in, B->perm_u, (int)n, 0, ibits + ubits, st);
-  scatter_ids_kernel<<<grid, block, 0, st>>>(B->k_out, n, R->n_users, ibits, R->coo_u, R->ucol, R->urow, d_dup);
-  // ---- item-major: a stable sort of the user-major entries on the item alone (32-bit keys, ibits key bits: 3 passes at
-  // ml-25m shape); payload = position in the user-major arrays.  The 64-bit key buffers are reused as 32-bit ones.
   uint32_t* k32_in = reinterpret_cast<uint32_t*>(B->k_in);
   uint32_t* k32_out = reinterpret_cast<uint32_t*>(B->k_out);
+  uint32_t* ukey_in = k32_in + n;
+  uint32_t* ukey_out = k32_out + n;
+  // ---- user-major: the item-sorted entries (sort_items) sorted again, stably, by user; payload = position in the raw input
+  user_keys_kernel<<<grid, block, 0, st>>>(d_u, B->v2_in, n, ukey_in);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, ukey_in, ukey_out, B->v2_in, B->perm_u, (int)n, 0, ubits, st);
+  MRS_TRY(ensure_scratch(e, tmp));
+  cub::DeviceRadixSort::SortPairs(e->scratch, tmp, ukey_in, ukey_out, B->v2_in, B->perm_u, (int)n, 0, ubits, st);
+  scatter_users_kernel<<<grid, block, 0, st>>>(ukey_out, B->perm_u, d_i, n, R->n_users, R->coo_u, R->ucol, R->urow, d_dup);
+  // ---- item-major: a stable sort of the user-major entries on the item alone (the users of an item stay ascending);
+  // payload = position in the user-major arrays
   item_keys_kernel<<<grid, block, 0, st>>>(R->ucol, n, k32_in, B->v2_in);
   cub::DeviceRadixSort::SortPairs(nullptr, tmp, k32_in, k32_out, B->v2_in, R->csc_src, (int)n, 0, ibits, st);
   MRS_TRY(ensure_scratch(e, tmp));
   cub::DeviceRadixSort::SortPairs(e->scratch, tmp, k32_in, k32_out, B->v2_in, R->csc_src, (int)n, 0, ibits, st);
   scatter_items_kernel<<<grid, block, 0, st>>>(k32_out, R->csc_src, R->coo_u, n, R->n_items, R->irow, R->icolp);
-  count_launch(12);
+  count_launch(10);
   MRS_CUDA(cudaGetLastError());
   return MRS_OK;
 }
@@ -326,6 +339,7 @@ void free_upload(mrs_upload* up) {
   use_engine(up->eng);
   if (up->ev_values) cudaEventSynchronize(up->ev_values);  // the copies read host memory and write these buffers
   dev_free(up->d_u); dev_free(up->d_i); dev_free(up->d_r); dev_free(up->d_c);
+  if (up->ev_items) cudaEventDestroy(up->ev_items);
   if (up->ev_ids) cudaEventDestroy(up->ev_ids);
   if (up->ev_values) cudaEventDestroy(up->ev_values);
   delete up;
@@ -348,14 +362,15 @@ int32_t upload_begin(mrs_engine* e, const int32_t* users, const int32_t* items, 
   if (rc == MRS_OK && codes) rc = dev_alloc(&up->d_c, (size_t)n + 16);
   cudaError_t ce = cudaSuccess;
   if (rc == MRS_OK) ce = cudaEventCreateWithFlags(&up->ev_ids, cudaEventDisableTiming);
+  if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventCreateWithFlags(&up->ev_items, cudaEventDisableTiming);
   if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventCreateWithFlags(&up->ev_values, cudaEventDisableTiming);
   // the staging buffers may be recycled blocks: stay behind whatever the compute stream still has queued on them
   if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(e->ev_order, e->stream);
   if (rc == MRS_OK && ce == cudaSuccess) ce = cudaStreamWaitEvent(e->copy_stream, e->ev_order, 0);
-  if (rc == MRS_OK && ce == cudaSuccess && n) {
-    ce = cudaMemcpyAsync(up->d_u, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->copy_stream);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(up->d_i, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->copy_stream);
-  }
+  // the items travel first: they are the least significant sort key, and their sort runs while the users follow
+  if (rc == MRS_OK && ce == cudaSuccess && n) ce = cudaMemcpyAsync(up->d_i, items, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->copy_stream);
+  if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(up->ev_items, e->copy_stream);
+  if (rc == MRS_OK && ce == cudaSuccess && n) ce = cudaMemcpyAsync(up->d_u, users, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->copy_stream);
   if (rc == MRS_OK && ce == cudaSuccess) ce = cudaEventRecord(up->ev_ids, e->copy_stream);
   if (rc == MRS_OK && ce == cudaSuccess && n && !codes) ce = cudaMemcpyAsync(up->d_r, ratings, sizeof(double) * n, cudaMemcpyHostToDevice, e->copy_stream);
   if (rc == MRS_OK && ce == cudaSuccess && n && codes) ce = cudaMemcpyAsync(up->d_c, codes, (size_t)n, cudaMemcpyHostToDevice, e->copy_stream);
@@ -387,9 +402,10 @@ int32_t ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items
     return code;
   };
   cudaError_t ce = cudaMemcpyAsync(d_stats, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, st);
-  if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, up->ev_ids, 0);
+  // ---- the items (they arrive first): id range, then their sort -- enqueued before we wait for the users
+  if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, up->ev_items ? up->ev_items : up->ev_ids, 0);
   if (ce == cudaSuccess && n) {
-    scan_ids_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_u, up->d_i, n, d_stats);
+    scan_id_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_i, n, d_stats + 1, d_stats + 2);
     count_launch();
   }
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_stats, d_stats, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
@@ -402,10 +418,26 @@ int32_t ratings_from_upload(mrs_upload* up, int32_t n_users_dim, int32_t n_items
   R = new mrs_ratings();
   R->eng = e;
   R->n = n;
-  R->n_users = std::max(n_users_dim, h_stats[0] + 1);
   R->n_items = std::max(n_items_dim, h_stats[1] + 1);
-  if (R->n_users < 1) R->n_users = 1;
   if (R->n_items < 1) R->n_items = 1;
+  R->n_users = 1;
+  s = sort_items(e, R, up->d_i, &B);
+  if (s != MRS_OK) return fail(s);
+  // ---- the users
+  ce = cudaStreamWaitEvent(st, up->ev_ids, 0);
+  if (ce == cudaSuccess && n) {
+    scan_id_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(up->d_u, n, d_stats, d_stats + 2);
+    count_launch();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_stats, d_stats, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { set_error("mrs_ratings_from_coo: %s", cudaGetErrorString(ce)); return fail(MRS_ERR_CUDA); }
+  if (n && h_stats[2] < 0) {
+    set_error("mrs_ratings_from_coo: negative user or item id (%d)", h_stats[2]);
+    return fail(MRS_ERR_INVALID);
+  }
+  R->n_users = std::max(n_users_dim, h_stats[0] + 1);
+  if (R->n_users < 1) R->n_users = 1;
   int32_t* d_dup = d_stats + 4;
   s = sort_ids(e, R, up->d_u, up->d_i, d_dup, &B);  // enqueued before we wait for the ratings
   if (s != MRS_OK) return fail(s);
