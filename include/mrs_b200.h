@@ -166,6 +166,11 @@ MRS_API int32_t mrs_fit(mrs_engine* e, const mrs_ratings* train, mrs_model** out
 MRS_API int32_t mrs_fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
 /* single-GPU asynchronous fit: mrs_fit_local and mrs_fit_finish fused (no exchange step, one kernel fewer) */
 MRS_API int32_t mrs_fit_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
+/* Users-only refit of an existing, fitted model of `train` (asynchronous): the user averages and the global average, which is
+ * all that predictor(ratings, weightedSumDeviation(...)) takes from the fit (P:557-586, P:489-549).  The per-item average
+ * deviation keeps the values of the last full fit (a model's train set never changes).  This is the fit of the timed kNN
+ * closure (predict/kNN.scala:42-45). */
+MRS_API int32_t mrs_fit_users_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
 /* The exchange buffer written by mrs_fit_local: n_doubles = 3*I+2 fp64 values on the device (I = item table size),
  * [ sum of deviations per item | count per item | sum of all ratings | count | sum of ratings per item ].
  * A sharded run all-reduces (sum) it across ranks between mrs_fit_local and mrs_fit_finish: this is the one

@@ -110,6 +110,28 @@ __global__ void __launch_bounds__(256) user_sum_kernel(const uint8_t* __restrict
   tl_end(tl, 0);
 }
 
+// Users-only refit (mrs_fit_users_async): user averages and the global average from K1's integer sums, in the item pass'
+// own words (one correctly rounded division per user, -1.0 = no ratings, P:222); re-arms the sums for the next K1.
+__global__ void __launch_bounds__(256) user_avg_kernel(uint32_t* __restrict__ usum, const int32_t* __restrict__ urow, int32_t n_users,
+                                                      unsigned long long* __restrict__ k1_part, double n_total, double* __restrict__ uavg,
+                                                      double* __restrict__ gavg, double* __restrict__ xbuf_tail) {
+  pdl_trigger();
+  pdl_wait();  // K1's sums are complete
+  for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users; u += gridDim.x * blockDim.x) {
+    const uint32_t S = usum[u];
+    const uint32_t cnt = (uint32_t)(urow[u + 1] - urow[u]);
+    usum[u] = 0;
+    uavg[u] = cnt ? (0.5 * (double)S) / (double)cnt : -1.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
+    k1_part[0] = 0; k1_part[1] = 0; k1_part[2] = 0;
+    xbuf_tail[0] = gs;
+    xbuf_tail[1] = n_total;
+    gavg[0] = n_total > 0.0 ? gs / n_total : 0.0;  // P:18 mean of an empty Seq is 0.0
+  }
+}
+
 // ---- K1b: per-user average (-1.0 sentinel for users without ratings) + global rating sum / count
 __global__ void __launch_bounds__(256) user_finalize_kernel(const int32_t* __restrict__ urow, const int32_t* __restrict__ seg_chunk_ptr,
                                                            const double* __restrict__ upart, int32_t n_users,
@@ -496,6 +518,28 @@ int32_t fit_local(mrs_engine* e, const mrs_ratings* R, mrs_model** inout, bool f
   MRS_REQUIRE(!push, MRS_ERR_UNSUPPORTED, "mrs_fit_local_push: the fused exchange needs a half-star coded rating set");
   MRS_TRY(launch_fit_local<double>(e, R, m));
   if (fused_finalize) return fit_finish(m);
+  return MRS_OK;
+}
+
+// Users-only refit of an existing model: what the personalized / kNN predictors need from the fit (P:557-586 uses the user
+// averages and the global average; the per-item average deviation belongs to the baseline predictor only and keeps the
+// values of the last full fit -- the train set of a model never changes).  Two small kernels instead of the three of a
+// full fit.
+int32_t fit_users(mrs_engine* e, const mrs_ratings* R, mrs_model** inout) {
+  MRS_REQUIRE(e && R && inout && *inout, MRS_ERR_INVALID, "mrs_fit_users_async: NULL argument (pass a fitted model of this train set)");
+  mrs_model* m = *inout;
+  MRS_REQUIRE(m->train == R && m->finished, MRS_ERR_INVALID, "mrs_fit_users_async: the model must have been fitted on this rating set");
+  if (R->value_kind != kValueCode || R->n == 0) return fit_local(e, R, inout, true, nullptr, false);  // fp64-valued sets: the full fit
+  use_engine(e);
+  m->host_valid = false;
+  user_sum_kernel<<<m->k1_blocks, 256, 0, e->stream>>>(R->uval16, R->vec_row, R->n_vec, m->usum, m->k1_part, e->d_timeline, 0);
+  mark(e, "user_sum");
+  MRS_CUDA(cudaGetLastError());
+  const int grid = std::max(1, std::min((R->n_users + 255) / 256, e->sm_count * 4));
+  MRS_CUDA(launch_pdl(user_avg_kernel, dim3(grid), dim3(256), 0, e->stream, m->usum, R->urow, R->n_users, m->k1_part, (double)R->n, m->uavg, m->gavg,
+                      m->xbuf + 2 * (size_t)R->n_items));
+  mark(e, "user_avg");
+  MRS_CUDA(cudaGetLastError());
   return MRS_OK;
 }
 

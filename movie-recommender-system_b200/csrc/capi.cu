@@ -324,6 +324,7 @@ extern "C" int32_t mrs_profile_end(mrs_engine* e, char* names_out, int64_t names
 // ------------------------------------------------------------------ fit
 extern "C" int32_t mrs_fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout) { return fit_local(e, train, inout, false); }
 extern "C" int32_t mrs_fit_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout) { return fit_local(e, train, inout, true); }
+extern "C" int32_t mrs_fit_users_async(mrs_engine* e, const mrs_ratings* train, mrs_model** inout) { return fit_users(e, train, inout); }
 extern "C" int32_t mrs_fit_finish(mrs_model* m) { return fit_finish(m); }
 
 extern "C" int32_t mrs_fit(mrs_engine* e, const mrs_ratings* train, mrs_model** out) {

@@ -417,6 +417,7 @@ int32_t launch_mae_tiled_baseline(const mrs_model* m, const mrs_ratings* T, doub
                                   const PushDev* big = nullptr, bool deliver = true);
 // baseline.cu
 int32_t fit_local(mrs_engine* e, const mrs_ratings* train, mrs_model** inout, bool fused_finalize, const PushDev* push = nullptr, bool no_finalize = false);
+int32_t fit_users(mrs_engine* e, const mrs_ratings* train, mrs_model** inout);
 int32_t fit_finish(mrs_model* m);
 int32_t mae_baseline_async(const mrs_model* m, int32_t pred_kind, const mrs_ratings* test, double* d_out2);
 int32_t predict_baseline_async(const mrs_model* m, int32_t pred_kind, const int32_t* d_users, const int32_t* d_items,

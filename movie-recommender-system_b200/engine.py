@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "MRS_ERR_INVALID", -2: "MRS_ERR_CUDA", -3: "MRS_ERR_NOMEM", -4:
 EXPORTS = [
     "mrs_last_error", "mrs_version", "mrs_launch_count", "mrs_engine_create", "mrs_engine_destroy", "mrs_engine_sync", "mrs_debug_timeline", "mrs_debug_cta_stamps", "mrs_debug_warp_stamps", "mrs_debug_fp64_fma_per_s",
     "mrs_graph_begin", "mrs_graph_end", "mrs_graph_launch", "mrs_graph_destroy", "mrs_profile_begin", "mrs_profile_end", "mrs_upload_begin", "mrs_upload_begin_codes", "mrs_ratings_from_coo_codes", "mrs_ratings_from_upload", "mrs_upload_destroy", "mrs_ratings_from_coo", "mrs_ratings_from_file", "mrs_ratings_from_text", "mrs_ratings_info", "mrs_ratings_bytes", "mrs_ratings_layout_info", "mrs_ratings_destroy",
-    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_connect_local", "mrs_multi_create", "mrs_multi_load", "mrs_multi_baseline_mae", "mrs_multi_model", "mrs_multi_owner", "mrs_multi_destroy", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_fit_local_push", "mrs_fit_finish_pull", "mrs_mae_push_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
+    "mrs_fit", "mrs_fit_local", "mrs_fit_async", "mrs_fit_users_async", "mrs_model_set_item_averages", "mrs_model_exchange_buffer", "mrs_fit_finish", "mrs_model_destroy", "mrs_exchange_create", "mrs_exchange_connect", "mrs_exchange_connect_local", "mrs_multi_create", "mrs_multi_load", "mrs_multi_baseline_mae", "mrs_multi_model", "mrs_multi_owner", "mrs_multi_destroy", "mrs_exchange_allreduce_async", "mrs_exchange_allreduce_indexed_async", "mrs_fit_local_push", "mrs_fit_finish_pull", "mrs_mae_push_async", "mrs_exchange_status", "mrs_exchange_set_timeout_ms", "mrs_exchange_stamps", "mrs_exchange_destroy",
     "mrs_model_scalar",
     "mrs_model_lookup", "mrs_model_vector", "mrs_fit_similarity", "mrs_fit_similarity_async", "mrs_fit_similarity_rows_async", "mrs_model_set_tie_order", "mrs_sim_set_k",
     "mrs_similarity", "mrs_neighbors", "mrs_sim_entry_values", "mrs_sim_destroy", "mrs_predict", "mrs_mae",
@@ -96,6 +96,7 @@ def lib():
         "mrs_fit": (i32, [vp, vp, P(vp)]),
         "mrs_fit_local": (i32, [vp, vp, P(vp)]),
         "mrs_fit_async": (i32, [vp, vp, P(vp)]),
+        "mrs_fit_users_async": (i32, [vp, vp, P(vp)]),
         "mrs_model_set_item_averages": (i32, [vp, i32]),
         "mrs_model_exchange_buffer": (i32, [vp, P(vp), P(i64)]),
         "mrs_fit_finish": (i32, [vp]),
@@ -432,6 +433,11 @@ class Model:
         _check(lib().mrs_fit_local(self.engine._h, self.train._h, C.byref(self._h)))
         between(*self.exchange_buffer())
         _check(lib().mrs_fit_finish(self._h))
+
+    def refit_users(self):
+        """Enqueue a users-only refit (user averages + global average): what the personalized / kNN predictors take from
+        the fit (P:557-586); the per-item average deviations keep the values of the last full fit."""
+        _check(lib().mrs_fit_users_async(self.engine._h, self.train._h, C.byref(self._h)))
 
     def set_item_averages(self, enabled):
         """Per-item rating averages are not needed by the baseline predictor; switching them off saves work in the fit."""

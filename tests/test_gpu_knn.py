@@ -272,3 +272,26 @@ def test_similarity_kernel_with_several_item_phases(eng, kind):
             assert ids.tolist() == oi.tolist() and sims.tolist() == os_.tolist()
     for h in (s, m, R):
         h.close()
+
+
+def test_users_only_refit_is_the_fit_of_the_knn_closure(eng, ml100k):
+    """mrs_fit_users_async: user averages and global average bit-identical to the full fit, item deviations untouched, and the
+    kNN MAE after a users-only refit equal to the one after a full refit (P:557-586 never reads the item deviations)."""
+    tr, te = ml100k["train"], ml100k["test"]
+    R, T = eng.ratings(*tr), eng.ratings(*te)
+    m = E.Model(eng, R)
+    ua, idev, g = m.vector(E.USER_AVG)[0].copy(), m.vector(E.ITEM_AVG_DEV)[0].copy(), m.global_avg
+    s = m.similarity(E.SIM_COSINE, 30)
+    want = m.mae(T, E.PRED_PERSONALIZED, s)
+    for _ in range(3):          # K1's sums are re-armed by the users-only kernel: repeated refits stay exact
+        m.refit_users()
+    s.refit(30)
+    eng.sync()
+    assert np.array_equal(m.vector(E.USER_AVG)[0], ua) and m.global_avg == g
+    assert np.array_equal(m.vector(E.ITEM_AVG_DEV)[0], idev)
+    assert m.mae(T, E.PRED_PERSONALIZED, s) == want
+    m.refit(); eng.sync()        # and a full fit after it finds its accumulators armed
+    assert np.array_equal(m.vector(E.ITEM_AVG_DEV)[0], idev) and np.array_equal(m.vector(E.USER_AVG)[0], ua)
+    assert m.mae(T, E.PRED_BASELINE) == pytest.approx(O.Oracle(*tr).mae(te, kind=O.BASELINE), rel=1e-6)
+    for h in (s, m, T, R):
+        h.close()

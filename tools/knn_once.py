@@ -8,13 +8,14 @@ import numpy as np, torch
 import mrs_b200
 from mrs_b200 import engine as E, synth
 d = synth.cached("ml100k")
-eng = E.Engine(0)
+stream = torch.cuda.Stream()
+eng = E.Engine(0, stream=stream.cuda_stream)
 R, T = eng.ratings(*d["train"]), eng.ratings(*d["test"])
 m = E.Model(eng, R)
 s = m.similarity(E.SIM_COSINE, 300)
 out2 = torch.zeros(2, dtype=torch.float64, device="cuda")
 def closure():
-    m.refit(); s.refit(300); m.mae_async(T, out2.data_ptr(), E.PRED_PERSONALIZED, s)
+    (m.refit() if os.environ.get("FULL_FIT") else m.refit_users()); s.refit(300); m.mae_async(T, out2.data_ptr(), E.PRED_PERSONALIZED, s)
 for _ in range(int(os.environ.get("REPS", "3"))):
     closure()
 torch.cuda.synchronize()
@@ -28,7 +29,7 @@ if not os.environ.get("NO_TIMING"):
     g = eng.capture(closure); g.launch(); torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
     for a, b in ev:
-        a.record(); g.launch(); b.record()
+        a.record(stream); g.launch(); b.record(stream)
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     print(f"closure (graph replay): median {1e3 * ms[len(ms) // 2]:.1f} us, min {1e3 * ms[0]:.1f} us")
