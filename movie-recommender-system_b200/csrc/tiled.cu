@@ -1,20 +1,23 @@
 // tiled.cu -- the item-deviation pass of the fit (P:155-186 / P:316-343) on a layout made for B200:
 //
-//   * users are cut into tiles of kTileUsers; a CTA stages the tile's fp64 user averages in shared memory
-//     (64 KB), so the 20 M random 8-byte gathers of the pass hit shared-memory banks instead of L2 sectors
-//     (capture A: 640 MB of L2 sector traffic, L1 hit rate 11 %);
+//   * users are cut into tiles of at most kTileCap users; a CTA builds the tile's 8-byte user records in shared memory
+//     (128 KB) from K1's integer code sums and the row pointer, so the 20 M random 8-byte gathers of the pass hit
+//     shared-memory banks instead of L2 sectors (first capture: 640 MB of L2 sector traffic, L1 hit rate 11 %);
 //   * inside a tile the entries are item-major; every (tile, item) segment is cut into units of <= kUnitLen
 //     entries, units are sorted by length and packed 32 to a "slice" in sliced-ELL order (entry j of lane l at
-//     row j, column l), so a warp streams a slice with one coalesced 128-byte load per row and every lane
-//     accumulates ITS unit sequentially: no cross-lane reduction, no atomics, a fixed summation order;
-//   * an entry is 4 bytes: valid bit | half-star code | 16-bit user id local to the tile.
+//     row j, column l); a warp streams a run of 128-byte rows through its own TMA ring (cp.async.bulk + mbarrier) and
+//     every lane accumulates ITS unit sequentially: no cross-lane reduction, a fixed summation order inside a unit;
+//   * an entry is 4 bytes.  Form 1 (every code <= kAlphaMaxCode): the top 15 bits of the fp64 number (code - 2)/8 and the
+//     byte offset of the user's record; form 0: valid bit | half-star code | local user.
 //
-// The finalisation kernel adds the units of an item in (tile, sub-chunk) order, so the pass is bit-reproducible.
-// Deviation = (r - avg) * (1 / scale): the two possible reciprocals of a user, 1/(5-avg) and 1/(avg-1), are computed
-// once per user with a correctly rounded division (user_avg_kernel) and staged in shared memory next to the average,
-// so the inner loop has no division.  d * fl(1/s) differs from the reference's fl(d / s) by <= 1 ulp -- far inside
-// the 1e-6 parity bound; the kNN path, whose neighbour ranking needs the exact bits, computes its own deviations
-// with a true division (knn.cu).
+// Deviation = N / D with N = c*code - S and D = 10c - S (N > 0) or S - 2c (N < 0): two exact small integers formed in
+// fp64 from the entry and the record (S = the user's code sum, c = rating count), one hardware reciprocal seed refined by
+// three DFMA, ONE rounding -- within 2 ulp of the reference's three (average, difference, quotient), far inside the 1e-6
+// parity bound; r > avg <=> N > 0 exactly, so the branch of scale() is the reference's.  The kNN path, whose neighbour
+// ranking needs the exact bits, computes its own deviations with true divisions (knn.cu).
+// Unit sums are handed over as integer atomics on a 2^-40 grid: exact, so the per-item sums do not depend on the order
+// in which warps, CTAs or ranks deliver them and the pass is bit-reproducible.  The rows of a tile are cut over its warps
+// at row granularity by a static partition laid down with the layout (item_partition_kernel).
 #include <cub/cub.cuh>
 
 #include <algorithm>
