@@ -2,7 +2,8 @@
 // and sorted COO.  Replaces `load(...).collect()` materialisation (P:35-49).  Not on the timed hot path of the
 // reference either (predict/Baseline.scala:40-42 load before timing); it is inside bench.py's e2e figure.
 //
-// The two sorts use cub::DeviceRadixSort (library code, like calling cuBLAS); everything else is ours.
+// The three stable sorts (by item, by user, and by item again for the item-major order) use cub::DeviceRadixSort (library
+// code, like calling cuBLAS); everything else is ours.
 #include <cub/cub.cuh>
 
 #include <algorithm>
