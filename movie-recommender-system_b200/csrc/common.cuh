@@ -112,6 +112,16 @@ struct PushDev {
 __device__ __forceinline__ double* push_slot(const PushDev& x, int p, int parity, int from) {
   return x.peer[p] + x.recv_off + ((size_t)parity * x.world + from) * x.cap;
 }
+// q-th destination of this rank's deliveries: the ranks start with their own successor and go round, so that the stores of
+// all ranks do not converge on one NVSwitch port at a time (with p = 0, 1, ... every rank writes to rank 0 first)
+__device__ __forceinline__ int push_peer(const PushDev& x, int q) {
+#ifdef MRS_PUSH_NOROTATE
+  return q;
+#else
+  const int p = x.rank + 1 + q;
+  return p >= x.world ? p - x.world : p;
+#endif
+}
 __device__ __forceinline__ void push_flag_raise(const PushDev& x, int p, unsigned long long epoch) {
   unsigned long long* f = reinterpret_cast<unsigned long long*>(x.peer[p]) + x.flag_off + x.rank;
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");

@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(kMaeThreads, 1) predict_mae_tiled_kernel(const
       const double ds = (double)__ldcg(fix + i) * kInvFix;
       fix_other[i] = 0;  // re-arm the buffer of the NEXT pass
       const double cnt = (double)(__ldg(f.icolp + i + 1) - __ldg(f.icolp + i));
-      for (int p = 0; p < x2.world; ++p) {
-        double* slot = push_slot(x2, p, xpar, x2.rank);
+      for (int q = 0; q < x2.world; ++q) {
+        double* slot = push_slot(x2, push_peer(x2, q), xpar, x2.rank);
         slot[j] = ds;
         slot[(size_t)K + j] = cnt;
       }

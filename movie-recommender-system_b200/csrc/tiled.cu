@@ -625,8 +625,8 @@ __global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restr
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double gs = 0.5 * (double)k1_part[0];  // integer sum of codes: exact, order independent
     k1_part[0] = 0; k1_part[1] = 0; k1_part[2] = 0;  // re-arm the sum and the hand-over counts for the next pass
-    for (int p = 0; p < x.world; ++p) {
-      double* slot = push_slot(x, p, parity, x.rank);
+    for (int q = 0; q < x.world; ++q) {
+      double* slot = push_slot(x, push_peer(x, q), parity, x.rank);
       slot[2 * (size_t)K] = gs;
       slot[2 * (size_t)K + 1] = n_total;
     }
@@ -637,8 +637,8 @@ __global__ void __launch_bounds__(256) item_tiled_push_kernel(long long* __restr
     const double ds = (double)xdev_fix[i] * (1.0 / kFixScale);
     xdev_fix[i] = 0;  // re-arm (items known on no rank never leave zero)
     const double cnt = (double)(__ldg(icolp + i + 1) - __ldg(icolp + i));
-    for (int p = 0; p < x.world; ++p) {
-      double* slot = push_slot(x, p, parity, x.rank);
+    for (int q = 0; q < x.world; ++q) {  // every rank starts with its own successor: no port of the switch takes all senders at once
+      double* slot = push_slot(x, push_peer(x, q), parity, x.rank);
       slot[j] = ds;
       slot[(size_t)K + j] = cnt;
     }
