@@ -545,7 +545,7 @@ template <typename VT, int SIMMODE>
 __global__ void __launch_bounds__(256) pers_mae_kernel(const int32_t* __restrict__ tu, const int32_t* __restrict__ ti,
                                                       const VT* __restrict__ tv, int64_t n, int32_t n_users, int32_t n_items,
                                                       const double* __restrict__ uavg, const double* __restrict__ gavg_p,
-                                                      const int32_t* __restrict__ icolp, const int32_t* __restrict__ irow,
+                                                      const int32_t* __restrict__ icolp, const int32_t* __restrict__ ccd,
                                                       const double* __restrict__ cdev, const int32_t* __restrict__ cidx,
                                                       const double* __restrict__ S, const int32_t* __restrict__ rank,
                                                       int32_t n_known, int32_t k, double* __restrict__ part,
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256) pers_mae_kernel(const int32_t* __restrict
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   double acc = 0.0;  // identical in every lane of the warp
   for (int64_t q = blockIdx.x * (int64_t)wpb + wid; q < n; q += (int64_t)gridDim.x * wpb) {
-    const double pr = predict_pair<SIMMODE>(tu[q], ti[q], lane, n_users, n_items, uavg, gavg, icolp, irow, cdev, cidx, S, rank, n_known, k);
+    const double pr = predict_pair<SIMMODE>(tu[q], ti[q], lane, n_users, n_items, uavg, gavg, icolp, ccd, cdev, cidx, S, rank, n_known, k);
     acc += fabs(decode_value(tv[q]) - pr);  // P:71
   }
   if (lane == 0) sh[wid] = acc;
@@ -592,14 +592,14 @@ template <int SIMMODE, bool WSD>
 __global__ void __launch_bounds__(256) pers_pairs_kernel(const int32_t* __restrict__ us, const int32_t* __restrict__ is, int64_t n,
                                                         int32_t n_users, int32_t n_items, const double* __restrict__ uavg,
                                                         const double* __restrict__ gavg_p, const int32_t* __restrict__ icolp,
-                                                        const int32_t* __restrict__ irow, const double* __restrict__ cdev,
+                                                        const int32_t* __restrict__ ccd, const double* __restrict__ cdev,
                                                         const int32_t* __restrict__ cidx, const double* __restrict__ S,
                                                         const int32_t* __restrict__ rank, int32_t n_known, int32_t k,
                                                         double* __restrict__ out) {
   const double gavg = gavg_p[0];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (int64_t q = blockIdx.x * (int64_t)wpb + wid; q < n; q += (int64_t)gridDim.x * wpb) {
-    const double pr = predict_pair<SIMMODE, WSD>(us[q], is[q], lane, n_users, n_items, uavg, gavg, icolp, irow, cdev, cidx, S, rank, n_known, k);
+    const double pr = predict_pair<SIMMODE, WSD>(us[q], is[q], lane, n_users, n_items, uavg, gavg, icolp, ccd, cdev, cidx, S, rank, n_known, k);
     if (lane == 0) out[q] = pr;
   }
 }
