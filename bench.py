@@ -380,6 +380,12 @@ def run_ours(args):
         "kernel_ms": per_kernel[dom], "per_kernel_ms": per_kernel,
         "step": {"algorithmic_bytes": alg_total, "achieved": alg_total / (step_ms_mean * 1e-3) / 1e9,
                  "frac": alg_total / (step_ms_mean * 1e-3) / 1e9 / peak},
+        # SURVEY 8(d) "also report test-only": the test pass alone (predict + |error| + reduction over this rank's test ratings)
+        "test_only": ({"ratings_per_s": float(te[0].size) / (per_kernel["predict_mae_tiled"] * 1e-3), "kernel": "predict_mae_tiled",
+                       "kernel_ms": per_kernel["predict_mae_tiled"], "algorithmic_bytes_per_launch": alg["predict_mae_tiled"],
+                       "achieved": alg["predict_mae_tiled"] / (per_kernel["predict_mae_tiled"] * 1e-3) / 1e9,
+                       "frac": alg["predict_mae_tiled"] / (per_kernel["predict_mae_tiled"] * 1e-3) / 1e9 / peak}
+                      if per_kernel.get("predict_mae_tiled") else None),
     }
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + layout build + fit + MAE + D2H per step
@@ -690,7 +696,14 @@ def bench_knn(eng, stream, torch):
                          "peak_source": "measured in this run (mrs_debug_fp64_fma_per_s: 8 DFMA chains per thread, all SMs)"},
                 "peak_source": "148 SMs x 1.965 GHz x 1 wavefront per clock (ncu: l1tex__data_pipe_lsu_wavefronts, profiles/r02_ncu_knn_similarity.txt)",
                 "traffic": None}
-    return {"roofline": knn_roof, "metric": "knn_k300_ml100k_fit_predict_mae_ms", "value": statistics.median(ms), "unit": "ms", "min_ms": min(ms),
+    # SURVEY 8(d) work counts of the closure: similarity products, keys ranked, prediction gathers, compulsory bytes
+    n_known = int((cnt_u > 0).sum())
+    ti_ok = te[1][te[1] < cnt_i.size]
+    knn_work = {"similarity_products_sparse": useful, "similarity_products_dense": float(n_known) ** 2 * float(cnt_i.size),
+                "similarity_products_executed": executed, "topk_keys": float(n_known) * float(n_known - 1),
+                "predict_gathers": float(cnt_i[ti_ok].sum()),
+                "compulsory_bytes": 12.0 * float(tr[0].size) + 12.0 * float(te[0].size) + 12.0 * float(n_known) * 300.0}
+    return {"roofline": knn_roof, "work": knn_work, "metric": "knn_k300_ml100k_fit_predict_mae_ms", "value": statistics.median(ms), "unit": "ms", "min_ms": min(ms),
             "mean_ms": sum(ms) / len(ms), "reps": reps, "launch_mode": mode, "mae": mae, "per_kernel_ms": per_kernel,
             "closure": "mrs_fit_users_async (user + global averages: all that predictor/weightedSumDeviation read from the fit, P:489-586) -> "
                        "mrs_fit_similarity_async(cosine, k=300) -> mrs_mae_async(PERSONALIZED)",
