@@ -694,7 +694,7 @@ def bench_knn(eng, stream, torch):
                 "kernel_ms": per_kernel.get("similarity"),
                 "fp64": {"achieved_macs_per_s": executed / sim_s if sim_s else None, "peak": fp64,
                          "peak_source": "measured in this run (mrs_debug_fp64_fma_per_s: 8 DFMA chains per thread, all SMs)"},
-                "peak_source": "148 SMs x 1.965 GHz x 1 wavefront per clock (ncu: l1tex__data_pipe_lsu_wavefronts, profiles/r02_ncu_knn_similarity.txt)",
+                "peak_source": "148 SMs x 1.965 GHz x 1 wavefront per clock (ncu: l1tex__data_pipe_lsu_wavefronts, profiles/r02_ncu_summary_knn.txt)",
                 "traffic": None}
     # SURVEY 8(d) work counts of the closure: similarity products, keys ranked, prediction gathers, compulsory bytes
     n_known = int((cnt_u > 0).sum())
